@@ -1,0 +1,145 @@
+/*
+ * kektordb_gpu.h — C ABI of the B200 (sm_100a) vector-search hot path for KektorDB.
+ *
+ * This header is the drop-in boundary: what the Go host binds through cgo
+ * (`//go:build cuda`), next to the existing native header
+ * native/compute/include/kektordb_compute.h:8-11 whose conventions it keeps:
+ * plain C, borrowed pointers valid for the call only, no exceptions across the
+ * boundary, int return (0 = ok, <0 = error), caller owns every buffer it passes,
+ * the library owns device memory behind the opaque handle.
+ *
+ * Every entry point cites the reference interface it stands in for (paths relative
+ * to the reference tree).  ids are the reference's internal ids: uint32, 0 reserved
+ * (pkg/core/hnsw/hnsw_index.go:590).  Scores are the raw float64 distances the
+ * reference returns (types.SearchResult{DocID uint32; Score float64},
+ * pkg/core/types/types.go:11-14): squared L2, or 1 - dot on unit vectors.
+ *
+ * There is no CPU fallback: without a CUDA device every call fails with
+ * KDBGPU_ERR_CUDA and kdbgpu_last_error() says why.
+ */
+#ifndef KEKTORDB_GPU_H
+#define KEKTORDB_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDBGPU_OK 0
+#define KDBGPU_ERR_INVALID (-1)  /* bad argument                                   */
+#define KDBGPU_ERR_CUDA (-2)     /* CUDA runtime / no device                       */
+#define KDBGPU_ERR_NOMEM (-3)    /* device or host allocation failed               */
+#define KDBGPU_ERR_STATE (-4)    /* call order (e.g. search before graph upload)   */
+#define KDBGPU_ERR_OVERFLOW (-5) /* a per-query candidate heap exceeded its bound  */
+
+/* distance.DistanceMetric (pkg/core/distance/distance_go.go:34-39) */
+#define KDBGPU_METRIC_L2 0     /* "euclidean": squared, no sqrt (:57-68) */
+#define KDBGPU_METRIC_COSINE 1 /* "cosine": 1 - dot on unit vectors (:122-128) */
+
+typedef struct kdbgpu_index kdbgpu_index;
+
+/* Exact per-batch counters, for the roofline accounting of SURVEY.md §8(d). */
+typedef struct {
+  uint64_t dist_evals; /* E: query x stored-vector distance evaluations            */
+  uint64_t hops;       /* H: candidate expansions (adjacency rows read)            */
+  uint64_t hops_l0;    /* of which on level 0 (rows of 2M ids; the rest M ids)      */
+  float kernel_ms;     /* device time of the traversal kernel(s), CUDA events      */
+  float total_ms;      /* device time of the whole call incl. H2D / D2H copies     */
+} kdbgpu_stats;
+
+/* ---- library ---------------------------------------------------------------------- */
+int kdbgpu_device_count(void);
+/* Message of the last failing call on this thread ("" if none).  Never NULL. */
+const char *kdbgpu_last_error(void);
+/* "kektordb_gpu <version> sm_100a" */
+const char *kdbgpu_version(void);
+
+/* ---- lifecycle: stands in for hnsw.New / Index.Close (hnsw_index.go:138, :3533) ------ */
+/* One handle mirrors one hnsw.Index on one GPU.  m is the index's M (mMax0 = 2*m, :149),
+ * capacity the highest internal id the mirror can hold. */
+int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacity, kdbgpu_index **out);
+int kdbgpu_index_destroy(kdbgpu_index *);
+
+/* ---- staging: the GPU mirror of Index.nodes / Node.vec (hnsw_node.go:13-39) ----------- */
+/* Rows exactly as the reference stores them (already unit-normalised for cosine,
+ * hnsw_index.go:485-493); row i is internal id first_id + i.  Source of the bytes in the
+ * reference: VectorArena.GetBytes (pkg/storage/mmap/arena.go:378). */
+int kdbgpu_upload_vectors(kdbgpu_index *, uint32_t first_id, uint32_t count, const float *rows);
+/* Same, from device memory on the handle's device (row_stride in floats). */
+int kdbgpu_upload_vectors_device(kdbgpu_index *, uint32_t first_id, uint32_t count, const float *d_rows,
+                                 size_t row_stride);
+/* Topology snapshot (what SnapshotData() exposes, hnsw_index.go:3064): n = nodeCounter;
+ * levels[i] = len(Connections)-1 of node i or -1 for a nil slot; node i owns rows
+ * node_row[i] .. node_row[i+1]-1 (level 0 first); row r lists nbrs[row_off[r] .. row_off[r+1]-1]
+ * in the reference's order.  entry / max_level = entrypointID / maxLevel. */
+int kdbgpu_set_graph(kdbgpu_index *, uint32_t n, const int32_t *levels, const uint64_t *node_row,
+                     const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level);
+/* Node.Deleted flags as a dense bitset over ids (bit i of word i/64); NULL clears all. */
+int kdbgpu_set_deleted(kdbgpu_index *, const uint64_t *bitset, size_t words);
+
+/* ---- query: stands in for (*Index).SearchWithScores (hnsw_index.go:343-468) ----------- */
+/* nq independent searches in one call (the Go shim's micro-batcher forms the batch).
+ *   queries   [nq][dim] raw float32; for cosine the library normalises a copy exactly as
+ *             normalize() does (hnsw_index.go:3030-3045).
+ *   k         results wanted per query; ef_search as passed to SearchWithScores
+ *             (ef = max(ef_search, k), :2377-2380; the needsRefine boost :387-399 is applied
+ *             by the caller).
+ *   allow     NULL = nil allow-list.  Otherwise a dense bitset over internal ids with the same
+ *             membership as the *roaring.Bitmap from DB.FindIDsByFilter (pkg/core/core.go:1766),
+ *             shared by the whole batch; semantics of :436-447, :2480-2485, :2545-2549.
+ *   out_ids / out_scores  [nq][k], ascending distance; rows are zero-filled past out_counts[q].
+ * A query whose search "fails" in the reference (nil entry, empty level result) yields count 0,
+ * as SearchWithScores does (:355-359). */
+int kdbgpu_search_batch(kdbgpu_index *, const float *queries, uint32_t nq, int k, int ef_search,
+                        const uint64_t *allow, size_t allow_words, uint32_t *out_ids, double *out_scores,
+                        uint32_t *out_counts, kdbgpu_stats *stats);
+/* Same with every buffer resident on the handle's device; enqueued on `stream` (a cudaStream_t,
+ * NULL = the handle's own stream) without host synchronisation.  d_allow may be NULL;
+ * allow_first_id is the smallest member of the allow-list (ignored when d_allow is NULL). */
+int kdbgpu_search_batch_device(kdbgpu_index *, const float *d_queries, uint32_t nq, int k, int ef_search,
+                               const uint64_t *d_allow, size_t allow_words, uint32_t allow_first_id,
+                               uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts,
+                               void *stream);
+
+/* ---- the literal inner-loop hook: DistanceFuncF32 over a candidate list ---------------- */
+/* out[i] = distFn(query, node ids[i]) — the closure at hnsw_index.go:2393-2396 evaluated for a
+ * whole neighbour list in one launch.  `query` must already be prepared (normalised for
+ * cosine), as inside searchLayerUnlocked. */
+int kdbgpu_distance_batch(kdbgpu_index *, const float *query, const uint32_t *ids, uint32_t n, double *out);
+
+/* ---- flat: BruteForceIndex.SearchWithScores (pkg/core/vector_index.go:104-162) ---------- */
+/* Exhaustive scan of the staged rows (deleted ids skipped, allow-list applied as a filter).
+ *   mode 0  reference arithmetic: sum of float64(q_i - x_i)^2 on the RAW query, any metric.
+ *   mode 1  exact float64 distance under the index metric (cosine: query normalised as in
+ *           searchInternal) — the ground truth used for recall.
+ * Ties are returned in ascending id order (the reference's order among ties is unspecified). */
+int kdbgpu_flat_search_batch(kdbgpu_index *, const float *queries, uint32_t nq, int k, int mode,
+                             const uint64_t *allow, size_t allow_words, uint32_t *out_ids,
+                             double *out_scores, uint32_t *out_counts, kdbgpu_stats *stats);
+
+/* ---- multi-GPU: merge of per-shard top-k (id-range shards) -------------- */
+/* d_ids / d_scores: [n_shards][nq][k] gathered candidates (global ids), d_counts [n_shards][nq].
+ * Writes the k best per query, ascending (distance, id).  Device buffers, async on `stream`. */
+int kdbgpu_merge_topk_device(kdbgpu_index *, int n_shards, uint32_t nq, int k, const uint32_t *d_ids,
+                             const double *d_scores, const uint32_t *d_counts, uint32_t *d_out_ids,
+                             double *d_out_scores, uint32_t *d_out_counts, void *stream);
+
+/* ---- introspection -------------------------------------------------------------------- */
+int kdbgpu_index_device(const kdbgpu_index *);
+uint32_t kdbgpu_index_count(const kdbgpu_index *);   /* n of the last kdbgpu_set_graph        */
+uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *);
+/* Resident CTAs the traversal kernel runs with for (k, ef) — queries in flight per launch. */
+int kdbgpu_search_concurrency(kdbgpu_index *, int k, int ef_search);
+
+/* ---- tuning hook (tests / benchmarks only; not bound by the Go shim) --------------------- */
+/* CTA shape of the traversal kernel: warps per CTA, bulk-copy slots per warp, candidate-heap
+ * entries kept in shared memory, cap on resident CTAs per SM (0 = no cap).  A value <= 0
+ * (< 0 for the cap) keeps the current setting.  Results never depend on the shape. */
+int kdbgpu_set_tuning(kdbgpu_index *, int nwarps, int slots, int cand_smem, int max_ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEKTORDB_GPU_H */

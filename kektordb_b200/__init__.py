@@ -1,0 +1,9 @@
+"""kektordb_b200 — B200 (sm_100a) vector-search hot path for KektorDB behind a C ABI.
+
+Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C ABI of
+include/kektordb_gpu.h), `ffi.py` (ctypes binding of that ABI), `index.py` (host-side mirror
+of hnsw.Index's search surface) and `build.py` (nvcc build, in-tree).
+"""
+from .index import Cosine, Euclidean, GpuIndex, SearchStats, dense_allow_list, effective_ef  # noqa: F401
+
+__all__ = ["GpuIndex", "SearchStats", "Cosine", "Euclidean", "dense_allow_list", "effective_ef"]

@@ -1,0 +1,659 @@
+// api.cu — the C ABI of include/kektordb_gpu.h: handle lifecycle, staging of the corpus and the
+// graph into HBM, and the batched query entry points.  No torch types, no exceptions across the
+// boundary, no CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kdb_internal.cuh"
+
+using namespace kdb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      (void)cudaGetLastError();                                                                     \
+      return fail(_e == cudaErrorMemoryAllocation ? KDBGPU_ERR_NOMEM : KDBGPU_ERR_CUDA, "%s: %s", #expr, \
+                  cudaGetErrorString(_e));                                                          \
+    }                                                                                               \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t reserve(size_t want, bool zero = false) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T));
+    if (e != cudaSuccess) return e;
+    n = want;
+    if (zero) e = cudaMemset(p, 0, want * sizeof(T));
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace
+
+struct kdbgpu_index {
+  int device = 0;
+  int dim = 0, metric = 0, m = 0;
+  uint32_t capacity = 0;
+  uint32_t stride = 0;
+  uint32_t n = 0;
+  uint32_t entry = 0;
+  int max_level = -1;
+  bool has_graph = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int num_sms = 0;
+  SearchTuning tuning;
+  std::mutex mu;  // one batch in flight per handle
+
+  DevBuf<float> vecs;
+  DevBuf<uint32_t> adj0, upper_adj, upper_first, deleted;
+  DevBuf<int8_t> levels;
+  bool has_deleted = false;
+  // per-call workspace
+  DevBuf<float> q_raw, q_prep;
+  DevBuf<uint32_t> out_ids, out_counts, allow, visited, ids_tmp;
+  DevBuf<double> out_scores, flat_dist, dist_tmp;
+  DevBuf<HeapEntry> cand_overflow;
+  DevBuf<unsigned long long> stats;
+  DevBuf<uint32_t> work_counter;
+  DevBuf<int> err_flag;
+  int ws_grid = 0;
+  uint32_t vis_words = 0;
+  uint32_t ovf_cap = 1u << 15;
+
+  DevIndex dev() const {
+    DevIndex d;
+    d.vecs = vecs.p;
+    d.adj0 = adj0.p;
+    d.upper_adj = upper_adj.p;
+    d.upper_first = upper_first.p;
+    d.levels = levels.p;
+    d.deleted = has_deleted ? deleted.p : nullptr;
+    d.stride = stride;
+    d.dim = (uint32_t)dim;
+    d.n = n;
+    d.deg0 = (uint32_t)(2 * m);
+    d.degu = (uint32_t)m;
+    d.entry = entry;
+    d.max_level = max_level;
+    d.metric = metric;
+    return d;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      ok = false;
+      (void)cudaGetLastError();
+      return;
+    }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
+      ok = false;
+      (void)cudaGetLastError();
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int ensure_search_workspace(kdbgpu_index *h, int grid) {
+  const uint32_t words = (((h->capacity + 1 + 31) / 32) + 3) & ~3u;
+  if (grid > h->ws_grid || words != h->vis_words) {
+    h->vis_words = words;
+    h->visited.release();
+    CUDA_TRY(h->visited.reserve((size_t)grid * words, true));
+    h->cand_overflow.release();
+    CUDA_TRY(h->cand_overflow.reserve((size_t)grid * h->ovf_cap));
+    h->ws_grid = grid;
+  }
+  CUDA_TRY(h->stats.reserve(4, true));
+  CUDA_TRY(h->work_counter.reserve(1, true));
+  CUDA_TRY(h->err_flag.reserve(1, true));
+  return KDBGPU_OK;
+}
+
+// queue one traversal launch on `stream`; buffers are device pointers
+int enqueue_search(kdbgpu_index *h, const float *d_q_prepared, uint32_t nq, int k, int ef, const uint32_t *d_allow,
+                   uint32_t allow_entry, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, cudaStream_t stream) {
+  DevIndex ix = h->dev();
+  const int occ = search_occupancy(ix, ef, h->tuning);
+  if (occ <= 0)
+    return fail(KDBGPU_ERR_INVALID, "search configuration does not fit shared memory (dim=%d ef=%d smem=%zu)", h->dim,
+                ef, search_smem_bytes(ix, ef, h->tuning));
+  int grid = occ * h->num_sms;
+  if ((uint32_t)grid > nq) grid = (int)nq;
+  int rc = ensure_search_workspace(h, occ * h->num_sms);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->work_counter.p, 0, sizeof(uint32_t), stream));
+  CUDA_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), stream));
+  SearchArgs a;
+  a.queries = d_q_prepared;
+  a.nq = nq;
+  a.k = k;
+  a.ef = ef;
+  a.allow = d_allow;
+  a.allow_entry = allow_entry;
+  a.out_ids = d_ids;
+  a.out_scores = d_scores;
+  a.out_counts = d_counts;
+  a.visited = h->visited.p;
+  a.vis_words = h->vis_words;
+  a.cand_overflow = h->cand_overflow.p;
+  a.ovf_cap = h->ovf_cap;
+  a.cand_smem = (uint32_t)h->tuning.cand_smem;
+  a.stats = h->stats.p;
+  a.work_counter = h->work_counter.p;
+  a.err_flag = h->err_flag.p;
+  CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
+  return KDBGPU_OK;
+}
+
+uint32_t first_set_bit(const uint64_t *bits, size_t words, bool *found) {
+  for (size_t w = 0; w < words; ++w)
+    if (bits[w]) {
+      *found = true;
+      return (uint32_t)(w * 64 + (size_t)__builtin_ctzll(bits[w]));
+    }
+  *found = false;
+  return 0;
+}
+
+// copy a host allow-list bitset into h->allow, padded/truncated to cover ids 0..capacity
+int stage_allow(kdbgpu_index *h, const uint64_t *allow, size_t allow_words, cudaStream_t stream) {
+  const size_t need32 = ((size_t)h->capacity + 1 + 31) / 32 + 2;
+  CUDA_TRY(h->allow.reserve(need32));
+  CUDA_TRY(cudaMemsetAsync(h->allow.p, 0, need32 * sizeof(uint32_t), stream));
+  size_t copy32 = allow_words * 2;
+  if (copy32 > need32) copy32 = need32;
+  CUDA_TRY(cudaMemcpyAsync(h->allow.p, allow, copy32 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  return KDBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kdbgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *kdbgpu_last_error(void) { return g_last_error.c_str(); }
+
+const char *kdbgpu_version(void) { return "kektordb_gpu 0.1.0 sm_100a"; }
+
+int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacity, kdbgpu_index **out) {
+  if (!out) return fail(KDBGPU_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (dim <= 0 || dim > 8192) return fail(KDBGPU_ERR_INVALID, "dim %d out of range (1..8192)", dim);
+  if (metric != KDBGPU_METRIC_L2 && metric != KDBGPU_METRIC_COSINE)
+    return fail(KDBGPU_ERR_INVALID, "unknown metric %d", metric);
+  if (m <= 0) m = 16;  // hnsw.New default (hnsw_index.go:140-142)
+  if (m > 128) return fail(KDBGPU_ERR_INVALID, "m %d too large (max 128)", m);
+  if (capacity == 0 || capacity > 0xfffffff0u) return fail(KDBGPU_ERR_INVALID, "capacity out of range");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return fail(KDBGPU_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+  }
+  if (device < 0 || device >= ndev) return fail(KDBGPU_ERR_INVALID, "device %d of %d", device, ndev);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(KDBGPU_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(KDBGPU_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  kdbgpu_index *h = new (std::nothrow) kdbgpu_index();
+  if (!h) return fail(KDBGPU_ERR_NOMEM, "host allocation failed");
+  h->device = device;
+  h->dim = dim;
+  h->metric = metric;
+  h->m = m;
+  h->capacity = capacity;
+  h->stride = ((uint32_t)dim + 31u) & ~31u;
+  h->num_sms = prop.multiProcessorCount;
+  const char *env;
+  if ((env = getenv("KDBGPU_NWARPS"))) h->tuning.nwarps = atoi(env);
+  if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
+  if ((env = getenv("KDBGPU_CAND_SMEM"))) h->tuning.cand_smem = atoi(env);
+  if ((env = getenv("KDBGPU_MAX_CTAS_PER_SM"))) h->tuning.max_ctas_per_sm = atoi(env);
+  auto cleanup = [&](int rc) {
+    kdbgpu_index_destroy(h);
+    return rc;
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  const size_t n1 = (size_t)capacity + 1;
+  if (e == cudaSuccess) e = h->vecs.reserve(n1 * h->stride, true);
+  if (e == cudaSuccess) e = h->adj0.reserve(n1 * (size_t)(2 * m), true);
+  if (e == cudaSuccess) e = h->levels.reserve(n1);
+  if (e == cudaSuccess) e = cudaMemset(h->levels.p, 0xff, n1);
+  if (e == cudaSuccess) e = h->upper_first.reserve(n1, true);
+  if (e == cudaSuccess) e = h->deleted.reserve((n1 + 31) / 32 + 2, true);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return cleanup(fail(e == cudaErrorMemoryAllocation ? KDBGPU_ERR_NOMEM : KDBGPU_ERR_CUDA,
+                        "index allocation failed: %s", cudaGetErrorString(e)));
+  }
+  *out = h;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_index_destroy(kdbgpu_index *h) {
+  if (!h) return KDBGPU_OK;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->vecs.release();
+  h->adj0.release();
+  h->upper_adj.release();
+  h->upper_first.release();
+  h->deleted.release();
+  h->levels.release();
+  h->q_raw.release();
+  h->q_prep.release();
+  h->out_ids.release();
+  h->out_counts.release();
+  h->allow.release();
+  h->visited.release();
+  h->ids_tmp.release();
+  h->out_scores.release();
+  h->flat_dist.release();
+  h->dist_tmp.release();
+  h->cand_overflow.release();
+  h->stats.release();
+  h->work_counter.release();
+  h->err_flag.release();
+  for (auto &e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  (void)cudaGetLastError();
+  delete h;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_upload_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, const float *rows) {
+  if (!h || (!rows && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (first_id == 0 || (uint64_t)first_id + count - 1 > h->capacity)
+    return fail(KDBGPU_ERR_INVALID, "ids %u..%llu outside 1..%u", first_id, (unsigned long long)first_id + count - 1,
+                h->capacity);
+  if (count == 0) return KDBGPU_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  // padded columns were zeroed at creation and are never written
+  CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), rows,
+                             (size_t)h->dim * sizeof(float), (size_t)h->dim * sizeof(float), count,
+                             cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_upload_vectors_device(kdbgpu_index *h, uint32_t first_id, uint32_t count, const float *d_rows,
+                                 size_t row_stride) {
+  if (!h || (!d_rows && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (first_id == 0 || (uint64_t)first_id + count - 1 > h->capacity || row_stride < (size_t)h->dim)
+    return fail(KDBGPU_ERR_INVALID, "ids %u..+%u outside 1..%u or bad stride", first_id, count, h->capacity);
+  if (count == 0) return KDBGPU_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), d_rows,
+                             row_stride * sizeof(float), (size_t)h->dim * sizeof(float), count,
+                             cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const uint64_t *node_row,
+                     const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level) {
+  if (!h || !levels || !node_row || !row_off) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (n > h->capacity) return fail(KDBGPU_ERR_INVALID, "n %u exceeds capacity %u", n, h->capacity);
+  if (max_level >= 0 && (entry == 0 || entry > n || levels[entry] < 0))
+    return fail(KDBGPU_ERR_INVALID, "entry point %u is not a live node", entry);
+  const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
+  const size_t n1 = (size_t)n + 1;
+  std::vector<uint32_t> adj0(n1 * deg0, 0u), upper_first(n1, 0u), upper;
+  std::vector<int8_t> lv(n1, (int8_t)-1);
+  size_t upper_rows = 0;
+  for (uint32_t id = 1; id <= n; ++id) {
+    const int32_t L = levels[id];
+    if (L < 0) continue;
+    if (L > 120) return fail(KDBGPU_ERR_INVALID, "node %u has level %d", id, L);
+    if (node_row[id + 1] - node_row[id] != (uint64_t)(L + 1))
+      return fail(KDBGPU_ERR_INVALID, "node %u: %llu rows for level %d", id,
+                  (unsigned long long)(node_row[id + 1] - node_row[id]), L);
+    lv[id] = (int8_t)L;
+    upper_first[id] = (uint32_t)upper_rows;
+    upper_rows += (size_t)L;
+  }
+  upper.assign((upper_rows + 1) * degu, 0u);
+  for (uint32_t id = 1; id <= n; ++id) {
+    const int32_t L = levels[id];
+    for (int32_t l = 0; l <= L; ++l) {
+      const uint64_t r = node_row[id] + (uint64_t)l;
+      const uint64_t b = row_off[r], e = row_off[r + 1];
+      const uint32_t cap = l == 0 ? deg0 : degu;
+      uint32_t *dst = l == 0 ? &adj0[(size_t)id * deg0] : &upper[((size_t)upper_first[id] + (size_t)(l - 1)) * degu];
+      uint32_t w = 0;
+      for (uint64_t i = b; i < e; ++i) {
+        const uint32_t nb = nbrs[i];
+        // nil / out-of-range neighbours are skipped by the reference with no side effect on
+        // results (hnsw_index.go:2553-2561); drop them here so rows hold live ids only
+        if (nb == 0 || nb > n || levels[nb] < 0) continue;
+        if (w >= cap)
+          return fail(KDBGPU_ERR_INVALID, "node %u level %d has more than %u neighbours", id, l, cap);
+        dst[w++] = nb;
+      }
+    }
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(h->upper_adj.reserve(upper.size()));
+  CUDA_TRY(cudaMemcpyAsync(h->adj0.p, adj0.data(), adj0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->upper_adj.p, upper.data(), upper.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                           h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->upper_first.p, upper_first.data(), n1 * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                           h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->levels.p, 0xff, (size_t)h->capacity + 1, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->levels.p, lv.data(), n1, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->n = n;
+  h->entry = entry;
+  h->max_level = max_level;
+  h->has_graph = true;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_set_deleted(kdbgpu_index *h, const uint64_t *bitset, size_t words) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const size_t need32 = h->deleted.n;
+  CUDA_TRY(cudaMemsetAsync(h->deleted.p, 0, need32 * sizeof(uint32_t), h->stream));
+  h->has_deleted = false;
+  if (bitset && words) {
+    size_t copy32 = words * 2;
+    if (copy32 > need32) copy32 = need32;
+    CUDA_TRY(cudaMemcpyAsync(h->deleted.p, bitset, copy32 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    for (size_t w = 0; w < words; ++w)
+      if (bitset[w]) {
+        h->has_deleted = true;
+        break;
+      }
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int ef_search,
+                        const uint64_t *allow, size_t allow_words, uint32_t *out_ids, double *out_scores,
+                        uint32_t *out_counts, kdbgpu_stats *stats) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (nq == 0) return KDBGPU_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (k <= 0 || k > 10000) return fail(KDBGPU_ERR_INVALID, "k %d outside 1..10000", k);  // http_handlers.go:37
+  if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called");
+  const int ef = ef_search < k ? k : ef_search;  // hnsw_index.go:2377-2380
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  // an empty index or an empty non-nil allow-list returns [] for every query (:383-385, :443-445)
+  bool allow_found = true;
+  uint32_t allow_first = 0;
+  if (allow) allow_first = first_set_bit(allow, allow_words, &allow_found);
+  if (h->max_level < 0 || !allow_found || (allow && allow_first > h->n)) {
+    memset(out_ids, 0, (size_t)nq * k * sizeof(uint32_t));
+    memset(out_scores, 0, (size_t)nq * k * sizeof(double));
+    memset(out_counts, 0, (size_t)nq * sizeof(uint32_t));
+    return KDBGPU_OK;
+  }
+  cudaStream_t s = h->stream;
+  CUDA_TRY(h->q_raw.reserve((size_t)nq * h->dim));
+  CUDA_TRY(h->q_prep.reserve((size_t)nq * h->stride));
+  CUDA_TRY(h->out_ids.reserve((size_t)nq * k));
+  CUDA_TRY(h->out_scores.reserve((size_t)nq * k));
+  CUDA_TRY(h->out_counts.reserve(nq));
+  CUDA_TRY(cudaEventRecord(h->ev[0], s));
+  CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries, (size_t)nq * h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  const uint32_t *d_allow = nullptr;
+  if (allow) {
+    int rc = stage_allow(h, allow, allow_words, s);
+    if (rc) return rc;
+    d_allow = h->allow.p;
+  }
+  CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
+  CUDA_TRY(cudaEventRecord(h->ev[1], s));
+  int rc = enqueue_search(h, h->q_prep.p, nq, k, ef, d_allow, allow_first, h->out_ids.p, h->out_scores.p,
+                          h->out_counts.p, s);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev[2], s));
+  CUDA_TRY(cudaMemcpyAsync(out_ids, h->out_ids.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(out_scores, h->out_scores.p, (size_t)nq * k * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(out_counts, h->out_counts.p, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  unsigned long long st[4] = {0, 0, 0, 0};
+  int err = 0;
+  CUDA_TRY(cudaMemcpyAsync(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&err, h->err_flag.p, sizeof err, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->dist_evals = st[0];
+    stats->hops = st[1];
+    stats->hops_l0 = st[2];
+    cudaEventElapsedTime(&stats->kernel_ms, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
+  }
+  if (err == KDBGPU_ERR_OVERFLOW)
+    return fail(KDBGPU_ERR_OVERFLOW, "candidate heap exceeded %u entries for at least one query",
+                h->ovf_cap + (uint32_t)h->tuning.cand_smem);
+  return KDBGPU_OK;
+}
+
+int kdbgpu_search_batch_device(kdbgpu_index *h, const float *d_queries, uint32_t nq, int k, int ef_search,
+                               const uint64_t *d_allow, size_t allow_words, uint32_t allow_first_id,
+                               uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (nq == 0) return KDBGPU_OK;
+  if (!d_queries || !d_out_ids || !d_out_scores || !d_out_counts) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (k <= 0 || k > 10000) return fail(KDBGPU_ERR_INVALID, "k %d outside 1..10000", k);
+  if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called");
+  if (d_allow && allow_words * 64 < (size_t)h->n + 1)
+    return fail(KDBGPU_ERR_INVALID, "device allow-list must cover ids 0..%u", h->n);
+  const int ef = ef_search < k ? k : ef_search;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->stream;
+  if (h->max_level < 0 || (d_allow && (allow_first_id == 0 || allow_first_id > h->n))) {
+    CUDA_TRY(cudaMemsetAsync(d_out_ids, 0, (size_t)nq * k * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemsetAsync(d_out_scores, 0, (size_t)nq * k * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)nq * sizeof(uint32_t), s));
+    return KDBGPU_OK;
+  }
+  CUDA_TRY(h->q_prep.reserve((size_t)nq * h->stride));
+  CUDA_TRY(launch_prep_queries(d_queries, (size_t)h->dim, h->q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
+  return enqueue_search(h, h->q_prep.p, nq, k, ef, reinterpret_cast<const uint32_t *>(d_allow), allow_first_id,
+                        d_out_ids, d_out_scores, d_out_counts, s);
+}
+
+int kdbgpu_distance_batch(kdbgpu_index *h, const float *query, const uint32_t *ids, uint32_t n, double *out) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (n == 0) return KDBGPU_OK;
+  if (!query || !ids || !out) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  CUDA_TRY(h->q_prep.reserve((size_t)h->stride));
+  CUDA_TRY(h->ids_tmp.reserve(n));
+  CUDA_TRY(h->dist_tmp.reserve(n));
+  CUDA_TRY(cudaMemsetAsync(h->q_prep.p, 0, (size_t)h->stride * sizeof(float), s));
+  CUDA_TRY(cudaMemcpyAsync(h->q_prep.p, query, (size_t)h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->ids_tmp.p, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  DevIndex ix = h->dev();
+  ix.n = h->capacity;  // any staged row may be addressed, graph or not
+  CUDA_TRY(launch_distance_batch(ix, h->q_prep.p, h->ids_tmp.p, n, h->dist_tmp.p, s));
+  CUDA_TRY(cudaMemcpyAsync(out, h->dist_tmp.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode,
+                             const uint64_t *allow, size_t allow_words, uint32_t *out_ids, double *out_scores,
+                             uint32_t *out_counts, kdbgpu_stats *stats) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (nq == 0) return KDBGPU_OK;
+  if (!queries || !out_ids || !out_scores || !out_counts) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (k <= 0 || k > 1024) return fail(KDBGPU_ERR_INVALID, "flat k %d outside 1..1024", k);
+  if (mode != 0 && mode != 1) return fail(KDBGPU_ERR_INVALID, "mode %d", mode);
+  if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called (it defines the live rows)");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  if (h->n == 0) {
+    memset(out_ids, 0, (size_t)nq * k * sizeof(uint32_t));
+    memset(out_scores, 0, (size_t)nq * k * sizeof(double));
+    memset(out_counts, 0, (size_t)nq * sizeof(uint32_t));
+    return KDBGPU_OK;
+  }
+  // BruteForceIndex treats an empty allow-list as unfiltered (vector_index.go:132)
+  const uint32_t *d_allow = nullptr;
+  if (allow) {
+    bool found = false;
+    (void)first_set_bit(allow, allow_words, &found);
+    if (found) {
+      int rc = stage_allow(h, allow, allow_words, s);
+      if (rc) return rc;
+      d_allow = h->allow.p;
+    }
+  }
+  // bound the dist[chunk][n] workspace to ~2 GiB
+  uint32_t chunk = (uint32_t)((2ull << 30) / ((size_t)h->n * sizeof(double)));
+  if (chunk < 16) chunk = 16;
+  chunk &= ~15u;
+  if (chunk > nq) chunk = nq;
+  CUDA_TRY(h->q_raw.reserve((size_t)chunk * h->dim));
+  CUDA_TRY(h->q_prep.reserve((size_t)chunk * h->stride));
+  CUDA_TRY(h->out_ids.reserve((size_t)chunk * k));
+  CUDA_TRY(h->out_scores.reserve((size_t)chunk * k));
+  CUDA_TRY(h->out_counts.reserve(chunk));
+  CUDA_TRY(h->flat_dist.reserve((size_t)chunk * h->n));
+  DevIndex ix = h->dev();
+  CUDA_TRY(cudaEventRecord(h->ev[0], s));
+  for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+    const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
+    CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries + (size_t)q0 * h->dim, (size_t)c * h->dim * sizeof(float),
+                             cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
+                                 mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
+    CUDA_TRY(launch_flat_distances(ix, h->q_raw.p, h->q_prep.p, c, mode, h->flat_dist.p, s));
+    CUDA_TRY(launch_flat_select(ix, h->flat_dist.p, c, k, d_allow, h->out_ids.p, h->out_scores.p, h->out_counts.p, s));
+    CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->dist_evals = (uint64_t)nq * h->n;
+    cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
+    stats->kernel_ms = stats->total_ms;
+  }
+  return KDBGPU_OK;
+}
+
+int kdbgpu_merge_topk_device(kdbgpu_index *h, int n_shards, uint32_t nq, int k, const uint32_t *d_ids,
+                             const double *d_scores, const uint32_t *d_counts, uint32_t *d_out_ids,
+                             double *d_out_scores, uint32_t *d_out_counts, void *stream) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (n_shards <= 0 || n_shards > 16) return fail(KDBGPU_ERR_INVALID, "n_shards %d outside 1..16", n_shards);
+  if (k <= 0) return fail(KDBGPU_ERR_INVALID, "k %d", k);
+  if (nq == 0) return KDBGPU_OK;
+  if (!d_ids || !d_scores || !d_counts || !d_out_ids || !d_out_scores || !d_out_counts)
+    return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  DeviceGuard g(h->device);
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->stream;
+  CUDA_TRY(launch_merge_topk(n_shards, nq, k, d_ids, d_scores, d_counts, d_out_ids, d_out_scores, d_out_counts, s));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_index_device(const kdbgpu_index *h) { return h ? h->device : -1; }
+uint32_t kdbgpu_index_count(const kdbgpu_index *h) { return h ? h->n : 0; }
+uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *h) {
+  if (!h) return 0;
+  return h->vecs.bytes() + h->adj0.bytes() + h->upper_adj.bytes() + h->upper_first.bytes() + h->deleted.bytes() +
+         h->levels.bytes() + h->visited.bytes() + h->cand_overflow.bytes() + h->flat_dist.bytes() + h->q_raw.bytes() +
+         h->q_prep.bytes() + h->out_ids.bytes() + h->out_scores.bytes() + h->allow.bytes();
+}
+int kdbgpu_search_concurrency(kdbgpu_index *h, int k, int ef_search) {
+  if (!h) return 0;
+  DeviceGuard g(h->device);
+  const int ef = ef_search < k ? k : ef_search;
+  return search_occupancy(h->dev(), ef, h->tuning) * h->num_sms;
+}
+
+// test/tuning hook (not part of the reference-facing surface): CTA shape of the traversal kernel
+int kdbgpu_set_tuning(kdbgpu_index *h, int nwarps, int slots, int cand_smem, int max_ctas_per_sm) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  SearchTuning t = h->tuning;
+  if (nwarps > 0) t.nwarps = nwarps;
+  if (slots > 0) t.slots = slots;
+  if (cand_smem > 0) t.cand_smem = cand_smem;
+  if (max_ctas_per_sm >= 0) t.max_ctas_per_sm = max_ctas_per_sm;
+  const bool ok = (t.nwarps == 2 && (t.slots == 2 || t.slots == 4)) ||
+                  (t.nwarps == 4 && (t.slots == 1 || t.slots == 2 || t.slots == 4)) ||
+                  (t.nwarps == 8 && (t.slots == 1 || t.slots == 2));
+  if (!ok) return fail(KDBGPU_ERR_INVALID, "unsupported CTA shape nwarps=%d slots=%d", t.nwarps, t.slots);
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->tuning = t;
+  return KDBGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// flat.cu — exhaustive scan (BruteForceIndex.SearchWithScores, reference
+// pkg/core/vector_index.go:104-162) and the k-way merge of per-shard results.
+//
+// Exact path: float64 distances in the reference's own arithmetic (sequential in the element
+// index, separate multiply and add), materialised as dist[nq][n] in HBM, then an exact per-query
+// top-k by radix select on the (distance, id) order.  It is both the product's flat path (mode 0)
+// and the ground truth for recall (mode 1).
+#include "kdb_internal.cuh"
+
+namespace kdb {
+namespace {
+
+constexpr int FT_ROWS = 64;   // corpus rows per CTA tile
+constexpr int FT_Q = 16;      // queries per CTA tile
+constexpr int FT_E = 32;      // elements per staged chunk
+constexpr int FT_THREADS = 256;
+
+// mode 0: sum += f64(q_e - x_e)^2, difference taken in f32 (vector_index.go:150-162), raw query
+// mode 1: cosine -> 1 - sum f64(q^_e)*f64(x_e);  L2 -> sum (f64(q_e) - f64(x_e))^2
+template <int MODE, int METRIC>
+__global__ void __launch_bounds__(FT_THREADS)
+    flat_distances_kernel(const DevIndex ix, const float *__restrict__ queries, size_t q_stride, uint32_t nq,
+                          double *__restrict__ dist) {
+  __shared__ float s_rows[FT_ROWS][FT_E + 1];
+  __shared__ float s_q[FT_Q][FT_E];
+  const uint32_t row0 = blockIdx.x * FT_ROWS;  // row r <-> id r + 1
+  const uint32_t q0 = blockIdx.y * FT_Q;
+  const int t = threadIdx.x;
+  const int qi = t >> 4;       // 0..15
+  const int rg = t & 15;       // rows rg, rg+16, rg+32, rg+48
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (uint32_t e0 = 0; e0 < ix.dim; e0 += FT_E) {
+    for (int i = t; i < FT_ROWS * FT_E; i += FT_THREADS) {
+      const int r = i / FT_E, e = i % FT_E;
+      const uint32_t row = row0 + r;
+      float v = 0.f;
+      if (row < ix.n && e0 + e < ix.dim) v = ix.vecs[(size_t)(row + 1) * ix.stride + e0 + e];
+      s_rows[r][e] = v;
+    }
+    for (int i = t; i < FT_Q * FT_E; i += FT_THREADS) {
+      const int qq = i / FT_E, e = i % FT_E;
+      float v = 0.f;
+      if (q0 + qq < nq && e0 + e < ix.dim) v = queries[(size_t)(q0 + qq) * q_stride + e0 + e];
+      s_q[qq][e] = v;
+    }
+    __syncthreads();
+    const int emax = (ix.dim - e0) < (uint32_t)FT_E ? (int)(ix.dim - e0) : FT_E;
+    for (int e = 0; e < emax; ++e) {
+      const float qf = s_q[qi][e];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xf = s_rows[rg + 16 * j][e];
+        if (MODE == 0) {
+          const double diff = static_cast<double>(__fsub_rn(qf, xf));
+          acc[j] = __dadd_rn(acc[j], __dmul_rn(diff, diff));
+        } else if (METRIC == KDBGPU_METRIC_COSINE) {
+          acc[j] = __dadd_rn(acc[j], __dmul_rn(static_cast<double>(qf), static_cast<double>(xf)));
+        } else {
+          const double diff = __dsub_rn(static_cast<double>(qf), static_cast<double>(xf));
+          acc[j] = __dadd_rn(acc[j], __dmul_rn(diff, diff));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (q0 + qi < nq) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t row = row0 + rg + 16 * j;
+      if (row < ix.n) {
+        double d = acc[j];
+        if (MODE == 1 && METRIC == KDBGPU_METRIC_COSINE) d = __dsub_rn(1.0, d);
+        dist[(size_t)(q0 + qi) * ix.n + row] = d;
+      }
+    }
+  }
+}
+
+// order-preserving map double -> uint64
+__device__ __forceinline__ unsigned long long dkey(double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_BITS = 11;
+constexpr int SEL_BINS = 1 << SEL_BITS;
+constexpr int SEL_MAXK = 1024;
+
+// One CTA per query.  Exact k smallest by (distance, id) among live, allowed rows.
+__global__ void __launch_bounds__(SEL_THREADS)
+    flat_select_kernel(const DevIndex ix, const double *__restrict__ dist, uint32_t nq, int k,
+                       const uint32_t *__restrict__ allow, uint32_t *__restrict__ out_ids,
+                       double *__restrict__ out_scores, uint32_t *__restrict__ out_counts) {
+  __shared__ uint32_t hist[SEL_BINS];
+  __shared__ unsigned long long s_prefix;
+  __shared__ uint32_t s_remaining, s_shift_done;
+  __shared__ unsigned long long s_keys[SEL_MAXK];
+  __shared__ uint32_t s_ids[SEL_MAXK];
+  __shared__ uint32_t s_count, s_ties_needed, s_valid;
+  const uint32_t q = blockIdx.x;
+  if (q >= nq) return;
+  const double *row = dist + (size_t)q * ix.n;
+  const int t = threadIdx.x;
+  auto live = [&](uint32_t r) -> bool {
+    const uint32_t id = r + 1;
+    if (ix.levels[id] < 0) return false;
+    if (ix.deleted && ((ix.deleted[id >> 5] >> (id & 31)) & 1u)) return false;
+    if (allow && !((allow[id >> 5] >> (id & 31)) & 1u)) return false;
+    return true;
+  };
+  // count live rows
+  if (t == 0) s_valid = 0;
+  __syncthreads();
+  {
+    uint32_t c = 0;
+    for (uint32_t r = t; r < ix.n; r += SEL_THREADS) c += live(r) ? 1u : 0u;
+    atomicAdd(&s_valid, c);
+  }
+  __syncthreads();
+  const uint32_t kk = s_valid < (uint32_t)k ? s_valid : (uint32_t)k;
+  if (kk == 0) {
+    for (int i = t; i < k; i += SEL_THREADS) {
+      out_ids[(size_t)q * k + i] = 0;
+      out_scores[(size_t)q * k + i] = 0.0;
+    }
+    if (t == 0) out_counts[q] = 0;
+    return;
+  }
+  // radix select of the kk-th smallest key, most significant digit first
+  if (t == 0) {
+    s_prefix = 0ULL;
+    s_remaining = kk;
+  }
+  __syncthreads();
+  int shift = 64;
+  while (shift > 0) {
+    const int bits = shift >= SEL_BITS ? SEL_BITS : shift;
+    shift -= bits;
+    for (int i = t; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    const int hi_shift = shift + bits;  // bits above the current digit
+    for (uint32_t r = t; r < ix.n; r += SEL_THREADS) {
+      if (!live(r)) continue;
+      const unsigned long long key = dkey(row[r]);
+      const bool match = hi_shift >= 64 ? true : ((key >> hi_shift) == (prefix >> hi_shift));
+      if (match) atomicAdd(&hist[(key >> shift) & ((1u << bits) - 1u)], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      uint32_t rem = s_remaining;
+      uint32_t b = 0;
+      for (; b < (1u << bits); ++b) {
+        if (hist[b] >= rem) break;
+        rem -= hist[b];
+      }
+      s_prefix = prefix | ((unsigned long long)b << shift);
+      s_remaining = rem;
+    }
+    __syncthreads();
+  }
+  const unsigned long long kth = s_prefix;  // key of the kk-th smallest
+  const uint32_t ties_needed = s_remaining;  // how many rows equal to kth are inside the top kk
+  if (t == 0) {
+    s_count = 0;
+    s_ties_needed = ties_needed;
+    (void)s_shift_done;
+  }
+  __syncthreads();
+  // strictly smaller keys: all of them
+  for (uint32_t r = t; r < ix.n; r += SEL_THREADS) {
+    if (!live(r)) continue;
+    const unsigned long long key = dkey(row[r]);
+    if (key < kth) {
+      const uint32_t pos = atomicAdd(&s_count, 1u);
+      s_keys[pos] = key;
+      s_ids[pos] = r + 1;
+    }
+  }
+  __syncthreads();
+  // ties at kth: smallest ids first — sequential scan in id order by chunks
+  {
+    __shared__ uint32_t s_tie_base;
+    if (t == 0) s_tie_base = s_count;
+    __syncthreads();
+    for (uint32_t r0 = 0; r0 < ix.n; r0 += SEL_THREADS) {
+      const uint32_t r = r0 + t;
+      bool is_tie = false;
+      if (r < ix.n && live(r)) is_tie = dkey(row[r]) == kth;
+      // block-wide ordered compaction via warp ballots
+      __shared__ uint32_t warp_cnt[SEL_THREADS / 32];
+      const uint32_t bal = __ballot_sync(0xffffffffu, is_tie);
+      if ((t & 31) == 0) warp_cnt[t >> 5] = __popc(bal);
+      __syncthreads();
+      uint32_t before = 0;
+      for (int w = 0; w < (t >> 5); ++w) before += warp_cnt[w];
+      uint32_t total = 0;
+      for (int w = 0; w < SEL_THREADS / 32; ++w) total += warp_cnt[w];
+      const uint32_t taken = s_tie_base - s_count;  // ties stored so far
+      if (is_tie) {
+        const uint32_t rank = taken + before + __popc(bal & ((1u << (t & 31)) - 1u));
+        if (rank < ties_needed) {
+          s_keys[s_count + rank] = kth;
+          s_ids[s_count + rank] = r + 1;
+        }
+      }
+      __syncthreads();
+      if (t == 0) s_tie_base += total;
+      __syncthreads();
+      if (s_tie_base - s_count >= ties_needed) break;
+    }
+  }
+  __syncthreads();
+  // sort the kk collected by (key, id): bitonic over the next power of two
+  uint32_t np2 = 1;
+  while (np2 < kk) np2 <<= 1;
+  for (uint32_t i = kk + t; i < np2; i += SEL_THREADS) {
+    s_keys[i] = ~0ULL;
+    s_ids[i] = 0xffffffffu;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= np2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = t; i < np2; i += SEL_THREADS) {
+        const uint32_t j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const unsigned long long ki = s_keys[i], kj = s_keys[j];
+          const uint32_t ii = s_ids[i], ij = s_ids[j];
+          const bool gt = ki > kj || (ki == kj && ii > ij);
+          if (gt == up) {
+            s_keys[i] = kj;
+            s_keys[j] = ki;
+            s_ids[i] = ij;
+            s_ids[j] = ii;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = t; i < k; i += SEL_THREADS) {
+    const bool ok = (uint32_t)i < kk;
+    out_ids[(size_t)q * k + i] = ok ? s_ids[i] : 0u;
+    out_scores[(size_t)q * k + i] = ok ? dkey_inv(s_keys[i]) : 0.0;
+  }
+  if (t == 0) out_counts[q] = kk;
+}
+
+// k-way merge of per-shard ascending lists by (distance, id); one thread per query.
+__global__ void merge_topk_kernel(int n_shards, uint32_t nq, int k, const uint32_t *__restrict__ ids,
+                                  const double *__restrict__ scores, const uint32_t *__restrict__ counts,
+                                  uint32_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                                  uint32_t *__restrict__ out_counts) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint32_t pos[16];
+  for (int s = 0; s < n_shards; ++s) pos[s] = 0;
+  int n = 0;
+  for (; n < k; ++n) {
+    int best = -1;
+    double bd = 0.0;
+    uint32_t bi = 0;
+    for (int s = 0; s < n_shards; ++s) {
+      const uint32_t c = counts[(size_t)s * nq + q];
+      if (pos[s] >= c || pos[s] >= (uint32_t)k) continue;
+      const size_t o = ((size_t)s * nq + q) * k + pos[s];
+      const double d = scores[o];
+      const uint32_t id = ids[o];
+      if (best < 0 || d < bd || (d == bd && id < bi)) {
+        best = s;
+        bd = d;
+        bi = id;
+      }
+    }
+    if (best < 0) break;
+    pos[best]++;
+    out_ids[(size_t)q * k + n] = bi;
+    out_scores[(size_t)q * k + n] = bd;
+  }
+  out_counts[q] = (uint32_t)n;
+  for (int i = n; i < k; ++i) {
+    out_ids[(size_t)q * k + i] = 0;
+    out_scores[(size_t)q * k + i] = 0.0;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_flat_distances(const DevIndex &ix, const float *queries_raw, const float *queries_prepared,
+                                  uint32_t nq, int mode, double *dist, cudaStream_t stream) {
+  if (nq == 0 || ix.n == 0) return cudaSuccess;
+  dim3 grid((ix.n + FT_ROWS - 1) / FT_ROWS, (nq + FT_Q - 1) / FT_Q);
+  if (mode == 0) {
+    flat_distances_kernel<0, KDBGPU_METRIC_L2><<<grid, FT_THREADS, 0, stream>>>(ix, queries_raw, ix.dim, nq, dist);
+  } else if (ix.metric == KDBGPU_METRIC_COSINE) {
+    flat_distances_kernel<1, KDBGPU_METRIC_COSINE>
+        <<<grid, FT_THREADS, 0, stream>>>(ix, queries_prepared, ix.stride, nq, dist);
+  } else {
+    flat_distances_kernel<1, KDBGPU_METRIC_L2><<<grid, FT_THREADS, 0, stream>>>(ix, queries_raw, ix.dim, nq, dist);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flat_select(const DevIndex &ix, const double *dist, uint32_t nq, int k, const uint32_t *allow,
+                               uint32_t *out_ids, double *out_scores, uint32_t *out_counts, cudaStream_t stream) {
+  if (nq == 0) return cudaSuccess;
+  if (k > SEL_MAXK) return cudaErrorInvalidValue;
+  flat_select_kernel<<<nq, SEL_THREADS, 0, stream>>>(ix, dist, nq, k, allow, out_ids, out_scores, out_counts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_topk(int n_shards, uint32_t nq, int k, const uint32_t *ids, const double *scores,
+                              const uint32_t *counts, uint32_t *out_ids, double *out_scores,
+                              uint32_t *out_counts, cudaStream_t stream) {
+  if (nq == 0) return cudaSuccess;
+  if (n_shards > 16) return cudaErrorInvalidValue;
+  merge_topk_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(n_shards, nq, k, ids, scores, counts, out_ids,
+                                                         out_scores, out_counts);
+  return cudaGetLastError();
+}
+
+}  // namespace kdb

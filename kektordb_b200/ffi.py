@@ -1,0 +1,76 @@
+"""ctypes binding of include/kektordb_gpu.h — the same C ABI the Go host binds through cgo.
+
+Loading fails loudly if the library has not been built; calling fails loudly (GpuError) when
+there is no CUDA device.  There is no CPU fallback anywhere behind this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+LIB_PATH = _build.LIB
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_OVERFLOW = -1, -2, -3, -4, -5
+METRIC_L2, METRIC_COSINE = 0, 1
+
+
+class GpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kektordb_gpu error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("dist_evals", C.c_uint64), ("hops", C.c_uint64), ("hops_l0", C.c_uint64),
+                ("kernel_ms", C.c_float), ("total_ms", C.c_float)]
+
+
+# every symbol include/kektordb_gpu.h declares: name -> (restype, argtypes)
+_vp, _u32, _i32, _sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
+SIGNATURES = {
+    "kdbgpu_device_count": (_i32, []),
+    "kdbgpu_last_error": (C.c_char_p, []),
+    "kdbgpu_version": (C.c_char_p, []),
+    "kdbgpu_index_create": (_i32, [_i32, _i32, _i32, _i32, _u32, C.POINTER(_vp)]),
+    "kdbgpu_index_destroy": (_i32, [_vp]),
+    "kdbgpu_upload_vectors": (_i32, [_vp, _u32, _u32, _vp]),
+    "kdbgpu_upload_vectors_device": (_i32, [_vp, _u32, _u32, _vp, _sz]),
+    "kdbgpu_set_graph": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _i32]),
+    "kdbgpu_set_deleted": (_i32, [_vp, _vp, _sz]),
+    "kdbgpu_search_batch": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, C.POINTER(Stats)]),
+    "kdbgpu_search_batch_device": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _u32, _vp, _vp, _vp, _vp]),
+    "kdbgpu_distance_batch": (_i32, [_vp, _vp, _vp, _u32, _vp]),
+    "kdbgpu_flat_search_batch": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, C.POINTER(Stats)]),
+    "kdbgpu_merge_topk_device": (_i32, [_vp, _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kdbgpu_index_device": (_i32, [_vp]),
+    "kdbgpu_index_count": (_u32, [_vp]),
+    "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),
+    "kdbgpu_search_concurrency": (_i32, [_vp, _i32, _i32]),
+    "kdbgpu_set_tuning": (_i32, [_vp, _i32, _i32, _i32, _i32]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libkektordb_gpu.so (built in-tree by kektordb_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python -m kektordb_b200.build` (nvcc, sm_100a). "
+                "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise GpuError(rc, lib().kdbgpu_last_error().decode("utf-8", "replace"))

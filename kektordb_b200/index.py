@@ -1,0 +1,190 @@
+"""Host-side mirror of the reference's hnsw.Index search surface over the C ABI.
+
+Same names and argument meaning as the reference (pkg/core/hnsw/hnsw_index.go):
+`SearchWithScores(query, k, allowList, efSearch)` (:343), metric strings "euclidean" /
+"cosine" (pkg/core/distance/distance_go.go:34-39), internal uint32 ids from 1, scores = raw
+float64 distances, failures yield empty results (:355-359).  The only addition is that a call
+takes a batch of queries — the batch a Go-side micro-batcher would form.
+
+All compute happens in libkektordb_gpu.so (hand-written sm_100a CUDA); this module only moves
+numpy buffers across the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import ffi
+
+Euclidean = "euclidean"
+Cosine = "cosine"
+_METRICS = {Euclidean: ffi.METRIC_L2, Cosine: ffi.METRIC_COSINE, "l2": ffi.METRIC_L2,
+            ffi.METRIC_L2: ffi.METRIC_L2, ffi.METRIC_COSINE: ffi.METRIC_COSINE}
+
+
+@dataclass
+class SearchStats:
+    dist_evals: int = 0
+    hops: int = 0
+    hops_l0: int = 0
+    kernel_ms: float = 0.0
+    total_ms: float = 0.0
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def effective_ef(ef_search: int, needs_refine: bool) -> int:
+    """The needsRefine boost of searchInternal (hnsw_index.go:387-399), applied by the caller."""
+    actual = ef_search
+    if needs_refine:
+        boosted = int(float(ef_search) * 2)
+        boosted = max(boosted, 80)
+        boosted = min(boosted, 200)
+        if boosted > actual:
+            actual = boosted
+    return actual
+
+
+def dense_allow_list(ids, n: int) -> np.ndarray:
+    """Dense uint64 bitset over internal ids 0..n with the membership of a roaring bitmap."""
+    words = np.zeros((n >> 6) + 1, dtype=np.uint64)
+    ids = np.asarray(ids, dtype=np.uint64)
+    if ids.size:
+        np.bitwise_or.at(words, (ids >> np.uint64(6)).astype(np.int64), np.uint64(1) << (ids & np.uint64(63)))
+    return words
+
+
+class GpuIndex:
+    """GPU mirror of one hnsw.Index: corpus rows + adjacency staged in HBM, searched on device."""
+
+    def __init__(self, dim: int, metric, m: int = 16, capacity: int = 1 << 20, device: int = 0):
+        if metric not in _METRICS:
+            raise ValueError(f"metric '{metric}' not supported for float32 precision")  # distance_go.go:155-157
+        self._lib = ffi.lib()
+        self.dim, self.m, self.capacity, self.device = int(dim), int(m) if m > 0 else 16, int(capacity), int(device)
+        self.metric = _METRICS[metric]
+        self.needs_refine = False
+        h = C.c_void_p()
+        ffi.check(self._lib.kdbgpu_index_create(device, dim, self.metric, m, capacity, C.byref(h)))
+        self._h = h
+
+    # -- lifecycle -------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.kdbgpu_index_destroy(self._h)
+            self._h = None
+
+    Close = close
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise ffi.GpuError(ffi.ERR_STATE, "index is closed")
+        return self._h
+
+    # -- staging ---------------------------------------------------------------------------
+    def upload_vectors(self, first_id: int, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"rows must be [count, {self.dim}]")
+        ffi.check(self._lib.kdbgpu_upload_vectors(self._handle(), first_id, rows.shape[0], _ptr(rows)))
+
+    def set_graph(self, n: int, levels, node_row, row_off, nbrs, entry: int, max_level: int) -> None:
+        levels = np.ascontiguousarray(levels, dtype=np.int32)
+        node_row = np.ascontiguousarray(node_row, dtype=np.uint64)
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
+        nbrs = np.ascontiguousarray(nbrs, dtype=np.uint32)
+        if levels.shape != (n + 1,) or node_row.shape != (n + 2,):
+            raise ValueError("levels must be [n+1] and node_row [n+2]")
+        if nbrs.size == 0:
+            nbrs = np.zeros(1, dtype=np.uint32)
+        ffi.check(self._lib.kdbgpu_set_graph(self._handle(), n, _ptr(levels), _ptr(node_row), _ptr(row_off),
+                                             _ptr(nbrs), entry, max_level))
+
+    def set_deleted(self, bitset: np.ndarray | None) -> None:
+        if bitset is None:
+            ffi.check(self._lib.kdbgpu_set_deleted(self._handle(), None, 0))
+            return
+        b = np.ascontiguousarray(bitset, dtype=np.uint64)
+        ffi.check(self._lib.kdbgpu_set_deleted(self._handle(), _ptr(b), b.size))
+
+    def set_tuning(self, nwarps: int = 0, slots: int = 0, cand_smem: int = 0, max_ctas_per_sm: int = -1) -> None:
+        ffi.check(self._lib.kdbgpu_set_tuning(self._handle(), nwarps, slots, cand_smem, max_ctas_per_sm))
+
+    # -- query -----------------------------------------------------------------------------
+    def SearchWithScores(self, query, k: int, allowList: np.ndarray | None = None, efSearch: int = 0):
+        """Batched (*Index).SearchWithScores.  `query` is [nq, dim] (or [dim]); allowList a dense
+        uint64 bitset or None.  Returns (ids [nq,k] uint32, scores [nq,k] float64, counts [nq], stats)."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        single = q.ndim == 1
+        if single:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [nq, {self.dim}]")
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        scores = np.zeros((nq, k), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.uint32)
+        st = ffi.Stats()
+        allow = None if allowList is None else np.ascontiguousarray(allowList, dtype=np.uint64)
+        ef = effective_ef(int(efSearch), self.needs_refine)
+        ffi.check(self._lib.kdbgpu_search_batch(self._handle(), _ptr(q), nq, k, ef, _ptr(allow),
+                                                0 if allow is None else allow.size, _ptr(ids), _ptr(scores),
+                                                _ptr(counts), C.byref(st)))
+        stats = SearchStats(st.dist_evals, st.hops, st.hops_l0, st.kernel_ms, st.total_ms)
+        return ids, scores, counts, stats
+
+    search_with_scores = SearchWithScores
+
+    def distance_batch(self, prepared_query, ids) -> np.ndarray:
+        q = np.ascontiguousarray(prepared_query, dtype=np.float32)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.zeros(ids.size, dtype=np.float64)
+        ffi.check(self._lib.kdbgpu_distance_batch(self._handle(), _ptr(q), _ptr(ids), ids.size, _ptr(out)))
+        return out
+
+    def flat_search(self, query, k: int, mode: int = 0, allowList: np.ndarray | None = None):
+        """BruteForceIndex.SearchWithScores (mode 0) / exact f64 ground truth (mode 1)."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), dtype=np.uint32)
+        scores = np.zeros((nq, k), dtype=np.float64)
+        counts = np.zeros(nq, dtype=np.uint32)
+        st = ffi.Stats()
+        allow = None if allowList is None else np.ascontiguousarray(allowList, dtype=np.uint64)
+        ffi.check(self._lib.kdbgpu_flat_search_batch(self._handle(), _ptr(q), nq, k, mode, _ptr(allow),
+                                                     0 if allow is None else allow.size, _ptr(ids), _ptr(scores),
+                                                     _ptr(counts), C.byref(st)))
+        return ids, scores, counts, SearchStats(st.dist_evals, 0, 0, st.kernel_ms, st.total_ms)
+
+    # -- introspection ---------------------------------------------------------------------
+    def Metric(self) -> str:
+        return Cosine if self.metric == ffi.METRIC_COSINE else Euclidean
+
+    def Precision(self) -> str:
+        return "float32"
+
+    def GetDimension(self) -> int:
+        return self.dim
+
+    @property
+    def count(self) -> int:
+        return int(self._lib.kdbgpu_index_count(self._handle()))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.kdbgpu_index_device_bytes(self._handle()))
+
+    def search_concurrency(self, k: int, ef_search: int) -> int:
+        return int(self._lib.kdbgpu_search_concurrency(self._handle(), k, ef_search))
