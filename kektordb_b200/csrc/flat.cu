@@ -252,42 +252,55 @@ __global__ void __launch_bounds__(SEL_THREADS)
   if (t == 0) out_counts[q] = kk;
 }
 
-// k-way merge of per-shard ascending lists by (distance, id); one thread per query.
-__global__ void merge_topk_kernel(int n_shards, uint32_t nq, int k, const uint32_t *__restrict__ ids,
-                                  const double *__restrict__ scores, const uint32_t *__restrict__ counts,
-                                  uint32_t *__restrict__ out_ids, double *__restrict__ out_scores,
-                                  uint32_t *__restrict__ out_counts) {
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+// Merge of per-shard results: the k smallest of the union by (distance, id).  One CTA per query;
+// every candidate computes its rank among all candidates (exact under ties, independent of the
+// order inside a shard's list) and writes itself to out[rank] if rank < k.
+__global__ void __launch_bounds__(128)
+    merge_topk_kernel(int n_shards, uint32_t nq, int k, const uint32_t *__restrict__ ids,
+                      const double *__restrict__ scores, const uint32_t *__restrict__ counts,
+                      uint32_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                      uint32_t *__restrict__ out_counts) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  const uint32_t q = blockIdx.x;
   if (q >= nq) return;
-  uint32_t pos[16];
-  for (int s = 0; s < n_shards; ++s) pos[s] = 0;
-  int n = 0;
-  for (; n < k; ++n) {
-    int best = -1;
-    double bd = 0.0;
-    uint32_t bi = 0;
-    for (int s = 0; s < n_shards; ++s) {
-      const uint32_t c = counts[(size_t)s * nq + q];
-      if (pos[s] >= c || pos[s] >= (uint32_t)k) continue;
-      const size_t o = ((size_t)s * nq + q) * k + pos[s];
-      const double d = scores[o];
-      const uint32_t id = ids[o];
-      if (best < 0 || d < bd || (d == bd && id < bi)) {
-        best = s;
-        bd = d;
-        bi = id;
-      }
+  const int total_cap = n_shards * k;
+  double *s_d = reinterpret_cast<double *>(merge_smem);
+  uint32_t *s_id = reinterpret_cast<uint32_t *>(s_d + total_cap);
+  __shared__ uint32_t s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < total_cap; i += blockDim.x) {
+    const int s = i / k, j = i % k;
+    uint32_t c = counts[(size_t)s * nq + q];
+    if (c > (uint32_t)k) c = (uint32_t)k;
+    if ((uint32_t)j < c) {
+      const size_t o = ((size_t)s * nq + q) * k + j;
+      const uint32_t pos = atomicAdd(&s_n, 1u);
+      s_d[pos] = scores[o];
+      s_id[pos] = ids[o];
     }
-    if (best < 0) break;
-    pos[best]++;
-    out_ids[(size_t)q * k + n] = bi;
-    out_scores[(size_t)q * k + n] = bd;
   }
-  out_counts[q] = (uint32_t)n;
-  for (int i = n; i < k; ++i) {
+  __syncthreads();
+  const uint32_t n = s_n;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = s_d[i];
+    const uint32_t id = s_id[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+      const double dj = s_d[j];
+      rank += (dj < d || (dj == d && s_id[j] < id)) ? 1u : 0u;
+    }
+    if (rank < (uint32_t)k) {
+      out_ids[(size_t)q * k + rank] = id;
+      out_scores[(size_t)q * k + rank] = d;
+    }
+  }
+  const uint32_t m = n < (uint32_t)k ? n : (uint32_t)k;
+  for (uint32_t i = m + threadIdx.x; i < (uint32_t)k; i += blockDim.x) {
     out_ids[(size_t)q * k + i] = 0;
     out_scores[(size_t)q * k + i] = 0.0;
   }
+  if (threadIdx.x == 0) out_counts[q] = m;
 }
 
 }  // namespace
@@ -319,9 +332,12 @@ cudaError_t launch_merge_topk(int n_shards, uint32_t nq, int k, const uint32_t *
                               const uint32_t *counts, uint32_t *out_ids, double *out_scores,
                               uint32_t *out_counts, cudaStream_t stream) {
   if (nq == 0) return cudaSuccess;
-  if (n_shards > 16) return cudaErrorInvalidValue;
-  merge_topk_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(n_shards, nq, k, ids, scores, counts, out_ids,
-                                                         out_scores, out_counts);
+  const size_t smem = (size_t)n_shards * k * (sizeof(double) + sizeof(uint32_t));
+  if (n_shards > 16 || smem > 96 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  merge_topk_kernel<<<nq, 128, smem, stream>>>(n_shards, nq, k, ids, scores, counts, out_ids, out_scores,
+                                               out_counts);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,389 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle in
+KDBO_ARITH_KERNEL mode.  The bar is bit-exact: same ids, same order, same float64 scores, same
+counters.  Against the oracle's reference-faithful arithmetic modes the bar is the north-star's:
+same top-k id sets (up to near-ties) and scores within 1e-5 — stated in each test."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gpu():
+    from kektordb_b200 import GpuIndex, ffi
+    assert ffi.lib().kdbgpu_device_count() > 0, "these tests need a CUDA device (no CPU fallback exists)"
+    return GpuIndex
+
+
+def _metric_name(metric):
+    return "cosine" if metric == O.METRIC_COSINE else "euclidean"
+
+
+def _mirror(oi, metric, m, capacity=None):
+    """Stage the oracle index's stored rows + topology into a GPU handle (what the Go shim does)."""
+    GpuIndex = _gpu()
+    g = oi.export_graph()
+    gi = GpuIndex(oi.dim, _metric_name(metric), m, capacity or max(g.n, 1))
+    if g.n:
+        gi.upload_vectors(1, oi.vectors()[1:])
+    gi.set_graph(g.n, g.levels, g.node_row, g.row_off, g.nbrs, g.entry, g.max_level)
+    if g.deleted.any():
+        gi.set_deleted(O.dense_bitset(np.where(g.deleted)[0], g.n))
+    return gi, g
+
+
+def _build(n, dim, metric, m, efc, seed, batch=512, data="normal", dup=False):
+    rng = np.random.default_rng(seed)
+    if data == "normal":
+        X = rng.standard_normal((n, dim)).astype(np.float32)
+    elif data == "uniform":
+        X = rng.random((n, dim)).astype(np.float32)
+    else:  # small integer grid: many exact distance ties
+        X = rng.integers(-2, 3, (n, dim)).astype(np.float32)
+    if dup:
+        X[rng.integers(0, n, n // 10)] = X[rng.integers(0, n, n // 10)]
+    oi = O.OracleIndex(dim, metric, m, efc, O.ARITH_KERNEL, n + 8)
+    oi.build_batched(X, rng.random(n), batch=batch, threads=8)
+    return oi, X, rng
+
+
+def _assert_same(gpu, ora):
+    gids, gsc, gcnt, gst = gpu
+    oids, osc, ocnt, ost = ora
+    assert np.array_equal(gcnt, ocnt.astype(np.uint32))
+    assert np.array_equal(gids, oids)
+    assert np.array_equal(gsc, osc)  # float64 bit patterns
+    assert gst.dist_evals == ost.dist_evals and gst.hops == ost.hops and gst.hops_l0 == ost.hops_l0
+
+
+# ---- the reference's own known answers, through the GPU distance hook ------------------------
+def test_distance_hook_known_answers():
+    GpuIndex = _gpu()
+    gi = GpuIndex(2, "euclidean", 4, 8)
+    gi.upload_vectors(1, np.array([[3, 4]], dtype=np.float32))
+    assert gi.distance_batch(np.array([1, 2], np.float32), [1])[0] == 8.0  # distance_test.go:37-45
+    gi.close()
+    gi = GpuIndex(3, "cosine", 4, 8)
+    v = O.normalize([1, 2, 3])
+    gi.upload_vectors(1, v[None, :])
+    assert abs(gi.distance_batch(v, [1])[0]) < 1e-6  # distance_test.go:46-56
+    w = np.array([[1, 2, 3]], np.float32)
+    gi.upload_vectors(2, w)
+    assert gi.distance_batch(np.array([1, 2, 3], np.float32), [2])[0] == 1.0 - 14.0  # lib.rs:435-441 (dot = 14)
+    gi.close()
+
+
+@pytest.mark.parametrize("dim", [1, 3, 4, 7, 33, 100, 128, 200, 768, 1536])
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_COSINE])
+def test_distance_hook_is_bit_exact(dim, metric):
+    GpuIndex = _gpu()
+    rng = np.random.default_rng(dim)
+    X = rng.standard_normal((300, dim)).astype(np.float32)
+    q = rng.standard_normal(dim).astype(np.float32)
+    if metric == O.METRIC_COSINE:  # cosine indexes only ever hold unit vectors (hnsw_index.go:485-493)
+        X, q = O.normalize_rows(X), O.normalize(q)
+    gi = GpuIndex(dim, _metric_name(metric), 4, 300)
+    gi.upload_vectors(1, X)
+    ids = rng.integers(1, 301, 500).astype(np.uint32)
+    got = gi.distance_batch(q, ids)
+    want = np.array([O.distance(metric, O.ARITH_KERNEL, q, X[i - 1]) for i in ids])
+    assert np.array_equal(got, want)
+    # and within the north-star tolerance of the reference-faithful orders
+    for arith in (O.ARITH_SEQ, O.ARITH_AVX2):
+        ref = np.array([O.distance(metric, arith, q, X[i - 1]) for i in ids[:64]])
+        assert np.max(np.abs(got[:64] - ref) / np.maximum(1.0, np.abs(ref))) < 1e-5
+    gi.close()
+
+
+# ---- SearchWithScores parity -----------------------------------------------------------------
+CONFIGS = [
+    # n, dim, metric, M, efC, k, ef, data      (C1 of BASELINE.json first)
+    (10000, 128, O.METRIC_COSINE, 16, 200, 10, 64, "normal"),
+    (3000, 100, O.METRIC_L2, 8, 60, 10, 40, "uniform"),
+    (2500, 768, O.METRIC_COSINE, 32, 100, 10, 128, "normal"),
+    (1500, 1536, O.METRIC_COSINE, 32, 80, 10, 128, "normal"),
+    (2000, 7, O.METRIC_L2, 4, 40, 3, 0, "normal"),      # efSearch = 0 -> ef = k
+    (2000, 33, O.METRIC_COSINE, 6, 40, 25, 10, "normal"),  # ef < k -> ef = k
+    (1500, 12, O.METRIC_L2, 5, 40, 10, 50, "grid"),     # integer grid: exact ties everywhere
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"n{c[0]}-d{c[1]}-{'cos' if c[2] else 'l2'}-M{c[3]}-ef{c[6]}")
+def test_search_is_bit_exact(cfg):
+    n, dim, metric, m, efc, k, ef, data = cfg
+    oi, X, rng = _build(n, dim, metric, m, efc, seed=n + dim, data=data, dup=True)
+    gi, g = _mirror(oi, metric, m)
+    Q = np.concatenate([rng.standard_normal((96, dim)).astype(np.float32), X[rng.integers(0, n, 32)]])
+    if data == "grid":
+        Q = rng.integers(-2, 3, (128, dim)).astype(np.float32)
+    _assert_same(gi.SearchWithScores(Q, k, None, ef), oi.search_batch(Q, k, ef, threads=8))
+    # 10 % allow-list (config 5's shape): membership tested before any distance work
+    allow = O.dense_bitset(np.where(rng.random(n + 1) < 0.1)[0][1:], n)
+    _assert_same(gi.SearchWithScores(Q, k, allow, ef), oi.search_batch(Q, k, ef, allow=allow, threads=8))
+    # soft deletes: traversed, never returned
+    dele = rng.choice(np.arange(1, n + 1), n // 8, replace=False)
+    for d in dele:
+        oi.delete(int(d))
+    gi.set_deleted(O.dense_bitset(dele, n))
+    _assert_same(gi.SearchWithScores(Q, k, None, ef), oi.search_batch(Q, k, ef, threads=8))
+    _assert_same(gi.SearchWithScores(Q, k, allow, ef), oi.search_batch(Q, k, ef, allow=allow, threads=8))
+    gi.close()
+
+
+def test_reference_arithmetic_agreement_within_tolerance():
+    """North-star bar against the reference-faithful arithmetic (sequential f32 = distance_go.go,
+    8-lane FMA = lib.rs): scores within 1e-5; top-k id sets equal except where a different
+    summation order flips a near-tie.  We require >= 99 % id agreement and exact score tolerance."""
+    oi, X, rng = _build(6000, 128, O.METRIC_COSINE, 16, 100, seed=77)
+    gi, g = _mirror(oi, O.METRIC_COSINE, 16)
+    Q = rng.standard_normal((256, 128)).astype(np.float32)
+    gids, gsc, gcnt, _ = gi.SearchWithScores(Q, 10, None, 64)
+    for arith in (O.ARITH_SEQ, O.ARITH_AVX2):
+        oi.set_arith(arith)
+        oids, osc, ocnt, _ = oi.search_batch(Q, 10, 64, threads=8)
+        agree = np.mean([len(set(gids[i]) & set(oids[i])) / 10 for i in range(len(Q))])
+        assert agree >= 0.99
+        same = gids == oids
+        assert np.max(np.abs(gsc[same] - osc[same])) < 1e-5
+        assert np.max(np.abs(np.sort(gsc, 1) - np.sort(osc, 1))) < 1e-3  # flipped near-ties stay close
+        # engine-side score 1/(1+d) (search_utils.go:48-52) inherits the tolerance
+        assert np.max(np.abs(1 / (1 + gsc[same]) - 1 / (1 + osc[same]))) < 1e-5
+    gi.close()
+
+
+def test_results_do_not_depend_on_cta_shape():
+    oi, X, rng = _build(4000, 256, O.METRIC_L2, 12, 80, seed=5)
+    gi, g = _mirror(oi, O.METRIC_L2, 12)
+    Q = rng.standard_normal((200, 256)).astype(np.float32)
+    want = oi.search_batch(Q, 10, 96, threads=8)
+    for nwarps, slots, cand_smem in ((2, 2, 64), (2, 4, 512), (4, 1, 16), (4, 2, 512), (4, 4, 256), (8, 1, 512), (8, 2, 32)):
+        gi.set_tuning(nwarps, slots, cand_smem, 0)
+        _assert_same(gi.SearchWithScores(Q, 10, None, 96), want)
+    gi.set_tuning(4, 2, 512, 1)  # one CTA per SM: persistent loop over many queries per CTA
+    _assert_same(gi.SearchWithScores(Q, 10, None, 96), want)
+    gi.close()
+
+
+def test_large_ef_and_k():
+    oi, X, rng = _build(3000, 64, O.METRIC_COSINE, 8, 60, seed=6)
+    gi, g = _mirror(oi, O.METRIC_COSINE, 8)
+    Q = rng.standard_normal((40, 64)).astype(np.float32)
+    _assert_same(gi.SearchWithScores(Q, 100, None, 400), oi.search_batch(Q, 100, 400, threads=8))
+    _assert_same(gi.SearchWithScores(Q, 1000, None, 0), oi.search_batch(Q, 1000, 0, threads=8))
+    gi.close()
+
+
+def test_edge_cases_empty_tiny_and_ragged():
+    GpuIndex = _gpu()
+    # empty index: maxLevel == -1 -> [] (hnsw_index.go:383-385)
+    oi = O.OracleIndex(8, O.METRIC_L2, 4, 10, O.ARITH_KERNEL, 16)
+    gi, g = _mirror(oi, O.METRIC_L2, 4, capacity=16)
+    ids, sc, cnt, _ = gi.SearchWithScores(np.ones((3, 8), np.float32), 5, None, 10)
+    assert cnt.tolist() == [0, 0, 0] and not ids.any()
+    gi.close()
+    # 1, 2 and 5 nodes: fewer than k results, never more (hnsw_stress_test.go:110-114)
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 5):
+        oi = O.OracleIndex(8, O.METRIC_COSINE, 4, 10, O.ARITH_KERNEL, 16)
+        oi.add_many(rng.standard_normal((n, 8)).astype(np.float32), rng.random(n))
+        gi, g = _mirror(oi, O.METRIC_COSINE, 4, capacity=16)
+        Q = rng.standard_normal((4, 8)).astype(np.float32)
+        got = gi.SearchWithScores(Q, 10, None, 20)
+        _assert_same(got, oi.search_batch(Q, 10, 20))
+        assert (got[2] == n).all()
+        # zero query on a cosine index stays zero -> every distance is exactly 1.0 (Appendix A rule 2)
+        got = gi.SearchWithScores(np.zeros((1, 8), np.float32), 10, None, 20)
+        _assert_same(got, oi.search_batch(np.zeros((1, 8), np.float32), 10, 20))
+        assert np.all(got[1][0, :n] == 1.0)
+        gi.close()
+    # nq == 0 is a no-op
+    oi, X, rng = _build(200, 8, O.METRIC_L2, 4, 20, seed=9)
+    gi, g = _mirror(oi, O.METRIC_L2, 4)
+    ids, sc, cnt, _ = gi.SearchWithScores(np.zeros((0, 8), np.float32), 5, None, 10)
+    assert ids.shape == (0, 5)
+    # search before any graph upload is a state error, not a crash
+    from kektordb_b200 import ffi
+    fresh = GpuIndex(8, "euclidean", 4, 16)
+    with pytest.raises(ffi.GpuError):
+        fresh.SearchWithScores(np.zeros((1, 8), np.float32), 5, None, 10)
+    fresh.close()
+    gi.close()
+
+
+def test_allow_list_semantics():
+    """hnsw_index.go:436-447, :2480-2485, :2545-2549 and pkg/engine/roaring_filters_test.go."""
+    oi, X, rng = _build(2500, 16, O.METRIC_L2, 6, 40, seed=10)
+    gi, g = _mirror(oi, O.METRIC_L2, 6)
+    Q = rng.standard_normal((64, 16)).astype(np.float32)
+    n = g.n
+    # empty non-nil list -> [] for every query
+    got = gi.SearchWithScores(Q, 5, O.dense_bitset([], n), 30)
+    assert not got[2].any()
+    # entry point excluded: the smallest member becomes the entry, even a level-0-only node
+    low = [i for i in range(1, n + 1) if g.levels[i] == 0 and i != g.entry][:60]
+    allow = O.dense_bitset(low, n)
+    got = gi.SearchWithScores(Q, 5, allow, 30)
+    _assert_same(got, oi.search_batch(Q, 5, 30, allow=allow, threads=4))
+    assert all(set(r[:c].tolist()) <= set(low) for r, c in zip(got[0], got[2]))
+    # a single allowed id far from everything; an allow-list that covers everything
+    for ids in ([n], list(range(1, n + 1)), [1, 2, 3]):
+        allow = O.dense_bitset(ids, n)
+        _assert_same(gi.SearchWithScores(Q, 5, allow, 30), oi.search_batch(Q, 5, 30, allow=allow, threads=4))
+    # a bitset shorter than the id range (ids beyond it are simply not members)
+    short = O.dense_bitset([5, 70, 100], 127)
+    _assert_same(gi.SearchWithScores(Q, 5, short, 30), oi.search_batch(Q, 5, 30, allow=short, threads=4))
+    gi.close()
+
+
+def test_filter_id_sets_on_identical_zero_vectors():
+    """pkg/engine/roaring_filters_test.go:14-150 replayed on the GPU: all-zero vectors, euclidean,
+    k=10 efSearch=100; every distance ties at 0 and the allow-list alone decides the id set."""
+    oi = O.OracleIndex(2, O.METRIC_L2, 16, 200, O.ARITH_KERNEL, 16)
+    oi.add_batch(np.zeros((5, 2), np.float32), np.full(5, 0.9))
+    oi.add(np.zeros(2, np.float32), 0.9)
+    gi, g = _mirror(oi, O.METRIC_L2, 16, capacity=16)
+    q = np.zeros((1, 2), np.float32)
+    for allowed in ({3, 4}, {1}, {2, 5}, {2, 3, 4, 5}, {3, 4, 5}):
+        allow = O.dense_bitset(sorted(allowed), g.n)
+        ids, sc, cnt, _ = gi.SearchWithScores(q, 10, allow, 100)
+        assert set(ids[0, :cnt[0]].tolist()) == allowed and np.all(sc == 0.0)
+        _assert_same(gi.SearchWithScores(q, 10, allow, 100), oi.search_batch(q, 10, 100, allow=allow))
+    gi.close()
+
+
+def test_nil_slots_in_the_graph():
+    """Vacuum nils node slots (optimizer.go:252-274); neighbours pointing at them are skipped
+    (hnsw_index.go:2553-2561)."""
+    oi, X, rng = _build(1200, 10, O.METRIC_L2, 6, 40, seed=11)
+    g = oi.export_graph()
+    nil = [i for i in rng.choice(np.arange(1, g.n + 1), 100, replace=False) if i != g.entry]
+    levels = g.levels.copy()
+    keep_rows, node_row, row_off, nbrs = [], [0], [0], []
+    for i in range(g.n + 1):
+        if i in nil:
+            levels[i] = -1
+        for l in range(levels[i] + 1 if levels[i] >= 0 else 0):
+            row = g.row(i, l)
+            nbrs.extend(row.tolist())  # still lists nil neighbours: the library must skip them
+            row_off.append(len(nbrs))
+        node_row.append(len(row_off) - 1)
+    g2 = O.Graph(g.n, levels, np.array(node_row, np.uint64), np.array(row_off, np.uint64),
+                 np.array(nbrs, np.uint32), g.deleted, g.entry, g.max_level)
+    o2 = O.OracleIndex(10, O.METRIC_L2, 6, 40, O.ARITH_KERNEL, g.n)
+    o2.import_graph(oi.vectors(), g2)
+    GpuIndex = _gpu()
+    gi = GpuIndex(10, "euclidean", 6, g.n)
+    gi.upload_vectors(1, oi.vectors()[1:])
+    gi.set_graph(g2.n, g2.levels, g2.node_row, g2.row_off, g2.nbrs, g2.entry, g2.max_level)
+    Q = rng.standard_normal((64, 10)).astype(np.float32)
+    got = gi.SearchWithScores(Q, 8, None, 40)
+    want = o2.search_batch(Q, 8, 40, threads=4)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert not np.isin(got[0], nil).any()
+    gi.close()
+
+
+@pytest.mark.parametrize("name", ["cosine_d48_m8", "l2_d20_m6_filtered"])
+def test_golden_fixtures(name):
+    """Committed fixtures (tests/golden/make_golden.py): stored rows, topology, queries and the
+    oracle's expected output; replayed without building anything."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    GpuIndex = _gpu()
+    n, dim, metric, m = int(z["n"]), int(z["dim"]), int(z["metric"]), int(z["m"])
+    gi = GpuIndex(dim, _metric_name(metric), m, n)
+    gi.upload_vectors(1, z["vectors"][1:])
+    gi.set_graph(n, z["levels"], z["node_row"], z["row_off"], z["nbrs"], int(z["entry"]), int(z["max_level"]))
+    if z["deleted"].any():
+        gi.set_deleted(O.dense_bitset(np.where(z["deleted"])[0], n))
+    allow = z["allow"] if z["allow"].size else None
+    ids, sc, cnt, st = gi.SearchWithScores(z["queries"], int(z["k"]), allow, int(z["ef"]))
+    assert np.array_equal(ids, z["ids"]) and np.array_equal(sc, z["scores"])
+    assert np.array_equal(cnt, z["counts"].astype(np.uint32))
+    assert st.dist_evals == int(z["dist_evals"]) and st.hops == int(z["hops"])
+    gi.close()
+
+
+# ---- flat path ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_COSINE])
+def test_flat_scan_is_bit_exact(metric):
+    oi, X, rng = _build(3000, 96, metric, 8, 40, seed=12, dup=True)
+    dele = rng.choice(np.arange(1, 3001), 200, replace=False)
+    for d in dele:
+        oi.delete(int(d))
+    gi, g = _mirror(oi, metric, 8)
+    Q = np.concatenate([rng.standard_normal((40, 96)).astype(np.float32), X[:8]])
+    allow = O.dense_bitset(np.where(rng.random(3001) < 0.2)[0][1:], 3000)
+    for mode in (0, 1):
+        for k in (1, 10, 100):
+            for al in (None, allow):
+                fi, fs, fc, _ = gi.flat_search(Q, k, mode, al)
+                wi, ws, wc = oi.flat_search_batch(Q, k, mode=mode, allow=al, threads=8)
+                assert np.array_equal(fc, wc.astype(np.uint32))
+                assert np.array_equal(fi, wi) and np.array_equal(fs, ws)
+    # an empty allow-list is "no filter" for the brute-force index (vector_index.go:132)
+    fi, _, _, _ = gi.flat_search(Q, 5, 0, O.dense_bitset([], 3000))
+    wi, _, _ = oi.flat_search_batch(Q, 5, mode=0)
+    assert np.array_equal(fi, wi)
+    gi.close()
+
+
+def test_hnsw_recall_against_flat_ground_truth():
+    """Recall@10 of the graph search measured against the GPU's own exact scan (which the test
+    above pins to the oracle): low-rank random-normal data, the benchmark's data model."""
+    rng = np.random.default_rng(13)
+    W = rng.standard_normal((16, 128)).astype(np.float32) / 4
+    X = rng.standard_normal((8000, 16)).astype(np.float32) @ W + 0.1 * rng.standard_normal((8000, 128)).astype(np.float32)
+    Qm = rng.standard_normal((200, 16)).astype(np.float32) @ W + 0.1 * rng.standard_normal((200, 128)).astype(np.float32)
+    oi = O.OracleIndex(128, O.METRIC_COSINE, 16, 200, O.ARITH_KERNEL, 8000)
+    oi.build_batched(X, rng.random(8000), batch=1000, threads=8)
+    gi, g = _mirror(oi, O.METRIC_COSINE, 16)
+    ids, sc, cnt, _ = gi.SearchWithScores(Qm, 10, None, 64)
+    gt, _, _, _ = gi.flat_search(Qm, 10, 1)
+    rec = np.mean([len(set(ids[i]) & set(gt[i])) / 10 for i in range(200)])
+    assert rec >= 0.95
+    assert np.all(np.diff(sc, axis=1) >= 0)  # ascending distances (hnsw_index.go:2596-2604)
+    # idempotence: a second call returns the same bits
+    again = gi.SearchWithScores(Qm, 10, None, 64)
+    assert np.array_equal(again[0], ids) and np.array_equal(again[1], sc)
+    # scores are exactly the distance hook's values for the returned ids
+    qn = O.normalize(Qm[0])
+    assert np.array_equal(gi.distance_batch(qn, ids[0]), sc[0])
+    gi.close()
+
+
+# ---- merge of per-shard results ---------------------------------------------------------------
+def test_merge_topk_kernel_matches_numpy():
+    import ctypes as C
+
+    import torch
+    from kektordb_b200 import ffi
+    GpuIndex = _gpu()
+    gi = GpuIndex(4, "euclidean", 4, 8)
+    rng = np.random.default_rng(14)
+    S, nq, k = 4, 300, 10
+    sc = np.sort(rng.integers(0, 30, (S, nq, k)).astype(np.float64) / 7, axis=2)  # ties across shards
+    ids = rng.permutation(S * nq * k).astype(np.uint32).reshape(S, nq, k) + 1
+    cnt = rng.integers(0, k + 1, (S, nq)).astype(np.uint32)
+    d_ids, d_sc, d_cnt = (torch.from_numpy(a).cuda() for a in (ids.astype(np.int32), sc, cnt.astype(np.int32)))
+    o_ids = torch.zeros((nq, k), dtype=torch.int32, device="cuda")
+    o_sc = torch.zeros((nq, k), dtype=torch.float64, device="cuda")
+    o_cnt = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ffi.check(ffi.lib().kdbgpu_merge_topk_device(gi._h, S, nq, k, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
+                                                 o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(),
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    for q in range(nq):
+        pool = [(sc[s, q, i], int(ids[s, q, i])) for s in range(S) for i in range(cnt[s, q])]
+        pool.sort()
+        want = pool[:k]
+        n = int(o_cnt[q])
+        assert n == len(want)
+        assert o_ids[q, :n].cpu().numpy().astype(np.uint32).tolist() == [w[1] for w in want]
+        assert o_sc[q, :n].cpu().numpy().tolist() == [w[0] for w in want]
+    gi.close()
