@@ -126,6 +126,23 @@ int kdbgpu_merge_topk_device(kdbgpu_index *, int n_shards, uint32_t nq, int k, c
                              const double *d_scores, const uint32_t *d_counts, uint32_t *d_out_ids,
                              double *d_out_scores, uint32_t *d_out_counts, void *stream);
 
+/* ---- graph construction on the device (extension; the reference builds on the CPU) --------- */
+/* (*Index).AddBatch (hnsw_index.go:1466, addBatchInternal :1479-2088) for `count` raw vectors that
+ * receive ids n+1 .. n+count.  level_draws[i] is the rand.Float64() of randomLevel (:2616-2625).
+ * ef_const <= 0 -> 200 (efConstruction default); AddBatchFast passes max(2M, 40) (:1470-1476).
+ * While the index holds fewer than ef_const nodes the whole batch goes through sequential single
+ * Adds (:1502-1513, Add :472-809), as in the reference.  Deterministic. */
+int kdbgpu_add_batch(kdbgpu_index *, uint32_t count, const float *rows, const double *level_draws, int ef_const);
+/* Same with the rows resident on the handle's device (row_stride in floats). */
+int kdbgpu_add_batch_device(kdbgpu_index *, uint32_t count, const float *d_rows, size_t row_stride,
+                            const double *level_draws, int ef_const);
+/* Read the topology back (same layout as kdbgpu_set_graph; levels [n+1], node_row [n+2],
+ * row_off [n_rows+1], nbrs [n_edges]) and the stored rows ([count][dim]). */
+int kdbgpu_get_graph_sizes(kdbgpu_index *, uint32_t *n, uint64_t *n_rows, uint64_t *n_edges, uint32_t *entry,
+                           int *max_level);
+int kdbgpu_get_graph(kdbgpu_index *, int32_t *levels, uint64_t *node_row, uint64_t *row_off, uint32_t *nbrs);
+int kdbgpu_download_vectors(kdbgpu_index *, uint32_t first_id, uint32_t count, float *rows);
+
 /* ---- introspection -------------------------------------------------------------------- */
 int kdbgpu_index_device(const kdbgpu_index *);
 uint32_t kdbgpu_index_count(const kdbgpu_index *);   /* n of the last kdbgpu_set_graph        */

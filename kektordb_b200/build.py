@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkektordb_gpu.so")
-SOURCES = ["api.cu", "search.cu", "flat.cu"]
-HEADERS = ["kdb_internal.cuh", os.path.join("..", "..", "include", "kektordb_gpu.h")]
+SOURCES = ["api.cu", "search.cu", "flat.cu", "build.cu"]
+HEADERS = ["kdb_internal.cuh", "searcher.cuh", os.path.join("..", "..", "include", "kektordb_gpu.h")]
 
 
 def nvcc_path() -> str:

@@ -1,6 +1,8 @@
 // api.cu — the C ABI of include/kektordb_gpu.h: handle lifecycle, staging of the corpus and the
 // graph into HBM, and the batched query entry points.  No torch types, no exceptions across the
 // boundary, no CPU fallback.
+#include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +15,36 @@
 #include "kdb_internal.cuh"
 
 using namespace kdb;
+
+namespace kdb {
+struct BuildLaunch {
+  uint32_t start_id, count;
+  uint32_t pre_entry;
+  int pre_max;
+  int efc;
+  uint32_t n_slots;
+  uint32_t up_base;
+  uint32_t n_rows;
+  const uint32_t *out_off;
+  const uint32_t *slot_node;
+  const uint8_t *slot_level;
+  uint32_t *cand_ids, *cand_cnt;
+  uint32_t *row_cnt, *row_off, *srcs, *active, *n_active, *work_counter;
+  uint32_t *adj0, *upper_adj;
+  const uint32_t *upper_node;
+  const uint8_t *upper_level;
+  double *scratch_d;
+  uint32_t *scratch_ids;
+  uint32_t scratch_cap;
+  int commit_grid;
+};
+size_t seq_add_smem_bytes(const DevIndex &ix, int efc, uint32_t cand_smem);
+int build_search_occupancy(const DevIndex &ix, int efc, uint32_t cand_smem);
+cudaError_t launch_add_batch(const DevIndex &ix, const SearchArgs &a, const BuildLaunch &L, int search_grid,
+                             cudaStream_t stream);
+cudaError_t launch_seq_add(const DevIndex &ix, const SearchArgs &a, uint32_t start_id, uint32_t count, int efc,
+                           uint32_t *adj0, uint32_t *upper_adj, uint32_t *entry_io, cudaStream_t stream);
+}  // namespace kdb
 
 namespace {
 
@@ -93,6 +125,16 @@ struct kdbgpu_index {
   int ws_grid = 0;
   uint32_t vis_words = 0;
   uint32_t ovf_cap = 1u << 15;
+  // construction state: host mirrors of levels / upper-row ownership, device build workspace
+  std::vector<int8_t> h_levels;
+  std::vector<uint32_t> h_upper_first;
+  uint32_t upper_rows_used = 0;
+  DevBuf<uint32_t> upper_node;
+  DevBuf<uint8_t> upper_level;
+  DevBuf<uint32_t> b_out_off, b_slot_node, b_cand_ids, b_cand_cnt, b_row_cnt, b_row_off, b_srcs, b_active,
+      b_scalars, b_scratch_ids;
+  DevBuf<uint8_t> b_slot_level;
+  DevBuf<double> b_scratch_d;
 
   DevIndex dev() const {
     DevIndex d;
@@ -277,6 +319,12 @@ int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacit
   if (e == cudaSuccess) e = cudaMemset(h->levels.p, 0xff, n1);
   if (e == cudaSuccess) e = h->upper_first.reserve(n1, true);
   if (e == cudaSuccess) e = h->deleted.reserve((n1 + 31) / 32 + 2, true);
+  const size_t up_rows = (size_t)((double)capacity / (double)(m > 1 ? m - 1 : 1) * 1.3) + 4096;
+  if (e == cudaSuccess) e = h->upper_adj.reserve(up_rows * (size_t)m, true);
+  if (e == cudaSuccess) e = h->upper_node.reserve(up_rows, true);
+  if (e == cudaSuccess) e = h->upper_level.reserve(up_rows, true);
+  h->h_levels.assign(n1, (int8_t)-1);
+  h->h_upper_first.assign(n1, 0u);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     return cleanup(fail(e == cudaErrorMemoryAllocation ? KDBGPU_ERR_NOMEM : KDBGPU_ERR_CUDA,
@@ -310,6 +358,20 @@ int kdbgpu_index_destroy(kdbgpu_index *h) {
   h->stats.release();
   h->work_counter.release();
   h->err_flag.release();
+  h->upper_node.release();
+  h->upper_level.release();
+  h->b_out_off.release();
+  h->b_slot_node.release();
+  h->b_cand_ids.release();
+  h->b_cand_cnt.release();
+  h->b_row_cnt.release();
+  h->b_row_off.release();
+  h->b_srcs.release();
+  h->b_active.release();
+  h->b_scalars.release();
+  h->b_scratch_ids.release();
+  h->b_slot_level.release();
+  h->b_scratch_d.release();
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -357,7 +419,8 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
     return fail(KDBGPU_ERR_INVALID, "entry point %u is not a live node", entry);
   const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
   const size_t n1 = (size_t)n + 1;
-  std::vector<uint32_t> adj0(n1 * deg0, 0u), upper_first(n1, 0u), upper;
+  std::vector<uint32_t> adj0(n1 * deg0, 0u), upper_first(n1, 0u), upper, upper_node;
+  std::vector<uint8_t> upper_level;
   std::vector<int8_t> lv(n1, (int8_t)-1);
   size_t upper_rows = 0;
   for (uint32_t id = 1; id <= n; ++id) {
@@ -369,6 +432,10 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
                   (unsigned long long)(node_row[id + 1] - node_row[id]), L);
     lv[id] = (int8_t)L;
     upper_first[id] = (uint32_t)upper_rows;
+    for (int32_t l = 1; l <= L; ++l) {
+      upper_node.push_back(id);
+      upper_level.push_back((uint8_t)l);
+    }
     upper_rows += (size_t)L;
   }
   upper.assign((upper_rows + 1) * degu, 0u);
@@ -393,15 +460,34 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
   }
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  CUDA_TRY(h->upper_adj.reserve(upper.size()));
-  CUDA_TRY(cudaMemcpyAsync(h->adj0.p, adj0.data(), adj0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->upper_adj.p, upper.data(), upper.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                           h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->upper_first.p, upper_first.data(), n1 * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                           h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->levels.p, 0xff, (size_t)h->capacity + 1, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->levels.p, lv.data(), n1, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if ((upper_rows + 1) * degu > h->upper_adj.n) {
+    const size_t rows = (upper_rows + 1) + (upper_rows + 1) / 4 + 1024;
+    h->upper_adj.release();
+    h->upper_node.release();
+    h->upper_level.release();
+    CUDA_TRY(h->upper_adj.reserve(rows * degu, true));
+    CUDA_TRY(h->upper_node.reserve(rows, true));
+    CUDA_TRY(h->upper_level.reserve(rows, true));
+  }
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaMemsetAsync(h->adj0.p, 0, h->adj0.bytes(), s));
+  CUDA_TRY(cudaMemsetAsync(h->upper_adj.p, 0, h->upper_adj.bytes(), s));
+  CUDA_TRY(cudaMemcpyAsync(h->adj0.p, adj0.data(), adj0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->upper_adj.p, upper.data(), upper.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  if (upper_rows) {
+    CUDA_TRY(cudaMemcpyAsync(h->upper_node.p, upper_node.data(), upper_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->upper_level.p, upper_level.data(), upper_rows, cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaMemsetAsync(h->upper_first.p, 0, h->upper_first.bytes(), s));
+  CUDA_TRY(cudaMemcpyAsync(h->upper_first.p, upper_first.data(), n1 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(h->levels.p, 0xff, (size_t)h->capacity + 1, s));
+  CUDA_TRY(cudaMemcpyAsync(h->levels.p, lv.data(), n1, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  std::fill(h->h_levels.begin(), h->h_levels.end(), (int8_t)-1);
+  std::fill(h->h_upper_first.begin(), h->h_upper_first.end(), 0u);
+  std::copy(lv.begin(), lv.end(), h->h_levels.begin());
+  std::copy(upper_first.begin(), upper_first.end(), h->h_upper_first.begin());
+  h->upper_rows_used = (uint32_t)upper_rows;
   h->n = n;
   h->entry = entry;
   h->max_level = max_level;
@@ -639,6 +725,328 @@ int kdbgpu_search_concurrency(kdbgpu_index *h, int k, int ef_search) {
   return search_occupancy(h->dev(), ef, h->tuning) * h->num_sms;
 }
 
+}  // extern "C"
+
+// ---- graph construction on the device ---------------------------------------
+namespace {
+
+// randomLevel (hnsw_index.go:2616-2625): floor(-ln(u) * 1/ln(m)), capped at current max + 1
+int random_level(double u, int m, int current_max) {
+  const double ml = 1.0 / log((double)m);
+  const double f = floor(-log(u) * ml);
+  int level = (f > 1e9 || f != f) ? 1000000000 : (int)f;
+  if (level > current_max + 1) return current_max + 1;
+  return level;
+}
+
+int grow_upper(kdbgpu_index *h, size_t need_rows, cudaStream_t s) {
+  if (need_rows <= h->upper_node.n && need_rows * (size_t)h->m <= h->upper_adj.n) return KDBGPU_OK;
+  const size_t rows = need_rows + need_rows / 2 + 4096;
+  DevBuf<uint32_t> adj, node;
+  DevBuf<uint8_t> lvl;
+  CUDA_TRY(adj.reserve(rows * (size_t)h->m, true));
+  CUDA_TRY(node.reserve(rows, true));
+  CUDA_TRY(lvl.reserve(rows, true));
+  const size_t used = h->upper_rows_used;
+  if (used) {
+    CUDA_TRY(cudaMemcpyAsync(adj.p, h->upper_adj.p, used * (size_t)h->m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(node.p, h->upper_node.p, used * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(lvl.p, h->upper_level.p, used, cudaMemcpyDeviceToDevice, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  h->upper_adj.release();
+  h->upper_node.release();
+  h->upper_level.release();
+  h->upper_adj = adj;
+  h->upper_node = node;
+  h->upper_level = lvl;
+  return KDBGPU_OK;
+}
+
+uint32_t next_pow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// rows: `count` raw vectors, on the host (row_stride == dim) or on the device
+int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t row_stride, bool rows_on_device,
+                   const double *level_draws, int ef_const) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (count == 0) return KDBGPU_OK;
+  if (!rows || !level_draws) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (ef_const <= 0) ef_const = 200;  // hnsw.New default (hnsw_index.go:143-145)
+  if (ef_const > 2048) return fail(KDBGPU_ERR_INVALID, "ef_const %d too large (max 2048)", ef_const);
+  if (h->m < 2) return fail(KDBGPU_ERR_INVALID, "construction needs m >= 2");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if ((uint64_t)h->n + count > h->capacity)
+    return fail(KDBGPU_ERR_INVALID, "batch of %u does not fit: %u of %u ids used", count, h->n, h->capacity);
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  const uint32_t start_id = h->n + 1;
+  const bool sequential = (uint64_t)h->n < (uint64_t)ef_const;  // :1502-1513
+  // stage the rows: cosine vectors are normalised exactly as normalize() (:1557-1559, :485-493)
+  const float *d_src = rows;
+  if (!rows_on_device) {
+    CUDA_TRY(h->q_raw.reserve((size_t)count * h->dim));
+    CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, rows, (size_t)count * h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    d_src = h->q_raw.p;
+    row_stride = (size_t)h->dim;
+  }
+  CUDA_TRY(launch_prep_queries(d_src, row_stride, h->vecs.p + (size_t)start_id * h->stride, count, (uint32_t)h->dim,
+                               h->stride, h->metric, s));
+  // levels (:647, :1738) and upper-row allocation
+  const int pre_max = h->max_level;
+  const uint32_t pre_entry = h->entry;
+  std::vector<int8_t> lv(count);
+  std::vector<uint32_t> uf(count, 0u), new_upper_node;
+  std::vector<uint8_t> new_upper_level;
+  int cur_max = pre_max;
+  uint32_t new_entry = pre_entry;
+  uint32_t cursor = h->upper_rows_used;
+  for (uint32_t i = 0; i < count; ++i) {
+    int L = random_level(level_draws[i], h->m, sequential ? cur_max : pre_max);
+    if (L > 120) L = 120;
+    lv[i] = (int8_t)L;
+    uf[i] = cursor;
+    for (int l = 1; l <= L; ++l) {
+      new_upper_node.push_back(start_id + i);
+      new_upper_level.push_back((uint8_t)l);
+    }
+    cursor += (uint32_t)L;
+    if (cur_max == -1) {  // first node of an empty index (:658-670)
+      cur_max = L;
+      new_entry = start_id + i;
+    } else if (L > cur_max) {  // :793-801 / phase 4 :2066-2080
+      cur_max = L;
+      new_entry = start_id + i;
+    }
+  }
+  int rc = grow_upper(h, (size_t)cursor + 1, s);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->levels.p + start_id, lv.data(), count, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->upper_first.p + start_id, uf.data(), (size_t)count * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(h->adj0.p + (size_t)start_id * 2 * h->m, 0, (size_t)count * 2 * h->m * sizeof(uint32_t), s));
+  const uint32_t n_new_upper = cursor - h->upper_rows_used;
+  if (n_new_upper) {
+    CUDA_TRY(cudaMemsetAsync(h->upper_adj.p + (size_t)h->upper_rows_used * h->m, 0,
+                             (size_t)n_new_upper * h->m * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemcpyAsync(h->upper_node.p + h->upper_rows_used, new_upper_node.data(),
+                             (size_t)n_new_upper * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->upper_level.p + h->upper_rows_used, new_upper_level.data(), n_new_upper,
+                             cudaMemcpyHostToDevice, s));
+  }
+  // the new nodes are registered (visible to id-range checks) but unlinked
+  h->n = start_id + count - 1;
+  DevIndex ix = h->dev();
+  ix.entry = pre_entry;
+  ix.max_level = pre_max;
+  SearchTuning bt;  // construction uses its own CTA shape: 4 warps, 1 slot
+  bt.nwarps = 4;
+  bt.slots = 1;
+  bt.cand_smem = h->tuning.cand_smem;
+  const int occ = sequential ? 1 : build_search_occupancy(ix, ef_const, (uint32_t)bt.cand_smem);
+  if (occ <= 0) return fail(KDBGPU_ERR_INVALID, "construction search does not fit shared memory (ef_const=%d)", ef_const);
+  const int full_grid = occ * h->num_sms;
+  rc = ensure_search_workspace(h, full_grid > h->ws_grid ? full_grid : h->ws_grid);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->work_counter.p, 0, sizeof(uint32_t), s));
+  CUDA_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
+  SearchArgs a;
+  a.queries = nullptr;
+  a.nq = count;
+  a.k = ef_const;
+  a.ef = ef_const;
+  a.allow = nullptr;
+  a.allow_entry = 0;
+  a.out_ids = nullptr;
+  a.out_scores = nullptr;
+  a.out_counts = nullptr;
+  a.visited = h->visited.p;
+  a.vis_words = h->vis_words;
+  a.cand_overflow = h->cand_overflow.p;
+  a.ovf_cap = h->ovf_cap;
+  a.cand_smem = (uint32_t)bt.cand_smem;
+  a.stats = h->stats.p;
+  a.work_counter = h->work_counter.p;
+  a.err_flag = h->err_flag.p;
+  CUDA_TRY(h->b_scalars.reserve(8, true));
+  if (sequential) {
+    if (seq_add_smem_bytes(ix, ef_const, a.cand_smem) > 227 * 1024)
+      return fail(KDBGPU_ERR_INVALID, "sequential construction does not fit shared memory");
+    const uint32_t io[2] = {pre_entry, (uint32_t)(pre_max + 1)};
+    CUDA_TRY(cudaMemcpyAsync(h->b_scalars.p + 2, io, sizeof io, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_seq_add(ix, a, start_id, count, ef_const, h->adj0.p, h->upper_adj.p, h->b_scalars.p + 2, s));
+  } else {
+    std::vector<uint32_t> out_off(count), slot_node;
+    std::vector<uint8_t> slot_level;
+    uint32_t n_slots = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+      out_off[i] = n_slots;
+      const int top = lv[i] < pre_max ? lv[i] : pre_max;
+      for (int l = 0; l <= top; ++l) {
+        slot_node.push_back(start_id + i);
+        slot_level.push_back((uint8_t)l);
+      }
+      n_slots += (uint32_t)(top + 1);
+    }
+    const uint32_t up_base = h->capacity + 1;
+    const uint32_t n_rows = up_base + cursor;
+    CUDA_TRY(h->b_out_off.reserve(count));
+    CUDA_TRY(h->b_slot_node.reserve(n_slots));
+    CUDA_TRY(h->b_slot_level.reserve(n_slots));
+    CUDA_TRY(h->b_cand_ids.reserve((size_t)n_slots * ef_const));
+    CUDA_TRY(h->b_cand_cnt.reserve(n_slots));
+    CUDA_TRY(h->b_row_cnt.reserve((size_t)n_rows + 2));
+    CUDA_TRY(h->b_row_off.reserve((size_t)n_rows + 2));
+    CUDA_TRY(h->b_active.reserve((size_t)n_rows + 2));
+    CUDA_TRY(h->b_srcs.reserve((size_t)n_slots * ef_const * 2));
+    const int commit_grid = h->num_sms * 6;
+    const uint32_t scratch_cap = next_pow2(2u * (uint32_t)h->m + count + 1);
+    CUDA_TRY(h->b_scratch_d.reserve((size_t)commit_grid * scratch_cap));
+    CUDA_TRY(h->b_scratch_ids.reserve((size_t)commit_grid * scratch_cap));
+    CUDA_TRY(cudaMemcpyAsync(h->b_out_off.p, out_off.data(), (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->b_slot_node.p, slot_node.data(), (size_t)n_slots * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->b_slot_level.p, slot_level.data(), n_slots, cudaMemcpyHostToDevice, s));
+    BuildLaunch L;
+    L.start_id = start_id;
+    L.count = count;
+    L.pre_entry = pre_entry;
+    L.pre_max = pre_max;
+    L.efc = ef_const;
+    L.n_slots = n_slots;
+    L.up_base = up_base;
+    L.n_rows = n_rows;
+    L.out_off = h->b_out_off.p;
+    L.slot_node = h->b_slot_node.p;
+    L.slot_level = h->b_slot_level.p;
+    L.cand_ids = h->b_cand_ids.p;
+    L.cand_cnt = h->b_cand_cnt.p;
+    L.row_cnt = h->b_row_cnt.p;
+    L.row_off = h->b_row_off.p;
+    L.srcs = h->b_srcs.p;
+    L.active = h->b_active.p;
+    L.n_active = h->b_scalars.p;
+    L.work_counter = h->b_scalars.p + 1;
+    L.adj0 = h->adj0.p;
+    L.upper_adj = h->upper_adj.p;
+    L.upper_node = h->upper_node.p;
+    L.upper_level = h->upper_level.p;
+    L.scratch_d = h->b_scratch_d.p;
+    L.scratch_ids = h->b_scratch_ids.p;
+    L.scratch_cap = scratch_cap;
+    L.commit_grid = commit_grid;
+    int grid = full_grid;
+    if ((uint32_t)grid > count) grid = (int)count;
+    CUDA_TRY(launch_add_batch(ix, a, L, grid, s));
+  }
+  int err = 0;
+  uint32_t io_back[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(&err, h->err_flag.p, sizeof err, cudaMemcpyDeviceToHost, s));
+  if (sequential) CUDA_TRY(cudaMemcpyAsync(io_back, h->b_scalars.p + 2, sizeof io_back, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  // commit host-side state
+  for (uint32_t i = 0; i < count; ++i) {
+    h->h_levels[start_id + i] = lv[i];
+    h->h_upper_first[start_id + i] = uf[i];
+  }
+  h->upper_rows_used = cursor;
+  h->entry = new_entry;
+  h->max_level = cur_max;
+  h->has_graph = true;
+  if (sequential && (io_back[0] != new_entry || (int)io_back[1] - 1 != cur_max))
+    return fail(KDBGPU_ERR_STATE, "entry point bookkeeping diverged (device %u/%d, host %u/%d)", io_back[0],
+                (int)io_back[1] - 1, new_entry, cur_max);
+  if (err == KDBGPU_ERR_OVERFLOW) return fail(KDBGPU_ERR_OVERFLOW, "a construction-time list exceeded its bound");
+  return KDBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kdbgpu_add_batch(kdbgpu_index *h, uint32_t count, const float *rows, const double *level_draws, int ef_const) {
+  return add_batch_impl(h, count, rows, h ? (size_t)h->dim : 0, false, level_draws, ef_const);
+}
+
+int kdbgpu_add_batch_device(kdbgpu_index *h, uint32_t count, const float *d_rows, size_t row_stride,
+                            const double *level_draws, int ef_const) {
+  if (h && row_stride < (size_t)h->dim) return fail(KDBGPU_ERR_INVALID, "row_stride smaller than dim");
+  return add_batch_impl(h, count, d_rows, row_stride, true, level_draws, ef_const);
+}
+
+int kdbgpu_get_graph_sizes(kdbgpu_index *h, uint32_t *n, uint64_t *n_rows, uint64_t *n_edges, uint32_t *entry,
+                           int *max_level) {
+  if (!h || !n || !n_rows || !n_edges || !entry || !max_level) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
+  std::vector<uint32_t> adj0((size_t)(h->n + 1) * deg0), upper((size_t)(h->upper_rows_used + 1) * degu);
+  CUDA_TRY(cudaMemcpy(adj0.data(), h->adj0.p, adj0.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(upper.data(), h->upper_adj.p, upper.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  uint64_t rows = 0, edges = 0;
+  for (uint32_t id = 1; id <= h->n; ++id) {
+    const int L = h->h_levels[id];
+    if (L < 0) continue;
+    rows += (uint64_t)(L + 1);
+    for (int l = 0; l <= L; ++l) {
+      const uint32_t cap = l == 0 ? deg0 : degu;
+      const uint32_t *r = l == 0 ? &adj0[(size_t)id * deg0] : &upper[((size_t)h->h_upper_first[id] + (size_t)(l - 1)) * degu];
+      for (uint32_t i = 0; i < cap && r[i]; ++i) edges++;
+    }
+  }
+  *n = h->n;
+  *n_rows = rows;
+  *n_edges = edges;
+  *entry = h->entry;
+  *max_level = h->max_level;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_get_graph(kdbgpu_index *h, int32_t *levels, uint64_t *node_row, uint64_t *row_off, uint32_t *nbrs) {
+  if (!h || !levels || !node_row || !row_off || !nbrs) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
+  std::vector<uint32_t> adj0((size_t)(h->n + 1) * deg0), upper((size_t)(h->upper_rows_used + 1) * degu);
+  CUDA_TRY(cudaMemcpy(adj0.data(), h->adj0.p, adj0.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(upper.data(), h->upper_adj.p, upper.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  uint64_t r = 0, e = 0;
+  levels[0] = -1;
+  node_row[0] = 0;
+  for (uint32_t id = 1; id <= h->n; ++id) {
+    const int L = h->h_levels[id];
+    levels[id] = L;
+    node_row[id] = r;
+    for (int l = 0; l <= L; ++l) {
+      const uint32_t cap = l == 0 ? deg0 : degu;
+      const uint32_t *row = l == 0 ? &adj0[(size_t)id * deg0] : &upper[((size_t)h->h_upper_first[id] + (size_t)(l - 1)) * degu];
+      row_off[r++] = e;
+      for (uint32_t i = 0; i < cap && row[i]; ++i) nbrs[e++] = row[i];
+    }
+  }
+  node_row[h->n + 1] = r;
+  row_off[r] = e;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_download_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, float *rows) {
+  if (!h || (!rows && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if ((uint64_t)first_id + count - 1 > h->capacity) return fail(KDBGPU_ERR_INVALID, "id range outside capacity");
+  if (count == 0) return KDBGPU_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaMemcpy2D(rows, (size_t)h->dim * sizeof(float), h->vecs.p + (size_t)first_id * h->stride,
+                        (size_t)h->stride * sizeof(float), (size_t)h->dim * sizeof(float), count,
+                        cudaMemcpyDeviceToHost));
+  return KDBGPU_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 // test/tuning hook (not part of the reference-facing surface): CTA shape of the traversal kernel
 int kdbgpu_set_tuning(kdbgpu_index *h, int nwarps, int slots, int cand_smem, int max_ctas_per_sm) {
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");

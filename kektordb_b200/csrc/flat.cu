@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(SEL_THREADS)
                        double *__restrict__ out_scores, uint32_t *__restrict__ out_counts) {
   __shared__ uint32_t hist[SEL_BINS];
   __shared__ unsigned long long s_prefix;
-  __shared__ uint32_t s_remaining, s_shift_done;
+  __shared__ uint32_t s_remaining;
   __shared__ unsigned long long s_keys[SEL_MAXK];
   __shared__ uint32_t s_ids[SEL_MAXK];
-  __shared__ uint32_t s_count, s_ties_needed, s_valid;
+  __shared__ uint32_t s_count, s_valid;
   const uint32_t q = blockIdx.x;
   if (q >= nq) return;
   const double *row = dist + (size_t)q * ix.n;
@@ -168,8 +168,6 @@ __global__ void __launch_bounds__(SEL_THREADS)
   const uint32_t ties_needed = s_remaining;  // how many rows equal to kth are inside the top kk
   if (t == 0) {
     s_count = 0;
-    s_ties_needed = ties_needed;
-    (void)s_shift_done;
   }
   __syncthreads();
   // strictly smaller keys: all of them

@@ -45,6 +45,12 @@ SIGNATURES = {
     "kdbgpu_distance_batch": (_i32, [_vp, _vp, _vp, _u32, _vp]),
     "kdbgpu_flat_search_batch": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, C.POINTER(Stats)]),
     "kdbgpu_merge_topk_device": (_i32, [_vp, _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "kdbgpu_add_batch": (_i32, [_vp, _u32, _vp, _vp, _i32]),
+    "kdbgpu_add_batch_device": (_i32, [_vp, _u32, _vp, _sz, _vp, _i32]),
+    "kdbgpu_get_graph_sizes": (_i32, [_vp, C.POINTER(_u32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.POINTER(_u32), C.POINTER(_i32)]),
+    "kdbgpu_get_graph": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "kdbgpu_download_vectors": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_index_device": (_i32, [_vp]),
     "kdbgpu_index_count": (_u32, [_vp]),
     "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),

@@ -117,6 +117,41 @@ class GpuIndex:
         b = np.ascontiguousarray(bitset, dtype=np.uint64)
         ffi.check(self._lib.kdbgpu_set_deleted(self._handle(), _ptr(b), b.size))
 
+    # -- construction on the device (extension of the reference surface) ---------------------------
+    def AddBatch(self, vectors, level_draws, ef_construction: int = 0) -> None:
+        """(*Index).AddBatch (hnsw_index.go:1466): ids are assigned in order from count+1;
+        level_draws are the rand.Float64() values of randomLevel."""
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        u = np.ascontiguousarray(level_draws, dtype=np.float64)
+        if v.ndim != 2 or v.shape[1] != self.dim or u.shape != (v.shape[0],):
+            raise ValueError(f"vectors must be [count, {self.dim}] with one level draw each")
+        ffi.check(self._lib.kdbgpu_add_batch(self._handle(), v.shape[0], _ptr(v), _ptr(u), ef_construction))
+
+    def add_batch_device(self, d_rows_ptr: int, count: int, row_stride: int, level_draws,
+                         ef_construction: int = 0) -> None:
+        u = np.ascontiguousarray(level_draws, dtype=np.float64)
+        assert u.shape == (count,)
+        ffi.check(self._lib.kdbgpu_add_batch_device(self._handle(), count, C.c_void_p(d_rows_ptr), row_stride,
+                                                    _ptr(u), ef_construction))
+
+    def get_graph(self):
+        """Topology read-back: (n, levels, node_row, row_off, nbrs, entry, max_level)."""
+        n, rows, edges = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        entry, max_level = C.c_uint32(), C.c_int()
+        ffi.check(self._lib.kdbgpu_get_graph_sizes(self._handle(), C.byref(n), C.byref(rows), C.byref(edges),
+                                                   C.byref(entry), C.byref(max_level)))
+        levels = np.zeros(n.value + 1, dtype=np.int32)
+        node_row = np.zeros(n.value + 2, dtype=np.uint64)
+        row_off = np.zeros(rows.value + 1, dtype=np.uint64)
+        nbrs = np.zeros(max(edges.value, 1), dtype=np.uint32)
+        ffi.check(self._lib.kdbgpu_get_graph(self._handle(), _ptr(levels), _ptr(node_row), _ptr(row_off), _ptr(nbrs)))
+        return n.value, levels, node_row, row_off, nbrs[: edges.value], entry.value, max_level.value
+
+    def download_vectors(self, first_id: int, count: int) -> np.ndarray:
+        out = np.zeros((count, self.dim), dtype=np.float32)
+        ffi.check(self._lib.kdbgpu_download_vectors(self._handle(), first_id, count, _ptr(out)))
+        return out
+
     def set_tuning(self, nwarps: int = 0, slots: int = 0, cand_smem: int = 0, max_ctas_per_sm: int = -1) -> None:
         ffi.check(self._lib.kdbgpu_set_tuning(self._handle(), nwarps, slots, cand_smem, max_ctas_per_sm))
 
