@@ -144,6 +144,9 @@ int kdbgpu_get_graph(kdbgpu_index *, int32_t *levels, uint64_t *node_row, uint64
 int kdbgpu_download_vectors(kdbgpu_index *, uint32_t first_id, uint32_t count, float *rows);
 
 /* ---- introspection -------------------------------------------------------------------- */
+/* Counters (dist_evals, hops, hops_l0) of the most recent traversal launch on this handle;
+ * synchronises the device.  For callers of the *_device entry points. */
+int kdbgpu_last_search_stats(kdbgpu_index *, kdbgpu_stats *stats);
 int kdbgpu_index_device(const kdbgpu_index *);
 uint32_t kdbgpu_index_count(const kdbgpu_index *);   /* n of the last kdbgpu_set_graph        */
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *);

@@ -710,6 +710,21 @@ int kdbgpu_merge_topk_device(kdbgpu_index *h, int n_shards, uint32_t nq, int k, 
   return KDBGPU_OK;
 }
 
+int kdbgpu_last_search_stats(kdbgpu_index *h, kdbgpu_stats *stats) {
+  if (!h || !stats) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  memset(stats, 0, sizeof *stats);
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  if (!h->stats.p) return KDBGPU_OK;
+  unsigned long long st[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost));
+  stats->dist_evals = st[0];
+  stats->hops = st[1];
+  stats->hops_l0 = st[2];
+  return KDBGPU_OK;
+}
+
 int kdbgpu_index_device(const kdbgpu_index *h) { return h ? h->device : -1; }
 uint32_t kdbgpu_index_count(const kdbgpu_index *h) { return h ? h->n : 0; }
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *h) {

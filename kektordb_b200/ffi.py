@@ -51,6 +51,7 @@ SIGNATURES = {
                                       C.POINTER(_u32), C.POINTER(_i32)]),
     "kdbgpu_get_graph": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "kdbgpu_download_vectors": (_i32, [_vp, _u32, _u32, _vp]),
+    "kdbgpu_last_search_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "kdbgpu_index_device": (_i32, [_vp]),
     "kdbgpu_index_count": (_u32, [_vp]),
     "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),

@@ -180,6 +180,21 @@ class GpuIndex:
 
     search_with_scores = SearchWithScores
 
+    def search_device(self, d_queries_ptr: int, nq: int, k: int, ef_search: int, d_ids_ptr: int, d_scores_ptr: int,
+                      d_counts_ptr: int, stream_ptr: int = 0, d_allow_ptr: int = 0, allow_words: int = 0,
+                      allow_first_id: int = 0) -> None:
+        """kdbgpu_search_batch_device: every buffer already resident on the handle's device; the
+        launch is queued on `stream_ptr` (a cudaStream_t) without host synchronisation."""
+        ffi.check(self._lib.kdbgpu_search_batch_device(
+            self._handle(), C.c_void_p(d_queries_ptr), nq, k, effective_ef(int(ef_search), self.needs_refine),
+            C.c_void_p(d_allow_ptr) if d_allow_ptr else None, allow_words, allow_first_id, C.c_void_p(d_ids_ptr),
+            C.c_void_p(d_scores_ptr), C.c_void_p(d_counts_ptr), C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def last_search_stats(self) -> SearchStats:
+        st = ffi.Stats()
+        ffi.check(self._lib.kdbgpu_last_search_stats(self._handle(), C.byref(st)))
+        return SearchStats(st.dist_evals, st.hops, st.hops_l0, 0.0, 0.0)
+
     def distance_batch(self, prepared_query, ids) -> np.ndarray:
         q = np.ascontiguousarray(prepared_query, dtype=np.float32)
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
