@@ -55,7 +55,9 @@ def parse_args():
     p.add_argument("--build-batch", type=int, default=16384)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--no-shard-extra", action="store_true")
+    p.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"])
+    p.add_argument("--overlap", type=int, default=3,
+                   help="batches in flight: consecutive steps alternate over this many streams / caller threads")
     return p.parse_args()
 
 
@@ -82,7 +84,7 @@ def build_schedule(n, ef_const, bmax):
     """AddBatch call sizes: the first call (index smaller than efConstruction) goes through
     sequential single Adds in the reference, so it is kept small; later calls never exceed the
     current index size (batch members do not see each other, hnsw_index.go:1789-1853)."""
-    sched = [min(n, max(256, ef_const))]
+    sched = [min(n, ef_const)]
     while sum(sched) < n:
         sched.append(min(bmax, sum(sched), n - sum(sched)))
     return sched
@@ -106,57 +108,104 @@ def recall_at_k(ids, gt):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """Samples SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md's clocks
+    line).  kind "nvml" polls NVML in-process every 50 ms (the same counters nvidia-smi prints,
+    without a second process hammering the driver); kind "smi" runs `nvidia-smi -lms 200`."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
-        self.thread = None
+    def __init__(self, gpu_index, kind="nvml"):
+        self.gpu, self.kind = gpu_index, kind
+        self.sm, self.smax, self.reasons, self.power = [], [], set(), []
+        self.proc = self.thread = None
+        self.stop_flag = False
 
     def start(self):
+        if self.kind == "none":
+            return
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            if self.kind == "nvml":
+                import pynvml
+                pynvml.nvmlInit()
+                idx = self.gpu
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                if vis:
+                    try:
+                        idx = int(vis.split(",")[self.gpu])
+                    except Exception:
+                        idx = self.gpu
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+                self.nv = pynvml
+                self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            else:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                     "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as ex:
+            self.kind, self.err = "failed", repr(ex)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll_nvml(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                 else nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                         getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.smax.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = get_reasons(self.h)
+                for name, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
+    def _read_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                self.sm.append(float(f[1]))
+                self.smax.append(float(f[2]))
+                self.power.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        if self.kind in ("none", "failed"):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+                    "note": "sampler " + (self.kind if self.kind == "none" else getattr(self, "err", "failed"))}
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.smax) if self.smax else None, "samples": len(self.sm),
+                "power_w_max": round(max(self.power), 1) if self.power else None, "reasons": sorted(self.reasons),
+                "source": self.kind}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,10 +278,13 @@ def main():
     recall_local = recall_at_k(ids0[:n_gt], gt_ids)
 
     # ---- device-resident timing (`value`) --------------------------------------------------------
-    stream = torch.cuda.Stream(device=dev)
-    d_ids = torch.zeros((B, k), dtype=torch.int32, device=dev)
-    d_sc = torch.zeros((B, k), dtype=torch.float64, device=dev)
-    d_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    n_ov = max(1, min(4, args.overlap)) if mode != "shard" else 1
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_ov)]
+    stream = streams[0]
+    d_ids_l = [torch.zeros((B, k), dtype=torch.int32, device=dev) for _ in range(n_ov)]
+    d_sc_l = [torch.zeros((B, k), dtype=torch.float64, device=dev) for _ in range(n_ov)]
+    d_cnt_l = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(n_ov)]
+    d_ids, d_sc, d_cnt = d_ids_l[0], d_sc_l[0], d_cnt_l[0]
     g_ids = g_sc = g_cnt = m_ids = m_sc = m_cnt = None
     if mode == "shard":
         g_ids = torch.zeros((world, B, k), dtype=torch.int32, device=dev)
@@ -242,8 +294,9 @@ def main():
 
     def step_device(i):
         q = Qd[i * B:(i + 1) * B]
-        gi.search_device(q.data_ptr(), B, k, ef, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
-                         stream.cuda_stream)
+        j = i % n_ov  # consecutive batches alternate streams so that one batch's tail overlaps the next one's head
+        gi.search_device(q.data_ptr(), B, k, ef, d_ids_l[j].data_ptr(), d_sc_l[j].data_ptr(), d_cnt_l[j].data_ptr(),
+                         streams[j].cuda_stream)
         if mode == "shard":  # the one exchange step: all-gather of per-shard top-k, then merge
             with torch.cuda.stream(stream):
                 gl = torch.where(d_ids > 0, d_ids + base, d_ids)
@@ -262,18 +315,20 @@ def main():
     for i in range(args.warmup):
         step_device(i)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_sampler)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tot_e = tot_h = tot_h0 = 0
     barrier()
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
+    ev0.record(streams[0])
+    for st_ in streams[1:]:
+        st_.wait_event(ev0)  # every stream starts after the start mark
     for i in range(args.warmup, n_steps_total):
         step_device(i)
-    with torch.cuda.stream(stream):
-        ev1.record(stream)
+    for st_ in streams[1:]:
+        streams[0].wait_stream(st_)  # the end mark follows the last kernel of every stream
+    ev1.record(streams[0])
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     # counters of the last launch stand for the per-step work (same graph, i.i.d. query batches)
@@ -285,9 +340,17 @@ def main():
     for i in range(args.warmup):
         gi.SearchWithScores(Qh_np[i * B:(i + 1) * B], k, None, ef)
     barrier()
+
+    def e2e_worker(j):  # one caller thread per in-flight batch; ctypes releases the GIL inside the C call
+        for i in range(args.warmup + j, n_steps_total, n_ov):
+            gi.SearchWithScores(Qh_np[i * B:(i + 1) * B], k, None, ef)
+
+    workers = [threading.Thread(target=e2e_worker, args=(j,)) for j in range(n_ov)]
     t0 = time.perf_counter()
-    for i in range(args.warmup, n_steps_total):
-        ids_e, sc_e, cnt_e, st_e = gi.SearchWithScores(Qh_np[i * B:(i + 1) * B], k, None, ef)
+    for t in workers:
+        t.start()
+    for t in workers:
+        t.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -320,23 +383,32 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    stride = (D + 31) // 32 * 32
+    stride = (D + 127) // 128 * 128
     bytes_per_launch = tot_e * stride * 4 + tot_h0 * (2 * args.m) * 4 + (tot_h - tot_h0) * args.m * 4
-    kernel_ms = dev_ms / args.steps if mode != "shard" else None
-    if kernel_ms is None:  # shard mode: time the traversal alone (the step also holds the collective)
+    # average duration of ONE traversal launch, run alone (overlapped launches would hide each other's tails)
+    kernel_ms = None
+    if True:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
-        gi.search_device(Qd[:B].data_ptr(), B, k, ef, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
-                         stream.cuda_stream)
+        nrep = 5
+        for r in range(nrep):
+            gi.search_device(Qd[r * B:(r + 1) * B].data_ptr(), B, k, ef, d_ids.data_ptr(), d_sc.data_ptr(),
+                             d_cnt.data_ptr(), stream.cuda_stream)
         with torch.cuda.stream(stream):
             e1.record(stream)
         torch.cuda.synchronize()
-        kernel_ms = e0.elapsed_time(e1)
-    achieved = bytes_per_launch / (kernel_ms / 1e3) / 1e9
+        kernel_ms = e0.elapsed_time(e1) / nrep
+    isolated = bytes_per_launch / (kernel_ms / 1e3) / 1e9
+    # over the timed region: K launches' algorithmic bytes / the region's device time (launches of
+    # consecutive batches overlap, so this is the kernel's sustained rate; shard mode also holds the
+    # collective in the region and reports the isolated launch instead)
+    launch_ms = dev_ms / args.steps if mode != "shard" else kernel_ms
+    achieved = bytes_per_launch / (launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(bytes_per_launch), "avg_launch_ms": round(kernel_ms, 4),
+                "algorithmic_bytes_per_launch": int(bytes_per_launch), "avg_launch_ms": round(launch_ms, 4),
+                "isolated_launch_ms": round(kernel_ms, 4), "isolated_frac": round(isolated / peak, 4),
                 "dist_evals_per_query": round(tot_e / B, 1), "hops_per_query": round(tot_h / B, 1)}
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof):
@@ -352,10 +424,6 @@ def main():
             cpu_baseline, parity = run_cpu_baseline(args, gi, Qh_np, ncores, ids0, sc0)
         except Exception as ex:  # the main line must still print
             cpu_baseline = {"error": repr(ex)}
-
-    extra_shard = None
-    if rank == 0 or dist is not None:
-        pass
 
     if rank == 0:
         line = {
@@ -373,7 +441,7 @@ def main():
                        "data_model": f"random-normal, low-rank covariance (latent {args.latent}, noise {args.noise}), "
                                      "seeds 42/4242; graph built on GPU (kdbgpu_add_batch), levels seed 1",
                        "l2_policy": "inputs larger than L2: 3.07 GB corpus, new query batch every step",
-                       "build_seconds": round(build_s, 2), "host_cores": ncores},
+                       "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "host_cores": ncores},
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s",
                     "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12 + B * 4 + 36,
                     "ms_per_step": round(e2e_ms / args.steps, 4)},

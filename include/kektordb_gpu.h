@@ -154,10 +154,10 @@ uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *);
 int kdbgpu_search_concurrency(kdbgpu_index *, int k, int ef_search);
 
 /* ---- tuning hook (tests / benchmarks only; not bound by the Go shim) --------------------- */
-/* CTA shape of the traversal kernel: warps per CTA, bulk-copy slots per warp, candidate-heap
- * entries kept in shared memory, cap on resident CTAs per SM (0 = no cap).  A value <= 0
+/* Shape of the traversal kernel (one warp per query): bulk-copy row slots per query, candidate-heap
+ * entries kept in shared memory, cap on resident query-warps per SM (0 = no cap).  A value <= 0
  * (< 0 for the cap) keeps the current setting.  Results never depend on the shape. */
-int kdbgpu_set_tuning(kdbgpu_index *, int nwarps, int slots, int cand_smem, int max_ctas_per_sm);
+int kdbgpu_set_tuning(kdbgpu_index *, int slots, int cand_smem, int max_ctas_per_sm);
 
 #ifdef __cplusplus
 }

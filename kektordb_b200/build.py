@@ -35,21 +35,37 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [
-        nvcc_path(), "-std=c++17", "-O3", "-lineinfo", "-shared",
+    common = [
+        nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-ccbin", host_cxx,
         "-Xcompiler", "-fPIC,-O2,-Wall",
         "--fmad=false",  # every FMA in the kernels is an explicit __fmaf_rn
         "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB,
-    ] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    ]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:  # one nvcc per translation unit, in parallel
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = common + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs, failed = [], False
+    for src, obj, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            failed = True
+            sys.stderr.write(out)
+        elif verbose:
+            sys.stderr.write(out)
+        objs.append(obj)
+    if failed:
+        raise RuntimeError("nvcc failed")
+    link = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", host_cxx, "-o", LIB] + objs + ["-lcudart"]
+    r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed")
-    if verbose:
-        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed")
     return LIB
 
 

@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <shared_mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -108,7 +110,42 @@ struct kdbgpu_index {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int num_sms = 0;
   SearchTuning tuning;
-  std::mutex mu;  // one batch in flight per handle
+  // searches hold `mu` shared (kNumSearchWs of them can be in flight, each on its own workspace and
+  // stream, so consecutive batches overlap on the device); everything that changes the mirror or
+  // uses the handle-level workspace holds it exclusively
+  std::shared_mutex mu;
+  struct SearchWs {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;  // completion of the last launch that used this workspace
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    DevBuf<float> q_raw, q_prep;
+    DevBuf<uint32_t> out_ids, out_counts, allow, visited, work_counter;
+    DevBuf<double> out_scores;
+    DevBuf<HeapEntry> cand_overflow;
+    DevBuf<unsigned long long> stats;
+    DevBuf<int> err_flag;
+    DevBuf<unsigned char> out_blob;  // host path: scores | ids | counts | stats | err, one D2H copy
+    unsigned char *h_out = nullptr;  // pinned staging for that copy
+    size_t h_out_bytes = 0;
+    int grid = 0;
+    uint32_t vis_words = 0;
+    bool busy = false;
+    void release() {
+      out_blob.release();
+      if (h_out) cudaFreeHost(h_out);
+      h_out = nullptr;
+      h_out_bytes = 0;
+      q_raw.release(); q_prep.release(); out_ids.release(); out_counts.release(); allow.release();
+      visited.release(); work_counter.release(); out_scores.release(); cand_overflow.release();
+      stats.release(); err_flag.release();
+    }
+  };
+  static constexpr int kNumSearchWs = 4;
+  SearchWs sws[kNumSearchWs];
+  std::mutex ws_mu;
+  std::condition_variable ws_cv;
+  unsigned ws_next = 0;
+  int last_ws = -1;
 
   DevBuf<float> vecs;
   DevBuf<uint32_t> adj0, upper_adj, upper_first, deleted;
@@ -193,9 +230,52 @@ int ensure_search_workspace(kdbgpu_index *h, int grid) {
   return KDBGPU_OK;
 }
 
-// queue one traversal launch on `stream`; buffers are device pointers
-int enqueue_search(kdbgpu_index *h, const float *d_q_prepared, uint32_t nq, int k, int ef, const uint32_t *d_allow,
-                   uint32_t allow_entry, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, cudaStream_t stream) {
+// ---- per-launch search workspaces ---------------------------------------------------------------
+int ensure_ws(kdbgpu_index *h, kdbgpu_index::SearchWs &w, int grid) {
+  const uint32_t words = (((h->capacity + 1 + 31) / 32) + 3) & ~3u;
+  if (grid > w.grid || words != w.vis_words) {
+    w.vis_words = words;
+    w.visited.release();
+    CUDA_TRY(w.visited.reserve((size_t)grid * words, true));
+    w.cand_overflow.release();
+    CUDA_TRY(w.cand_overflow.reserve((size_t)grid * h->ovf_cap));
+    w.grid = grid;
+  }
+  CUDA_TRY(w.stats.reserve(4, true));
+  CUDA_TRY(w.work_counter.reserve(1, true));
+  CUDA_TRY(w.err_flag.reserve(1, true));
+  return KDBGPU_OK;
+}
+
+// blocks until one of the workspaces is free (host-buffer path: at most kNumSearchWs batches in flight)
+int acquire_ws(kdbgpu_index *h) {
+  std::unique_lock<std::mutex> lk(h->ws_mu);
+  for (;;) {
+    for (int i = 0; i < kdbgpu_index::kNumSearchWs; ++i) {
+      const int j = (int)((h->ws_next + (unsigned)i) % kdbgpu_index::kNumSearchWs);
+      if (!h->sws[j].busy) {
+        h->sws[j].busy = true;
+        h->ws_next = (unsigned)j + 1;
+        return j;
+      }
+    }
+    h->ws_cv.wait(lk);
+  }
+}
+void release_ws(kdbgpu_index *h, int j) {
+  {
+    std::lock_guard<std::mutex> lk(h->ws_mu);
+    h->sws[j].busy = false;
+  }
+  h->ws_cv.notify_one();
+}
+
+// queue one traversal launch on `stream` using workspace `w`; buffers are device pointers.  The
+// launch waits for the previous user of the workspace and records its own completion on w.done.
+int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_prepared, uint32_t nq, int k, int ef,
+                   const uint32_t *d_allow, uint32_t allow_entry, uint32_t *d_ids, double *d_scores,
+                   uint32_t *d_counts, cudaStream_t stream, unsigned long long *d_stats = nullptr,
+                   int *d_err = nullptr) {
   DevIndex ix = h->dev();
   const int occ = search_occupancy(ix, ef, h->tuning);
   if (occ <= 0)
@@ -203,11 +283,17 @@ int enqueue_search(kdbgpu_index *h, const float *d_q_prepared, uint32_t nq, int 
                 ef, search_smem_bytes(ix, ef, h->tuning));
   int grid = occ * h->num_sms;
   if ((uint32_t)grid > nq) grid = (int)nq;
-  int rc = ensure_search_workspace(h, occ * h->num_sms);
+  int rc = ensure_ws(h, w, occ * h->num_sms);
   if (rc) return rc;
-  CUDA_TRY(cudaMemsetAsync(h->work_counter.p, 0, sizeof(uint32_t), stream));
-  CUDA_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), stream));
-  CUDA_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), stream));
+  CUDA_TRY(cudaMemsetAsync(w.work_counter.p, 0, sizeof(uint32_t), stream));
+  if (d_stats && d_err) {  // contiguous in the caller's blob: stats[4] then err
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long) + sizeof(long long), stream));
+  } else {
+    d_stats = w.stats.p;
+    d_err = w.err_flag.p;
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), stream));
+    CUDA_TRY(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
+  }
   SearchArgs a;
   a.queries = d_q_prepared;
   a.nq = nq;
@@ -218,14 +304,14 @@ int enqueue_search(kdbgpu_index *h, const float *d_q_prepared, uint32_t nq, int 
   a.out_ids = d_ids;
   a.out_scores = d_scores;
   a.out_counts = d_counts;
-  a.visited = h->visited.p;
-  a.vis_words = h->vis_words;
-  a.cand_overflow = h->cand_overflow.p;
+  a.visited = w.visited.p;
+  a.vis_words = w.vis_words;
+  a.cand_overflow = w.cand_overflow.p;
   a.ovf_cap = h->ovf_cap;
   a.cand_smem = (uint32_t)h->tuning.cand_smem;
-  a.stats = h->stats.p;
-  a.work_counter = h->work_counter.p;
-  a.err_flag = h->err_flag.p;
+  a.stats = d_stats;
+  a.work_counter = w.work_counter.p;
+  a.err_flag = d_err;
   CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
   return KDBGPU_OK;
 }
@@ -240,14 +326,15 @@ uint32_t first_set_bit(const uint64_t *bits, size_t words, bool *found) {
   return 0;
 }
 
-// copy a host allow-list bitset into h->allow, padded/truncated to cover ids 0..capacity
-int stage_allow(kdbgpu_index *h, const uint64_t *allow, size_t allow_words, cudaStream_t stream) {
+// copy a host allow-list bitset into `dst`, padded/truncated to cover ids 0..capacity
+int stage_allow(kdbgpu_index *h, DevBuf<uint32_t> &dst, const uint64_t *allow, size_t allow_words,
+                cudaStream_t stream) {
   const size_t need32 = ((size_t)h->capacity + 1 + 31) / 32 + 2;
-  CUDA_TRY(h->allow.reserve(need32));
-  CUDA_TRY(cudaMemsetAsync(h->allow.p, 0, need32 * sizeof(uint32_t), stream));
+  CUDA_TRY(dst.reserve(need32));
+  CUDA_TRY(cudaMemsetAsync(dst.p, 0, need32 * sizeof(uint32_t), stream));
   size_t copy32 = allow_words * 2;
   if (copy32 > need32) copy32 = need32;
-  CUDA_TRY(cudaMemcpyAsync(h->allow.p, allow, copy32 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(dst.p, allow, copy32 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
   return KDBGPU_OK;
 }
 
@@ -299,10 +386,9 @@ int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacit
   h->metric = metric;
   h->m = m;
   h->capacity = capacity;
-  h->stride = ((uint32_t)dim + 31u) & ~31u;
+  h->stride = ((uint32_t)dim + 127u) & ~127u;  // whole float4 columns for every lane (searcher.cuh)
   h->num_sms = prop.multiProcessorCount;
   const char *env;
-  if ((env = getenv("KDBGPU_NWARPS"))) h->tuning.nwarps = atoi(env);
   if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
   if ((env = getenv("KDBGPU_CAND_SMEM"))) h->tuning.cand_smem = atoi(env);
   if ((env = getenv("KDBGPU_MAX_CTAS_PER_SM"))) h->tuning.max_ctas_per_sm = atoi(env);
@@ -312,6 +398,11 @@ int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacit
   };
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  for (auto &w : h->sws) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&w.ev[i]);
+  }
   const size_t n1 = (size_t)capacity + 1;
   if (e == cudaSuccess) e = h->vecs.reserve(n1 * h->stride, true);
   if (e == cudaSuccess) e = h->adj0.reserve(n1 * (size_t)(2 * m), true);
@@ -337,7 +428,14 @@ int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacit
 int kdbgpu_index_destroy(kdbgpu_index *h) {
   if (!h) return KDBGPU_OK;
   DeviceGuard g(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();
+  for (auto &w : h->sws) {
+    w.release();
+    if (w.done) cudaEventDestroy(w.done);
+    for (auto &e : w.ev)
+      if (e) cudaEventDestroy(e);
+    if (w.stream) cudaStreamDestroy(w.stream);
+  }
   h->vecs.release();
   h->adj0.release();
   h->upper_adj.release();
@@ -386,8 +484,9 @@ int kdbgpu_upload_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, co
     return fail(KDBGPU_ERR_INVALID, "ids %u..%llu outside 1..%u", first_id, (unsigned long long)first_id + count - 1,
                 h->capacity);
   if (count == 0) return KDBGPU_OK;
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   // padded columns were zeroed at creation and are never written
   CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), rows,
                              (size_t)h->dim * sizeof(float), (size_t)h->dim * sizeof(float), count,
@@ -402,8 +501,9 @@ int kdbgpu_upload_vectors_device(kdbgpu_index *h, uint32_t first_id, uint32_t co
   if (first_id == 0 || (uint64_t)first_id + count - 1 > h->capacity || row_stride < (size_t)h->dim)
     return fail(KDBGPU_ERR_INVALID, "ids %u..+%u outside 1..%u or bad stride", first_id, count, h->capacity);
   if (count == 0) return KDBGPU_OK;
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), d_rows,
                              row_stride * sizeof(float), (size_t)h->dim * sizeof(float), count,
                              cudaMemcpyDeviceToDevice, h->stream));
@@ -458,8 +558,9 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
       }
     }
   }
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   if ((upper_rows + 1) * degu > h->upper_adj.n) {
     const size_t rows = (upper_rows + 1) + (upper_rows + 1) / 4 + 1024;
     h->upper_adj.release();
@@ -497,8 +598,9 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
 
 int kdbgpu_set_deleted(kdbgpu_index *h, const uint64_t *bitset, size_t words) {
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   const size_t need32 = h->deleted.n;
   CUDA_TRY(cudaMemsetAsync(h->deleted.p, 0, need32 * sizeof(uint32_t), h->stream));
   h->has_deleted = false;
@@ -524,9 +626,9 @@ int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int 
   if (nq == 0) return KDBGPU_OK;
   if (!queries || !out_ids || !out_scores || !out_counts) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (k <= 0 || k > 10000) return fail(KDBGPU_ERR_INVALID, "k %d outside 1..10000", k);  // http_handlers.go:37
-  if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called");
   const int ef = ef_search < k ? k : ef_search;  // hnsw_index.go:2377-2380
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::shared_lock<std::shared_mutex> lk(h->mu);
+  if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called");
   DeviceGuard g(h->device);
   // an empty index or an empty non-nil allow-list returns [] for every query (:383-385, :443-445)
   bool allow_found = true;
@@ -538,41 +640,65 @@ int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     memset(out_counts, 0, (size_t)nq * sizeof(uint32_t));
     return KDBGPU_OK;
   }
-  cudaStream_t s = h->stream;
-  CUDA_TRY(h->q_raw.reserve((size_t)nq * h->dim));
-  CUDA_TRY(h->q_prep.reserve((size_t)nq * h->stride));
-  CUDA_TRY(h->out_ids.reserve((size_t)nq * k));
-  CUDA_TRY(h->out_scores.reserve((size_t)nq * k));
-  CUDA_TRY(h->out_counts.reserve(nq));
-  CUDA_TRY(cudaEventRecord(h->ev[0], s));
-  CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries, (size_t)nq * h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  const int wi = acquire_ws(h);
+  kdbgpu_index::SearchWs &w = h->sws[wi];
+  struct Release {
+    kdbgpu_index *h;
+    int wi;
+    ~Release() { release_ws(h, wi); }
+  } releaser{h, wi};
+  cudaStream_t s = w.stream;
+  CUDA_TRY(cudaStreamWaitEvent(s, w.done, 0));
+  CUDA_TRY(w.q_raw.reserve((size_t)nq * h->dim));
+  CUDA_TRY(w.q_prep.reserve((size_t)nq * h->stride));
+  // results, counters and the error flag live in one device blob -> a single D2H copy
+  const size_t nk = (size_t)nq * k;
+  const size_t o_ids = nk * sizeof(double);
+  const size_t o_counts = o_ids + nk * sizeof(uint32_t);
+  const size_t o_stats = (o_counts + (size_t)nq * sizeof(uint32_t) + 7) & ~(size_t)7;
+  const size_t o_err = o_stats + 4 * sizeof(unsigned long long);
+  const size_t blob_bytes = o_err + sizeof(long long);
+  CUDA_TRY(w.out_blob.reserve(blob_bytes));
+  if (w.h_out_bytes < blob_bytes) {
+    if (w.h_out) cudaFreeHost(w.h_out);
+    w.h_out = nullptr;
+    w.h_out_bytes = 0;
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&w.h_out), blob_bytes + blob_bytes / 4, cudaHostAllocDefault));
+    w.h_out_bytes = blob_bytes + blob_bytes / 4;
+  }
+  unsigned char *blob = w.out_blob.p;
+  CUDA_TRY(cudaEventRecord(w.ev[0], s));
+  CUDA_TRY(cudaMemcpyAsync(w.q_raw.p, queries, (size_t)nq * h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
   const uint32_t *d_allow = nullptr;
   if (allow) {
-    int rc = stage_allow(h, allow, allow_words, s);
+    int rc = stage_allow(h, w.allow, allow, allow_words, s);
     if (rc) return rc;
-    d_allow = h->allow.p;
+    d_allow = w.allow.p;
   }
-  CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
-  CUDA_TRY(cudaEventRecord(h->ev[1], s));
-  int rc = enqueue_search(h, h->q_prep.p, nq, k, ef, d_allow, allow_first, h->out_ids.p, h->out_scores.p,
-                          h->out_counts.p, s);
+  CUDA_TRY(launch_prep_queries(w.q_raw.p, (size_t)h->dim, w.q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
+  CUDA_TRY(cudaEventRecord(w.ev[1], s));
+  int rc = enqueue_search(h, w, w.q_prep.p, nq, k, ef, d_allow, allow_first, reinterpret_cast<uint32_t *>(blob + o_ids),
+                          reinterpret_cast<double *>(blob), reinterpret_cast<uint32_t *>(blob + o_counts), s,
+                          reinterpret_cast<unsigned long long *>(blob + o_stats), reinterpret_cast<int *>(blob + o_err));
   if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(h->ev[2], s));
-  CUDA_TRY(cudaMemcpyAsync(out_ids, h->out_ids.p, (size_t)nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(out_scores, h->out_scores.p, (size_t)nq * k * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(out_counts, h->out_counts.p, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  unsigned long long st[4] = {0, 0, 0, 0};
-  int err = 0;
-  CUDA_TRY(cudaMemcpyAsync(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&err, h->err_flag.p, sizeof err, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  CUDA_TRY(cudaEventRecord(w.ev[2], s));
+  CUDA_TRY(cudaMemcpyAsync(w.h_out, blob, blob_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord(w.ev[3], s));
+  CUDA_TRY(cudaEventRecord(w.done, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  memcpy(out_scores, w.h_out, nk * sizeof(double));
+  memcpy(out_ids, w.h_out + o_ids, nk * sizeof(uint32_t));
+  memcpy(out_counts, w.h_out + o_counts, (size_t)nq * sizeof(uint32_t));
+  unsigned long long st[4];
+  int err = 0;
+  memcpy(st, w.h_out + o_stats, sizeof st);
+  memcpy(&err, w.h_out + o_err, sizeof err);
   if (stats) {
     stats->dist_evals = st[0];
     stats->hops = st[1];
     stats->hops_l0 = st[2];
-    cudaEventElapsedTime(&stats->kernel_ms, h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
+    cudaEventElapsedTime(&stats->kernel_ms, w.ev[1], w.ev[2]);
+    cudaEventElapsedTime(&stats->total_ms, w.ev[0], w.ev[3]);
   }
   if (err == KDBGPU_ERR_OVERFLOW)
     return fail(KDBGPU_ERR_OVERFLOW, "candidate heap exceeded %u entries for at least one query",
@@ -587,30 +713,43 @@ int kdbgpu_search_batch_device(kdbgpu_index *h, const float *d_queries, uint32_t
   if (nq == 0) return KDBGPU_OK;
   if (!d_queries || !d_out_ids || !d_out_scores || !d_out_counts) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (k <= 0 || k > 10000) return fail(KDBGPU_ERR_INVALID, "k %d outside 1..10000", k);
+  const int ef = ef_search < k ? k : ef_search;
+  std::shared_lock<std::shared_mutex> lk(h->mu);
   if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called");
   if (d_allow && allow_words * 64 < (size_t)h->n + 1)
     return fail(KDBGPU_ERR_INVALID, "device allow-list must cover ids 0..%u", h->n);
-  const int ef = ef_search < k ? k : ef_search;
-  std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->stream;
+  // asynchronous path: workspaces rotate; reuse is ordered on the device through w.done
+  int wi;
+  {
+    std::lock_guard<std::mutex> wl(h->ws_mu);
+    wi = (int)(h->ws_next % kdbgpu_index::kNumSearchWs);
+    h->ws_next = (unsigned)wi + 1;
+    h->last_ws = wi;
+  }
+  kdbgpu_index::SearchWs &w = h->sws[wi];
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : w.stream;
   if (h->max_level < 0 || (d_allow && (allow_first_id == 0 || allow_first_id > h->n))) {
     CUDA_TRY(cudaMemsetAsync(d_out_ids, 0, (size_t)nq * k * sizeof(uint32_t), s));
     CUDA_TRY(cudaMemsetAsync(d_out_scores, 0, (size_t)nq * k * sizeof(double), s));
     CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)nq * sizeof(uint32_t), s));
     return KDBGPU_OK;
   }
-  CUDA_TRY(h->q_prep.reserve((size_t)nq * h->stride));
-  CUDA_TRY(launch_prep_queries(d_queries, (size_t)h->dim, h->q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
-  return enqueue_search(h, h->q_prep.p, nq, k, ef, reinterpret_cast<const uint32_t *>(d_allow), allow_first_id,
-                        d_out_ids, d_out_scores, d_out_counts, s);
+  CUDA_TRY(cudaStreamWaitEvent(s, w.done, 0));
+  CUDA_TRY(w.q_prep.reserve((size_t)nq * h->stride));
+  CUDA_TRY(launch_prep_queries(d_queries, (size_t)h->dim, w.q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
+  int rc = enqueue_search(h, w, w.q_prep.p, nq, k, ef, reinterpret_cast<const uint32_t *>(d_allow), allow_first_id,
+                          d_out_ids, d_out_scores, d_out_counts, s);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(w.done, s));
+  return KDBGPU_OK;
 }
 
 int kdbgpu_distance_batch(kdbgpu_index *h, const float *query, const uint32_t *ids, uint32_t n, double *out) {
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
   if (n == 0) return KDBGPU_OK;
   if (!query || !ids || !out) return fail(KDBGPU_ERR_INVALID, "NULL argument");
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t s = h->stream;
   CUDA_TRY(h->q_prep.reserve((size_t)h->stride));
@@ -637,7 +776,7 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
   if (k <= 0 || k > 1024) return fail(KDBGPU_ERR_INVALID, "flat k %d outside 1..1024", k);
   if (mode != 0 && mode != 1) return fail(KDBGPU_ERR_INVALID, "mode %d", mode);
   if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called (it defines the live rows)");
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t s = h->stream;
   if (h->n == 0) {
@@ -652,7 +791,7 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
     bool found = false;
     (void)first_set_bit(allow, allow_words, &found);
     if (found) {
-      int rc = stage_allow(h, allow, allow_words, s);
+      int rc = stage_allow(h, h->allow, allow, allow_words, s);
       if (rc) return rc;
       d_allow = h->allow.p;
     }
@@ -713,12 +852,12 @@ int kdbgpu_merge_topk_device(kdbgpu_index *h, int n_shards, uint32_t nq, int k, 
 int kdbgpu_last_search_stats(kdbgpu_index *h, kdbgpu_stats *stats) {
   if (!h || !stats) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   memset(stats, 0, sizeof *stats);
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  if (!h->stats.p) return KDBGPU_OK;
+  if (h->last_ws < 0 || !h->sws[h->last_ws].stats.p) return KDBGPU_OK;
   unsigned long long st[4] = {0, 0, 0, 0};
   CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpy(st, h->stats.p, sizeof st, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(st, h->sws[h->last_ws].stats.p, sizeof st, cudaMemcpyDeviceToHost));
   stats->dist_evals = st[0];
   stats->hops = st[1];
   stats->hops_l0 = st[2];
@@ -730,7 +869,8 @@ uint32_t kdbgpu_index_count(const kdbgpu_index *h) { return h ? h->n : 0; }
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *h) {
   if (!h) return 0;
   return h->vecs.bytes() + h->adj0.bytes() + h->upper_adj.bytes() + h->upper_first.bytes() + h->deleted.bytes() +
-         h->levels.bytes() + h->visited.bytes() + h->cand_overflow.bytes() + h->flat_dist.bytes() + h->q_raw.bytes() +
+         h->levels.bytes() + h->visited.bytes() + h->cand_overflow.bytes() + h->sws[0].visited.bytes() * kdbgpu_index::kNumSearchWs +
+         h->sws[0].cand_overflow.bytes() * kdbgpu_index::kNumSearchWs + h->flat_dist.bytes() + h->q_raw.bytes() +
          h->q_prep.bytes() + h->out_ids.bytes() + h->out_scores.bytes() + h->allow.bytes();
 }
 int kdbgpu_search_concurrency(kdbgpu_index *h, int k, int ef_search) {
@@ -793,10 +933,11 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   if (ef_const <= 0) ef_const = 200;  // hnsw.New default (hnsw_index.go:143-145)
   if (ef_const > 2048) return fail(KDBGPU_ERR_INVALID, "ef_const %d too large (max 2048)", ef_const);
   if (h->m < 2) return fail(KDBGPU_ERR_INVALID, "construction needs m >= 2");
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   if ((uint64_t)h->n + count > h->capacity)
     return fail(KDBGPU_ERR_INVALID, "batch of %u does not fit: %u of %u ids used", count, h->n, h->capacity);
   DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   cudaStream_t s = h->stream;
   const uint32_t start_id = h->n + 1;
   const bool sequential = (uint64_t)h->n < (uint64_t)ef_const;  // :1502-1513
@@ -857,9 +998,7 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   DevIndex ix = h->dev();
   ix.entry = pre_entry;
   ix.max_level = pre_max;
-  SearchTuning bt;  // construction uses its own CTA shape: 4 warps, 1 slot
-  bt.nwarps = 4;
-  bt.slots = 1;
+  SearchTuning bt;  // construction uses its own fixed shape (build.cu)
   bt.cand_smem = h->tuning.cand_smem;
   const int occ = sequential ? 1 : build_search_occupancy(ix, ef_const, (uint32_t)bt.cand_smem);
   if (occ <= 0) return fail(KDBGPU_ERR_INVALID, "construction search does not fit shared memory (ef_const=%d)", ef_const);
@@ -995,7 +1134,7 @@ int kdbgpu_add_batch_device(kdbgpu_index *h, uint32_t count, const float *d_rows
 int kdbgpu_get_graph_sizes(kdbgpu_index *h, uint32_t *n, uint64_t *n_rows, uint64_t *n_edges, uint32_t *entry,
                            int *max_level) {
   if (!h || !n || !n_rows || !n_edges || !entry || !max_level) return fail(KDBGPU_ERR_INVALID, "NULL argument");
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
   std::vector<uint32_t> adj0((size_t)(h->n + 1) * deg0), upper((size_t)(h->upper_rows_used + 1) * degu);
@@ -1022,7 +1161,7 @@ int kdbgpu_get_graph_sizes(kdbgpu_index *h, uint32_t *n, uint64_t *n_rows, uint6
 
 int kdbgpu_get_graph(kdbgpu_index *h, int32_t *levels, uint64_t *node_row, uint64_t *row_off, uint32_t *nbrs) {
   if (!h || !levels || !node_row || !row_off || !nbrs) return fail(KDBGPU_ERR_INVALID, "NULL argument");
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
   std::vector<uint32_t> adj0((size_t)(h->n + 1) * deg0), upper((size_t)(h->upper_rows_used + 1) * degu);
@@ -1051,7 +1190,7 @@ int kdbgpu_download_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, 
   if (!h || (!rows && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if ((uint64_t)first_id + count - 1 > h->capacity) return fail(KDBGPU_ERR_INVALID, "id range outside capacity");
   if (count == 0) return KDBGPU_OK;
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   CUDA_TRY(cudaMemcpy2D(rows, (size_t)h->dim * sizeof(float), h->vecs.p + (size_t)first_id * h->stride,
                         (size_t)h->stride * sizeof(float), (size_t)h->dim * sizeof(float), count,
@@ -1063,18 +1202,14 @@ int kdbgpu_download_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, 
 
 extern "C" {
 // test/tuning hook (not part of the reference-facing surface): CTA shape of the traversal kernel
-int kdbgpu_set_tuning(kdbgpu_index *h, int nwarps, int slots, int cand_smem, int max_ctas_per_sm) {
+int kdbgpu_set_tuning(kdbgpu_index *h, int slots, int cand_smem, int max_ctas_per_sm) {
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
   SearchTuning t = h->tuning;
-  if (nwarps > 0) t.nwarps = nwarps;
   if (slots > 0) t.slots = slots;
   if (cand_smem > 0) t.cand_smem = cand_smem;
   if (max_ctas_per_sm >= 0) t.max_ctas_per_sm = max_ctas_per_sm;
-  const bool ok = (t.nwarps == 2 && (t.slots == 2 || t.slots == 4)) ||
-                  (t.nwarps == 4 && (t.slots == 1 || t.slots == 2 || t.slots == 4)) ||
-                  (t.nwarps == 8 && (t.slots == 1 || t.slots == 2));
-  if (!ok) return fail(KDBGPU_ERR_INVALID, "unsupported CTA shape nwarps=%d slots=%d", t.nwarps, t.slots);
-  std::lock_guard<std::mutex> lk(h->mu);
+  if (!search_slots_supported(t.slots)) return fail(KDBGPU_ERR_INVALID, "unsupported slot count %d", t.slots);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
   h->tuning = t;
   return KDBGPU_OK;
 }

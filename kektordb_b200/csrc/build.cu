@@ -131,28 +131,22 @@ struct BuildSearchArgs {
   uint32_t *cand_cnt;       // [n_slots]
 };
 
-// phase 1 (:1789-1853)
-template <int NWARPS, int SLOTS, int METRIC>
-__global__ void __launch_bounds__(NWARPS * 32)
+// phase 1 (:1789-1853): one warp per new node
+template <int SLOTS, int METRIC, int CPL>
+__global__ void __launch_bounds__(32)
     build_search_kernel(const DevIndex ix, const SearchArgs a, const BuildSearchArgs b) {
   extern __shared__ __align__(128) unsigned char smem[];
-  Searcher<NWARPS, SLOTS, METRIC> s(ix, a, smem);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NWARPS * SLOTS; ++i) mbar_init(&s.sm.bars[i], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  const int tid = threadIdx.x;
+  Searcher<SLOTS, METRIC, CPL> s(ix, a, smem);
+  s.init_barriers();
+  const int lane = s.lane;
   for (;;) {
-    if (tid == 0) s.sm.ctl->q = atomicAdd(a.work_counter, 1u);
-    __syncthreads();
-    const uint32_t i = s.sm.ctl->q;
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(a.work_counter, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
     if (i >= b.count) break;
     const uint32_t id = b.start_id + i;
     const int node_level = ix.levels[id];
-    const float4 *src = reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.stride);
-    for (uint32_t c = tid; c < (ix.stride >> 2); c += NWARPS * 32) s.sm.q4[c] = src[c];
-    __syncthreads();
+    s.load_query(ix.vecs + (size_t)id * ix.stride);
     uint32_t ep = b.pre_entry;
     for (int l = b.pre_max; l > node_level; --l) {  // zoom in (:1819-1824)
       const int n = s.search_layer(l, 1, ep);
@@ -163,20 +157,21 @@ __global__ void __launch_bounds__(NWARPS * 32)
     for (int l = node_level < b.pre_max ? node_level : b.pre_max; l >= 0; --l) {  // (:1827-1850)
       const int n = s.search_layer(l, b.efc, ep);
       uint32_t *out = b.cand_ids + (size_t)(slot0 + l) * b.efc;
-      if (tid == 0) {
+      uint32_t first = 0;
+      if (lane == 0) {
         for (int j = n - 1; j >= 0; --j) out[j] = s.res.pop().id;  // ascending, as :2596-2604
         b.cand_cnt[slot0 + l] = n > 0 ? (uint32_t)n : 0u;
-        if (n > 0) s.sm.ctl->cur = out[0];
+        if (n > 0) first = out[0];
       }
-      s.clear_visited(l > 0);  // (has the barriers that publish ctl->cur)
-      if (n > 0) ep = s.sm.ctl->cur;
-      __syncthreads();
+      first = __shfl_sync(0xffffffffu, first, 0);
+      s.clear_visited(l > 0);
+      if (n > 0) ep = first;
     }
-    if (tid == 0 && s.overflow) {
+    if (lane == 0 && s.overflow) {
       atomicExch(a.err_flag, KDBGPU_ERR_OVERFLOW);
       s.overflow = false;
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -403,12 +398,15 @@ struct SeqAddArgs {
   uint32_t *entry_io;  // [0] = entry, [1] = max_level + 1 (0 = empty index)
 };
 
+constexpr int kSeqSlots = 4;
+
 template <int METRIC>
-__global__ void __launch_bounds__(128) seq_add_kernel(const DevIndex ix_in, const SearchArgs a, const SeqAddArgs b) {
+__global__ void __launch_bounds__(32) seq_add_kernel(const DevIndex ix_in, const SearchArgs a, const SeqAddArgs b) {
   extern __shared__ __align__(128) unsigned char smem[];
   DevIndex ix = ix_in;
-  Searcher<4, 1, METRIC> s(ix, a, smem);
-  const size_t base = smem_layout(ix.stride, a.ef, 4, 1, a.cand_smem, nullptr, nullptr);
+  Searcher<kSeqSlots, METRIC, 0> s(ix, a, smem);
+  const size_t base = smem_layout(ix.stride, a.ef, kSeqSlots, a.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
+                                  true, nullptr, nullptr);
   float4 *q2 = reinterpret_cast<float4 *>(smem + base);
   const int LL = (b.efc + kMaxDeg + 3) & ~1;  // list length, even so the f64 array after it stays aligned
   double *cd = reinterpret_cast<double *>(smem + base + (size_t)ix.stride * sizeof(float));
@@ -419,12 +417,8 @@ __global__ void __launch_bounds__(128) seq_add_kernel(const DevIndex ix_in, cons
   uint32_t *aid = reinterpret_cast<uint32_t *>(ad + (kMaxDeg + 2));
   uint32_t *fwd = aid + (kMaxDeg + 2);
   __shared__ int s_flag;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&s.sm.bars[i], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, warp = 0;
+  s.init_barriers();
   uint32_t entry = b.entry_io[0];
   int cur_max = (int)b.entry_io[1] - 1;
   for (uint32_t it = 0; it < b.count; ++it) {
@@ -437,8 +431,7 @@ __global__ void __launch_bounds__(128) seq_add_kernel(const DevIndex ix_in, cons
       continue;
     }
     __syncthreads();
-    stage_vector(ix, s.sm.q4, id, tid, 128);
-    __syncthreads();
+    s.load_query(ix.vecs + (size_t)id * ix.stride);
     uint32_t ep = entry;
     for (int l = cur_max; l > level; --l) {  // :685-690
       const int n = s.search_layer(l, 1, ep);
@@ -457,11 +450,12 @@ __global__ void __launch_bounds__(128) seq_add_kernel(const DevIndex ix_in, cons
       s.clear_visited(l > 0);
       if (n < 0) continue;  // :702-704
       const int max_m = l == 0 ? (int)ix.deg0 : (int)ix.degu;  // :707-710
-      const int ns = select_neighbors_dev<METRIC>(ix, cd, cid, (uint32_t)n, max_m, q2, sel, disc, &s_flag, tid, 128);
+      const int ns = select_neighbors_dev<METRIC>(ix, cd, cid, (uint32_t)n, max_m, q2, sel, disc, &s_flag, tid, 32);
       uint32_t *rowp = row_ptr(b.adj0, b.upper_adj, ix, id, l);
-      if (tid < max_m) fwd[tid] = tid < ns ? cid[sel[tid]] : 0u;
+      for (int i = tid; i < max_m; i += 32) fwd[i] = i < ns ? cid[sel[i]] : 0u;
       __syncthreads();
-      if (tid < max_m) rowp[tid] = fwd[tid];  // forward links (:717-722)
+      for (int i = tid; i < max_m; i += 32) rowp[i] = fwd[i];  // forward links (:717-722)
+      __threadfence_block();
       __syncthreads();
       for (int si = 0; si < ns; ++si) {  // reverse links (:725-783)
         const uint32_t nb = fwd[si];
@@ -480,7 +474,7 @@ __global__ void __launch_bounds__(128) seq_add_kernel(const DevIndex ix_in, cons
         }
         // prune (:753-771): candidates in list order + the new node last, NOT sorted
         __syncthreads();
-        stage_vector(ix, q2, nb, tid, 128);
+        stage_vector(ix, q2, nb, tid, 32);
         __syncthreads();
         uint32_t na = 0;
         for (uint32_t j = 0; j < ccount; ++j) {  // uniform over the CTA
@@ -493,16 +487,15 @@ __global__ void __launch_bounds__(128) seq_add_kernel(const DevIndex ix_in, cons
         if (tid == 0) aid[na] = id;
         na++;
         __syncthreads();
-        for (uint32_t j = warp; j < na; j += 4) {
+        for (uint32_t j = warp; j < na; j += 1) {
           const double dv = dist_to_node<METRIC>(ix, q2, aid[j], lane);
           if (lane == 0) ad[j] = dv;
         }
         __syncthreads();
-        const int nbest = select_neighbors_dev<METRIC>(ix, ad, aid, na, max_m, q2, sel, disc, &s_flag, tid, 128);
-        uint32_t mine = 0;
-        if (tid < max_m) mine = tid < nbest ? aid[sel[tid]] : 0u;
+        const int nbest = select_neighbors_dev<METRIC>(ix, ad, aid, na, max_m, q2, sel, disc, &s_flag, tid, 32);
+        for (int i = tid; i < max_m; i += 32) fwd[kMaxDeg + i] = i < nbest ? aid[sel[i]] : 0u;
         __syncthreads();
-        if (tid < max_m) nrow[tid] = mine;  // :774-782
+        for (int i = tid; i < max_m; i += 32) nrow[i] = fwd[kMaxDeg + i];  // :774-782
         __threadfence_block();
         __syncthreads();
       }
@@ -522,22 +515,64 @@ __global__ void __launch_bounds__(128) seq_add_kernel(const DevIndex ix_in, cons
   }
 }
 
-template <int NW, int SL>
+constexpr int kBuildSlots = 8;
+
+__host__ inline int build_cpl_of(const DevIndex &ix) {
+  const uint32_t c = ix.stride / 128;
+  return (c == 1 || c == 2 || c == 4 || c == 6 || c == 8 || c == 12) ? (int)c : 0;
+}
+
+template <int METRIC, int CPL>
+cudaError_t launch_build_search_one(const DevIndex &ix, const SearchArgs &a, const BuildSearchArgs &b, int grid,
+                                    size_t smem, cudaStream_t stream) {
+  auto kern = build_search_kernel<kBuildSlots, METRIC, CPL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32, smem, stream>>>(ix, a, b);
+  return cudaGetLastError();
+}
+template <int METRIC, int CPL>
+int build_search_occ_one(size_t smem) {
+  auto kern = build_search_kernel<kBuildSlots, METRIC, CPL>;
+  int nb = 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return nb;
+}
+#define KDB_BUILD_DISPATCH(EXPR)                                  \
+  if (ix.metric == KDBGPU_METRIC_COSINE) {                        \
+    constexpr int MT = KDBGPU_METRIC_COSINE;                      \
+    switch (build_cpl_of(ix)) {                                   \
+      case 1: { constexpr int CP = 1; EXPR; } break;              \
+      case 2: { constexpr int CP = 2; EXPR; } break;              \
+      case 4: { constexpr int CP = 4; EXPR; } break;              \
+      case 6: { constexpr int CP = 6; EXPR; } break;              \
+      case 8: { constexpr int CP = 8; EXPR; } break;              \
+      case 12: { constexpr int CP = 12; EXPR; } break;            \
+      default: { constexpr int CP = 0; EXPR; } break;             \
+    }                                                             \
+  } else {                                                        \
+    constexpr int MT = KDBGPU_METRIC_L2;                          \
+    switch (build_cpl_of(ix)) {                                   \
+      case 1: { constexpr int CP = 1; EXPR; } break;              \
+      case 2: { constexpr int CP = 2; EXPR; } break;              \
+      case 4: { constexpr int CP = 4; EXPR; } break;              \
+      case 6: { constexpr int CP = 6; EXPR; } break;              \
+      case 8: { constexpr int CP = 8; EXPR; } break;              \
+      case 12: { constexpr int CP = 12; EXPR; } break;            \
+      default: { constexpr int CP = 0; EXPR; } break;             \
+    }                                                             \
+  }
+
 cudaError_t launch_build_search_cfg(const DevIndex &ix, const SearchArgs &a, const BuildSearchArgs &b, int grid,
                                     size_t smem, cudaStream_t stream) {
-  cudaError_t e;
-  if (ix.metric == KDBGPU_METRIC_COSINE) {
-    auto kern = build_search_kernel<NW, SL, KDBGPU_METRIC_COSINE>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, NW * 32, smem, stream>>>(ix, a, b);
-  } else {
-    auto kern = build_search_kernel<NW, SL, KDBGPU_METRIC_L2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, NW * 32, smem, stream>>>(ix, a, b);
-  }
-  return cudaGetLastError();
+  cudaError_t e = cudaErrorInvalidConfiguration;
+  KDB_BUILD_DISPATCH(e = (launch_build_search_one<MT, CP>(ix, a, b, grid, smem, stream)))
+  return e;
 }
 
 }  // namespace
@@ -573,29 +608,23 @@ size_t commit_smem_bytes(const DevIndex &ix) {
 }
 
 size_t seq_add_smem_bytes(const DevIndex &ix, int efc, uint32_t cand_smem) {
-  const size_t base = smem_layout(ix.stride, efc, 4, 1, cand_smem, nullptr, nullptr);
+  const size_t base = smem_layout(ix.stride, efc, kSeqSlots, cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, true,
+                                  nullptr, nullptr);
   const size_t lists = (size_t)((efc + kMaxDeg + 3) & ~1) + 2;
   return base + (size_t)ix.stride * sizeof(float) + lists * (sizeof(double) + 3 * sizeof(uint32_t)) +
-         (size_t)(kMaxDeg + 2) * (sizeof(double) + 2 * sizeof(uint32_t)) + 64;
+         (size_t)(kMaxDeg + 2) * (sizeof(double) + sizeof(uint32_t)) + 2 * (size_t)kMaxDeg * sizeof(uint32_t) + 64;
+}
+
+size_t build_search_smem(const DevIndex &ix, int efc, uint32_t cand_smem) {
+  return smem_layout(ix.stride, efc, kBuildSlots, cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
+                     build_cpl_of(ix) == 0, nullptr, nullptr);
 }
 
 int build_search_occupancy(const DevIndex &ix, int efc, uint32_t cand_smem) {
-  const size_t smem = smem_layout(ix.stride, efc, 4, 1, cand_smem, nullptr, nullptr);
+  const size_t smem = build_search_smem(ix, efc, cand_smem);
+  if (smem > 227 * 1024) return 0;
   int nb = 0;
-  cudaError_t e;
-  if (ix.metric == KDBGPU_METRIC_COSINE) {
-    auto kern = build_search_kernel<4, 1, KDBGPU_METRIC_COSINE>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, smem);
-  } else {
-    auto kern = build_search_kernel<4, 1, KDBGPU_METRIC_L2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, smem);
-  }
-  if (e != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 0;
-  }
+  KDB_BUILD_DISPATCH(nb = (build_search_occ_one<MT, CP>(smem)))
   return nb;
 }
 
@@ -612,8 +641,8 @@ cudaError_t launch_add_batch(const DevIndex &ix, const SearchArgs &a, const Buil
   b.out_off = L.out_off;
   b.cand_ids = L.cand_ids;
   b.cand_cnt = L.cand_cnt;
-  const size_t smem = smem_layout(ix.stride, L.efc, 4, 1, a.cand_smem, nullptr, nullptr);
-  e = launch_build_search_cfg<4, 1>(ix, a, b, search_grid, smem, stream);
+  const size_t smem = build_search_smem(ix, L.efc, a.cand_smem);
+  e = launch_build_search_cfg(ix, a, b, search_grid, smem, stream);
   if (e != cudaSuccess) return e;
   RequestArgs r;
   r.slot_node = L.slot_node;
@@ -675,11 +704,11 @@ cudaError_t launch_seq_add(const DevIndex &ix, const SearchArgs &a, uint32_t sta
   if (ix.metric == KDBGPU_METRIC_COSINE) {
     auto kern = seq_add_kernel<KDBGPU_METRIC_COSINE>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    kern<<<1, 128, smem, stream>>>(ix, a, b);
+    kern<<<1, 32, smem, stream>>>(ix, a, b);
   } else {
     auto kern = seq_add_kernel<KDBGPU_METRIC_L2>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    kern<<<1, 128, smem, stream>>>(ix, a, b);
+    kern<<<1, 32, smem, stream>>>(ix, a, b);
   }
   return cudaGetLastError();
 }

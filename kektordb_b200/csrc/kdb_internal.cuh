@@ -2,7 +2,8 @@
 //
 // Layout of the GPU mirror of one hnsw.Index (reference: pkg/core/hnsw/hnsw_node.go:13-39,
 // hnsw_index.go:77) — see DESIGN.md §3:
-//   vecs       [(cap+1)][stride] f32, stride = dim rounded up to 32 floats (128-byte rows, zero padded)
+//   vecs       [(cap+1)][stride] f32, stride = dim rounded up to 128 floats (one float4 column per lane
+//              and pass; 512-byte-aligned rows, zero padded)
 //   adj0       [(cap+1)][deg0]   u32, deg0 = 2M, zero padded (id 0 is the nil slot)
 //   upper_adj  [rows][degu]      u32, degu = M; node i, level l>=1 -> row upper_first[i] + l-1
 //   levels     [(cap+1)]         i8,  -1 = nil node
@@ -59,11 +60,11 @@ struct SearchArgs {
 };
 
 struct SearchTuning {
-  int nwarps = 4;      // warps per CTA (one query per CTA)
-  int slots = 2;       // row slots per warp (bulk copies in flight per warp)
-  int cand_smem = 512; // candidate-heap entries in shared memory
+  int slots = 4;            // row slots per query-warp (bulk copies in flight per query), power of two
+  int cand_smem = 192;      // candidate-heap entries held in shared memory (the rest spills to HBM)
   int max_ctas_per_sm = 0;  // 0 = whatever fits
 };
+bool search_slots_supported(int slots);
 
 size_t search_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t);
 // returns resident CTAs per SM (0 = configuration does not fit)

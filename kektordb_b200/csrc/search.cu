@@ -1,18 +1,8 @@
-// search.cu — HNSW traversal on sm_100a: one CTA per query, persistent over the batch.
+// search.cu — the query-side kernels on sm_100a: the persistent HNSW traversal (one warp per
+// query, see searcher.cuh), exact query preparation, and the batched distance hook.
 //
-// Stands in for (*Index).searchInternal / searchLayerUnlocked
-// (reference pkg/core/hnsw/hnsw_index.go:369-468, :2351-2611) with the heaps of
-// hnsw_heap.go:18-156 and the visited BitSet of bitset.go.  Per hop the CTA
-//   A. (lane 0)   pops the nearest candidate, tests the early exit (:2497-2506)
-//   B. (warp 0)   reads the adjacency row, test-and-sets the visited bitset, applies the
-//                 allow-list BEFORE any distance (:2537-2549), compacts the survivors in row order
-//   C. (all warps) gathers the survivors' rows HBM -> shared memory with 1-D bulk copies
-//                 (cp.async.bulk + mbarrier, per-warp slots) and reduces query x row in the
-//                 fixed "kernel order" (kdb_internal.cuh)
-//   D. (lane 0)   applies the result/candidate heap updates sequentially in row order (:2571-2591)
-// Distances of one hop are computed in parallel but applied in the reference's order, and the two
-// binary heaps are the reference's own algorithms, so ids, order and scores are bit-identical to
-// the oracle in KDBO_ARITH_KERNEL mode — ties included.
+// hnsw_search_kernel stands in for (*Index).searchInternal / searchLayerUnlocked (reference
+// pkg/core/hnsw/hnsw_index.go:369-468, :2351-2611).
 #include "searcher.cuh"
 
 namespace kdb {
@@ -21,24 +11,20 @@ using namespace dev;
 
 namespace {
 
-template <int NWARPS, int SLOTS, int METRIC>
-__global__ void __launch_bounds__(NWARPS * 32) hnsw_search_kernel(const DevIndex ix, const SearchArgs a) {
+// One warp per CTA, persistent over the batch: queries are claimed from a global counter.
+template <int SLOTS, int METRIC, int CPL>
+__global__ void __launch_bounds__(32) hnsw_search_kernel(const DevIndex ix, const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  Searcher<NWARPS, SLOTS, METRIC> s(ix, a, smem);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NWARPS * SLOTS; ++i) mbar_init(&s.sm.bars[i], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
+  Searcher<SLOTS, METRIC, CPL> s(ix, a, smem);
+  s.init_barriers();
   for (;;) {
-    if (threadIdx.x == 0) s.sm.ctl->q = atomicAdd(a.work_counter, 1u);
-    __syncthreads();
-    const uint32_t q = s.sm.ctl->q;
+    uint32_t q = 0;
+    if (s.lane == 0) q = atomicAdd(a.work_counter, 1u);
+    q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= a.nq) break;
     s.run_query(q);
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (s.lane == 0) {
     atomicAdd(&a.stats[0], s.st_e);
     atomicAdd(&a.stats[1], s.st_h);
     atomicAdd(&a.stats[2], s.st_h0);
@@ -103,36 +89,26 @@ __global__ void distance_batch_kernel(const DevIndex ix, const float *__restrict
   }
 }
 
-template <int NW, int SL>
-cudaError_t launch_cfg(const DevIndex &ix, const SearchArgs &a, int grid, size_t smem, cudaStream_t stream) {
-  cudaError_t e;
-  if (ix.metric == KDBGPU_METRIC_COSINE) {
-    auto kern = hnsw_search_kernel<NW, SL, KDBGPU_METRIC_COSINE>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, NW * 32, smem, stream>>>(ix, a);
-  } else {
-    auto kern = hnsw_search_kernel<NW, SL, KDBGPU_METRIC_L2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, NW * 32, smem, stream>>>(ix, a);
-  }
-  return cudaGetLastError();
+// CPL (float4 columns per lane) instantiated at compile time; other row lengths use the generic path
+__host__ inline int cpl_of(const DevIndex &ix) {
+  const uint32_t c = ix.stride / 128;
+  return (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8 || c == 12) ? (int)c : 0;
 }
 
-template <int NW, int SL>
-int occupancy_cfg(const DevIndex &ix, size_t smem) {
+template <int SL, int METRIC, int CPL>
+cudaError_t launch_one(const DevIndex &ix, const SearchArgs &a, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = hnsw_search_kernel<SL, METRIC, CPL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32, smem, stream>>>(ix, a);
+  return cudaGetLastError();
+}
+template <int SL, int METRIC, int CPL>
+int occupancy_one(size_t smem) {
+  auto kern = hnsw_search_kernel<SL, METRIC, CPL>;
   int nb = 0;
-  cudaError_t e;
-  if (ix.metric == KDBGPU_METRIC_COSINE) {
-    auto kern = hnsw_search_kernel<NW, SL, KDBGPU_METRIC_COSINE>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem);
-  } else {
-    auto kern = hnsw_search_kernel<NW, SL, KDBGPU_METRIC_L2>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem);
-  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     return 0;
@@ -140,30 +116,59 @@ int occupancy_cfg(const DevIndex &ix, size_t smem) {
   return nb;
 }
 
-#define KDB_DISPATCH_CFG(NWv, SLv, EXPR)           \
-  if (t.nwarps == NWv && t.slots == SLv) {         \
-    constexpr int NW = NWv;                        \
-    constexpr int SL = SLv;                        \
-    EXPR;                                          \
+#define KDB_CASE_CPL(SLv, METRICv, CPLv, EXPR) \
+  case CPLv: {                                 \
+    constexpr int SL = SLv;                    \
+    constexpr int MT = METRICv;                \
+    constexpr int CP = CPLv;                   \
+    EXPR;                                      \
+  } break;
+#define KDB_SWITCH_CPL(SLv, METRICv, EXPR) \
+  switch (cpl) {                           \
+    KDB_CASE_CPL(SLv, METRICv, 1, EXPR)    \
+    KDB_CASE_CPL(SLv, METRICv, 2, EXPR)    \
+    KDB_CASE_CPL(SLv, METRICv, 3, EXPR)    \
+    KDB_CASE_CPL(SLv, METRICv, 4, EXPR)    \
+    KDB_CASE_CPL(SLv, METRICv, 6, EXPR)    \
+    KDB_CASE_CPL(SLv, METRICv, 8, EXPR)    \
+    KDB_CASE_CPL(SLv, METRICv, 12, EXPR)   \
+    default: {                             \
+      constexpr int SL = SLv;              \
+      constexpr int MT = METRICv;          \
+      constexpr int CP = 0;                \
+      EXPR;                                \
+    } break;                               \
+  }
+#define KDB_SWITCH_METRIC(SLv, EXPR)                   \
+  if (ix.metric == KDBGPU_METRIC_COSINE) {             \
+    KDB_SWITCH_CPL(SLv, KDBGPU_METRIC_COSINE, EXPR)    \
+  } else {                                             \
+    KDB_SWITCH_CPL(SLv, KDBGPU_METRIC_L2, EXPR)        \
+  }
+#define KDB_DISPATCH(EXPR)                       \
+  switch (t.slots) {                             \
+    case 2: { KDB_SWITCH_METRIC(2, EXPR) } break;   \
+    case 4: { KDB_SWITCH_METRIC(4, EXPR) } break;   \
+    case 8: { KDB_SWITCH_METRIC(8, EXPR) } break;   \
+    case 16: { KDB_SWITCH_METRIC(16, EXPR) } break; \
+    default: break;                              \
   }
 
 }  // namespace
 
+bool search_slots_supported(int slots) { return slots == 2 || slots == 4 || slots == 8 || slots == 16; }
+
 size_t search_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t) {
-  return smem_layout(ix.stride, ef, t.nwarps, t.slots, (uint32_t)t.cand_smem, nullptr, nullptr);
+  return smem_layout(ix.stride, ef, t.slots, (uint32_t)t.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
+                     cpl_of(ix) == 0, nullptr, nullptr);
 }
 
 int search_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
   const size_t smem = search_smem_bytes(ix, ef, t);
   if (smem > 227 * 1024) return 0;
+  const int cpl = cpl_of(ix);
   int nb = -1;
-  KDB_DISPATCH_CFG(2, 2, nb = (occupancy_cfg<NW, SL>(ix, smem)))
-  KDB_DISPATCH_CFG(2, 4, nb = (occupancy_cfg<NW, SL>(ix, smem)))
-  KDB_DISPATCH_CFG(4, 1, nb = (occupancy_cfg<NW, SL>(ix, smem)))
-  KDB_DISPATCH_CFG(4, 2, nb = (occupancy_cfg<NW, SL>(ix, smem)))
-  KDB_DISPATCH_CFG(4, 4, nb = (occupancy_cfg<NW, SL>(ix, smem)))
-  KDB_DISPATCH_CFG(8, 1, nb = (occupancy_cfg<NW, SL>(ix, smem)))
-  KDB_DISPATCH_CFG(8, 2, nb = (occupancy_cfg<NW, SL>(ix, smem)))
+  KDB_DISPATCH(nb = (occupancy_one<SL, MT, CP>(smem)))
   if (nb < 0) return 0;
   if (t.max_ctas_per_sm > 0 && nb > t.max_ctas_per_sm) nb = t.max_ctas_per_sm;
   return nb;
@@ -172,14 +177,9 @@ int search_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
 cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
                           cudaStream_t stream) {
   const size_t smem = search_smem_bytes(ix, a.ef, t);
+  const int cpl = cpl_of(ix);
   cudaError_t e = cudaErrorInvalidConfiguration;
-  KDB_DISPATCH_CFG(2, 2, e = (launch_cfg<NW, SL>(ix, a, grid, smem, stream)))
-  KDB_DISPATCH_CFG(2, 4, e = (launch_cfg<NW, SL>(ix, a, grid, smem, stream)))
-  KDB_DISPATCH_CFG(4, 1, e = (launch_cfg<NW, SL>(ix, a, grid, smem, stream)))
-  KDB_DISPATCH_CFG(4, 2, e = (launch_cfg<NW, SL>(ix, a, grid, smem, stream)))
-  KDB_DISPATCH_CFG(4, 4, e = (launch_cfg<NW, SL>(ix, a, grid, smem, stream)))
-  KDB_DISPATCH_CFG(8, 1, e = (launch_cfg<NW, SL>(ix, a, grid, smem, stream)))
-  KDB_DISPATCH_CFG(8, 2, e = (launch_cfg<NW, SL>(ix, a, grid, smem, stream)))
+  KDB_DISPATCH(e = (launch_one<SL, MT, CP>(ix, a, grid, smem, stream)))
   return e;
 }
 

@@ -1,27 +1,34 @@
-// searcher.cuh — the per-CTA HNSW layer search shared by the query kernel (search.cu) and the
-// graph-construction kernels (build.cu).  Everything here is device code in namespace kdb::dev.
+// searcher.cuh — the per-query HNSW layer search shared by the query kernel (search.cu) and the
+// graph-construction kernels (build.cu).  Device code, namespace kdb::dev.
 //
-// Stands in for searchLayerUnlocked (reference pkg/core/hnsw/hnsw_index.go:2351-2611) with the
-// heaps of hnsw_heap.go:18-156 and the visited BitSet of bitset.go; see search.cu for the phase
-// description.
+// ONE WARP PER QUERY.  Stands in for searchLayerUnlocked (reference
+// pkg/core/hnsw/hnsw_index.go:2351-2611) with the heaps of hnsw_heap.go:18-156 and the visited
+// BitSet of bitset.go.  Per hop the warp
+//   A. (lane 0)    pops the nearest candidate and tests the early exit (:2497-2506)
+//   B. (all lanes) reads the adjacency row (one neighbour per lane), test-and-sets the visited
+//                  bitset, applies the allow-list BEFORE any distance (:2537-2549) and compacts
+//                  the survivors in row order
+//   C. (all lanes) streams the survivors' rows HBM -> shared memory with 1-D bulk copies
+//                  (cp.async.bulk + mbarrier, SLOTS rows in flight), reduces query x row in the
+//                  fixed "kernel order" (kdb_internal.cuh) ...
+//   D. (lane 0)    ... and applies the heap update of each row right after its reduction, in row
+//                  order (:2571-2591), while the later rows of the hop are still in flight.
+// No CTA-wide barrier exists on this path: a CTA is a single warp, the SM interleaves ~7 of them.
+// The two binary heaps are the reference's own algorithms run by lane 0, so ids, order and scores
+// are bit-identical to the oracle in KDBO_ARITH_KERNEL mode — ties included.
 #pragma once
 #include "kdb_internal.cuh"
 
 namespace kdb {
 namespace dev {
 
-constexpr int kMaxDeg = 256;    // max neighbours per adjacency row (2M <= 256)
-constexpr int kMarkCap = 512;   // visited marks logged per upper-level search before full clear
+constexpr int kMaxDeg = 256;   // max neighbours per adjacency row (2M <= 256)
+constexpr int kMarkCap = 256;  // visited marks logged per upper-level search before a full clear
 
 struct Ctl {
-  uint32_t cur;
-  uint32_t n_eval;
-  int done;
-  uint32_t expanded;
-  uint32_t q;
-  int res_n;
   uint32_t n_marked;
-  uint32_t pad;
+  uint32_t cur;  // scratch word for callers (build kernels publish the next entry point here)
+  uint32_t pad[2];
 };
 
 struct SmemPtrs {
@@ -30,7 +37,6 @@ struct SmemPtrs {
   uint64_t *bars;
   HeapEntry *res;
   HeapEntry *cand;
-  double *eval_d;
   uint32_t *eval_id;
   uint32_t *eval_del;
   uint32_t *marked;
@@ -39,29 +45,28 @@ struct SmemPtrs {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// shared-memory carve-up, identical on host (sizing) and device (pointers)
-__host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int nwarps, int slots, uint32_t cand_smem,
-                                              unsigned char *base, SmemPtrs *p) {
+// shared-memory carve-up of one warp-CTA, identical on host (sizing) and device (pointers)
+__host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots, uint32_t cand_smem, uint32_t deg_max,
+                                              bool q_in_smem, unsigned char *base, SmemPtrs *p) {
+  const uint32_t dm = (deg_max + 31u) & ~31u;
   size_t off = 0;
-  size_t o_slots = off;
-  off += (size_t)nwarps * slots * stride * sizeof(float);
-  size_t o_q = off;
-  off += (size_t)stride * sizeof(float);
-  size_t o_res = off;
+  const size_t o_slots = off;
+  off += (size_t)slots * stride * sizeof(float);
+  const size_t o_q = off;
+  if (q_in_smem) off += (size_t)stride * sizeof(float);
+  const size_t o_res = off;
   off += (size_t)(ef + 1) * sizeof(HeapEntry);
-  size_t o_cand = off;
+  const size_t o_cand = off;
   off += (size_t)cand_smem * sizeof(HeapEntry);
-  size_t o_evald = off;
-  off += (size_t)kMaxDeg * sizeof(double);
-  size_t o_bars = off;
-  off += (size_t)nwarps * slots * sizeof(uint64_t);
-  size_t o_evalid = off;
-  off += (size_t)kMaxDeg * sizeof(uint32_t);
-  size_t o_evaldel = off;
-  off += (size_t)kMaxDeg * sizeof(uint32_t);
-  size_t o_marked = off;
+  const size_t o_bars = off;
+  off += (size_t)slots * sizeof(uint64_t);
+  const size_t o_evalid = off;
+  off += (size_t)dm * sizeof(uint32_t);
+  const size_t o_evaldel = off;
+  off += (size_t)dm * sizeof(uint32_t);
+  const size_t o_marked = off;
   off += (size_t)kMarkCap * sizeof(uint32_t);
-  size_t o_ctl = off;
+  const size_t o_ctl = off;
   off += sizeof(Ctl);
   off = align_up(off, 128);
   if (p) {
@@ -69,7 +74,6 @@ __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int nwarp
     p->q4 = reinterpret_cast<float4 *>(base + o_q);
     p->res = reinterpret_cast<HeapEntry *>(base + o_res);
     p->cand = reinterpret_cast<HeapEntry *>(base + o_cand);
-    p->eval_d = reinterpret_cast<double *>(base + o_evald);
     p->bars = reinterpret_cast<uint64_t *>(base + o_bars);
     p->eval_id = reinterpret_cast<uint32_t *>(base + o_evalid);
     p->eval_del = reinterpret_cast<uint32_t *>(base + o_evaldel);
@@ -180,23 +184,26 @@ __device__ __forceinline__ bool bit_test(const uint32_t *bits, uint32_t id) {
   return (bits[id >> 5] >> (id & 31)) & 1u;
 }
 
-template <int NWARPS, int SLOTS, int METRIC>
+// CPL = float4 columns per lane = stride / 128 when known at compile time (query held in
+// registers, reduction fully unrolled); CPL == 0 is the generic path (query in shared memory).
+template <int SLOTS, int METRIC, int CPL>
 struct Searcher {
+  static_assert((SLOTS & (SLOTS - 1)) == 0, "SLOTS must be a power of two");
   const DevIndex &ix;
   const SearchArgs &a;
   SmemPtrs sm;
   uint32_t *vis;
-  const int tid, lane, warp;
-  uint32_t phase_bits;  // parity of each of this warp's slot barriers
-  CandHeap cand;
-  ResHeap res;
+  const int lane;
+  uint32_t phase_bits;  // parity of each slot barrier
+  CandHeap cand;        // meaningful on lane 0
+  ResHeap res;          // meaningful on lane 0
   unsigned long long st_e, st_h, st_h0;
   bool overflow;
+  float4 qreg[CPL > 0 ? CPL : 1];
 
   __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem)
-      : ix(ix_), a(a_), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), phase_bits(0),
-        st_e(0), st_h(0), st_h0(0), overflow(false) {
-    smem_layout(ix.stride, a.ef, NWARPS, SLOTS, a.cand_smem, smem, &sm);
+      : ix(ix_), a(a_), lane(threadIdx.x & 31), phase_bits(0), st_e(0), st_h(0), st_h0(0), overflow(false) {
+    smem_layout(ix.stride, a.ef, SLOTS, a.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, CPL == 0, smem, &sm);
     vis = a.visited + (size_t)blockIdx.x * a.vis_words;
     cand.s = sm.cand;
     cand.g = a.cand_overflow + (size_t)blockIdx.x * a.ovf_cap;
@@ -207,44 +214,106 @@ struct Searcher {
     res.n = 0;
   }
 
-  // Phase C: rows eval_id[0..n_eval) -> eval_d.  Warp w owns rows w, w+NWARPS, ...; each of its
-  // SLOTS shared-memory slots has an mbarrier; the warp keeps SLOTS bulk copies in flight.
-  __device__ __forceinline__ void gather() {
-    const uint32_t n_eval = sm.ctl->n_eval;
-    const uint32_t nrows = n_eval > (uint32_t)warp ? (n_eval - warp + NWARPS - 1) / NWARPS : 0;
+  __device__ __forceinline__ void init_barriers() {
+    if (lane == 0) {
+      for (int i = 0; i < SLOTS; ++i) mbar_init(&sm.bars[i], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void load_query(const float *src_row) {
+    const float4 *src = reinterpret_cast<const float4 *>(src_row);
+    if (CPL > 0) {
+#pragma unroll
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) qreg[t] = src[lane + 32 * t];
+    } else {
+      for (uint32_t c = lane; c < (ix.stride >> 2); c += 32) sm.q4[c] = src[c];
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void issue_row(uint32_t j, uint32_t id) {  // lane 0
+    const uint32_t slot = j & (SLOTS - 1);
     const uint32_t row_bytes = ix.stride * sizeof(float);
-    const uint32_t nchunks = ix.stride >> 2;
-    float *wslots = sm.slots + (size_t)warp * SLOTS * ix.stride;
-    uint64_t *wbars = sm.bars + warp * SLOTS;
-    auto issue = [&](uint32_t j) {
-      if (lane == 0) {
-        const uint32_t slot = j % SLOTS;
-        const uint32_t id = sm.eval_id[warp + j * NWARPS];
-        mbar_expect_tx(&wbars[slot], row_bytes);
-        bulk_g2s(wslots + (size_t)slot * ix.stride, ix.vecs + (size_t)id * ix.stride, row_bytes, &wbars[slot]);
+    mbar_expect_tx(&sm.bars[slot], row_bytes);
+    bulk_g2s(sm.slots + (size_t)slot * ix.stride, ix.vecs + (size_t)id * ix.stride, row_bytes, &sm.bars[slot]);
+  }
+
+  __device__ __forceinline__ void wait_slot(uint32_t j) {
+    const uint32_t slot = j & (SLOTS - 1);
+    mbar_wait(&sm.bars[slot], (phase_bits >> slot) & 1u);
+    phase_bits ^= 1u << slot;
+  }
+
+  // lane partial of query x row held in slot (j mod SLOTS): (a0 + a1) + (a2 + a3), kernel order
+  __device__ __forceinline__ float lane_partial(uint32_t j) const {
+    const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots + (size_t)(j & (SLOTS - 1)) * ix.stride);
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+    if (CPL > 0) {
+#pragma unroll
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) {
+        const float4 q = qreg[t];
+        const float4 b = r4[lane + 32 * t];
+        if (METRIC == KDBGPU_METRIC_COSINE) {
+          ax = __fmaf_rn(q.x, b.x, ax);
+          ay = __fmaf_rn(q.y, b.y, ay);
+          az = __fmaf_rn(q.z, b.z, az);
+          aw = __fmaf_rn(q.w, b.w, aw);
+        } else {
+          const float dx = __fsub_rn(q.x, b.x), dy = __fsub_rn(q.y, b.y), dz = __fsub_rn(q.z, b.z),
+                      dw = __fsub_rn(q.w, b.w);
+          ax = __fmaf_rn(dx, dx, ax);
+          ay = __fmaf_rn(dy, dy, ay);
+          az = __fmaf_rn(dz, dz, az);
+          aw = __fmaf_rn(dw, dw, aw);
+        }
       }
-    };
-    const uint32_t pro = nrows < (uint32_t)SLOTS ? nrows : (uint32_t)SLOTS;
-    for (uint32_t j = 0; j < pro; ++j) issue(j);
-    for (uint32_t j = 0; j < nrows; ++j) {
-      const uint32_t slot = j % SLOTS;
-      mbar_wait(&wbars[slot], (phase_bits >> slot) & 1u);
-      phase_bits ^= 1u << slot;
-      const float s = warp_reduce_row<METRIC>(sm.q4, reinterpret_cast<const float4 *>(wslots + (size_t)slot * ix.stride),
-                                              nchunks, lane);
-      if (lane == 0) sm.eval_d[warp + j * NWARPS] = to_distance<METRIC>(s);
-      __syncwarp();
-      if (j + SLOTS < nrows) {
-        fence_proxy_async();  // generic-proxy reads of the slot precede the async-proxy overwrite
-        issue(j + SLOTS);
+    } else {
+      const uint32_t nchunks = ix.stride >> 2;
+#pragma unroll 4
+      for (uint32_t c = lane; c < nchunks; c += 32) {
+        const float4 q = sm.q4[c];
+        const float4 b = r4[c];
+        if (METRIC == KDBGPU_METRIC_COSINE) {
+          ax = __fmaf_rn(q.x, b.x, ax);
+          ay = __fmaf_rn(q.y, b.y, ay);
+          az = __fmaf_rn(q.z, b.z, az);
+          aw = __fmaf_rn(q.w, b.w, aw);
+        } else {
+          const float dx = __fsub_rn(q.x, b.x), dy = __fsub_rn(q.y, b.y), dz = __fsub_rn(q.z, b.z),
+                      dw = __fsub_rn(q.w, b.w);
+          ax = __fmaf_rn(dx, dx, ax);
+          ay = __fmaf_rn(dy, dy, ay);
+          az = __fmaf_rn(dz, dz, az);
+          aw = __fmaf_rn(dw, dw, aw);
+        }
+      }
+    }
+    return __fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw));
+  }
+
+  // lane 0: the reference's per-neighbour result update (:2571-2591)
+  __device__ __forceinline__ void heap_update(float s, uint32_t j, int ef) {
+    HeapEntry e;
+    e.d = to_distance<METRIC>(s);
+    e.id = sm.eval_id[j];
+    e.pad = 0;
+    bool admit = res.n < ef;  // worstDist = MaxFloat64 while results is empty
+    if (!admit) admit = e.d < res.a[0].d;
+    if (admit) {
+      if (!cand.push(e)) overflow = true;  // :2581
+      if (!sm.eval_del[j]) {              // :2584
+        res.push(e);
+        if (res.n > ef) (void)res.pop();  // :2587-2589
       }
     }
   }
 
-  __device__ __forceinline__ void mark_logged(uint32_t id, bool log) {  // lane-0 only helper
+  __device__ __forceinline__ void mark_logged(uint32_t id, bool log) {  // lane 0
     atomicOr(&vis[id >> 5], 1u << (id & 31));
     if (log) {
-      uint32_t m = sm.ctl->n_marked;
+      const uint32_t m = sm.ctl->n_marked;
       if (m < (uint32_t)kMarkCap) sm.marked[m] = id;
       sm.ctl->n_marked = m + 1;
     }
@@ -252,159 +321,158 @@ struct Searcher {
 
   // visited.Clear() (bitset.go:44-48): only this search's marks if they were logged, else all words
   __device__ __forceinline__ void clear_visited(bool logged) {
-    __syncthreads();
+    __syncwarp();
     const uint32_t m = sm.ctl->n_marked;
     if (logged && m <= (uint32_t)kMarkCap) {
-      for (uint32_t i = tid; i < m; i += NWARPS * 32) vis[sm.marked[i] >> 5] = 0u;
+      for (uint32_t i = lane; i < m; i += 32) vis[sm.marked[i] >> 5] = 0u;
     } else {
       uint4 *v4 = reinterpret_cast<uint4 *>(vis);
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      for (uint32_t i = tid; i < (a.vis_words >> 2); i += NWARPS * 32) v4[i] = z;
+      for (uint32_t i = lane; i < (a.vis_words >> 2); i += 32) v4[i] = z;
     }
-    __syncthreads();
+    __syncwarp();
   }
 
-  // searchLayerUnlocked (hnsw_index.go:2351-2611).  Returns the number of results left in the
-  // max-heap `res` (not yet drained), or -1 if the entry node is nil (:2466-2468).
+  // searchLayerUnlocked (hnsw_index.go:2351-2611).  Returns (on every lane) the number of results
+  // left in the max-heap `res` (not yet drained), or -1 if the entry node is nil (:2466-2468).
   __device__ int search_layer(const int level, const int ef, const uint32_t ep) {
     const bool log_marks = level > 0;
     if (ep == 0 || ep > ix.n || ix.levels[ep] < 0) return -1;
-    if (tid == 0) {
-      sm.ctl->n_eval = 1;
+    // dist(query, entry) (:2471)
+    if (lane == 0) {
       sm.ctl->n_marked = 0;
-      sm.eval_id[0] = ep;
+      issue_row(0, ep);
     }
-    __syncthreads();
-    gather();  // dist(query, entry) (:2471)
-    __syncthreads();
-    if (tid == 0) {
+    __syncwarp();
+    wait_slot(0);
+    float s0 = lane_partial(0);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s0 = __fadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, o));
+    __syncwarp();  // all lanes are done reading the slot
+    if (lane == 0) {
       cand.n = 0;
       res.n = 0;
       HeapEntry e;
-      e.d = sm.eval_d[0];
+      e.d = to_distance<METRIC>(s0);
       e.id = ep;
       e.pad = 0;
-      cand.push(e);              // :2478
+      cand.push(e);                // :2478
       mark_logged(ep, log_marks);  // :2479
-      bool ep_valid = true;      // :2481-2485 (an empty allow-list never reaches the kernel)
+      bool ep_valid = true;        // :2481-2485 (an empty allow-list never reaches the kernel)
       if (a.allow != nullptr && !bit_test(a.allow, ep)) ep_valid = false;
       const bool del = ix.deleted != nullptr && bit_test(ix.deleted, ep);
       if (ep_valid && !del) res.push(e);  // :2487-2489
       st_e += 1;
     }
+    __syncwarp();
     for (;;) {  // :2495
-      if (tid == 0) {
-        int done = 0;
-        if (cand.n == 0 || overflow) {
-          done = 1;
+      // ---- A: pop + early exit (lane 0), broadcast
+      uint32_t cur = 0xffffffffu;
+      if (lane == 0 && cand.n > 0 && !overflow) {
+        const HeapEntry c = cand.pop();
+        if (!(res.n >= ef && c.d > res.a[0].d)) cur = c.id;  // :2501-2506
+      }
+      cur = __shfl_sync(0xffffffffu, cur, 0);
+      if (cur == 0xffffffffu) break;
+      // ---- B: adjacency row -> ordered list of neighbours to evaluate
+      uint32_t n_eval = 0;
+      // "level >= len(currentNode.Connections)" -> continue (:2521-2524)
+      const bool expand = (level == 0) || (ix.levels[cur] >= level);
+      if (expand) {
+        const uint32_t *row;
+        uint32_t deg;
+        if (level == 0) {
+          deg = ix.deg0;
+          row = ix.adj0 + (size_t)cur * deg;
         } else {
-          const HeapEntry cur = cand.pop();
-          if (res.n >= ef && cur.d > res.a[0].d) {  // :2501-2506
-            done = 1;
-          } else {
-            sm.ctl->cur = cur.id;
-          }
+          deg = ix.degu;
+          row = ix.upper_adj + ((size_t)ix.upper_first[cur] + (uint32_t)(level - 1)) * deg;
         }
-        sm.ctl->done = done;
+        for (uint32_t base = 0; base < deg; base += 32) {  // :2537
+          const uint32_t idx = base + lane;
+          const uint32_t id = idx < deg ? row[idx] : 0u;  // plain load: build kernels mutate rows
+          const bool act = id != 0u;                      // rows are compacted at upload; 0 = padding
+          if (__ballot_sync(0xffffffffu, act) == 0u) break;
+          // a repeated id inside the row is visited by its first occurrence (:2539-2542)
+          const uint32_t same = __match_any_sync(0xffffffffu, id);
+          const bool leader = act && ((__ffs(same) - 1) == lane);
+          bool fresh = false;
+          if (leader) {
+            const uint32_t bit = 1u << (id & 31);
+            const uint32_t old = atomicOr(&vis[id >> 5], bit);  // visited.Has + visited.Add
+            fresh = (old & bit) == 0u;
+          }
+          if (log_marks) {
+            const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
+            const uint32_t m0 = sm.ctl->n_marked;
+            if (fresh) {
+              const uint32_t pos = m0 + __popc(fm & ((1u << lane) - 1u));
+              if (pos < (uint32_t)kMarkCap) sm.marked[pos] = id;
+            }
+            __syncwarp();
+            if (lane == 0) sm.ctl->n_marked = m0 + __popc(fm);
+            __syncwarp();
+          }
+          // allow-list before any distance work (:2545-2549)
+          const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id));
+          uint32_t del = 0u;
+          if (keep && ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
+          const uint32_t km = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
+            sm.eval_id[pos] = id;
+            sm.eval_del[pos] = del;
+          }
+          n_eval += __popc(km);
+        }
+        __syncwarp();
       }
-      __syncthreads();
-      if (sm.ctl->done) break;
-      const uint32_t cur = sm.ctl->cur;
-      if (warp == 0) {  // phase B
-        uint32_t n_eval = 0;
-        // "level >= len(currentNode.Connections)" -> continue (:2521-2524)
-        const bool expand = (level == 0) || (ix.levels[cur] >= level);
-        if (expand) {
-          const uint32_t *row;
-          uint32_t deg;
-          if (level == 0) {
-            deg = ix.deg0;
-            row = ix.adj0 + (size_t)cur * deg;
-          } else {
-            deg = ix.degu;
-            row = ix.upper_adj + ((size_t)ix.upper_first[cur] + (uint32_t)(level - 1)) * deg;
-          }
-          for (uint32_t base = 0; base < deg; base += 32) {  // :2537
-            const uint32_t idx = base + lane;
-            const uint32_t id = idx < deg ? row[idx] : 0u;  // plain load: build kernels mutate rows
-            const bool act = id != 0u;  // rows are compacted at upload; 0 = padding
-            if (__ballot_sync(0xffffffffu, act) == 0u) break;
-            // a repeated id inside the row is visited by its first occurrence (:2539-2542)
-            const uint32_t same = __match_any_sync(0xffffffffu, id);
-            const bool leader = act && ((__ffs(same) - 1) == lane);
-            bool fresh = false;
-            if (leader) {
-              const uint32_t bit = 1u << (id & 31);
-              const uint32_t old = atomicOr(&vis[id >> 5], bit);  // visited.Has + visited.Add
-              fresh = (old & bit) == 0u;
-            }
-            if (log_marks) {
-              const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
-              const uint32_t m0 = sm.ctl->n_marked;
-              if (fresh) {
-                const uint32_t pos = m0 + __popc(fm & ((1u << lane) - 1u));
-                if (pos < (uint32_t)kMarkCap) sm.marked[pos] = id;
-              }
-              __syncwarp();
-              if (lane == 0) sm.ctl->n_marked = m0 + __popc(fm);
-              __syncwarp();
-            }
-            // allow-list before any distance work (:2545-2549)
-            const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id));
-            uint32_t del = 0u;
-            if (keep && ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
-            const uint32_t km = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-              const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
-              sm.eval_id[pos] = id;
-              sm.eval_del[pos] = del;
-            }
-            n_eval += __popc(km);
-          }
+      // ---- C + D: stream the rows, two per iteration (independent reductions interleave), and
+      // apply each heap update as soon as its distance exists
+      if (lane == 0) {
+        const uint32_t pro = n_eval < (uint32_t)SLOTS ? n_eval : (uint32_t)SLOTS;
+        for (uint32_t j = 0; j < pro; ++j) issue_row(j, sm.eval_id[j]);
+      }
+      for (uint32_t j = 0; j < n_eval; j += 2) {
+        const bool two = j + 1 < n_eval;
+        wait_slot(j);
+        if (two) wait_slot(j + 1);
+        float sa = lane_partial(j);  // :2566
+        float sb = two ? lane_partial(j + 1) : 0.f;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
+          sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
         }
+        __syncwarp();  // all lanes are done reading both slots
         if (lane == 0) {
-          sm.ctl->n_eval = n_eval;
-          sm.ctl->expanded = expand ? 1u : 0u;
+          // refill the slots first: keeps SLOTS rows in flight while the heaps are updated
+          if (j + SLOTS < n_eval) {
+            fence_proxy_async();  // generic-proxy reads of the slots precede the async-proxy overwrite
+            issue_row(j + SLOTS, sm.eval_id[j + SLOTS]);
+            if (j + 1 + SLOTS < n_eval) issue_row(j + 1 + SLOTS, sm.eval_id[j + 1 + SLOTS]);
+          }
+          heap_update(sa, j, ef);
+          if (two) heap_update(sb, j + 1, ef);
         }
       }
-      __syncthreads();
-      gather();  // phase C (:2566)
-      __syncthreads();
-      if (tid == 0) {  // phase D (:2571-2591)
-        const uint32_t n_eval = sm.ctl->n_eval;
-        for (uint32_t i = 0; i < n_eval; ++i) {
-          HeapEntry e;
-          e.d = sm.eval_d[i];
-          e.id = sm.eval_id[i];
-          e.pad = 0;
-          bool admit = res.n < ef;  // worstDist = MaxFloat64 while results is empty
-          if (!admit) admit = e.d < res.a[0].d;
-          if (admit) {
-            if (!cand.push(e)) overflow = true;  // :2581
-            if (!sm.eval_del[i]) {              // :2584
-              res.push(e);
-              if (res.n > ef) (void)res.pop();  // :2587-2589
-            }
-          }
-        }
+      if (lane == 0) {
         st_e += n_eval;
-        if (sm.ctl->expanded) {
+        if (expand) {
           st_h += 1;
           if (level == 0) st_h0 += 1;
         }
       }
+      __syncwarp();
     }
-    if (tid == 0) sm.ctl->res_n = res.n;
-    __syncthreads();
-    return sm.ctl->res_n;
+    const int n = __shfl_sync(0xffffffffu, res.n, 0);
+    __syncwarp();
+    return n;
   }
 
   // searchInternal (hnsw_index.go:369-468) for query q
   __device__ void run_query(uint32_t q) {
-    const uint32_t nchunks = ix.stride >> 2;
-    const float4 *src = reinterpret_cast<const float4 *>(a.queries + (size_t)q * ix.stride);
-    for (uint32_t c = tid; c < nchunks; c += NWARPS * 32) sm.q4[c] = src[c];
-    __syncthreads();
+    load_query(a.queries + (size_t)q * ix.stride);
     uint32_t ep = ix.entry;
     if (a.allow != nullptr && !bit_test(a.allow, ep)) ep = a.allow_entry;  // :436-447
     bool failed = ix.max_level < 0;
@@ -418,7 +486,7 @@ struct Searcher {
     if (!failed) {
       const int n = search_layer(0, a.ef, ep);  // :462
       if (n > 0) {
-        if (tid == 0) {  // :2596-2610 drain from the back, keep the first k
+        if (lane == 0) {  // :2596-2610 drain from the back, keep the first k
           for (int i = n - 1; i >= 0; --i) {
             const HeapEntry e = res.pop();
             if (i < a.k) {
@@ -431,7 +499,7 @@ struct Searcher {
       }
       clear_visited(false);
     }
-    if (tid == 0) {
+    if (lane == 0) {
       if (overflow) {
         atomicExch(a.err_flag, KDBGPU_ERR_OVERFLOW);
         overflow = false;
@@ -443,9 +511,9 @@ struct Searcher {
       }
       a.out_counts[q] = (uint32_t)count;
     }
+    __syncwarp();
   }
 };
-
 
 }  // namespace dev
 }  // namespace kdb

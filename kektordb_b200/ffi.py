@@ -56,7 +56,7 @@ SIGNATURES = {
     "kdbgpu_index_count": (_u32, [_vp]),
     "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),
     "kdbgpu_search_concurrency": (_i32, [_vp, _i32, _i32]),
-    "kdbgpu_set_tuning": (_i32, [_vp, _i32, _i32, _i32, _i32]),
+    "kdbgpu_set_tuning": (_i32, [_vp, _i32, _i32, _i32]),
 }
 
 _lib = None

@@ -152,8 +152,8 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_download_vectors(self._handle(), first_id, count, _ptr(out)))
         return out
 
-    def set_tuning(self, nwarps: int = 0, slots: int = 0, cand_smem: int = 0, max_ctas_per_sm: int = -1) -> None:
-        ffi.check(self._lib.kdbgpu_set_tuning(self._handle(), nwarps, slots, cand_smem, max_ctas_per_sm))
+    def set_tuning(self, slots: int = 0, cand_smem: int = 0, max_ctas_per_sm: int = -1) -> None:
+        ffi.check(self._lib.kdbgpu_set_tuning(self._handle(), slots, cand_smem, max_ctas_per_sm))
 
     # -- query -----------------------------------------------------------------------------
     def SearchWithScores(self, query, k: int, allowList: np.ndarray | None = None, efSearch: int = 0):

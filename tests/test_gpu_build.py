@@ -1,0 +1,99 @@
+"""Device-side graph construction (kdbgpu_add_batch) against the oracle's
+restatement of (*Index).AddBatch / addBatchInternal (hnsw_index.go:1466-2088): the adjacency is
+identical after every call — sequential single-Add fallback (:1502-1513) and batch path alike."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(n, dim, metric, m, efc, batches, seed, data="normal"):
+    from kektordb_b200 import GpuIndex
+    rng = np.random.default_rng(seed)
+    X = (rng.standard_normal((n, dim)) if data == "normal" else rng.integers(-2, 3, (n, dim))).astype(np.float32)
+    u = rng.random(n)
+    om = O.METRIC_COSINE if metric == "cosine" else O.METRIC_L2
+    oi = O.OracleIndex(dim, om, m, efc, O.ARITH_KERNEL, n)
+    gi = GpuIndex(dim, metric, m, n)
+    pos = 0
+    for b in batches:
+        b = min(b, n - pos)
+        if b <= 0:
+            break
+        gi.AddBatch(X[pos:pos + b], u[pos:pos + b], efc)
+        oi.add_batch(X[pos:pos + b], u[pos:pos + b], efc, threads=8)
+        pos += b
+        g = oi.export_graph()
+        gn, levels, node_row, row_off, nbrs, entry, max_level = gi.get_graph()
+        assert (gn, entry, max_level) == (g.n, g.entry, g.max_level)
+        assert np.array_equal(levels, g.levels)
+        assert np.array_equal(row_off, g.row_off)
+        assert np.array_equal(nbrs, g.nbrs)
+    assert np.array_equal(gi.download_vectors(1, n), oi.vectors()[1:])  # normalize() is bit-exact too
+    return gi, oi, X, rng
+
+
+def test_sequential_fallback_and_batches_small():
+    gi, oi, X, rng = _compare(300, 16, "euclidean", 4, 20, [10, 5, 5, 30, 50, 200], 1)
+    gi.close()
+
+
+def test_cosine_batches():
+    gi, oi, X, rng = _compare(1500, 32, "cosine", 8, 40, [40, 60, 100, 300, 1000], 2)
+    # and the graph it built is searched identically by both sides
+    Q = rng.standard_normal((64, 32)).astype(np.float32)
+    ids, sc, cnt, st = gi.SearchWithScores(Q, 10, None, 50)
+    oids, osc, ocnt, ost = oi.search_batch(Q, 10, 50, threads=8)
+    assert np.array_equal(ids, oids) and np.array_equal(sc, osc)
+    gi.close()
+
+
+def test_exact_ties_everywhere():
+    gi, oi, X, rng = _compare(1200, 12, "euclidean", 6, 30, [30, 70, 300, 800], 3, data="grid")
+    gi.close()
+
+
+def test_reference_defaults_m16_efc200():
+    gi, oi, X, rng = _compare(5000, 128, "cosine", 16, 200, [200, 300, 500, 1000, 3000], 4)
+    gi.close()
+
+
+def test_hub_rows_longer_than_the_shared_memory_list():
+    """A batch much larger than the graph: some rows receive > 1024 requests and take the
+    global-scratch path of the commit kernel."""
+    gi, oi, X, rng = _compare(4000, 8, "euclidean", 4, 24, [24, 3976], 5)
+    gi.close()
+
+
+def test_add_after_import():
+    """set_graph (import of a CPU-built index) followed by AddBatch keeps extending the same graph."""
+    from kektordb_b200 import GpuIndex
+    rng = np.random.default_rng(6)
+    X = rng.standard_normal((2000, 24)).astype(np.float32)
+    u = rng.random(2000)
+    oi = O.OracleIndex(24, O.METRIC_COSINE, 8, 40, O.ARITH_KERNEL, 2000)
+    oi.build_batched(X[:1200], u[:1200], batch=300, threads=4)
+    g = oi.export_graph()
+    gi = GpuIndex(24, "cosine", 8, 2000)
+    gi.upload_vectors(1, oi.vectors()[1:])
+    gi.set_graph(g.n, g.levels, g.node_row, g.row_off, g.nbrs, g.entry, g.max_level)
+    gi.AddBatch(X[1200:], u[1200:], 40)
+    oi.add_batch(X[1200:], u[1200:], 40, threads=4)
+    g = oi.export_graph()
+    gn, levels, node_row, row_off, nbrs, entry, max_level = gi.get_graph()
+    assert (gn, entry, max_level) == (g.n, g.entry, g.max_level)
+    assert np.array_equal(levels, g.levels) and np.array_equal(row_off, g.row_off) and np.array_equal(nbrs, g.nbrs)
+    gi.close()
+
+
+def test_capacity_is_enforced():
+    from kektordb_b200 import GpuIndex, ffi
+    gi = GpuIndex(8, "euclidean", 4, 50)
+    rng = np.random.default_rng(7)
+    gi.AddBatch(rng.standard_normal((40, 8)).astype(np.float32), rng.random(40), 10)
+    with pytest.raises(ffi.GpuError):
+        gi.AddBatch(rng.standard_normal((20, 8)).astype(np.float32), rng.random(20), 10)
+    assert gi.count == 40
+    gi.close()

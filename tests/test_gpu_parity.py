@@ -161,10 +161,10 @@ def test_results_do_not_depend_on_cta_shape():
     gi, g = _mirror(oi, O.METRIC_L2, 12)
     Q = rng.standard_normal((200, 256)).astype(np.float32)
     want = oi.search_batch(Q, 10, 96, threads=8)
-    for nwarps, slots, cand_smem in ((2, 2, 64), (2, 4, 512), (4, 1, 16), (4, 2, 512), (4, 4, 256), (8, 1, 512), (8, 2, 32)):
-        gi.set_tuning(nwarps, slots, cand_smem, 0)
+    for slots, cand_smem in ((2, 512), (4, 16), (4, 512), (8, 256), (8, 32), (16, 128)):
+        gi.set_tuning(slots, cand_smem, 0)
         _assert_same(gi.SearchWithScores(Q, 10, None, 96), want)
-    gi.set_tuning(4, 2, 512, 1)  # one CTA per SM: persistent loop over many queries per CTA
+    gi.set_tuning(8, 192, 1)  # one query-warp per SM: persistent loop over many queries per warp
     _assert_same(gi.SearchWithScores(Q, 10, None, 96), want)
     gi.close()
 
