@@ -52,6 +52,8 @@ def parse_args():
     p.add_argument("--batch", type=int, default=1024)
     p.add_argument("--latent", type=int, default=32)
     p.add_argument("--noise", type=float, default=0.1)
+    p.add_argument("--data-model", default="lowrank", choices=["lowrank", "iid"],
+                   help="lowrank: x = zW + noise*e (default); iid: isotropic N(0,1) (recall collapses, DESIGN.md §6)")
     p.add_argument("--build-batch", type=int, default=16384)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -65,7 +67,16 @@ def parse_args():
 # data + index construction (setup, untimed)
 # ------------------------------------------------------------------------------------------------
 def make_data(torch, n, dim, latent, noise, seed, device):
-    """Random-normal vectors with low-rank covariance: x = z W + noise * e, z ~ N(0, I_latent)."""
+    """Random-normal vectors with low-rank covariance: x = z W + noise * e, z ~ N(0, I_latent).
+    latent <= 0 selects i.i.d. isotropic N(0, 1)."""
+    if latent <= 0:
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        out = torch.empty(n, dim, device=device, dtype=torch.float32)
+        for i in range(0, n, 1 << 18):
+            c = min(1 << 18, n - i)
+            out[i:i + c] = torch.randn(c, dim, generator=g, device=device)
+        return out
     g = torch.Generator(device=device)
     g.manual_seed(777)
     W = torch.randn(latent, dim, generator=g, device=device) / latent ** 0.5
@@ -226,6 +237,8 @@ def oracle_from_gpu(gi, m, efc, arith):
 
 def main():
     args = parse_args()
+    if args.data_model == "iid":
+        args.latent = 0
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,8 +265,8 @@ def main():
     # ---- setup (untimed): corpus, graph, queries -------------------------------------------------
     X = make_data(torch, N, D, args.latent, args.noise, 42, dev)
     if mode == "shard":
-        n_local = N // world
-        base = rank * n_local
+        from kektordb_b200.sharding import shard_range
+        base, n_local = shard_range(N, world, rank)
         Xl = X[base:base + n_local].contiguous()
         del X
         X = Xl
@@ -300,9 +313,9 @@ def main():
         if mode == "shard":  # the one exchange step: all-gather of per-shard top-k, then merge
             with torch.cuda.stream(stream):
                 gl = torch.where(d_ids > 0, d_ids + base, d_ids)
-                dist.all_gather_into_tensor(g_ids, gl)
-                dist.all_gather_into_tensor(g_sc, d_sc)
-                dist.all_gather_into_tensor(g_cnt, d_cnt)
+                dist.all_gather_into_tensor(g_ids.view(world * B, k), gl)
+                dist.all_gather_into_tensor(g_sc.view(world * B, k), d_sc)
+                dist.all_gather_into_tensor(g_cnt.view(world * B), d_cnt)
             ffi.check(ffi.lib().kdbgpu_merge_topk_device(gi._h, world, B, k, g_ids.data_ptr(), g_sc.data_ptr(),
                                                          g_cnt.data_ptr(), m_ids.data_ptr(), m_sc.data_ptr(),
                                                          m_cnt.data_ptr(), stream.cuda_stream))
@@ -438,7 +451,8 @@ def main():
                        "parallelism": {"single": "1 GPU", "replica": f"{world} replicas, queries split, no collective",
                                        "shard": f"corpus split by id range over {world} GPUs, NCCL all-gather of "
                                                 f"per-shard top-{k} + merge kernel"}[mode],
-                       "data_model": f"random-normal, low-rank covariance (latent {args.latent}, noise {args.noise}), "
+                       "data_model": (f"random-normal, low-rank covariance (latent {args.latent}, noise {args.noise}), "
+                                      if args.latent > 0 else "random-normal, i.i.d. isotropic, ") +
                                      "seeds 42/4242; graph built on GPU (kdbgpu_add_batch), levels seed 1",
                        "l2_policy": "inputs larger than L2: 3.07 GB corpus, new query batch every step",
                        "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "host_cores": ncores},
@@ -466,9 +480,9 @@ def shard_recall(torch, dist, ffi, gi, Qgt, k, base, world, m_ids, m_sc, m_cnt, 
     fc = np.concatenate([fc, np.zeros(pad, np.uint32)]).astype(np.int32)
     t_i, t_s, t_c = (torch.from_numpy(a).to(dev) for a in (fi, fs, fc))
     gi2, gs2, gc2 = torch.zeros_like(g_ids), torch.zeros_like(g_sc), torch.zeros_like(g_cnt)
-    dist.all_gather_into_tensor(gi2, t_i)
-    dist.all_gather_into_tensor(gs2, t_s)
-    dist.all_gather_into_tensor(gc2, t_c)
+    dist.all_gather_into_tensor(gi2.view(world * B, k), t_i)
+    dist.all_gather_into_tensor(gs2.view(world * B, k), t_s)
+    dist.all_gather_into_tensor(gc2.view(world * B), t_c)
     e_ids, e_sc, e_cnt = torch.zeros_like(d_ids), torch.zeros_like(d_sc), torch.zeros_like(d_cnt)
     torch.cuda.synchronize()
     ffi.check(ffi.lib().kdbgpu_merge_topk_device(gi._h, world, B, k, gi2.data_ptr(), gs2.data_ptr(), gc2.data_ptr(),
@@ -478,9 +492,9 @@ def shard_recall(torch, dist, ffi, gi, Qgt, k, base, world, m_ids, m_sc, m_cnt, 
     gi.search_device(Qd[:B].data_ptr(), B, k, ef, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), stream.cuda_stream)
     with torch.cuda.stream(stream):
         gl = torch.where(d_ids > 0, d_ids + base, d_ids)
-        dist.all_gather_into_tensor(g_ids, gl)
-        dist.all_gather_into_tensor(g_sc, d_sc)
-        dist.all_gather_into_tensor(g_cnt, d_cnt)
+        dist.all_gather_into_tensor(g_ids.view(world * B, k), gl)
+        dist.all_gather_into_tensor(g_sc.view(world * B, k), d_sc)
+        dist.all_gather_into_tensor(g_cnt.view(world * B), d_cnt)
     ffi.check(ffi.lib().kdbgpu_merge_topk_device(gi._h, world, B, k, g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(),
                                                  m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr(), stream.cuda_stream))
     torch.cuda.synchronize()
