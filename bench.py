@@ -349,26 +349,62 @@ def main():
     tot_e, tot_h, tot_h0 = st_last.dist_evals, st_last.hops, st_last.hops_l0
 
     # ---- end-to-end timing through the C ABI with host buffers (`e2e`) -----------------------------
-    out_ids = torch.empty((B, k), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
-    for i in range(args.warmup):
-        gi.SearchWithScores(Qh_np[i * B:(i + 1) * B], k, None, ef)
-    barrier()
-
-    def e2e_worker(j):  # one caller thread per in-flight batch; ctypes releases the GIL inside the C call
-        for i in range(args.warmup + j, n_steps_total, n_ov):
+    if mode != "shard":
+        for i in range(args.warmup):
             gi.SearchWithScores(Qh_np[i * B:(i + 1) * B], k, None, ef)
+        barrier()
 
-    workers = [threading.Thread(target=e2e_worker, args=(j,)) for j in range(n_ov)]
-    t0 = time.perf_counter()
-    for t in workers:
-        t.start()
-    for t in workers:
-        t.join()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        def e2e_worker(j):  # one caller thread per in-flight batch; ctypes releases the GIL inside the C call
+            torch.cuda.set_device(local_rank)
+            for i in range(args.warmup + j, n_steps_total, n_ov):
+                gi.SearchWithScores(Qh_np[i * B:(i + 1) * B], k, None, ef)
+
+        workers = [threading.Thread(target=e2e_worker, args=(j,)) for j in range(n_ov)]
+        t0 = time.perf_counter()
+        for t in workers:
+            t.start()
+        for t in workers:
+            t.join()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_d2h = B * k * 12 + B * 4 + 40
+    else:
+        # sharded: H2D of the batch, per-shard search, all-gather, merge, D2H of the merged top-k
+        h_ids = torch.empty((B, k), dtype=torch.int32, pin_memory=True)
+        h_sc = torch.empty((B, k), dtype=torch.float64, pin_memory=True)
+        h_cnt = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        q_stage = torch.empty((B, D), dtype=torch.float32, device=dev)
+
+        def e2e_step(i):
+            with torch.cuda.stream(stream):
+                q_stage.copy_(Qh[i * B:(i + 1) * B], non_blocking=True)
+            gi.search_device(q_stage.data_ptr(), B, k, ef, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
+                             stream.cuda_stream)
+            with torch.cuda.stream(stream):
+                gl = torch.where(d_ids > 0, d_ids + base, d_ids)
+                dist.all_gather_into_tensor(g_ids.view(world * B, k), gl)
+                dist.all_gather_into_tensor(g_sc.view(world * B, k), d_sc)
+                dist.all_gather_into_tensor(g_cnt.view(world * B), d_cnt)
+            ffi.check(ffi.lib().kdbgpu_merge_topk_device(gi._h, world, B, k, g_ids.data_ptr(), g_sc.data_ptr(),
+                                                         g_cnt.data_ptr(), m_ids.data_ptr(), m_sc.data_ptr(),
+                                                         m_cnt.data_ptr(), stream.cuda_stream))
+            with torch.cuda.stream(stream):
+                h_ids.copy_(m_ids, non_blocking=True)
+                h_sc.copy_(m_sc, non_blocking=True)
+                h_cnt.copy_(m_cnt, non_blocking=True)
+            stream.synchronize()
+
+        for i in range(args.warmup):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.warmup, n_steps_total):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_d2h = B * k * 12 + B * 4
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    del out_ids
 
     # ---- reduce over ranks: max time, summed work --------------------------------------------------
     times = torch.tensor([dev_ms, e2e_s * 1e3, recall_local], dtype=torch.float64, device=dev)
@@ -457,7 +493,7 @@ def main():
                        "l2_policy": "inputs larger than L2: 3.07 GB corpus, new query batch every step",
                        "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "host_cores": ncores},
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s",
-                    "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12 + B * 4 + 36,
+                    "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": e2e_d2h,
                     "ms_per_step": round(e2e_ms / args.steps, 4)},
             "gpu_launches": 2 * args.steps + (args.steps if mode == "shard" else 0),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,

@@ -16,6 +16,10 @@
  *
  * There is no CPU fallback: without a CUDA device every call fails with
  * KDBGPU_ERR_CUDA and kdbgpu_last_error() says why.
+ *
+ * Threading: any thread may call; searches on one handle run concurrently (up to 4 batches in
+ * flight), calls that change the mirror are exclusive.  A call leaves the handle's device as the
+ * calling thread's current CUDA device.
  */
 #ifndef KEKTORDB_GPU_H
 #define KEKTORDB_GPU_H

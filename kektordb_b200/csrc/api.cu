@@ -195,22 +195,22 @@ struct kdbgpu_index {
 
 namespace {
 
+// Makes the handle's device current for the calling thread.  It is deliberately NOT restored on
+// return: restoring a device the thread never used would create a primary context there (CUDA 12
+// cudaSetDevice semantics) — costly in multi-process, one-rank-per-GPU deployments.
 struct DeviceGuard {
-  int prev = -1;
   bool ok = true;
   explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
       ok = false;
       (void)cudaGetLastError();
       return;
     }
-    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
+    if (cur != dev && cudaSetDevice(dev) != cudaSuccess) {
       ok = false;
       (void)cudaGetLastError();
     }
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
   }
 };
 
