@@ -118,10 +118,25 @@ int kdbgpu_distance_batch(kdbgpu_index *, const float *query, const uint32_t *id
  *   mode 0  reference arithmetic: sum of float64(q_i - x_i)^2 on the RAW query, any metric.
  *   mode 1  exact float64 distance under the index metric (cosine: query normalised as in
  *           searchInternal) — the ground truth used for recall.
- * Ties are returned in ascending id order (the reference's order among ties is unspecified). */
+ * Ties are returned in ascending id order (the reference's order among ties is unspecified).
+ *
+ * mode | KDBGPU_FLAT_PREFILTER: same results, bit for bit, found through a bf16 tensor-core
+ * (tcgen05) Q x K^T pass that only NOMINATES rows; the nominated rows are re-scored in the float64
+ * arithmetic above and a per-query certificate proves no other row can enter the top k (a query
+ * whose certificate does not close is answered by the exhaustive scan).  stats->dist_evals = exact
+ * float64 evaluations, stats->hops = queries answered by the exhaustive scan, stats->kernel_ms =
+ * device time of the two tensor-core passes. */
+#define KDBGPU_FLAT_PREFILTER 0x10
 int kdbgpu_flat_search_batch(kdbgpu_index *, const float *queries, uint32_t nq, int k, int mode,
                              const uint64_t *allow, size_t allow_words, uint32_t *out_ids,
                              double *out_scores, uint32_t *out_counts, kdbgpu_stats *stats);
+
+/* Validation hook for the pre-filter (tests only): the approximate scores the tensor-core pass
+ * assigns, out_scores [nq][n] (row r = id r+1; exact distance = score + |q|^2 for L2 / mode 0,
+ * = score + 1 for cosine mode 1; +inf for rows that may not be nominated), and out_bound [nq], the
+ * certified bound on |approximate - exact| the thresholds are built from.  nq * n <= 2^30. */
+int kdbgpu_flat_prefilter_scores(kdbgpu_index *, const float *queries, uint32_t nq, int mode, float *out_scores,
+                                 float *out_bound);
 
 /* ---- multi-GPU: merge of per-shard top-k (id-range shards) -------------- */
 /* d_ids / d_scores: [n_shards][nq][k] gathered candidates (global ids), d_counts [n_shards][nq].

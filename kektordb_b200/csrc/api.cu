@@ -172,6 +172,13 @@ struct kdbgpu_index {
       b_scalars, b_scratch_ids;
   DevBuf<uint8_t> b_slot_level;
   DevBuf<double> b_scratch_d;
+  // tensor-core flat pre-filter: bf16 mirror of the rows (built lazily, dropped when rows change)
+  DevBuf<uint16_t> x_bf16, tq_bf16;
+  DevBuf<float> x_sumsq, x_resid2, x_max, tc_beta, tq_sumsq, tq_resid2, t_gmin, t_theta, t_bound;
+  DevBuf<uint32_t> t_cnt, t_bufid, t_flags;
+  DevBuf<unsigned long long> t_nres;
+  bool tc_valid = false;
+  uint32_t tc_n = 0;
 
   DevIndex dev() const {
     DevIndex d;
@@ -338,6 +345,205 @@ int stage_allow(kdbgpu_index *h, DevBuf<uint32_t> &dst, const uint64_t *allow, s
   return KDBGPU_OK;
 }
 
+
+// ---- flat scan -------------------------------------------------------------------------------------
+// exhaustive float64 scan (flat.cu); caller holds the handle exclusively
+int flat_scan_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, const uint32_t *d_allow,
+                   uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+  cudaStream_t s = h->stream;
+  // bound the dist[chunk][n] workspace to ~2 GiB
+  uint32_t chunk = (uint32_t)((2ull << 30) / ((size_t)h->n * sizeof(double)));
+  if (chunk < 16) chunk = 16;
+  chunk &= ~15u;
+  if (chunk > nq) chunk = nq;
+  CUDA_TRY(h->q_raw.reserve((size_t)chunk * h->dim));
+  CUDA_TRY(h->q_prep.reserve((size_t)chunk * h->stride));
+  CUDA_TRY(h->out_ids.reserve((size_t)chunk * k));
+  CUDA_TRY(h->out_scores.reserve((size_t)chunk * k));
+  CUDA_TRY(h->out_counts.reserve(chunk));
+  CUDA_TRY(h->flat_dist.reserve((size_t)chunk * h->n));
+  DevIndex ix = h->dev();
+  for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+    const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
+    CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries + (size_t)q0 * h->dim, (size_t)c * h->dim * sizeof(float),
+                             cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
+                                 mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
+    CUDA_TRY(launch_flat_distances(ix, h->q_raw.p, h->q_prep.p, c, mode, h->flat_dist.p, s));
+    CUDA_TRY(launch_flat_select(ix, h->flat_dist.p, c, k, d_allow, h->out_ids.p, h->out_scores.p, h->out_counts.p, s));
+    CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  return KDBGPU_OK;
+}
+
+// ---- flat scan with the tensor-core pre-filter (flat_tc.cu) ---------------------------------------
+struct TcPlan {
+  uint32_t bm, bn, n_pad, dp, n_groups;
+  int use_norm;
+  float alpha;
+};
+
+// bf16 mirror of the rows (lazily), beta for this call's liveness / allow-list
+int tc_prepare(kdbgpu_index *h, int mode, const uint32_t *d_allow, int k, TcPlan *P, cudaStream_t s) {
+  P->bm = flat_tc_bm();
+  P->bn = flat_tc_bn();
+  P->n_pad = (h->n + P->bn - 1) / P->bn * P->bn;
+  P->dp = ((uint32_t)h->dim + flat_tc_bk() - 1) / flat_tc_bk() * flat_tc_bk();
+  P->n_groups = P->n_pad / 32;
+  P->use_norm = (mode == 0 || h->metric == KDBGPU_METRIC_L2) ? 1 : 0;
+  P->alpha = P->use_norm ? -2.f : -1.f;  // L2: |x|^2 - 2<q,x> (+|q|^2) ; cosine: -<q^,x> (+1)
+  (void)k;
+  if (!h->tc_valid || h->tc_n != h->n) {
+    CUDA_TRY(h->x_bf16.reserve((size_t)P->n_pad * P->dp));
+    CUDA_TRY(h->x_sumsq.reserve(P->n_pad));
+    CUDA_TRY(h->x_resid2.reserve(P->n_pad));
+    CUDA_TRY(h->x_max.reserve(2));
+    CUDA_TRY(launch_to_bf16(h->vecs.p + h->stride, h->stride, h->n, (uint32_t)h->dim, h->x_bf16.p, P->dp, P->n_pad,
+                            h->x_sumsq.p, h->x_resid2.p, s));
+    CUDA_TRY(launch_tc_max(h->x_sumsq.p, h->x_resid2.p, h->n, h->x_max.p, s));
+    h->tc_valid = true;
+    h->tc_n = h->n;
+  }
+  CUDA_TRY(h->tc_beta.reserve(P->n_pad));
+  CUDA_TRY(launch_tc_beta(h->dev(), h->x_sumsq.p, d_allow, P->use_norm, P->n_pad, h->tc_beta.p, s));
+  return KDBGPU_OK;
+}
+
+// H2D of `c` raw queries, normalisation where the mode asks for it, bf16 copy + norms
+int tc_stage_queries(kdbgpu_index *h, const float *queries, uint32_t c, uint32_t c_pad, int mode, const TcPlan &P,
+                     cudaStream_t s) {
+  CUDA_TRY(h->q_raw.reserve((size_t)c * h->dim));
+  CUDA_TRY(h->q_prep.reserve((size_t)c * h->stride));
+  CUDA_TRY(h->tq_bf16.reserve((size_t)c_pad * P.dp));
+  CUDA_TRY(h->tq_sumsq.reserve(c_pad));
+  CUDA_TRY(h->tq_resid2.reserve(c_pad));
+  CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries, (size_t)c * h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
+                               mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
+  const bool prepared = mode == 1 && h->metric == KDBGPU_METRIC_COSINE;
+  CUDA_TRY(launch_to_bf16(prepared ? h->q_prep.p : h->q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim, c,
+                          (uint32_t)h->dim, h->tq_bf16.p, P.dp, c_pad, h->tq_sumsq.p, h->tq_resid2.p, s));
+  return KDBGPU_OK;
+}
+
+FlatTcLaunch tc_launch_desc(kdbgpu_index *h, const TcPlan &P, uint32_t c, uint32_t c_pad) {
+  FlatTcLaunch L;
+  memset(&L, 0, sizeof L);
+  L.q_bf16 = h->tq_bf16.p;
+  L.x_bf16 = h->x_bf16.p;
+  L.nq = c;
+  L.nq_pad = c_pad;
+  L.n = h->n;
+  L.n_pad = P.n_pad;
+  L.dp = P.dp;
+  L.alpha = P.alpha;
+  L.beta = h->tc_beta.p;
+  const uint64_t tiles = (uint64_t)(c_pad / P.bm) * (P.n_pad / P.bn);
+  L.grid = tiles < (uint64_t)h->num_sms ? (int)tiles : h->num_sms;
+  return L;
+}
+
+int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, const uint32_t *d_allow,
+                        uint32_t *out_ids, double *out_scores, uint32_t *out_counts, uint64_t *evals,
+                        uint64_t *fallbacks, float *gemm_ms) {
+  cudaStream_t s = h->stream;
+  TcPlan P;
+  int rc = tc_prepare(h, mode, d_allow, k, &P, s);
+  if (rc) return rc;
+  const uint32_t cap = k <= 256 ? 2048u : 4096u;
+  if (P.n_groups < (uint32_t)k || h->n <= cap || tc_rescore_smem((uint32_t)h->dim, cap) > 200 * 1024) {
+    // too few rows for a threshold to exist (or to be worth it): the exhaustive scan answers
+    *evals = (uint64_t)nq * h->n;
+    *fallbacks = nq;
+    return flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
+  }
+  // chunk so that gmin[chunk][n_groups] stays within 512 MiB
+  uint32_t chunk = (uint32_t)((512ull << 20) / ((size_t)P.n_groups * sizeof(float)));
+  chunk = chunk / P.bm * P.bm;
+  if (chunk < P.bm) chunk = P.bm;
+  if (chunk > 4096) chunk = 4096;
+  const uint32_t nq_pad = (nq + P.bm - 1) / P.bm * P.bm;
+  if (chunk > nq_pad) chunk = nq_pad;
+  CUDA_TRY(h->t_gmin.reserve((size_t)chunk * P.n_groups));
+  CUDA_TRY(h->t_theta.reserve(chunk));
+  CUDA_TRY(h->t_bound.reserve(chunk));
+  CUDA_TRY(h->t_cnt.reserve(chunk));
+  CUDA_TRY(h->t_flags.reserve(chunk));
+  CUDA_TRY(h->t_bufid.reserve((size_t)chunk * cap));
+  CUDA_TRY(h->t_nres.reserve(1));
+  CUDA_TRY(h->out_ids.reserve((size_t)chunk * k));
+  CUDA_TRY(h->out_scores.reserve((size_t)chunk * k));
+  CUDA_TRY(h->out_counts.reserve(chunk));
+  CUDA_TRY(cudaMemsetAsync(h->t_nres.p, 0, sizeof(unsigned long long), s));
+  DevIndex ix = h->dev();
+  const bool prepared = mode == 1 && h->metric == KDBGPU_METRIC_COSINE;
+  std::vector<uint32_t> flags(nq, 0u);
+  *gemm_ms = 0.f;
+  for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+    const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
+    const uint32_t c_pad = (c + P.bm - 1) / P.bm * P.bm;
+    rc = tc_stage_queries(h, queries + (size_t)q0 * h->dim, c, c_pad, mode, P, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->t_cnt.p, 0, (size_t)c_pad * sizeof(uint32_t), s));
+    FlatTcLaunch L = tc_launch_desc(h, P, c, c_pad);
+    L.gmin = h->t_gmin.p;
+    L.theta = h->t_theta.p;
+    L.cnt = h->t_cnt.p;
+    L.buf_id = h->t_bufid.p;
+    L.cap = cap;
+    CUDA_TRY(cudaEventRecord(h->ev[1], s));
+    L.epi = 1;  // pass A: group minima
+    CUDA_TRY(launch_flat_tc(L, s));
+    CUDA_TRY(launch_tc_threshold(h->t_gmin.p, P.n_groups, c, k, h->tq_sumsq.p, h->tq_resid2.p, h->x_max.p, P.alpha,
+                                 P.use_norm, P.dp, h->t_theta.p, h->t_bound.p, s));
+    L.epi = 2;  // pass B: ids below theta
+    CUDA_TRY(launch_flat_tc(L, s));
+    CUDA_TRY(cudaEventRecord(h->ev[2], s));
+    CUDA_TRY(launch_tc_rescore(ix, mode, prepared ? h->q_prep.p : h->q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim,
+                               c, k, h->t_cnt.p, h->t_bufid.p, cap, h->t_theta.p, h->t_bound.p, h->tq_sumsq.p,
+                               h->out_ids.p, h->out_scores.p, h->out_counts.p, h->t_flags.p, h->t_nres.p, s));
+    CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(flags.data() + q0, h->t_flags.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+    *gemm_ms += ms;
+  }
+  unsigned long long nres = 0;
+  CUDA_TRY(cudaMemcpy(&nres, h->t_nres.p, sizeof nres, cudaMemcpyDeviceToHost));
+  // queries whose certificate did not close (candidate buffer overflow) take the exhaustive scan
+  std::vector<uint32_t> redo;
+  for (uint32_t q = 0; q < nq; ++q)
+    if (flags[q]) redo.push_back(q);
+  if (!redo.empty()) {
+    const size_t r = redo.size();
+    std::vector<float> rq(r * (size_t)h->dim);
+    std::vector<uint32_t> rid(r * (size_t)k), rcnt(r);
+    std::vector<double> rsc(r * (size_t)k);
+    for (size_t i = 0; i < r; ++i)
+      memcpy(&rq[i * h->dim], queries + (size_t)redo[i] * h->dim, (size_t)h->dim * sizeof(float));
+    rc = flat_scan_impl(h, rq.data(), (uint32_t)r, k, mode, d_allow, rid.data(), rsc.data(), rcnt.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < r; ++i) {
+      memcpy(out_ids + (size_t)redo[i] * k, &rid[i * k], (size_t)k * sizeof(uint32_t));
+      memcpy(out_scores + (size_t)redo[i] * k, &rsc[i * k], (size_t)k * sizeof(double));
+      out_counts[redo[i]] = rcnt[i];
+    }
+  }
+  *evals = nres + (uint64_t)redo.size() * h->n;
+  *fallbacks = redo.size();
+  return KDBGPU_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -470,6 +676,9 @@ int kdbgpu_index_destroy(kdbgpu_index *h) {
   h->b_scratch_ids.release();
   h->b_slot_level.release();
   h->b_scratch_d.release();
+  h->x_bf16.release(); h->tq_bf16.release(); h->x_sumsq.release(); h->x_resid2.release(); h->x_max.release();
+  h->tc_beta.release(); h->tq_sumsq.release(); h->tq_resid2.release(); h->t_gmin.release(); h->t_theta.release();
+  h->t_bound.release(); h->t_cnt.release(); h->t_bufid.release(); h->t_flags.release(); h->t_nres.release();
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -487,6 +696,7 @@ int kdbgpu_upload_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, co
   std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
+  h->tc_valid = false;
   // padded columns were zeroed at creation and are never written
   CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), rows,
                              (size_t)h->dim * sizeof(float), (size_t)h->dim * sizeof(float), count,
@@ -504,6 +714,7 @@ int kdbgpu_upload_vectors_device(kdbgpu_index *h, uint32_t first_id, uint32_t co
   std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
+  h->tc_valid = false;
   CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), d_rows,
                              row_stride * sizeof(float), (size_t)h->dim * sizeof(float), count,
                              cudaMemcpyDeviceToDevice, h->stream));
@@ -774,6 +985,8 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
   if (nq == 0) return KDBGPU_OK;
   if (!queries || !out_ids || !out_scores || !out_counts) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (k <= 0 || k > 1024) return fail(KDBGPU_ERR_INVALID, "flat k %d outside 1..1024", k);
+  const bool prefilter = (mode & KDBGPU_FLAT_PREFILTER) != 0;
+  mode &= ~KDBGPU_FLAT_PREFILTER;
   if (mode != 0 && mode != 1) return fail(KDBGPU_ERR_INVALID, "mode %d", mode);
   if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called (it defines the live rows)");
   std::unique_lock<std::shared_mutex> lk(h->mu);
@@ -796,41 +1009,67 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
       d_allow = h->allow.p;
     }
   }
-  // bound the dist[chunk][n] workspace to ~2 GiB
-  uint32_t chunk = (uint32_t)((2ull << 30) / ((size_t)h->n * sizeof(double)));
-  if (chunk < 16) chunk = 16;
-  chunk &= ~15u;
-  if (chunk > nq) chunk = nq;
-  CUDA_TRY(h->q_raw.reserve((size_t)chunk * h->dim));
-  CUDA_TRY(h->q_prep.reserve((size_t)chunk * h->stride));
-  CUDA_TRY(h->out_ids.reserve((size_t)chunk * k));
-  CUDA_TRY(h->out_scores.reserve((size_t)chunk * k));
-  CUDA_TRY(h->out_counts.reserve(chunk));
-  CUDA_TRY(h->flat_dist.reserve((size_t)chunk * h->n));
-  DevIndex ix = h->dev();
   CUDA_TRY(cudaEventRecord(h->ev[0], s));
-  for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
-    const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
-    CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries + (size_t)q0 * h->dim, (size_t)c * h->dim * sizeof(float),
-                             cudaMemcpyHostToDevice, s));
-    CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
-                                 mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
-    CUDA_TRY(launch_flat_distances(ix, h->q_raw.p, h->q_prep.p, c, mode, h->flat_dist.p, s));
-    CUDA_TRY(launch_flat_select(ix, h->flat_dist.p, c, k, d_allow, h->out_ids.p, h->out_scores.p, h->out_counts.p, s));
-    CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
-                             cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
-                             cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+  uint64_t evals = 0, fallbacks = 0;
+  float gemm_ms = 0.f;
+  int rc;
+  if (prefilter)
+    rc = flat_prefilter_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts, &evals, &fallbacks,
+                             &gemm_ms);
+  else {
+    rc = flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
+    evals = (uint64_t)nq * h->n;
   }
+  if (rc) return rc;
   CUDA_TRY(cudaEventRecord(h->ev[3], s));
   CUDA_TRY(cudaStreamSynchronize(s));
   if (stats) {
-    stats->dist_evals = (uint64_t)nq * h->n;
+    stats->dist_evals = evals;
+    stats->hops = fallbacks;
     cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
-    stats->kernel_ms = stats->total_ms;
+    stats->kernel_ms = prefilter ? gemm_ms : stats->total_ms;
   }
+  return KDBGPU_OK;
+}
+
+int kdbgpu_flat_prefilter_scores(kdbgpu_index *h, const float *queries, uint32_t nq, int mode, float *out_scores,
+                                 float *out_bound) {
+  if (!h || !queries || !out_scores) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (mode != 0 && mode != 1) return fail(KDBGPU_ERR_INVALID, "mode %d", mode);
+  if (!h->has_graph || h->n == 0) return fail(KDBGPU_ERR_STATE, "no rows staged");
+  if (nq == 0) return KDBGPU_OK;
+  if ((uint64_t)nq * h->n > (1ull << 30)) return fail(KDBGPU_ERR_INVALID, "validation hook: nq * n too large");
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  TcPlan P;
+  int rc = tc_prepare(h, mode, nullptr, 1, &P, s);
+  if (rc) return rc;
+  const uint32_t c_pad = (nq + P.bm - 1) / P.bm * P.bm;
+  rc = tc_stage_queries(h, queries, nq, c_pad, mode, P, s);
+  if (rc) return rc;
+  DevBuf<float> S;
+  CUDA_TRY(S.reserve((size_t)nq * h->n));
+  CUDA_TRY(h->t_gmin.reserve(1));
+  CUDA_TRY(h->t_theta.reserve(c_pad));
+  CUDA_TRY(h->t_bound.reserve(c_pad));
+  FlatTcLaunch L = tc_launch_desc(h, P, nq, c_pad);
+  L.epi = 0;
+  L.S = S.p;
+  L.ldS = h->n;
+  cudaError_t e = launch_flat_tc(L, s);
+  // bound[q] through the threshold kernel on a dummy one-group input
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->t_gmin.p, 0, sizeof(float), s);
+  if (e == cudaSuccess)
+    e = launch_tc_threshold(h->t_gmin.p, 0, nq, 1, h->tq_sumsq.p, h->tq_resid2.p, h->x_max.p, P.alpha, P.use_norm, P.dp,
+                            h->t_theta.p, h->t_bound.p, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out_scores, S.p, (size_t)nq * h->n * sizeof(float), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && out_bound)
+    e = cudaMemcpyAsync(out_bound, h->t_bound.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  S.release();
+  CUDA_TRY(e);
   return KDBGPU_OK;
 }
 
@@ -939,6 +1178,7 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   DeviceGuard g(h->device);
   CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   cudaStream_t s = h->stream;
+  h->tc_valid = false;
   const uint32_t start_id = h->n + 1;
   const bool sequential = (uint64_t)h->n < (uint64_t)ef_const;  // :1502-1513
   // stage the rows: cosine vectors are normalised exactly as normalize() (:1557-1559, :485-493)

@@ -1,0 +1,658 @@
+// flat_tc.cu — the tensor-core pre-filter of the flat scan (BASELINE config 3): a persistent,
+// warp-specialised tcgen05 GEMM  S[q][x] = alpha * <q~, x~> + beta[x]  over bf16 copies of the
+// queries and the corpus, fp32 accumulation in TMEM, operands staged by TMA (128-byte swizzle) through
+// a 4-stage mbarrier ring, two accumulator stages so the epilogue of one tile overlaps the MMAs of
+// the next.  It never decides a result by itself: it only nominates candidates, which flat.cu /
+// rescore re-evaluates in the reference's float64 arithmetic under a certificate (see api.cu).
+//
+//   tile        128 queries (UMMA M, TMEM lanes) x 256 corpus rows (UMMA N, TMEM columns), K = 64 per block
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2-5   epilogue: tcgen05.ld the accumulator, thread = query, columns = corpus rows
+//                 EPI_GROUPMIN min score of every 32-row group per query  (pass A -> per-query threshold)
+//                 EPI_EMIT     append id where score < theta[q]           (pass B -> candidates)
+//                 EPI_STORE    write every score (validation only)
+//
+// Replaces the O(N*D) scalar loop of BruteForceIndex.SearchWithScores
+// (reference pkg/core/vector_index.go:104-162) as far as candidate nomination goes.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "kdb_internal.cuh"
+
+namespace kdb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // bf16 elements = 128 bytes = one swizzle row
+constexpr int UK = 16;  // K of one tcgen05.mma.kind::f16
+constexpr int STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t A_BYTES = BM * BK * 2;
+constexpr uint32_t B_BYTES = BN * BK * 2;
+constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of BN columns
+
+enum { EPI_STORE = 0, EPI_GROUPMIN = 1, EPI_EMIT = 2 };
+constexpr int GROUP = 32;                 // corpus rows per group minimum (one tcgen05.ld.x32)
+constexpr int GROUPS_PER_TILE = BN / GROUP;
+
+struct TcArgs {
+  uint32_t nq_tiles, n_ctiles, k_blocks;
+  uint32_t nq, n;
+  float alpha;
+  const float *beta;  // [n_ctiles * BN], +inf = row excluded (padding, nil, deleted, not allowed)
+  float *S;           // EPI_STORE: [nq_tiles*BM][ldS]
+  size_t ldS;
+  float *gmin;         // EPI_GROUPMIN: [nq_tiles*BM][n_ctiles*GROUPS_PER_TILE]
+  const float *theta;  // EPI_EMIT: [nq_tiles*BM]
+  uint32_t *cnt;       // [nq]
+  uint32_t *buf_id;    // [nq][cap]
+  uint32_t cap;
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_smem_desc(const void *p) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(p) & 0x3FFFF) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
+__device__ __forceinline__ uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    flat_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX, const TcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *tiles = smem;  // [STAGES][A | B], every tile 1024-byte aligned (SWIZZLE_128B atom)
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t *empty = full + STAGES;
+  uint64_t *tmem_full = empty + STAGES;
+  uint64_t *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *s_beta = reinterpret_cast<float *>(tmem_ptr + 4);  // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 4);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t total_tiles = a.nq_tiles * a.n_ctiles;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const uint32_t ct = tile / a.nq_tiles, qt = tile % a.nq_tiles;
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          unsigned char *sa = tiles + (size_t)stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmQ, (int)(kb * BK), (int)(qt * BM), &full[stage]);
+          tma_load_2d(sa + A_BYTES, &tmX, (int)(kb * BK), (int)(ct * BN), &full[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc();
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);  // TMA bytes have landed
+          tc_fence_after();
+          const unsigned char *sa = tiles + (size_t)stage * STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advancing K inside the 128-byte swizzled row: +32 bytes = +2 in the (addr >> 4) field
+            umma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | (uint32_t)k) != 0u);
+          }
+          tc_commit(&empty[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1u;
+        if (acc == 0u) acc_phase ^= 1u;
+      }
+    }
+  } else {  // ===== epilogue warps 2..5 =====
+    const uint32_t quarter = (uint32_t)warp & 3u;  // the TMEM lane quarter this warp may read
+    const uint32_t et = (uint32_t)(threadIdx.x - 64);  // 0..127
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t ct = tile / a.nq_tiles, qt = tile % a.nq_tiles;
+      const uint32_t q = qt * BM + quarter * 32u + (uint32_t)lane;
+      float *sb = s_beta + acc * BN;
+      sb[et] = a.beta[(size_t)ct * BN + et];
+      sb[et + 128] = a.beta[(size_t)ct * BN + et + 128];
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      float theta = 0.f;
+      if (EPI == EPI_EMIT) theta = a.theta[q];
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        float best = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float score = __fmaf_rn(a.alpha, __uint_as_float(r[j]), sb[c0 + j]);
+          if (EPI == EPI_GROUPMIN) {
+            best = fminf(best, score);
+          } else if (EPI == EPI_EMIT) {
+            if (score < theta && q < a.nq) {
+              const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
+              if (pos < a.cap) a.buf_id[(size_t)q * a.cap + pos] = ct * BN + c0 + (uint32_t)j + 1u;  // internal id
+            }
+          } else {
+            const uint32_t col = ct * BN + c0 + (uint32_t)j;
+            if (q < a.nq && col < a.n) a.S[(size_t)q * a.ldS + col] = score;
+          }
+        }
+        if (EPI == EPI_GROUPMIN)
+          a.gmin[(size_t)q * ((size_t)a.n_ctiles * GROUPS_PER_TILE) + (size_t)ct * GROUPS_PER_TILE + c0 / GROUP] = best;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1u;
+      if (acc == 0u) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// f32 rows [rows][src_stride] -> bf16 [rows_pad][dp] (zero padded); per row, rounded UP to f32:
+// sumsq = sum v^2 and resid2 = sum (v - bf16(v))^2, both accumulated in f64 (they feed the error
+// certificate, so they must never under-estimate)
+__global__ void to_bf16_kernel(const float *__restrict__ src, size_t src_stride, uint32_t rows, uint32_t dim,
+                               __nv_bfloat16 *__restrict__ dst, uint32_t dp, uint32_t rows_pad,
+                               float *__restrict__ sumsq, float *__restrict__ resid2) {
+  const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows_pad) return;
+  double acc = 0.0, racc = 0.0;
+  for (uint32_t e = lane; e < dp; e += 32) {
+    float v = 0.f;
+    if (r < rows && e < dim) v = src[(size_t)r * src_stride + e];
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    dst[(size_t)r * dp + e] = b;
+    const double dv = (double)v, dr = dv - (double)__bfloat162float(b);
+    acc += dv * dv;
+    racc += dr * dr;
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    racc += __shfl_xor_sync(0xffffffffu, racc, o);
+  }
+  if (lane == 0) {
+    if (sumsq) sumsq[r] = __double2float_ru(acc * (1.0 + 1e-12));
+    if (resid2) resid2[r] = __double2float_ru(racc * (1.0 + 1e-12));
+  }
+}
+
+size_t tc_smem_bytes() {
+  return 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 2 * BN * sizeof(float);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over [rows][dp] (dp contiguous), box = 64 x box_rows, 128-byte swizzle
+bool make_tmap(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t dp, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {dp, rows};
+  const cuuint64_t gstride[1] = {dp * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// ---- launchers (api.cu) --------------------------------------------------------------------------
+uint32_t flat_tc_bm() { return BM; }
+uint32_t flat_tc_bn() { return BN; }
+uint32_t flat_tc_bk() { return BK; }
+uint32_t flat_tc_groups_per_tile() { return GROUPS_PER_TILE; }
+
+cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, uint32_t dim, void *dst, uint32_t dp,
+                           uint32_t rows_pad, float *sumsq, float *resid2, cudaStream_t stream) {
+  if (rows_pad == 0) return cudaSuccess;
+  const int wpb = 8;
+  to_bf16_kernel<<<(rows_pad + wpb - 1) / wpb, wpb * 32, 0, stream>>>(src, src_stride, rows, dim,
+                                                                      reinterpret_cast<__nv_bfloat16 *>(dst), dp,
+                                                                      rows_pad, sumsq, resid2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flat_tc(const FlatTcLaunch &L, cudaStream_t stream) {
+  CUtensorMap tmQ, tmX;
+  if (!make_tmap(&tmQ, L.q_bf16, L.nq_pad, L.dp, BM) || !make_tmap(&tmX, L.x_bf16, L.n_pad, L.dp, BN))
+    return cudaErrorInvalidValue;
+  TcArgs a;
+  a.nq_tiles = L.nq_pad / BM;
+  a.n_ctiles = L.n_pad / BN;
+  a.k_blocks = L.dp / BK;
+  a.nq = L.nq;
+  a.n = L.n;
+  a.alpha = L.alpha;
+  a.beta = L.beta;
+  a.S = L.S;
+  a.ldS = L.ldS;
+  a.gmin = L.gmin;
+  a.theta = L.theta;
+  a.cnt = L.cnt;
+  a.buf_id = L.buf_id;
+  a.cap = L.cap;
+  const size_t smem = tc_smem_bytes();
+  cudaError_t e;
+#define KDB_TC_LAUNCH(EPIv)                                                                              \
+  {                                                                                                      \
+    auto kern = flat_tc_kernel<EPIv>;                                                                    \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return e;                                                                      \
+    kern<<<L.grid, TC_THREADS, smem, stream>>>(tmQ, tmX, a);                                             \
+  }
+  if (L.epi == EPI_STORE) KDB_TC_LAUNCH(EPI_STORE)
+  else if (L.epi == EPI_GROUPMIN) KDB_TC_LAUNCH(EPI_GROUPMIN)
+  else KDB_TC_LAUNCH(EPI_EMIT)
+#undef KDB_TC_LAUNCH
+  return cudaGetLastError();
+}
+
+// ---- pass plumbing: beta vector, per-query thresholds, exact re-score + certificate ---------------
+namespace {
+
+constexpr float kInf = __builtin_huge_valf();
+
+// beta[r] for corpus row r (id r+1): sumsq (L2) or 0 (cosine); +inf when the row must not be nominated
+__global__ void tc_beta_kernel(const DevIndex ix, const float *__restrict__ sumsq, const uint32_t *__restrict__ allow,
+                               int use_norm, uint32_t n_pad, float *__restrict__ beta) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_pad) return;
+  const uint32_t id = r + 1;
+  bool ok = r < ix.n && ix.levels[id] >= 0;
+  if (ok && ix.deleted) ok = !((ix.deleted[id >> 5] >> (id & 31)) & 1u);
+  if (ok && allow) ok = (allow[id >> 5] >> (id & 31)) & 1u;
+  beta[r] = ok ? (use_norm ? sumsq[r] : 0.f) : kInf;
+}
+
+// out[0] = max sumsq, out[1] = max resid2 over rows < n (non-negative floats order like their bits)
+__global__ void tc_max_kernel(const float *__restrict__ sumsq, const float *__restrict__ resid2, uint32_t n,
+                              float *__restrict__ out) {
+  float m0 = 0.f, m1 = 0.f;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    m0 = fmaxf(m0, sumsq[i]);
+    m1 = fmaxf(m1, resid2[i]);
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m0));
+    atomicMax(reinterpret_cast<unsigned int *>(out) + 1, __float_as_uint(m1));
+  }
+}
+
+__device__ __forceinline__ uint32_t fkey(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) { return __uint_as_float((k >> 31) ? (k & 0x7fffffffu) : ~k); }
+
+constexpr int TH_THREADS = 256;
+constexpr int TH_BINS = 2048;
+// One CTA per query.  tau = k-th smallest group minimum (radix select, 11+11+10 bits): k distinct
+// groups hold a row scoring <= tau, so at least k rows score <= tau.  With e[q] bounding
+// |approximate - true| score for every row of the corpus and `slack` the float64 path's own
+// rounding, theta = tau + 2(e + slack) makes every row left out of {score < theta} provably farther
+// than the k-th nominated row.  bound[q] = e + slack is handed to the certificate.
+__global__ void __launch_bounds__(TH_THREADS)
+    tc_threshold_kernel(const float *__restrict__ gmin, uint32_t n_groups, uint32_t nq, int k,
+                        const float *__restrict__ qsumsq, const float *__restrict__ qresid2,
+                        const float *__restrict__ xmax, float alpha, int use_norm, uint32_t dp,
+                        float *__restrict__ theta, float *__restrict__ bound) {
+  __shared__ uint32_t hist[TH_BINS];
+  __shared__ uint32_t part[TH_THREADS];
+  __shared__ uint32_t s_prefix, s_rem;
+  const uint32_t q = blockIdx.x;
+  if (q >= nq) return;
+  const float *row = gmin + (size_t)q * n_groups;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    s_prefix = 0u;
+    s_rem = (uint32_t)k;
+  }
+  __syncthreads();
+  bool enough = true;
+  int shift = 32;
+  for (int pass = 0; pass < 3 && enough; ++pass) {
+    const int bits = pass < 2 ? 11 : 10;
+    shift -= bits;
+    for (int i = t; i < TH_BINS; i += TH_THREADS) hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const int hi = shift + bits;
+    for (uint32_t i = t; i < n_groups; i += TH_THREADS) {
+      const uint32_t key = fkey(row[i]);
+      if (hi >= 32 || (key >> hi) == (prefix >> hi)) atomicAdd(&hist[(key >> shift) & ((1u << bits) - 1u)], 1u);
+    }
+    __syncthreads();
+    const int per = TH_BINS / TH_THREADS;  // 8 bins per thread
+    uint32_t mine = 0;
+    for (int j = 0; j < per; ++j) mine += hist[t * per + j];
+    part[t] = mine;
+    __syncthreads();
+    if (t == 0) {
+      uint32_t rem = s_rem, c = 0;
+      int chunk = 0;
+      for (; chunk < TH_THREADS; ++chunk) {
+        if (c + part[chunk] >= rem) break;
+        c += part[chunk];
+      }
+      if (chunk == TH_THREADS) {
+        s_rem = 0xffffffffu;  // fewer than k values in total
+      } else {
+        rem -= c;
+        int b = chunk * per;
+        for (;; ++b) {
+          if (hist[b] >= rem) break;
+          rem -= hist[b];
+        }
+        s_prefix = prefix | ((uint32_t)b << shift);
+        s_rem = rem;
+      }
+    }
+    __syncthreads();
+    if (s_rem == 0xffffffffu) enough = false;
+  }
+  if (t == 0) {
+    const float up = 1.000001f;
+    const float qn = sqrtf(qsumsq[q]) * up, qr = sqrtf(qresid2[q]) * up;
+    const float xn = sqrtf(xmax[0]) * up, xr = sqrtf(xmax[1]) * up;
+    // |<q~,x~>_tc - <q,x>| <= |q - q~||x| + |q~||x - x~|  (bf16 rounding of the operands)
+    //                         + dp * 2^-21 |q~||x~|        (fp32 accumulation inside the tensor core)
+    const float dot_err = qr * xn + (qn + qr) * xr + (float)dp * 4.76837158203125e-7f * (qn + qr) * (xn + xr);
+    const float e = fabsf(alpha) * dot_err * 1.0001f + 1e-6f * (fabsf(alpha) * qn * xn + (use_norm ? xmax[0] : 0.f)) + 1e-12f;
+    const float slack = 4.76837158203125e-7f * (qn + xn) * (qn + xn) + 1e-9f;  // f64 path vs real arithmetic, |q|^2 in f32
+    const float tau = enough ? fkey_inv(s_prefix) : kInf;
+    theta[q] = tau < kInf ? tau + 2.f * (e + slack) * 1.0001f : kInf;
+    bound[q] = e + slack;
+  }
+}
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+// One CTA per query: exact distances of the nominated rows in the reference's arithmetic (flat.cu's
+// flat_distances_kernel order), ascending (distance, id), first k out, and the certificate
+//   theta - bound  >  (k-th exact distance) - qconst
+// i.e. every row that was NOT nominated is provably farther than the k-th result.  flags[q] != 0
+// sends the query to the exhaustive float64 scan.
+template <int MODE, int METRIC>
+__global__ void __launch_bounds__(RS_THREADS)
+    tc_rescore_kernel(const DevIndex ix, const float *__restrict__ queries, size_t q_stride, uint32_t nq, int k,
+                      const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ buf_id, uint32_t cap,
+                      const float *__restrict__ theta, const float *__restrict__ bound, const float *__restrict__ qsumsq,
+                      uint32_t *__restrict__ out_ids, double *__restrict__ out_scores, uint32_t *__restrict__ out_counts,
+                      uint32_t *__restrict__ flags, unsigned long long *__restrict__ n_rescored) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  const uint32_t q = blockIdx.x;
+  if (q >= nq) return;
+  uint32_t cap2 = 1;
+  while (cap2 < cap) cap2 <<= 1;
+  double *s_d = reinterpret_cast<double *>(rs_smem);
+  uint32_t *s_id = reinterpret_cast<uint32_t *>(s_d + cap2);
+  float *s_q = reinterpret_cast<float *>(s_id + cap2);
+  float *s_tile = s_q + ((ix.dim + 3u) & ~3u);  // [RS_WARPS][32][33]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t c_all = cnt[q];
+  const bool overflow = c_all > cap;
+  const uint32_t c = overflow ? cap : c_all;
+  uint32_t c2 = 1;  // sort only what is there
+  while (c2 < c) c2 <<= 1;
+  for (uint32_t e = tid; e < ix.dim; e += RS_THREADS) s_q[e] = queries[(size_t)q * q_stride + e];
+  for (uint32_t i = tid; i < c2; i += RS_THREADS) {
+    s_id[i] = i < c ? buf_id[(size_t)q * cap + i] : 0xffffffffu;
+    s_d[i] = __longlong_as_double(0x7ff0000000000000LL);
+  }
+  __syncthreads();
+  float *tile = s_tile + (size_t)warp * 32 * 33;
+  for (uint32_t base = warp * 32; base < c; base += RS_WARPS * 32) {
+    const uint32_t mine = base + lane < c ? s_id[base + lane] : 0u;
+    double acc = 0.0;
+    for (uint32_t e0 = 0; e0 < ix.dim; e0 += 32) {
+      for (int r = 0; r < 32; ++r) {  // coalesced: 128 bytes of row r per step
+        const uint32_t id = __shfl_sync(0xffffffffu, mine, r);
+        float v = 0.f;
+        if (id != 0u && e0 + lane < ix.dim) v = ix.vecs[(size_t)id * ix.stride + e0 + lane];
+        tile[r * 33 + lane] = v;
+      }
+      __syncwarp();
+      const int emax = (ix.dim - e0) < 32u ? (int)(ix.dim - e0) : 32;
+      for (int e = 0; e < emax; ++e) {
+        const float qf = s_q[e0 + e], xf = tile[lane * 33 + e];
+        if (MODE == 0) {
+          const double diff = static_cast<double>(__fsub_rn(qf, xf));
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+        } else if (METRIC == KDBGPU_METRIC_COSINE) {
+          acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(qf), static_cast<double>(xf)));
+        } else {
+          const double diff = __dsub_rn(static_cast<double>(qf), static_cast<double>(xf));
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+        }
+      }
+      __syncwarp();
+    }
+    if (MODE == 1 && METRIC == KDBGPU_METRIC_COSINE) acc = __dsub_rn(1.0, acc);
+    if (base + lane < c) s_d[base + lane] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) atomicAdd(n_rescored, (unsigned long long)c);
+  // ascending (distance, id)
+  for (uint32_t size = 2; size <= c2; size <<= 1)
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < c2; i += RS_THREADS) {
+        const uint32_t j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const double di = s_d[i], dj = s_d[j];
+          const uint32_t ii = s_id[i], ij = s_id[j];
+          const bool gt = di > dj || (di == dj && ii > ij);
+          if (gt == up) {
+            s_d[i] = dj;
+            s_d[j] = di;
+            s_id[i] = ij;
+            s_id[j] = ii;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  const uint32_t kk = c < (uint32_t)k ? c : (uint32_t)k;
+  for (int i = tid; i < k; i += RS_THREADS) {
+    const bool ok = (uint32_t)i < kk;
+    out_ids[(size_t)q * k + i] = ok ? s_id[i] : 0u;
+    out_scores[(size_t)q * k + i] = ok ? s_d[i] : 0.0;
+  }
+  if (tid == 0) {
+    out_counts[q] = kk;
+    uint32_t flag = overflow ? 1u : 0u;
+    const float th = theta[q];
+    if (!flag && th < kInf) {
+      if (kk < (uint32_t)k) {
+        flag = 2u;  // fewer nominated rows than k although rows were withheld
+      } else {
+        // exact distance -> score units of the pre-filter: L2  d = score + |q|^2 ; cosine d = 1 + score
+        double qconst;
+        if (MODE == 0 || METRIC == KDBGPU_METRIC_L2) qconst = (double)qsumsq[q];
+        else qconst = 1.0;
+        const double kth_score = s_d[kk - 1] - qconst;
+        if (!((double)th - (double)bound[q] > kth_score)) flag = 3u;
+      }
+    }
+    flags[q] = flag;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_tc_beta(const DevIndex &ix, const float *sumsq, const uint32_t *allow, int use_norm, uint32_t n_pad,
+                           float *beta, cudaStream_t stream) {
+  tc_beta_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(ix, sumsq, allow, use_norm, n_pad, beta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_max(const float *sumsq, const float *resid2, uint32_t n, float *out2, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  if (n) tc_max_kernel<<<296, 256, 0, stream>>>(sumsq, resid2, n, out2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_threshold(const float *gmin, uint32_t n_groups, uint32_t nq, int k, const float *qsumsq,
+                                const float *qresid2, const float *xmax, float alpha, int use_norm, uint32_t dp,
+                                float *theta, float *bound, cudaStream_t stream) {
+  tc_threshold_kernel<<<nq, TH_THREADS, 0, stream>>>(gmin, n_groups, nq, k, qsumsq, qresid2, xmax, alpha, use_norm, dp,
+                                                    theta, bound);
+  return cudaGetLastError();
+}
+
+size_t tc_rescore_smem(uint32_t dim, uint32_t cap) {
+  uint32_t cap2 = 1;
+  while (cap2 < cap) cap2 <<= 1;
+  return (size_t)cap2 * (sizeof(double) + sizeof(uint32_t)) + (size_t)((dim + 3u) & ~3u) * sizeof(float) +
+         (size_t)RS_WARPS * 32 * 33 * sizeof(float);
+}
+
+cudaError_t launch_tc_rescore(const DevIndex &ix, int mode, const float *queries, size_t q_stride, uint32_t nq, int k,
+                              const uint32_t *cnt, const uint32_t *buf_id, uint32_t cap, const float *theta,
+                              const float *bound, const float *qsumsq, uint32_t *out_ids, double *out_scores,
+                              uint32_t *out_counts, uint32_t *flags, unsigned long long *n_rescored,
+                              cudaStream_t stream) {
+  const size_t smem = tc_rescore_smem(ix.dim, cap);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e;
+#define KDB_RS_LAUNCH(MODEv, METRICv)                                                                          \
+  {                                                                                                            \
+    auto kern = tc_rescore_kernel<MODEv, METRICv>;                                                             \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+    if (e != cudaSuccess) return e;                                                                            \
+    kern<<<nq, RS_THREADS, smem, stream>>>(ix, queries, q_stride, nq, k, cnt, buf_id, cap, theta, bound, qsumsq, \
+                                           out_ids, out_scores, out_counts, flags, n_rescored);                \
+  }
+  if (mode == 0) KDB_RS_LAUNCH(0, KDBGPU_METRIC_L2)
+  else if (ix.metric == KDBGPU_METRIC_COSINE) KDB_RS_LAUNCH(1, KDBGPU_METRIC_COSINE)
+  else KDB_RS_LAUNCH(1, KDBGPU_METRIC_L2)
+#undef KDB_RS_LAUNCH
+  return cudaGetLastError();
+}
+
+}  // namespace kdb

@@ -85,6 +85,43 @@ cudaError_t launch_flat_select(const DevIndex &ix, const double *dist, uint32_t 
                                const uint32_t *allow, uint32_t *out_ids, double *out_scores,
                                uint32_t *out_counts, cudaStream_t stream);
 
+// flat scan, tensor-core pre-filter (flat_tc.cu): S[q][x] = alpha * <q~, x~> + beta[x] over bf16
+// copies, used only to nominate candidates that are then re-scored exactly under a certificate
+struct FlatTcLaunch {
+  const void *q_bf16;  // [nq_pad][dp]
+  const void *x_bf16;  // [n_pad][dp]
+  uint32_t nq, nq_pad, n, n_pad, dp;
+  float alpha;
+  const float *beta;  // [n_pad], +inf = row excluded
+  int epi;            // 0 store every score (validation), 1 group minima, 2 emit ids below theta
+  float *S;
+  size_t ldS;
+  float *gmin;         // [nq_pad][n_pad / 32]
+  const float *theta;  // [nq_pad]
+  uint32_t *cnt, *buf_id;
+  uint32_t cap;
+  int grid;
+};
+uint32_t flat_tc_bm();
+uint32_t flat_tc_bn();
+uint32_t flat_tc_bk();
+uint32_t flat_tc_groups_per_tile();
+cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, uint32_t dim, void *dst, uint32_t dp,
+                           uint32_t rows_pad, float *sumsq, float *resid2, cudaStream_t stream);
+cudaError_t launch_flat_tc(const FlatTcLaunch &L, cudaStream_t stream);
+cudaError_t launch_tc_beta(const DevIndex &ix, const float *sumsq, const uint32_t *allow, int use_norm, uint32_t n_pad,
+                           float *beta, cudaStream_t stream);
+cudaError_t launch_tc_max(const float *sumsq, const float *resid2, uint32_t n, float *out2, cudaStream_t stream);
+cudaError_t launch_tc_threshold(const float *gmin, uint32_t n_groups, uint32_t nq, int k, const float *qsumsq,
+                                const float *qresid2, const float *xmax, float alpha, int use_norm, uint32_t dp,
+                                float *theta, float *bound, cudaStream_t stream);
+size_t tc_rescore_smem(uint32_t dim, uint32_t cap);
+cudaError_t launch_tc_rescore(const DevIndex &ix, int mode, const float *queries, size_t q_stride, uint32_t nq, int k,
+                              const uint32_t *cnt, const uint32_t *buf_id, uint32_t cap, const float *theta,
+                              const float *bound, const float *qsumsq, uint32_t *out_ids, double *out_scores,
+                              uint32_t *out_counts, uint32_t *flags, unsigned long long *n_rescored,
+                              cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

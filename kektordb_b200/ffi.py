@@ -15,6 +15,7 @@ LIB_PATH = _build.LIB
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_OVERFLOW = -1, -2, -3, -4, -5
 METRIC_L2, METRIC_COSINE = 0, 1
+FLAT_PREFILTER = 0x10
 
 
 class GpuError(RuntimeError):
@@ -44,6 +45,7 @@ SIGNATURES = {
     "kdbgpu_search_batch_device": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _u32, _vp, _vp, _vp, _vp]),
     "kdbgpu_distance_batch": (_i32, [_vp, _vp, _vp, _u32, _vp]),
     "kdbgpu_flat_search_batch": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, C.POINTER(Stats)]),
+    "kdbgpu_flat_prefilter_scores": (_i32, [_vp, _vp, _u32, _i32, _vp, _vp]),
     "kdbgpu_merge_topk_device": (_i32, [_vp, _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kdbgpu_add_batch": (_i32, [_vp, _u32, _vp, _vp, _i32]),
     "kdbgpu_add_batch_device": (_i32, [_vp, _u32, _vp, _sz, _vp, _i32]),

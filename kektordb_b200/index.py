@@ -202,8 +202,13 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_distance_batch(self._handle(), _ptr(q), _ptr(ids), ids.size, _ptr(out)))
         return out
 
-    def flat_search(self, query, k: int, mode: int = 0, allowList: np.ndarray | None = None):
-        """BruteForceIndex.SearchWithScores (mode 0) / exact f64 ground truth (mode 1)."""
+    def flat_search(self, query, k: int, mode: int = 0, allowList: np.ndarray | None = None,
+                    prefilter: bool = False):
+        """BruteForceIndex.SearchWithScores (mode 0) / exact f64 ground truth (mode 1).  With
+        `prefilter` the same answer is found through the tensor-core nomination pass
+        (KDBGPU_FLAT_PREFILTER); stats.hops then counts queries the exhaustive scan answered."""
+        if prefilter:
+            mode |= ffi.FLAT_PREFILTER
         q = np.ascontiguousarray(query, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -216,7 +221,20 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_flat_search_batch(self._handle(), _ptr(q), nq, k, mode, _ptr(allow),
                                                      0 if allow is None else allow.size, _ptr(ids), _ptr(scores),
                                                      _ptr(counts), C.byref(st)))
-        return ids, scores, counts, SearchStats(st.dist_evals, 0, 0, st.kernel_ms, st.total_ms)
+        return ids, scores, counts, SearchStats(st.dist_evals, st.hops, 0, st.kernel_ms, st.total_ms)
+
+    def flat_prefilter_scores(self, query, mode: int = 0):
+        """Validation hook: approximate scores [nq, n] of the tensor-core pass and the certified
+        per-query bound on their error."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        n = self.count
+        out = np.zeros((q.shape[0], n), dtype=np.float32)
+        bound = np.zeros(q.shape[0], dtype=np.float32)
+        ffi.check(self._lib.kdbgpu_flat_prefilter_scores(self._handle(), _ptr(q), q.shape[0], mode, _ptr(out),
+                                                         _ptr(bound)))
+        return out, bound
 
     # -- introspection ---------------------------------------------------------------------
     def Metric(self) -> str:
