@@ -175,7 +175,9 @@ struct kdbgpu_index {
   // tensor-core flat pre-filter: bf16 mirror of the rows (built lazily, dropped when rows change)
   DevBuf<uint16_t> x_bf16, tq_bf16;
   DevBuf<float> x_sumsq, x_resid2, x_max, tc_beta, tq_sumsq, tq_resid2, t_gmin, t_theta, t_bound;
-  DevBuf<uint32_t> t_cnt, t_bufid, t_flags;
+  DevBuf<uint32_t> t_cnt, t_subcnt, t_flags, t_fcnt, t_fid;
+  DevBuf<uint2> t_sub, t_ovf;
+  DevBuf<float> t_thf;
   DevBuf<unsigned long long> t_nres;
   bool tc_valid = false;
   uint32_t tc_n = 0;
@@ -455,26 +457,45 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
   TcPlan P;
   int rc = tc_prepare(h, mode, d_allow, k, &P, s);
   if (rc) return rc;
-  const uint32_t cap = k <= 256 ? 2048u : 4096u;
-  if (P.n_groups < (uint32_t)k || h->n <= cap || tc_rescore_smem((uint32_t)h->dim, cap) > 200 * 1024) {
+  const uint32_t cap = 2048u;                      // spill slots per query beyond the per-(query, CTA) slots
+  const uint32_t sub_slots = flat_tc_sub_slots();
+  const uint32_t want = 8192u;                     // nominees per query the sampling aims below
+  const uint32_t fcap = k <= 256 ? 1024u : 4096u;  // survivors of the refinement, re-scored exactly
+  // pass A may look at every ct_stride-th corpus tile only: any k rows bound the k-th best score from
+  // above, a sample just makes theta looser (about ct_stride * k nominees instead of k)
+  const uint32_t n_ctiles = P.n_pad / P.bn, gpt = flat_tc_groups_per_tile();
+  uint32_t ct_stride = want / (6u * (uint32_t)k);
+  if (ct_stride > 8) ct_stride = 8;
+  while (ct_stride > 1 && (uint64_t)((n_ctiles + ct_stride - 1) / ct_stride) * gpt < 4ull * (uint64_t)k) --ct_stride;
+  if (ct_stride < 1) ct_stride = 1;
+  const char *env_stride = getenv("KDBGPU_FLAT_SAMPLE");
+  if (env_stride && atoi(env_stride) >= 1 && atoi(env_stride) <= 64) ct_stride = (uint32_t)atoi(env_stride);
+  const uint32_t n_groups = (n_ctiles + ct_stride - 1) / ct_stride * gpt;
+  if (n_groups < (uint32_t)k || h->n <= cap || tc_rescore_smem((uint32_t)h->dim, fcap) > 200 * 1024) {
     // too few rows for a threshold to exist (or to be worth it): the exhaustive scan answers
     *evals = (uint64_t)nq * h->n;
     *fallbacks = nq;
     return flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
   }
   // chunk so that gmin[chunk][n_groups] stays within 512 MiB
-  uint32_t chunk = (uint32_t)((512ull << 20) / ((size_t)P.n_groups * sizeof(float)));
+  uint32_t chunk = (uint32_t)((512ull << 20) / ((size_t)n_groups * sizeof(float)));
   chunk = chunk / P.bm * P.bm;
   if (chunk < P.bm) chunk = P.bm;
-  if (chunk > 4096) chunk = 4096;
+  if (chunk > flat_tc_max_queries()) chunk = flat_tc_max_queries();
   const uint32_t nq_pad = (nq + P.bm - 1) / P.bm * P.bm;
   if (chunk > nq_pad) chunk = nq_pad;
-  CUDA_TRY(h->t_gmin.reserve((size_t)chunk * P.n_groups));
+  const uint32_t emit_grid = (uint32_t)h->num_sms;
+  CUDA_TRY(h->t_gmin.reserve((size_t)chunk * n_groups));
   CUDA_TRY(h->t_theta.reserve(chunk));
   CUDA_TRY(h->t_bound.reserve(chunk));
+  CUDA_TRY(h->t_thf.reserve(chunk));
   CUDA_TRY(h->t_cnt.reserve(chunk));
+  CUDA_TRY(h->t_fcnt.reserve(chunk));
   CUDA_TRY(h->t_flags.reserve(chunk));
-  CUDA_TRY(h->t_bufid.reserve((size_t)chunk * cap));
+  CUDA_TRY(h->t_sub.reserve((size_t)chunk * emit_grid * sub_slots));
+  CUDA_TRY(h->t_subcnt.reserve((size_t)chunk * emit_grid));
+  CUDA_TRY(h->t_ovf.reserve((size_t)chunk * cap));
+  CUDA_TRY(h->t_fid.reserve((size_t)chunk * fcap));
   CUDA_TRY(h->t_nres.reserve(1));
   CUDA_TRY(h->out_ids.reserve((size_t)chunk * k));
   CUDA_TRY(h->out_scores.reserve((size_t)chunk * k));
@@ -493,19 +514,31 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     FlatTcLaunch L = tc_launch_desc(h, P, c, c_pad);
     L.gmin = h->t_gmin.p;
     L.theta = h->t_theta.p;
-    L.cnt = h->t_cnt.p;
-    L.buf_id = h->t_bufid.p;
+    L.sub = h->t_sub.p;
+    L.sub_cnt = h->t_subcnt.p;
+    L.ovf_cnt = h->t_cnt.p;
+    L.ovf = h->t_ovf.p;
     L.cap = cap;
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
-    L.epi = 1;  // pass A: group minima
+    L.epi = 1;  // pass A: group minima over the sampled tiles
+    L.ct_stride = ct_stride;
+    {
+      const uint64_t tiles = (uint64_t)(c_pad / P.bm) * ((n_ctiles + ct_stride - 1) / ct_stride);
+      L.grid = tiles < (uint64_t)h->num_sms ? (int)tiles : h->num_sms;
+    }
     CUDA_TRY(launch_flat_tc(L, s));
-    CUDA_TRY(launch_tc_threshold(h->t_gmin.p, P.n_groups, c, k, h->tq_sumsq.p, h->tq_resid2.p, h->x_max.p, P.alpha,
+    CUDA_TRY(launch_tc_threshold(h->t_gmin.p, n_groups, c, k, h->tq_sumsq.p, h->tq_resid2.p, h->x_max.p, P.alpha,
                                  P.use_norm, P.dp, h->t_theta.p, h->t_bound.p, s));
-    L.epi = 2;  // pass B: ids below theta
+    L.epi = 2;  // pass B: ids + scores below theta, every tile
+    L.ct_stride = 1;
+    L.grid = tc_launch_desc(h, P, c, c_pad).grid;
     CUDA_TRY(launch_flat_tc(L, s));
+    const uint32_t grid_b = (uint32_t)L.grid;
     CUDA_TRY(cudaEventRecord(h->ev[2], s));
+    CUDA_TRY(launch_tc_refine(h->t_sub.p, h->t_subcnt.p, grid_b, h->t_cnt.p, h->t_ovf.p, cap, c, k, h->t_theta.p,
+                              h->t_bound.p, h->t_fcnt.p, h->t_fid.p, fcap, h->t_thf.p, h->t_flags.p, s));
     CUDA_TRY(launch_tc_rescore(ix, mode, prepared ? h->q_prep.p : h->q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim,
-                               c, k, h->t_cnt.p, h->t_bufid.p, cap, h->t_theta.p, h->t_bound.p, h->tq_sumsq.p,
+                               c, k, h->t_fcnt.p, h->t_fid.p, fcap, h->t_thf.p, h->t_bound.p, h->tq_sumsq.p,
                                h->out_ids.p, h->out_scores.p, h->out_counts.p, h->t_flags.p, h->t_nres.p, s));
     CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
                              cudaMemcpyDeviceToHost, s));
@@ -678,7 +711,7 @@ int kdbgpu_index_destroy(kdbgpu_index *h) {
   h->b_scratch_d.release();
   h->x_bf16.release(); h->tq_bf16.release(); h->x_sumsq.release(); h->x_resid2.release(); h->x_max.release();
   h->tc_beta.release(); h->tq_sumsq.release(); h->tq_resid2.release(); h->t_gmin.release(); h->t_theta.release();
-  h->t_bound.release(); h->t_cnt.release(); h->t_bufid.release(); h->t_flags.release(); h->t_nres.release();
+  h->t_bound.release(); h->t_fcnt.release(); h->t_fid.release(); h->t_sub.release(); h->t_ovf.release(); h->t_subcnt.release(); h->t_thf.release(); h->t_cnt.release(); h->t_flags.release(); h->t_nres.release();
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);

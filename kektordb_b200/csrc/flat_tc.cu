@@ -38,9 +38,12 @@ constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of BN columns
 enum { EPI_STORE = 0, EPI_GROUPMIN = 1, EPI_EMIT = 2 };
 constexpr int GROUP = 32;                 // corpus rows per group minimum (one tcgen05.ld.x32)
 constexpr int GROUPS_PER_TILE = BN / GROUP;
+constexpr int SUB = 32;                   // nominee slots per (query, CTA)
+constexpr int MAX_Q_PER_LAUNCH = 2048;    // per-CTA nominee counters live in shared memory
 
 struct TcArgs {
-  uint32_t nq_tiles, n_ctiles, k_blocks;
+  uint32_t nq_tiles, n_ctiles, k_blocks;  // n_ctiles = corpus tiles this launch visits
+  uint32_t ct_stride;                     // visited tile i is corpus tile i * ct_stride (pass A samples)
   uint32_t nq, n;
   float alpha;
   const float *beta;  // [n_ctiles * BN], +inf = row excluded (padding, nil, deleted, not allowed)
@@ -48,8 +51,12 @@ struct TcArgs {
   size_t ldS;
   float *gmin;         // EPI_GROUPMIN: [nq_tiles*BM][n_ctiles*GROUPS_PER_TILE]
   const float *theta;  // EPI_EMIT: [nq_tiles*BM]
-  uint32_t *cnt;       // [nq]
-  uint32_t *buf_id;    // [nq][cap]
+  // EPI_EMIT: nominees of query q found by CTA c go to sub[q][c][0..SUB) without any atomic (the CTA
+  // counts them in shared memory); what does not fit spills to ovf[q][0..cap) through ovf_cnt[q]
+  uint2 *sub;          // [nq_pad][gridDim.x][SUB]  {id, score bits}
+  uint32_t *sub_cnt;   // [nq_pad][gridDim.x]
+  uint32_t *ovf_cnt;   // [nq_pad]
+  uint2 *ovf;          // [nq_pad][cap]
   uint32_t cap;
 };
 
@@ -119,6 +126,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t *tmem_empty = tmem_full + 2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
   float *s_beta = reinterpret_cast<float *>(tmem_ptr + 4);  // [2][BN]
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_beta + 2 * BN);  // [nq_tiles * BM], EPI_EMIT only
+  if (EPI == EPI_EMIT)
+    for (uint32_t i = threadIdx.x; i < a.nq_tiles * BM; i += TC_THREADS) s_cnt[i] = 0u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (lane == 0) {  // ===== TMA producer =====
       uint32_t stage = 0, phase = 0;
       for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const uint32_t ct = tile / a.nq_tiles, qt = tile % a.nq_tiles;
+        const uint32_t ct = (tile / a.nq_tiles) * a.ct_stride, qt = tile % a.nq_tiles;
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -201,7 +211,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t et = (uint32_t)(threadIdx.x - 64);  // 0..127
     uint32_t acc = 0, acc_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const uint32_t ct = tile / a.nq_tiles, qt = tile % a.nq_tiles;
+      const uint32_t cti = tile / a.nq_tiles, qt = tile % a.nq_tiles;
+      const uint32_t ct = cti * a.ct_stride;
       const uint32_t q = qt * BM + quarter * 32u + (uint32_t)lane;
       float *sb = s_beta + acc * BN;
       sb[et] = a.beta[(size_t)ct * BN + et];
@@ -210,36 +221,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       float theta = 0.f;
-      if (EPI == EPI_EMIT) theta = a.theta[q];
+      uint32_t my_cnt = 0u, my_cnt0 = 0u;
+      if (EPI == EPI_EMIT) {
+        theta = a.theta[q];
+        my_cnt = my_cnt0 = s_cnt[q];  // this thread is the only one in the CTA that serves query q
+      }
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
-        float best = __int_as_float(0x7f800000);
+        float sc[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float score = __fmaf_rn(a.alpha, __uint_as_float(r[j]), sb[c0 + j]);
-          if (EPI == EPI_GROUPMIN) {
-            best = fminf(best, score);
-          } else if (EPI == EPI_EMIT) {
-            if (score < theta && q < a.nq) {
-              const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
-              if (pos < a.cap) a.buf_id[(size_t)q * a.cap + pos] = ct * BN + c0 + (uint32_t)j + 1u;  // internal id
-            }
-          } else {
+        for (int j4 = 0; j4 < 8; ++j4) {  // beta: 8 broadcast LDS.128 instead of 32 dependent LDS.32
+          const float4 b4 = *reinterpret_cast<const float4 *>(sb + c0 + 4 * j4);
+          sc[4 * j4 + 0] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 0]), b4.x);
+          sc[4 * j4 + 1] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 1]), b4.y);
+          sc[4 * j4 + 2] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 2]), b4.z);
+          sc[4 * j4 + 3] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 3]), b4.w);
+        }
+        if (EPI == EPI_STORE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
             const uint32_t col = ct * BN + c0 + (uint32_t)j;
-            if (q < a.nq && col < a.n) a.S[(size_t)q * a.ldS + col] = score;
+            if (q < a.nq && col < a.n) a.S[(size_t)q * a.ldS + col] = sc[j];
+          }
+        } else {
+          float m[16];  // min tree: independent chains
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = fminf(sc[j], sc[j + 16]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = fminf(m[j], m[j + 8]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = fminf(m[j], m[j + 4]);
+          const float best = fminf(fminf(m[0], m[1]), fminf(m[2], m[3]));
+          if (EPI == EPI_GROUPMIN) {
+            a.gmin[(size_t)q * ((size_t)a.n_ctiles * GROUPS_PER_TILE) + (size_t)cti * GROUPS_PER_TILE + c0 / GROUP] = best;
+          } else if (best < theta && q < a.nq) {  // a group holding at least one nominee of this query
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mask |= (sc[j] < theta) ? (1u << j) : 0u;  // predicated, no branches
+            while (mask) {
+              const int j = __ffs((int)mask) - 1;
+              mask &= mask - 1u;
+              // sc[j] for a run-time j: 5-level select tree over the register-resident scores
+              float v16[16], v8[8], v4[4];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v16[i] = (j & 16) ? sc[i + 16] : sc[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] = (j & 8) ? v16[i + 8] : v16[i];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v4[i] = (j & 4) ? v8[i + 4] : v8[i];
+              const float v2a = (j & 2) ? v4[2] : v4[0], v2b = (j & 2) ? v4[3] : v4[1];
+              const float v = (j & 1) ? v2b : v2a;
+              const uint2 rec = make_uint2(ct * BN + c0 + (uint32_t)j + 1u, __float_as_uint(v));  // internal id
+              const uint32_t pos = my_cnt++;
+              if (pos < (uint32_t)SUB) {
+                a.sub[((size_t)q * gridDim.x + blockIdx.x) * SUB + pos] = rec;
+              } else {
+                const uint32_t p = atomicAdd(&a.ovf_cnt[q], 1u);
+                if (p < a.cap) a.ovf[(size_t)q * a.cap + p] = rec;
+              }
+            }
           }
         }
-        if (EPI == EPI_GROUPMIN)
-          a.gmin[(size_t)q * ((size_t)a.n_ctiles * GROUPS_PER_TILE) + (size_t)ct * GROUPS_PER_TILE + c0 / GROUP] = best;
       }
+      if (EPI == EPI_EMIT && my_cnt != my_cnt0) s_cnt[q] = my_cnt;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1u;
       if (acc == 0u) acc_phase ^= 1u;
+    }
+    if (EPI == EPI_EMIT) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (uint32_t i = et; i < a.nq_tiles * BM; i += 128) a.sub_cnt[(size_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
     }
   }
   tc_fence_before();
@@ -280,8 +336,9 @@ __global__ void to_bf16_kernel(const float *__restrict__ src, size_t src_stride,
   }
 }
 
-size_t tc_smem_bytes() {
-  return 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 2 * BN * sizeof(float);
+size_t tc_smem_bytes(uint32_t nq_pad_emit) {
+  return 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 2 * BN * sizeof(float) +
+         (size_t)nq_pad_emit * sizeof(uint32_t);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -320,6 +377,8 @@ uint32_t flat_tc_bm() { return BM; }
 uint32_t flat_tc_bn() { return BN; }
 uint32_t flat_tc_bk() { return BK; }
 uint32_t flat_tc_groups_per_tile() { return GROUPS_PER_TILE; }
+uint32_t flat_tc_sub_slots() { return SUB; }
+uint32_t flat_tc_max_queries() { return MAX_Q_PER_LAUNCH; }
 
 cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, uint32_t dim, void *dst, uint32_t dp,
                            uint32_t rows_pad, float *sumsq, float *resid2, cudaStream_t stream) {
@@ -337,7 +396,8 @@ cudaError_t launch_flat_tc(const FlatTcLaunch &L, cudaStream_t stream) {
     return cudaErrorInvalidValue;
   TcArgs a;
   a.nq_tiles = L.nq_pad / BM;
-  a.n_ctiles = L.n_pad / BN;
+  a.ct_stride = L.ct_stride ? L.ct_stride : 1u;
+  a.n_ctiles = (L.n_pad / BN + a.ct_stride - 1) / a.ct_stride;
   a.k_blocks = L.dp / BK;
   a.nq = L.nq;
   a.n = L.n;
@@ -347,10 +407,13 @@ cudaError_t launch_flat_tc(const FlatTcLaunch &L, cudaStream_t stream) {
   a.ldS = L.ldS;
   a.gmin = L.gmin;
   a.theta = L.theta;
-  a.cnt = L.cnt;
-  a.buf_id = L.buf_id;
+  a.sub = reinterpret_cast<uint2 *>(L.sub);
+  a.sub_cnt = L.sub_cnt;
+  a.ovf_cnt = L.ovf_cnt;
+  a.ovf = reinterpret_cast<uint2 *>(L.ovf);
   a.cap = L.cap;
-  const size_t smem = tc_smem_bytes();
+  if (L.epi == EPI_EMIT && (L.nq_pad > MAX_Q_PER_LAUNCH || L.grid > 256)) return cudaErrorInvalidValue;
+  const size_t smem = tc_smem_bytes(L.epi == EPI_EMIT ? L.nq_pad : 0);
   cudaError_t e;
 #define KDB_TC_LAUNCH(EPIv)                                                                              \
   {                                                                                                      \
@@ -488,66 +551,232 @@ __global__ void __launch_bounds__(TH_THREADS)
   }
 }
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RF_THREADS = 256;
+// One CTA per query.  Pass B nominated every row scoring below the (loose, sample-based) theta and
+// kept its approximate score.  tau' = the k-th smallest of those scores is the k-th smallest
+// approximate score of the WHOLE corpus (every row below theta is in the buffer, and at least k are),
+// so only rows scoring below theta' = tau' + 2 * bound can still enter the exact top k: they go on to
+// the float64 re-score; the rest are dropped under the same certificate.
+// flags[q]: 0 ok, 1 nomination buffer overflow, 2 survivor buffer overflow, 4 fewer than k nominees
+// although rows were withheld.
+__global__ void __launch_bounds__(RF_THREADS)
+    tc_refine_kernel(const uint2 *__restrict__ sub, const uint32_t *__restrict__ sub_cnt, uint32_t grid,
+                     const uint32_t *__restrict__ ovf_cnt, const uint2 *__restrict__ ovf, uint32_t cap, uint32_t nq, int k,
+                     const float *__restrict__ theta, const float *__restrict__ bound, uint32_t *__restrict__ fcnt,
+                     uint32_t *__restrict__ fid, uint32_t fcap, float *__restrict__ theta_final,
+                     uint32_t *__restrict__ flags) {
+  __shared__ uint32_t hist[TH_BINS];
+  __shared__ uint32_t part[RF_THREADS];
+  __shared__ uint32_t s_sub[256];
+  __shared__ uint32_t s_prefix, s_rem, s_out, s_total;
+  const uint32_t q = blockIdx.x;
+  if (q >= nq) return;
+  const int t = threadIdx.x;
+  const float th = theta[q];
+  const uint32_t n_ovf = ovf_cnt[q];
+  if (n_ovf > cap) {  // the spill buffer lost nominees: nothing can be certified
+    if (t == 0) {
+      flags[q] = 1u;
+      fcnt[q] = 0u;
+      theta_final[q] = th;
+    }
+    return;
+  }
+  if (t == 0) s_total = 0u;
+  __syncthreads();
+  for (uint32_t i = t; i < grid; i += RF_THREADS) {
+    uint32_t v = sub_cnt[(size_t)q * grid + i];
+    if (v > (uint32_t)SUB) v = SUB;
+    s_sub[i] = v;
+    atomicAdd(&s_total, v);
+  }
+  __syncthreads();
+  const uint32_t c = s_total + n_ovf;
+  const uint2 *qsub = sub + (size_t)q * grid * SUB;
+  const uint2 *qovf = ovf + (size_t)q * cap;
+  const uint32_t n_slots = grid * SUB + n_ovf;
+  // record i of this query's nominee space, or id 0 for an empty slot
+  auto rec_at = [&](uint32_t i) -> uint2 {
+    if (i < grid * SUB) {
+      if ((i % SUB) < s_sub[i / SUB]) return qsub[i];
+      return make_uint2(0u, 0u);
+    }
+    return qovf[i - grid * SUB];
+  };
+  float thf = th;  // theta = +inf (nothing withheld) or fewer than k nominees: keep them all
+  if (c >= (uint32_t)k && th < kInf) {
+    if (t == 0) {
+      s_prefix = 0u;
+      s_rem = (uint32_t)k;
+    }
+    __syncthreads();
+    int shift = 32;
+    for (int pass = 0; pass < 3; ++pass) {
+      const int bits = pass < 2 ? 11 : 10;
+      shift -= bits;
+      for (int i = t; i < TH_BINS; i += RF_THREADS) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const int hi = shift + bits;
+      for (uint32_t i = t; i < n_slots; i += RF_THREADS) {
+        const uint2 r = rec_at(i);
+        if (r.x == 0u) continue;
+        const uint32_t key = fkey(__uint_as_float(r.y));
+        if (hi >= 32 || (key >> hi) == (prefix >> hi)) atomicAdd(&hist[(key >> shift) & ((1u << bits) - 1u)], 1u);
+      }
+      __syncthreads();
+      const int per = TH_BINS / RF_THREADS;
+      uint32_t mine = 0;
+      for (int j = 0; j < per; ++j) mine += hist[t * per + j];
+      part[t] = mine;
+      __syncthreads();
+      if (t == 0) {
+        uint32_t rem = s_rem, acc = 0;
+        int chunk = 0;
+        for (; chunk < RF_THREADS - 1; ++chunk) {
+          if (acc + part[chunk] >= rem) break;
+          acc += part[chunk];
+        }
+        rem -= acc;
+        int b = chunk * per;
+        for (; b < TH_BINS - 1; ++b) {
+          if (hist[b] >= rem) break;
+          rem -= hist[b];
+        }
+        s_prefix = prefix | ((uint32_t)b << shift);
+        s_rem = rem;
+      }
+      __syncthreads();
+    }
+    const float tau = fkey_inv(s_prefix);
+    const float tf = tau + 2.f * bound[q] * 1.0001f;
+    thf = tf < th ? tf : th;
+  }
+  if (t == 0) s_out = 0u;
+  __syncthreads();
+  for (uint32_t i = t; i < n_slots; i += RF_THREADS) {
+    const uint2 r = rec_at(i);
+    if (r.x != 0u && __uint_as_float(r.y) < thf) {
+      const uint32_t pos = atomicAdd(&s_out, 1u);
+      if (pos < fcap) fid[(size_t)q * fcap + pos] = r.x;
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    const uint32_t n_out = s_out;
+    uint32_t flag = 0u;
+    if (n_out > fcap) flag = 2u;
+    else if (n_out < (uint32_t)k && th < kInf) flag = 4u;
+    fcnt[q] = n_out > fcap ? fcap : n_out;
+    theta_final[q] = thf;
+    flags[q] = flag;
+  }
+}
 
-// One CTA per query: exact distances of the nominated rows in the reference's arithmetic (flat.cu's
-// flat_distances_kernel order), ascending (distance, id), first k out, and the certificate
-//   theta - bound  >  (k-th exact distance) - qconst
-// i.e. every row that was NOT nominated is provably farther than the k-th result.  flags[q] != 0
-// sends the query to the exhaustive float64 scan.
+// one term of the flat scan's float64 sum, exactly as flat.cu's flat_distances_kernel forms it
+template <int MODE, int METRIC>
+__device__ __forceinline__ double exact_term(float qf, float xf) {
+  if (MODE == 0) {
+    const double diff = static_cast<double>(__fsub_rn(qf, xf));
+    return __dmul_rn(diff, diff);
+  } else if (METRIC == KDBGPU_METRIC_COSINE) {
+    return __dmul_rn(static_cast<double>(qf), static_cast<double>(xf));
+  } else {
+    const double diff = __dsub_rn(static_cast<double>(qf), static_cast<double>(xf));
+    return __dmul_rn(diff, diff);
+  }
+}
+
+constexpr int RS_THREADS = 128;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_CHUNK = 128;           // floats of every row per step: 512 contiguous bytes per request
+constexpr int RS_LD = RS_CHUNK + 4;     // padded tile row (conflict-free LDS.128 with lane = row)
+
+// One CTA per query: exact distances of the surviving rows in the reference's arithmetic (flat.cu's
+// flat_distances_kernel order: sequential in the element index, float64), ascending (distance, id),
+// first k out, and the certificate
+//   theta' - bound  >  (k-th exact distance) - qconst
+// i.e. every row that was dropped is provably farther than the k-th result.  flags[q] != 0 sends the
+// query to the exhaustive float64 scan.
 template <int MODE, int METRIC>
 __global__ void __launch_bounds__(RS_THREADS)
     tc_rescore_kernel(const DevIndex ix, const float *__restrict__ queries, size_t q_stride, uint32_t nq, int k,
-                      const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ buf_id, uint32_t cap,
-                      const float *__restrict__ theta, const float *__restrict__ bound, const float *__restrict__ qsumsq,
-                      uint32_t *__restrict__ out_ids, double *__restrict__ out_scores, uint32_t *__restrict__ out_counts,
-                      uint32_t *__restrict__ flags, unsigned long long *__restrict__ n_rescored) {
+                      const uint32_t *__restrict__ fcnt, const uint32_t *__restrict__ fid, uint32_t fcap,
+                      const float *__restrict__ theta_final, const float *__restrict__ bound,
+                      const float *__restrict__ qsumsq, uint32_t *__restrict__ out_ids, double *__restrict__ out_scores,
+                      uint32_t *__restrict__ out_counts, uint32_t *__restrict__ flags,
+                      unsigned long long *__restrict__ n_rescored) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   const uint32_t q = blockIdx.x;
   if (q >= nq) return;
   uint32_t cap2 = 1;
-  while (cap2 < cap) cap2 <<= 1;
+  while (cap2 < fcap) cap2 <<= 1;
   double *s_d = reinterpret_cast<double *>(rs_smem);
   uint32_t *s_id = reinterpret_cast<uint32_t *>(s_d + cap2);
   float *s_q = reinterpret_cast<float *>(s_id + cap2);
-  float *s_tile = s_q + ((ix.dim + 3u) & ~3u);  // [RS_WARPS][32][33]
+  float *s_tile = s_q + ((ix.dim + RS_CHUNK - 1) / RS_CHUNK) * RS_CHUNK;  // [RS_WARPS][2][32][RS_LD]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t c_all = cnt[q];
-  const bool overflow = c_all > cap;
-  const uint32_t c = overflow ? cap : c_all;
+  const uint32_t c = flags[q] ? 0u : fcnt[q];
   uint32_t c2 = 1;  // sort only what is there
   while (c2 < c) c2 <<= 1;
-  for (uint32_t e = tid; e < ix.dim; e += RS_THREADS) s_q[e] = queries[(size_t)q * q_stride + e];
+  const uint32_t dim_pad = ((ix.dim + RS_CHUNK - 1) / RS_CHUNK) * RS_CHUNK;
+  for (uint32_t e = tid; e < dim_pad; e += RS_THREADS) s_q[e] = e < ix.dim ? queries[(size_t)q * q_stride + e] : 0.f;
   for (uint32_t i = tid; i < c2; i += RS_THREADS) {
-    s_id[i] = i < c ? buf_id[(size_t)q * cap + i] : 0xffffffffu;
+    s_id[i] = i < c ? fid[(size_t)q * fcap + i] : 0xffffffffu;
     s_d[i] = __longlong_as_double(0x7ff0000000000000LL);
   }
   __syncthreads();
-  float *tile = s_tile + (size_t)warp * 32 * 33;
+  float *tile = s_tile + (size_t)warp * 2 * 32 * RS_LD;  // two stages per warp
+  const uint32_t n_chunks = (ix.dim + RS_CHUNK - 1) / RS_CHUNK;
   for (uint32_t base = warp * 32; base < c; base += RS_WARPS * 32) {
     const uint32_t mine = base + lane < c ? s_id[base + lane] : 0u;
-    double acc = 0.0;
-    for (uint32_t e0 = 0; e0 < ix.dim; e0 += 32) {
-      for (int r = 0; r < 32; ++r) {  // coalesced: 128 bytes of row r per step
+    // rows are stored with stride >= dim rounded up to 128 floats, zero padded (kdb_internal.cuh), so a
+    // whole 512-byte chunk of every row can be requested; lane l moves bytes [16l, 16l+16) of each row
+    auto issue = [&](uint32_t ci) {
+      float *dst = tile + (size_t)(ci & 1u) * 32 * RS_LD + 4 * lane;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
         const uint32_t id = __shfl_sync(0xffffffffu, mine, r);
-        float v = 0.f;
-        if (id != 0u && e0 + lane < ix.dim) v = ix.vecs[(size_t)id * ix.stride + e0 + lane];
-        tile[r * 33 + lane] = v;
+        if (id != 0u) {
+          const float *src = ix.vecs + (size_t)id * ix.stride + (size_t)ci * RS_CHUNK + 4 * lane;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + r * RS_LD)), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc = 0.0;
+    issue(0);
+    for (uint32_t ci = 0; ci < n_chunks; ++ci) {
+      if (ci + 1 < n_chunks) {
+        issue(ci + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
       __syncwarp();
-      const int emax = (ix.dim - e0) < 32u ? (int)(ix.dim - e0) : 32;
-      for (int e = 0; e < emax; ++e) {
-        const float qf = s_q[e0 + e], xf = tile[lane * 33 + e];
-        if (MODE == 0) {
-          const double diff = static_cast<double>(__fsub_rn(qf, xf));
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-        } else if (METRIC == KDBGPU_METRIC_COSINE) {
-          acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(qf), static_cast<double>(xf)));
-        } else {
-          const double diff = __dsub_rn(static_cast<double>(qf), static_cast<double>(xf));
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      const uint32_t e0 = ci * RS_CHUNK;
+      const int emax = (ix.dim - e0) < (uint32_t)RS_CHUNK ? (int)(ix.dim - e0) : RS_CHUNK;
+      const float *trow = tile + (size_t)(ci & 1u) * 32 * RS_LD + lane * RS_LD;
+      if (mine != 0u) {
+        int e = 0;
+        // 16 elements at a time: the products do not depend on the running sum, so they are formed
+        // first (independent) and only the 16 additions stay on the loop-carried chain — the order of
+        // the additions, and therefore every rounding, is still the reference's
+        for (; e + 16 <= emax; e += 16) {
+          double term[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 x4 = *reinterpret_cast<const float4 *>(trow + e + 4 * g);
+            const float4 q4 = *reinterpret_cast<const float4 *>(s_q + e0 + e + 4 * g);
+            term[4 * g + 0] = exact_term<MODE, METRIC>(q4.x, x4.x);
+            term[4 * g + 1] = exact_term<MODE, METRIC>(q4.y, x4.y);
+            term[4 * g + 2] = exact_term<MODE, METRIC>(q4.z, x4.z);
+            term[4 * g + 3] = exact_term<MODE, METRIC>(q4.w, x4.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc = __dadd_rn(acc, term[j]);
         }
+        for (; e < emax; ++e) acc = __dadd_rn(acc, exact_term<MODE, METRIC>(s_q[e0 + e], trow[e]));
       }
       __syncwarp();
     }
@@ -584,16 +813,16 @@ __global__ void __launch_bounds__(RS_THREADS)
   }
   if (tid == 0) {
     out_counts[q] = kk;
-    uint32_t flag = overflow ? 1u : 0u;
-    const float th = theta[q];
+    uint32_t flag = flags[q];
+    const float th = theta_final[q];
     if (!flag && th < kInf) {
+      // exact distance -> score units of the pre-filter: L2  d = score + |q|^2 ; cosine d = 1 + score
+      double qconst;
+      if (MODE == 0 || METRIC == KDBGPU_METRIC_L2) qconst = (double)qsumsq[q];
+      else qconst = 1.0;
       if (kk < (uint32_t)k) {
-        flag = 2u;  // fewer nominated rows than k although rows were withheld
+        flag = 3u;
       } else {
-        // exact distance -> score units of the pre-filter: L2  d = score + |q|^2 ; cosine d = 1 + score
-        double qconst;
-        if (MODE == 0 || METRIC == KDBGPU_METRIC_L2) qconst = (double)qsumsq[q];
-        else qconst = 1.0;
         const double kth_score = s_d[kk - 1] - qconst;
         if (!((double)th - (double)bound[q] > kth_score)) flag = 3u;
       }
@@ -625,28 +854,40 @@ cudaError_t launch_tc_threshold(const float *gmin, uint32_t n_groups, uint32_t n
   return cudaGetLastError();
 }
 
-size_t tc_rescore_smem(uint32_t dim, uint32_t cap) {
+cudaError_t launch_tc_refine(const void *sub, const uint32_t *sub_cnt, uint32_t grid, const uint32_t *ovf_cnt,
+                             const void *ovf, uint32_t cap, uint32_t nq, int k, const float *theta, const float *bound,
+                             uint32_t *fcnt, uint32_t *fid, uint32_t fcap, float *theta_final, uint32_t *flags,
+                             cudaStream_t stream) {
+  if (grid > 256) return cudaErrorInvalidValue;
+  tc_refine_kernel<<<nq, RF_THREADS, 0, stream>>>(reinterpret_cast<const uint2 *>(sub), sub_cnt, grid, ovf_cnt,
+                                                 reinterpret_cast<const uint2 *>(ovf), cap, nq, k, theta, bound, fcnt,
+                                                 fid, fcap, theta_final, flags);
+  return cudaGetLastError();
+}
+
+size_t tc_rescore_smem(uint32_t dim, uint32_t fcap) {
   uint32_t cap2 = 1;
-  while (cap2 < cap) cap2 <<= 1;
-  return (size_t)cap2 * (sizeof(double) + sizeof(uint32_t)) + (size_t)((dim + 3u) & ~3u) * sizeof(float) +
-         (size_t)RS_WARPS * 32 * 33 * sizeof(float);
+  while (cap2 < fcap) cap2 <<= 1;
+  return (size_t)cap2 * (sizeof(double) + sizeof(uint32_t)) +
+         (size_t)((dim + RS_CHUNK - 1) / RS_CHUNK) * RS_CHUNK * sizeof(float) +
+         (size_t)RS_WARPS * 2 * 32 * RS_LD * sizeof(float);
 }
 
 cudaError_t launch_tc_rescore(const DevIndex &ix, int mode, const float *queries, size_t q_stride, uint32_t nq, int k,
-                              const uint32_t *cnt, const uint32_t *buf_id, uint32_t cap, const float *theta,
+                              const uint32_t *fcnt, const uint32_t *fid, uint32_t fcap, const float *theta_final,
                               const float *bound, const float *qsumsq, uint32_t *out_ids, double *out_scores,
                               uint32_t *out_counts, uint32_t *flags, unsigned long long *n_rescored,
                               cudaStream_t stream) {
-  const size_t smem = tc_rescore_smem(ix.dim, cap);
+  const size_t smem = tc_rescore_smem(ix.dim, fcap);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e;
-#define KDB_RS_LAUNCH(MODEv, METRICv)                                                                          \
-  {                                                                                                            \
-    auto kern = tc_rescore_kernel<MODEv, METRICv>;                                                             \
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
-    if (e != cudaSuccess) return e;                                                                            \
-    kern<<<nq, RS_THREADS, smem, stream>>>(ix, queries, q_stride, nq, k, cnt, buf_id, cap, theta, bound, qsumsq, \
-                                           out_ids, out_scores, out_counts, flags, n_rescored);                \
+#define KDB_RS_LAUNCH(MODEv, METRICv)                                                                              \
+  {                                                                                                                \
+    auto kern = tc_rescore_kernel<MODEv, METRICv>;                                                                 \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    if (e != cudaSuccess) return e;                                                                                \
+    kern<<<nq, RS_THREADS, smem, stream>>>(ix, queries, q_stride, nq, k, fcnt, fid, fcap, theta_final, bound,      \
+                                           qsumsq, out_ids, out_scores, out_counts, flags, n_rescored);            \
   }
   if (mode == 0) KDB_RS_LAUNCH(0, KDBGPU_METRIC_L2)
   else if (ix.metric == KDBGPU_METRIC_COSINE) KDB_RS_LAUNCH(1, KDBGPU_METRIC_COSINE)

@@ -96,9 +96,13 @@ struct FlatTcLaunch {
   int epi;            // 0 store every score (validation), 1 group minima, 2 emit ids below theta
   float *S;
   size_t ldS;
-  float *gmin;         // [nq_pad][n_pad / 32]
+  float *gmin;         // [nq_pad][visited tiles * 8]
+  uint32_t ct_stride;  // visit every ct_stride-th corpus tile (0/1 = all); pass A may sample
   const float *theta;  // [nq_pad]
-  uint32_t *cnt, *buf_id;
+  void *sub;          // [nq_pad][grid][sub slots] {id, score}: nominees per (query, CTA), no atomics
+  uint32_t *sub_cnt;  // [nq_pad][grid]
+  uint32_t *ovf_cnt;  // [nq_pad] spill beyond the sub slots
+  void *ovf;          // [nq_pad][cap]
   uint32_t cap;
   int grid;
 };
@@ -115,9 +119,15 @@ cudaError_t launch_tc_max(const float *sumsq, const float *resid2, uint32_t n, f
 cudaError_t launch_tc_threshold(const float *gmin, uint32_t n_groups, uint32_t nq, int k, const float *qsumsq,
                                 const float *qresid2, const float *xmax, float alpha, int use_norm, uint32_t dp,
                                 float *theta, float *bound, cudaStream_t stream);
-size_t tc_rescore_smem(uint32_t dim, uint32_t cap);
+uint32_t flat_tc_sub_slots();
+uint32_t flat_tc_max_queries();
+cudaError_t launch_tc_refine(const void *sub, const uint32_t *sub_cnt, uint32_t grid, const uint32_t *ovf_cnt,
+                             const void *ovf, uint32_t cap, uint32_t nq, int k, const float *theta, const float *bound,
+                             uint32_t *fcnt, uint32_t *fid, uint32_t fcap, float *theta_final, uint32_t *flags,
+                             cudaStream_t stream);
+size_t tc_rescore_smem(uint32_t dim, uint32_t fcap);
 cudaError_t launch_tc_rescore(const DevIndex &ix, int mode, const float *queries, size_t q_stride, uint32_t nq, int k,
-                              const uint32_t *cnt, const uint32_t *buf_id, uint32_t cap, const float *theta,
+                              const uint32_t *fcnt, const uint32_t *fid, uint32_t fcap, const float *theta_final,
                               const float *bound, const float *qsumsq, uint32_t *out_ids, double *out_scores,
                               uint32_t *out_counts, uint32_t *flags, unsigned long long *n_rescored,
                               cudaStream_t stream);
