@@ -58,6 +58,9 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"])
+    p.add_argument("--workload", default="hnsw", choices=["hnsw", "flat", "hybrid"],
+                   help="hnsw = BASELINE configs[1] (the headline); flat = configs[2] (tensor-core flat top-100); "
+                        "hybrid = configs[4] (1536-d HNSW + 10 %% allow-list) — see bench_extra.py")
     p.add_argument("--overlap", type=int, default=3,
                    help="batches in flight: consecutive steps alternate over this many streams / caller threads")
     return p.parse_args()
@@ -252,6 +255,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.workload != "hnsw":
+        if world > 1:
+            raise SystemExit("--workload flat/hybrid are single-GPU lines")
+        import bench_extra
+        if args.workload == "flat" and args.data_model == "lowrank" and "--data-model" not in sys.argv:
+            args.latent = 0  # configs[2] is quoted on plain random-normal vectors; exact search has no recall issue
+        return (bench_extra.run_flat if args.workload == "flat" else bench_extra.run_hybrid)(args, torch, sys.modules[__name__])
     dist = None
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist_mod

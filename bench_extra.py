@@ -1,0 +1,310 @@
+"""bench_extra.py — the other single-GPU configurations of BASELINE.json, behind `bench.py --workload`:
+
+  flat    configs[2]: 1M x 768-d L2, flat brute force, top-100, 1024 queries per step.  The product path
+          is kdbgpu_flat_search_batch(mode 0 | KDBGPU_FLAT_PREFILTER): tcgen05 bf16 Q x K^T nomination +
+          exact float64 re-score under a certificate — results bit-identical to the exhaustive float64
+          scan (BruteForceIndex.SearchWithScores, reference pkg/core/vector_index.go:104-162).
+  hybrid  configs[4]: 1M x 1536-d cosine HNSW with an allow-list of 10 % selectivity (the dense form of
+          the roaring bitmap DB.FindIDsByFilter returns, reference pkg/core/core.go:1766), top-10.
+
+Same JSON contract as bench.py's main line (value / e2e / roofline / cpu_baseline / clocks).  They are
+extra lines: the driver's headline stays `bench.py` with no --workload flag (configs[1]).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm_gbs": 6650.0, "bf16_tflops": 1650.0, "bf16_tflops_sustained": None, "src": "fallback (B200_PROFILING.md)"}
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            out.update({"hbm_gbs": float(j["hbm_gbs"]), "bf16_tflops": float(j["bf16_tflops"]),
+                        "bf16_tflops_sustained": j.get("bf16_tflops_sustained"), "src": "measured (MEASURED_PEAKS.json)"})
+        except Exception:
+            pass
+    return out
+
+
+def _rows_only_graph(gi, n):
+    """Flat scans need rows and liveness only: every node on level 0, no links."""
+    lv = np.zeros(n + 1, np.int32)
+    lv[0] = -1
+    gi.set_graph(n, lv, np.concatenate([[0], np.arange(n + 1)]).astype(np.uint64), np.zeros(n + 1, np.uint64),
+                 np.zeros(1, np.uint32), 1, 0)
+
+
+def run_flat(args, torch, bench):
+    from kektordb_b200 import GpuIndex
+    N, D, B = args.n, args.dim, args.batch
+    k = args.k if args.k != 10 else 100  # configs[2] asks for top-100
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    ncores = len(os.sched_getaffinity(0))
+    n_total = args.warmup + args.steps
+    X = bench.make_data(torch, N, D, args.latent, args.noise, 42, dev)
+    gi = GpuIndex(D, "euclidean", 8, N, device=local_rank)
+    ffi = bench_ffi()
+    ffi.check(ffi.lib().kdbgpu_upload_vectors_device(gi._h, 1, N, X.data_ptr(), D))
+    _rows_only_graph(gi, N)
+    Qd = bench.make_data(torch, n_total * B, D, args.latent, args.noise, 4242, dev)
+    Qh = torch.empty((n_total * B, D), dtype=torch.float32, pin_memory=True)
+    Qh.copy_(Qd)
+    torch.cuda.synchronize()
+    Q = Qh.numpy()
+
+    if args.impl == "reference":
+        return _flat_reference_arm(args, gi, X, Q, k, ncores)
+
+    # parity (untimed): pre-filter vs exhaustive float64 scan on the GPU, and vs the CPU oracle
+    n_par = 32
+    a = gi.flat_search(Q[:n_par], k, 0)
+    b0 = gi.flat_search(Q[:B], k, 0, prefilter=True)  # also the first warm-up (builds the bf16 mirror)
+    parity = {"queries": n_par, "vs_exhaustive_f64_scan": {
+        "ids_equal": bool(np.array_equal(a[0], b0[0][:n_par])), "scores_bit_equal": bool(np.array_equal(a[1], b0[1][:n_par]))}}
+    for i in range(args.warmup):
+        gi.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True)
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank, args.clock_sampler)
+    sampler.start()
+    comp_ms = tens_ms = 0.0
+    rescored = fallbacks = 0
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_total):
+        _, _, _, st = gi.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True)
+        comp_ms += st.kernel_ms
+        tens_ms += st.hops_l0 / 1e6
+        rescored += st.dist_evals
+        fallbacks += st.hops
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    pk = _peaks()
+    value = B * args.steps / (comp_ms / 1e3)
+    e2e = B * args.steps / e2e_s
+    dp = (D + 63) // 64 * 64
+    n_pad = (N + 255) // 256 * 256
+    flops_full = 2.0 * B * n_pad * dp                      # one full Q x K^T pass (pass B, the dominant kernel)
+    stride = int(os.environ.get("KDBGPU_FLAT_SAMPLE", "0")) or max(1, min(8, 8192 // (6 * k)))
+    flops_step = flops_full * (1.0 + 1.0 / stride)         # + the sampled threshold pass
+    achieved = flops_step * args.steps / (tens_ms / 1e3) / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, par2 = _flat_cpu_baseline(args, gi, Q, k, ncores, b0)
+        parity["vs_cpu_oracle"] = par2
+    line = {
+        "metric": f"top-{k} queries/sec, exact, {N}x{D}-d L2 flat brute force (batch={B})",
+        "value": round(value, 1), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(comp_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 nomination (tcgen05, f32 accumulate) + f64 exact re-score", "data": "synthetic",
+        "recall_at_k": 1.0 if parity["vs_exhaustive_f64_scan"]["ids_equal"] else None,
+        "config": {"workload": f"{N}x{D} L2 flat, top-{k}, batch={B} queries/step, 1xB200 (BASELINE configs[2])",
+                   "data_model": "random-normal, i.i.d. isotropic" if args.latent <= 0 else
+                                 f"random-normal, low-rank covariance (latent {args.latent})",
+                   "l2_policy": "inputs larger than L2: 1.5 GB bf16 corpus + 3.07 GB f32 rows, new queries every step",
+                   "pass_a_tile_stride": stride, "host_cores": ncores,
+                   "value_is": "device time of every kernel of the call (CUDA events inside the library), copies excluded"},
+        "e2e": {"value": round(e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
+                "d2h_bytes_per_step": B * k * 12 + B * 8, "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+        "gpu_launches": 8 * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "flat_tc_kernel (threshold pass + nomination pass)",
+                     "achieved": round(achieved, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None, "peak_source": pk["src"],
+                     "peak_sustained": pk["bf16_tflops_sustained"],
+                     "flops_per_step": flops_step, "tensor_passes_ms_per_step": round(tens_ms / args.steps, 4),
+                     "exact_rescored_rows_per_query": round(rescored / (B * args.steps), 1),
+                     "queries_sent_to_exhaustive_scan": int(fallbacks)},
+        "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def bench_ffi():
+    from kektordb_b200 import ffi
+    return ffi
+
+
+def _oracle_flat_index(gi, X_rows, n):
+    from oracle import oracle as O
+    oi = O.OracleIndex(gi.dim, O.METRIC_L2, 8, 16, O.ARITH_KERNEL, n)
+    lv = np.zeros(n + 1, np.int32)
+    lv[0] = -1
+    g = O.Graph(n, lv, np.concatenate([[0], np.arange(n + 1)]).astype(np.uint64), np.zeros(n + 1, np.uint64),
+                np.zeros(0, np.uint32), np.zeros(n + 1, np.uint8), 1, 0)
+    oi.import_graph(X_rows, g)
+    return oi
+
+
+def _download_rows(gi, n):
+    vec = np.zeros((n + 1, gi.dim), dtype=np.float32)
+    step = 1 << 17
+    for i in range(1, n + 1, step):
+        c = min(step, n + 1 - i)
+        vec[i:i + c] = gi.download_vectors(i, c)
+    return vec
+
+
+def _flat_cpu_baseline(args, gi, Q, k, ncores, gpu_first):
+    oi = _oracle_flat_index(gi, _download_rows(gi, args.n), args.n)
+    n_par = 8
+    wi, ws, wc = oi.flat_search_batch(Q[:n_par], k, mode=0, threads=ncores)
+    par = {"queries": n_par, "ids_equal": bool(np.array_equal(wi, gpu_first[0][:n_par])),
+           "scores_bit_equal": bool(np.array_equal(ws, gpu_first[1][:n_par]))}
+    done, t0 = 0, time.perf_counter()
+    while True:
+        oi.flat_search_batch(Q[done:done + ncores], k, mode=0, threads=ncores)
+        done += ncores
+        el = time.perf_counter() - t0
+        if el >= args.cpu_seconds or done >= 512:
+            break
+    return {"value": round(done / el, 2), "unit": "queries/s", "cores": ncores, "kind": "port",
+            "sample": f"{done} queries of the same workload in {el:.1f} s, oracle restatement of "
+                      "BruteForceIndex.SearchWithScores (float64 scan + sort), one query per thread"}, par
+
+
+def _flat_reference_arm(args, gi, X, Q, k, ncores):
+    oi = _oracle_flat_index(gi, _download_rows(gi, args.n), args.n)
+    gi.close()
+    B = min(args.batch, 2 * ncores)  # a bounded sample per step: the CPU scan needs ~0.5 core-seconds per query
+    for i in range(min(args.warmup, 1)):
+        oi.flat_search_batch(Q[:B], k, mode=0, threads=ncores)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        oi.flat_search_batch(Q[i * B:(i + 1) * B], k, mode=0, threads=ncores)
+    el = time.perf_counter() - t0
+    v = B * args.steps / el
+    print(json.dumps({
+        "impl": "reference", "metric": f"top-{k} queries/sec, exact, {args.n}x{args.dim}-d L2 flat brute force",
+        "value": round(v, 2), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(el / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.n}x{args.dim} L2 flat, top-{k}; each step = {B} queries (bounded sample of the "
+                               f"{args.batch}-query batch)", "parallelism": f"CPU only, {ncores} threads"},
+        "cpu_baseline": {"value": round(v, 2), "unit": "queries/s", "cores": ncores, "kind": "port",
+                         "sample": f"{args.steps} steps of {B} queries, oracle restatement of BruteForceIndex"},
+        "e2e": {"value": round(v, 2), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+def run_hybrid(args, torch, bench):
+    """configs[4]: HNSW + allow-list (10 % selectivity).  Semantics of the reference: non-members are
+    marked visited and skipped before any distance and are never traversed through
+    (hnsw_index.go:2542-2549); the smallest member replaces a non-member entry point (:437-446)."""
+    from kektordb_b200 import GpuIndex, dense_allow_list
+    from oracle import oracle as O
+    N, B, k, ef = args.n, args.batch, args.k, args.ef
+    D = args.dim if args.dim != 768 else 1536
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    ncores = len(os.sched_getaffinity(0))
+    n_total = args.warmup + args.steps
+    X = bench.make_data(torch, N, D, args.latent, args.noise, 42, dev)
+    gi, build_s = bench.build_index(torch, GpuIndex, X, args.m, args.efc, args.build_batch, 1, local_rank)
+    del X
+    Qd = bench.make_data(torch, n_total * B, D, args.latent, args.noise, 4242, dev)
+    Qh = torch.empty((n_total * B, D), dtype=torch.float32, pin_memory=True)
+    Qh.copy_(Qd)
+    torch.cuda.synchronize()
+    Q = Qh.numpy()
+    sel = float(os.environ.get("KDB_SELECTIVITY", "0.1"))
+    member = np.random.default_rng(7).random(N + 1) < sel
+    member[0] = False
+    allow = dense_allow_list(np.where(member)[0], N)
+
+    if args.impl == "reference":
+        oi = bench.oracle_from_gpu(gi, args.m, args.efc, O.ARITH_AVX2)
+        gi.close()
+        for i in range(args.warmup):
+            oi.search_batch(Q[i * B:(i + 1) * B], k, ef, allow=allow, threads=ncores)
+        t0 = time.perf_counter()
+        for i in range(args.warmup, n_total):
+            oi.search_batch(Q[i * B:(i + 1) * B], k, ef, allow=allow, threads=ncores)
+        el = time.perf_counter() - t0
+        v = B * args.steps / el
+        print(json.dumps({"impl": "reference", "metric": f"top-{k} queries/sec, {N}x{D}-d cosine HNSW + allow-list {sel:.0%}",
+                          "value": round(v, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"{N}x{D} cosine HNSW M={args.m} efSearch={ef} top-{k}, allow-list {sel:.0%}",
+                                     "parallelism": f"CPU only, {ncores} threads"},
+                          "cpu_baseline": {"value": round(v, 1), "unit": "queries/s", "cores": ncores, "kind": "port",
+                                           "sample": f"{args.steps} steps of {B} queries, oracle port"},
+                          "e2e": {"value": round(v, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return 0
+
+    ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, allow, ef)
+    n_gt = min(256, B)
+    gt_ids, _, gt_cnt, _ = gi.flat_search(Q[:n_gt], k, 1, allow, prefilter=True)
+    recall = bench.recall_at_k(ids0[:n_gt], gt_ids)
+    only_members = bool(member[ids0[ids0 > 0]].all())
+    for i in range(args.warmup):
+        gi.SearchWithScores(Q[i * B:(i + 1) * B], k, allow, ef)
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank, args.clock_sampler)
+    sampler.start()
+    kern_ms, E, H, H0 = 0.0, 0, 0, 0
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_total):
+        _, _, _, st = gi.SearchWithScores(Q[i * B:(i + 1) * B], k, allow, ef)
+        kern_ms += st.kernel_ms
+        E, H, H0 = E + st.dist_evals, H + st.hops, H0 + st.hops_l0
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    pk = _peaks()
+    stride = (D + 127) // 128 * 128
+    byts = E * stride * 4 + H0 * 2 * args.m * 4 + (H - H0) * args.m * 4
+    achieved = byts / (kern_ms / 1e3) / 1e9
+    cpu = parity = None
+    if not args.no_cpu_baseline:
+        oi = bench.oracle_from_gpu(gi, args.m, args.efc, O.ARITH_KERNEL)
+        npar = min(256, B)
+        pid, psc, pcnt, pst = oi.search_batch(Q[:npar], k, ef, allow=allow, threads=ncores)
+        parity = {"queries": npar, "ids_equal": bool(np.array_equal(pid, ids0[:npar])),
+                  "scores_bit_equal": bool(np.array_equal(psc, sc0[:npar])),
+                  "counts_equal": bool(np.array_equal(pcnt.astype(np.uint32), cnt0[:npar])),
+                  "results_are_allow_list_members": only_members}
+        oi.set_arith(O.ARITH_AVX2)
+        oi.search_batch(Q[:npar], k, ef, allow=allow, threads=ncores)
+        done, t1, i = 0, time.perf_counter(), 0
+        while True:
+            oi.search_batch(Q[(i % n_total) * B:(i % n_total + 1) * B], k, ef, allow=allow, threads=ncores)
+            done += B
+            i += 1
+            el = time.perf_counter() - t1
+            if el >= args.cpu_seconds or i >= 64:
+                break
+        cpu = {"value": round(done / el, 1), "unit": "queries/s", "cores": ncores, "kind": "port",
+               "sample": f"{done} queries in {el:.1f} s, oracle port, AVX2-FMA order, same graph and allow-list"}
+    line = {
+        "metric": f"top-{k} queries/sec @ recall@{k}, {N}x{D}-d cosine HNSW + allow-list ({sel:.0%} selectivity)",
+        "value": round(B * args.steps / (kern_ms / 1e3), 1), "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(kern_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "recall_at_10": round(recall, 4),
+        "config": {"workload": f"{N}x{D} cosine, HNSW M={args.m} efC={args.efc} efSearch={ef}, top-{k}, allow-list "
+                               f"Bernoulli({sel}) seed 7 shared by the batch, batch={B} (BASELINE configs[4])",
+                   "l2_policy": "inputs larger than L2", "build_seconds": round(build_s, 2), "host_cores": ncores,
+                   "value_is": "device time of the traversal kernel (CUDA events inside the library), one batch in flight"},
+        "e2e": {"value": round(B * args.steps / e2e_s, 1), "unit": "queries/s",
+                "h2d_bytes_per_step": B * D * 4 + allow.nbytes, "d2h_bytes_per_step": B * k * 12 + B * 4 + 40,
+                "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk["src"],
+                     "dist_evals_per_query": round(E / (B * args.steps), 1), "hops_per_query": round(H / (B * args.steps), 1)},
+        "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    return 0

@@ -125,7 +125,8 @@ int kdbgpu_distance_batch(kdbgpu_index *, const float *query, const uint32_t *id
  * arithmetic above and a per-query certificate proves no other row can enter the top k (a query
  * whose certificate does not close is answered by the exhaustive scan).  stats->dist_evals = exact
  * float64 evaluations, stats->hops = queries answered by the exhaustive scan, stats->kernel_ms =
- * device time of the two tensor-core passes. */
+ * device time of all kernels of the call (copies excluded), stats->hops_l0 = device time of the
+ * tensor-core passes alone, in nanoseconds. */
 #define KDBGPU_FLAT_PREFILTER 0x10
 int kdbgpu_flat_search_batch(kdbgpu_index *, const float *queries, uint32_t nq, int k, int mode,
                              const uint64_t *allow, size_t allow_words, uint32_t *out_ids,

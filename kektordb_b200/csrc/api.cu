@@ -418,13 +418,14 @@ int tc_prepare(kdbgpu_index *h, int mode, const uint32_t *d_allow, int k, TcPlan
 
 // H2D of `c` raw queries, normalisation where the mode asks for it, bf16 copy + norms
 int tc_stage_queries(kdbgpu_index *h, const float *queries, uint32_t c, uint32_t c_pad, int mode, const TcPlan &P,
-                     cudaStream_t s) {
+                     cudaStream_t s, cudaEvent_t after_h2d = nullptr) {
   CUDA_TRY(h->q_raw.reserve((size_t)c * h->dim));
   CUDA_TRY(h->q_prep.reserve((size_t)c * h->stride));
   CUDA_TRY(h->tq_bf16.reserve((size_t)c_pad * P.dp));
   CUDA_TRY(h->tq_sumsq.reserve(c_pad));
   CUDA_TRY(h->tq_resid2.reserve(c_pad));
   CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries, (size_t)c * h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (after_h2d) CUDA_TRY(cudaEventRecord(after_h2d, s));
   CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
                                mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
   const bool prepared = mode == 1 && h->metric == KDBGPU_METRIC_COSINE;
@@ -452,7 +453,7 @@ FlatTcLaunch tc_launch_desc(kdbgpu_index *h, const TcPlan &P, uint32_t c, uint32
 
 int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, const uint32_t *d_allow,
                         uint32_t *out_ids, double *out_scores, uint32_t *out_counts, uint64_t *evals,
-                        uint64_t *fallbacks, float *gemm_ms) {
+                        uint64_t *fallbacks, float *gemm_ms, float *compute_ms) {
   cudaStream_t s = h->stream;
   TcPlan P;
   int rc = tc_prepare(h, mode, d_allow, k, &P, s);
@@ -505,10 +506,12 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
   const bool prepared = mode == 1 && h->metric == KDBGPU_METRIC_COSINE;
   std::vector<uint32_t> flags(nq, 0u);
   *gemm_ms = 0.f;
+  *compute_ms = 0.f;
+  cudaEvent_t ev_c0 = h->sws[0].ev[0], ev_c1 = h->sws[0].ev[1];  // handle is held exclusively: no search uses them
   for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
     const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
     const uint32_t c_pad = (c + P.bm - 1) / P.bm * P.bm;
-    rc = tc_stage_queries(h, queries + (size_t)q0 * h->dim, c, c_pad, mode, P, s);
+    rc = tc_stage_queries(h, queries + (size_t)q0 * h->dim, c, c_pad, mode, P, s, ev_c0);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(h->t_cnt.p, 0, (size_t)c_pad * sizeof(uint32_t), s));
     FlatTcLaunch L = tc_launch_desc(h, P, c, c_pad);
@@ -540,6 +543,7 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     CUDA_TRY(launch_tc_rescore(ix, mode, prepared ? h->q_prep.p : h->q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim,
                                c, k, h->t_fcnt.p, h->t_fid.p, fcap, h->t_thf.p, h->t_bound.p, h->tq_sumsq.p,
                                h->out_ids.p, h->out_scores.p, h->out_counts.p, h->t_flags.p, h->t_nres.p, s));
+    CUDA_TRY(cudaEventRecord(ev_c1, s));
     CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
                              cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
@@ -550,6 +554,8 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
     *gemm_ms += ms;
+    cudaEventElapsedTime(&ms, ev_c0, ev_c1);
+    *compute_ms += ms;
   }
   unsigned long long nres = 0;
   CUDA_TRY(cudaMemcpy(&nres, h->t_nres.p, sizeof nres, cudaMemcpyDeviceToHost));
@@ -1044,11 +1050,11 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
   }
   CUDA_TRY(cudaEventRecord(h->ev[0], s));
   uint64_t evals = 0, fallbacks = 0;
-  float gemm_ms = 0.f;
+  float gemm_ms = 0.f, compute_ms = 0.f;
   int rc;
   if (prefilter)
     rc = flat_prefilter_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts, &evals, &fallbacks,
-                             &gemm_ms);
+                             &gemm_ms, &compute_ms);
   else {
     rc = flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
     evals = (uint64_t)nq * h->n;
@@ -1060,7 +1066,10 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
     stats->dist_evals = evals;
     stats->hops = fallbacks;
     cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
-    stats->kernel_ms = prefilter ? gemm_ms : stats->total_ms;
+    // pre-filter: kernel_ms = every kernel of the call (no copies); hops_l0 = the two tensor-core
+    // passes + threshold alone, in nanoseconds
+    stats->kernel_ms = prefilter && compute_ms > 0.f ? compute_ms : stats->total_ms;
+    stats->hops_l0 = prefilter ? (uint64_t)(gemm_ms * 1e6f) : 0;
   }
   return KDBGPU_OK;
 }

@@ -687,9 +687,9 @@ __device__ __forceinline__ double exact_term(float qf, float xf) {
   }
 }
 
-constexpr int RS_THREADS = 128;
+constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_CHUNK = 128;           // floats of every row per step: 512 contiguous bytes per request
+constexpr int RS_CHUNK = 64;            // floats of every row per step: 256 contiguous bytes per request
 constexpr int RS_LD = RS_CHUNK + 4;     // padded tile row (conflict-free LDS.128 with lane = row)
 
 // One CTA per query: exact distances of the surviving rows in the reference's arithmetic (flat.cu's
@@ -733,12 +733,14 @@ __global__ void __launch_bounds__(RS_THREADS)
     // rows are stored with stride >= dim rounded up to 128 floats, zero padded (kdb_internal.cuh), so a
     // whole 512-byte chunk of every row can be requested; lane l moves bytes [16l, 16l+16) of each row
     auto issue = [&](uint32_t ci) {
-      float *dst = tile + (size_t)(ci & 1u) * 32 * RS_LD + 4 * lane;
+      constexpr int LPR = RS_CHUNK / 4;  // lanes (16 bytes each) per row chunk
+      constexpr int RPI = 32 / LPR;      // rows covered by one warp-wide request
+      float *dst = tile + (size_t)(ci & 1u) * 32 * RS_LD + (lane / LPR) * RS_LD + 4 * (lane % LPR);
 #pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const uint32_t id = __shfl_sync(0xffffffffu, mine, r);
+      for (int r = 0; r < 32; r += RPI) {
+        const uint32_t id = __shfl_sync(0xffffffffu, mine, r + lane / LPR);
         if (id != 0u) {
-          const float *src = ix.vecs + (size_t)id * ix.stride + (size_t)ci * RS_CHUNK + 4 * lane;
+          const float *src = ix.vecs + (size_t)id * ix.stride + (size_t)ci * RS_CHUNK + 4 * (lane % LPR);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + r * RS_LD)), "l"(src) : "memory");
         }
       }

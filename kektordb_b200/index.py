@@ -221,7 +221,7 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_flat_search_batch(self._handle(), _ptr(q), nq, k, mode, _ptr(allow),
                                                      0 if allow is None else allow.size, _ptr(ids), _ptr(scores),
                                                      _ptr(counts), C.byref(st)))
-        return ids, scores, counts, SearchStats(st.dist_evals, st.hops, 0, st.kernel_ms, st.total_ms)
+        return ids, scores, counts, SearchStats(st.dist_evals, st.hops, st.hops_l0, st.kernel_ms, st.total_ms)
 
     def flat_prefilter_scores(self, query, mode: int = 0):
         """Validation hook: approximate scores [nq, n] of the tensor-core pass and the certified
