@@ -34,6 +34,15 @@ def _peaks():
     return out
 
 
+def _flat_traffic():
+    """DRAM bytes of one nomination-pass launch from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_flat.json")
+    try:
+        return int(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def _rows_only_graph(gi, n):
     """Flat scans need rows and liveness only: every node on level 0, no links."""
     lv = np.zeros(n + 1, np.int32)
@@ -117,7 +126,7 @@ def run_flat(args, torch, bench):
         "gpu_launches": 8 * args.steps,
         "roofline": {"bound": "tensor", "kernel": "flat_tc_kernel (threshold pass + nomination pass)",
                      "achieved": round(achieved, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None, "peak_source": pk["src"],
+                     "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": _flat_traffic(), "peak_source": pk["src"],
                      "peak_sustained": pk["bf16_tflops_sustained"],
                      "flops_per_step": flops_step, "tensor_passes_ms_per_step": round(tens_ms / args.steps, 4),
                      "exact_rescored_rows_per_query": round(rescored / (B * args.steps), 1),
