@@ -58,9 +58,11 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"])
-    p.add_argument("--workload", default="hnsw", choices=["hnsw", "flat", "hybrid"],
+    p.add_argument("--workload", default="hnsw", choices=["hnsw", "flat", "hybrid", "quantized"],
                    help="hnsw = BASELINE configs[1] (the headline); flat = configs[2] (tensor-core flat top-100); "
-                        "hybrid = configs[4] (1536-d HNSW + 10 %% allow-list) — see bench_extra.py")
+                        "hybrid = configs[4] (1536-d HNSW + 10 %% allow-list); quantized = configs[1]'s corpus held "
+                        "as int8 (cosine) or float16 (euclidean) rows, SURVEY.md §8 f-4 — see bench_extra.py")
+    p.add_argument("--precision", default="int8", choices=["int8", "float16"], help="--workload quantized only")
     p.add_argument("--overlap", type=int, default=3,
                    help="batches in flight: consecutive steps alternate over this many streams / caller threads")
     return p.parse_args()
@@ -104,9 +106,9 @@ def build_schedule(n, ef_const, bmax):
     return sched
 
 
-def build_index(torch, GpuIndex, X, m, efc, bmax, level_seed, device_index):
+def build_index(torch, GpuIndex, X, m, efc, bmax, level_seed, device_index, metric="cosine"):
     n, dim = X.shape
-    gi = GpuIndex(dim, "cosine", m, n, device=device_index)
+    gi = GpuIndex(dim, metric, m, n, device=device_index)
     u = np.random.default_rng(level_seed).random(n)
     pos = 0
     t0 = time.time()
@@ -257,11 +259,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if args.workload != "hnsw":
         if world > 1:
-            raise SystemExit("--workload flat/hybrid are single-GPU lines")
+            raise SystemExit("--workload flat/hybrid/quantized are single-GPU lines")
         import bench_extra
         if args.workload == "flat" and args.data_model == "lowrank" and "--data-model" not in sys.argv:
             args.latent = 0  # configs[2] is quoted on plain random-normal vectors; exact search has no recall issue
-        return (bench_extra.run_flat if args.workload == "flat" else bench_extra.run_hybrid)(args, torch, sys.modules[__name__])
+        fn = {"flat": bench_extra.run_flat, "hybrid": bench_extra.run_hybrid, "quantized": bench_extra.run_quantized}
+        return fn[args.workload](args, torch, sys.modules[__name__])
     dist = None
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist_mod

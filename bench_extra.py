@@ -7,6 +7,10 @@
   hybrid  configs[4]: 1M x 1536-d cosine HNSW with an allow-list of 10 % selectivity (the dense form of
           the roaring bitmap DB.FindIDsByFilter returns, reference pkg/core/core.go:1766), top-10.
 
+  quantized  configs[1]'s corpus and graph with the rows held as int8 (cosine) or float16 (euclidean) —
+          the reference's other two precisions (distance.Int8 / distance.Float16).  The
+          traversal kernel is HBM-bound, so 1 / 2 bytes per element instead of 4 is the lever.
+
 Same JSON contract as bench.py's main line (value / e2e / roofline / cpu_baseline / clocks).  They are
 extra lines: the driver's headline stays `bench.py` with no --workload flag (configs[1]).
 """
@@ -313,6 +317,200 @@ def run_hybrid(args, torch, bench):
         "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk["src"],
                      "dist_evals_per_query": round(E / (B * args.steps), 1), "hops_per_query": round(H / (B * args.steps), 1)},
+        "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+def run_quantized(args, torch, bench):
+    """the HNSW traversal over int8 (cosine) / float16 (euclidean) rows.  Distances follow
+    the reference's arithmetic for the precision (hnsw_index.go:2398-2449, distance_go.go:93-118); int8
+    results are bit-identical to the CPU path in any summation order (integer dot), float16 ones in
+    kernel order.  The graph is the float32 GPU build over the same rows (device-side construction is
+    float32-only; DB.Compress would rebuild with the quantized distances) — both arms search the same graph."""
+    import threading
+    from kektordb_b200 import GpuIndex, ffi
+    from oracle import oracle as O
+    N, D, B, k, ef = args.n, args.dim, args.batch, args.k, args.ef
+    prec = args.precision
+    metric = "cosine" if prec == "int8" else "euclidean"
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    ncores = len(os.sched_getaffinity(0))
+    n_total = args.warmup + args.steps
+    X = bench.make_data(torch, N, D, args.latent, args.noise, 42, dev)
+    gf, build_s = bench.build_index(torch, GpuIndex, X, args.m, args.efc, args.build_batch, 1, local_rank, metric)
+    del X
+    Qd = bench.make_data(torch, n_total * B, D, args.latent, args.noise, 4242, dev)
+    Qh = torch.empty((n_total * B, D), dtype=torch.float32, pin_memory=True)
+    Qh.copy_(Qd)
+    torch.cuda.synchronize()
+    Q = Qh.numpy()
+    # exact float32 ground truth for recall, from the float32 index
+    n_gt = min(256, B)
+    gt_ids, _, _, _ = gf.flat_search(Q[:n_gt], k, 1, prefilter=True)
+    # the quantized mirror: stored float32 rows -> TrainQuantizer -> converted on the device; same topology
+    V = _download_rows(gf, N)
+    graph = gf.get_graph()
+    gf.close()
+    gi = GpuIndex(D, metric, args.m, N, device=local_rank, precision=prec)
+    t0 = time.time()
+    abs_max = gi.TrainQuantizer(V[1:]) if prec == "int8" else None
+    step = 1 << 17
+    for i in range(1, N + 1, step):
+        gi.upload_vectors(i, V[i:i + step])
+    gi.set_graph(*graph)
+    stage_s = time.time() - t0
+    del V
+    oprec = O.PREC_I8 if prec == "int8" else O.PREC_F16
+
+    def oracle_index(arith):
+        n, levels, node_row, row_off, nbrs, entry, max_level = graph
+        rows = np.zeros((n + 1, D), dtype=np.int8 if prec == "int8" else np.uint16)
+        for i in range(1, n + 1, step):
+            c = min(step, n + 1 - i)
+            rows[i:i + c] = gi.download_rows_raw(i, c)
+        oi = O.OracleIndex(D, O.METRIC_COSINE if prec == "int8" else O.METRIC_L2, args.m, args.efc, arith, n, precision=oprec)
+        if prec == "int8":
+            oi.set_quantizer(abs_max)
+        oi.import_graph(rows, O.Graph(n, levels, node_row, row_off, nbrs, np.zeros(n + 1, np.uint8), entry, max_level))
+        return oi
+
+    metric_name = f"top-{k} queries/sec @ recall@{k}, {N}x{D}-d {metric} HNSW over {prec} rows (M={args.m}, efSearch={ef}, batch={B})"
+    if args.impl == "reference":
+        oi = oracle_index(O.ARITH_AVX2)
+        gi.close()
+        for i in range(args.warmup):
+            oi.search_batch(Q[i * B:(i + 1) * B], k, ef, threads=ncores)
+        t1 = time.perf_counter()
+        for i in range(args.warmup, n_total):
+            oi.search_batch(Q[i * B:(i + 1) * B], k, ef, threads=ncores)
+        el = time.perf_counter() - t1
+        v = B * args.steps / el
+        print(json.dumps({"impl": "reference", "metric": metric_name, "value": round(v, 1), "unit": "queries/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": prec, "data": "synthetic",
+                          "config": {"workload": f"{N}x{D} {metric} HNSW over {prec} rows, efSearch={ef}, top-{k}",
+                                     "parallelism": f"CPU only, {ncores} threads"},
+                          "cpu_baseline": {"value": round(v, 1), "unit": "queries/s", "cores": ncores, "kind": "port",
+                                           "sample": f"{args.steps} steps of {B} queries, oracle port"},
+                          "e2e": {"value": round(v, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return 0
+
+    ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, None, ef)
+    recall = bench.recall_at_k(ids0[:n_gt], gt_ids)
+    # ---- device-resident timing: consecutive batches alternate over n_ov streams (as bench.py's headline)
+    n_ov = max(1, min(4, args.overlap))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_ov)]
+    d_ids = [torch.zeros((B, k), dtype=torch.int32, device=dev) for _ in range(n_ov)]
+    d_sc = [torch.zeros((B, k), dtype=torch.float64, device=dev) for _ in range(n_ov)]
+    d_cnt = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(n_ov)]
+
+    def step_device(i):
+        j = i % n_ov
+        gi.search_device(Qd[i * B:(i + 1) * B].data_ptr(), B, k, ef, d_ids[j].data_ptr(), d_sc[j].data_ptr(),
+                         d_cnt[j].data_ptr(), streams[j].cuda_stream)
+
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank, args.clock_sampler)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(streams[0])
+    for s_ in streams[1:]:
+        s_.wait_event(ev0)
+    for i in range(args.warmup, n_total):
+        step_device(i)
+    for s_ in streams[1:]:
+        streams[0].wait_stream(s_)
+    ev1.record(streams[0])
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    st = gi.last_search_stats()
+    # isolated launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(streams[0])
+    for r in range(5):
+        gi.search_device(Qd[r * B:(r + 1) * B].data_ptr(), B, k, ef, d_ids[0].data_ptr(), d_sc[0].data_ptr(),
+                         d_cnt[0].data_ptr(), streams[0].cuda_stream)
+    e1.record(streams[0])
+    torch.cuda.synchronize()
+    iso_ms = e0.elapsed_time(e1) / 5
+    # ---- e2e through the C ABI with host buffers, n_ov caller threads
+    for i in range(args.warmup):
+        gi.SearchWithScores(Q[i * B:(i + 1) * B], k, None, ef)
+
+    def worker(j):
+        torch.cuda.set_device(local_rank)
+        for i in range(args.warmup + j, n_total, n_ov):
+            gi.SearchWithScores(Q[i * B:(i + 1) * B], k, None, ef)
+
+    ws = [threading.Thread(target=worker, args=(j,)) for j in range(n_ov)]
+    t1 = time.perf_counter()
+    for t in ws:
+        t.start()
+    for t in ws:
+        t.join()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t1
+    clocks = sampler.stop()
+    pk = _peaks()
+    esize = 1 if prec == "int8" else 2
+    row_bytes = (D * esize + 127) // 128 * 128
+    byts = st.dist_evals * (row_bytes + (4 if prec == "int8" else 0)) + st.hops_l0 * 2 * args.m * 4 + \
+        (st.hops - st.hops_l0) * args.m * 4
+    launch_ms = dev_ms / args.steps
+    achieved = byts / (launch_ms / 1e3) / 1e9
+    cpu = parity = None
+    if not args.no_cpu_baseline:
+        oi = oracle_index(O.ARITH_KERNEL)
+        npar = min(256, B)
+        pid, psc, pcnt, pst = oi.search_batch(Q[:npar], k, ef, threads=ncores)
+        parity = {"queries": npar, "ids_equal": bool(np.array_equal(pid, ids0[:npar])),
+                  "scores_bit_equal": bool(np.array_equal(psc, sc0[:npar])),
+                  "counts_equal": bool(np.array_equal(pcnt.astype(np.uint32), cnt0[:npar]))}
+        oi.set_arith(O.ARITH_AVX2)
+        rid, rsc, _, _ = oi.search_batch(Q[:npar], k, ef, threads=ncores)
+        parity["ids_equal_vs_reference_order"] = bool(np.array_equal(rid, ids0[:npar]))
+        same = rid == ids0[:npar]
+        parity["max_abs_score_diff_vs_reference_order"] = float(np.max(np.abs(rsc[same] - sc0[:npar][same]))) if same.any() else None
+        done, t2, i = 0, time.perf_counter(), 0
+        while True:
+            oi.search_batch(Q[(i % n_total) * B:(i % n_total + 1) * B], k, ef, threads=ncores)
+            done += B
+            i += 1
+            el = time.perf_counter() - t2
+            if el >= args.cpu_seconds or i >= 64:
+                break
+        cpu = {"value": round(done / el, 1), "unit": "queries/s", "cores": ncores, "kind": "port",
+               "sample": f"{done} queries in {el:.1f} s, oracle port over the same {prec} rows and graph, "
+                         + ("exact int32 dot (dotProductGoInt8), " if prec == "int8" else "AVX2-FMA + F16C order (lib.rs:101-141), ")
+                         + "one query per thread"}
+    line = {
+        "metric": metric_name, "value": round(B * args.steps / (dev_ms / 1e3), 1), "unit": "queries/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(launch_ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "i8 dot -> f64" if prec == "int8" else "f16 rows, f32 accumulate",
+        "data": "synthetic", "recall_at_10": round(recall, 4),
+        "config": {"workload": f"{N}x{D} {metric}, HNSW M={args.m} efC={args.efc} efSearch={ef}, top-{k}, batch={B}, rows held as "
+                               f"{prec} ({row_bytes} B per row); recall is against the exact float32 scan",
+                   "graph": "float32 GPU build over the same rows (kdbgpu_add_batch); same graph for both arms",
+                   "quantizer_abs_max": abs_max, "l2_policy": "inputs larger than L2, new query batch every step",
+                   "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "stage_seconds": round(stage_s, 2),
+                   "host_cores": ncores},
+        "e2e": {"value": round(B * args.steps / e2e_s, 1), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
+                "d2h_bytes_per_step": B * k * 12 + B * 4 + 40, "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk["src"],
+                     "algorithmic_bytes_per_launch": int(byts), "avg_launch_ms": round(launch_ms, 4),
+                     "isolated_launch_ms": round(iso_ms, 4),
+                     "isolated_frac": round(byts / (iso_ms / 1e3) / 1e9 / pk["hbm_gbs"], 4),
+                     "dist_evals_per_query": round(st.dist_evals / B, 1), "hops_per_query": round(st.hops / B, 1)},
         "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

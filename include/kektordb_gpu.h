@@ -42,6 +42,13 @@ extern "C" {
 #define KDBGPU_METRIC_L2 0     /* "euclidean": squared, no sqrt (:57-68) */
 #define KDBGPU_METRIC_COSINE 1 /* "cosine": 1 - dot on unit vectors (:122-128) */
 
+/* distance.PrecisionType (distance_go.go:41-46).  The reference offers float16 for "euclidean"
+ * only and int8 for "cosine" only (float16Funcs / int8Funcs, :139-146). */
+#define KDBGPU_PRECISION_F32 0
+#define KDBGPU_PRECISION_F16 1  /* rows = float16 bits (uint16), squaredEuclideanGoFloat16 (:93-105)      */
+#define KDBGPU_PRECISION_INT8 2 /* rows = int8 + per-row f32 norm, dotProductGoInt8 (:108-118) scaled as  */
+                                /* in searchLayerUnlocked (hnsw_index.go:2398-2449)                       */
+
 typedef struct kdbgpu_index kdbgpu_index;
 
 /* Exact per-batch counters, for the roofline accounting of SURVEY.md §8(d). */
@@ -64,13 +71,38 @@ const char *kdbgpu_version(void);
 /* One handle mirrors one hnsw.Index on one GPU.  m is the index's M (mMax0 = 2*m, :149),
  * capacity the highest internal id the mirror can hold. */
 int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacity, kdbgpu_index **out);
+/* hnsw.New with its precision argument (hnsw_index.go:138).  A float16 / int8 handle keeps the rows
+ * in their stored form (2 / 1 bytes per element: the traversal kernel is HBM-bound, so bytes per row
+ * are what it pays for) and answers kdbgpu_search_batch / kdbgpu_distance_batch with the reference's
+ * arithmetic for that precision; the flat scan and device-side construction are float32-only. */
+int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m, uint32_t capacity,
+                           kdbgpu_index **out);
 int kdbgpu_index_destroy(kdbgpu_index *);
+int kdbgpu_index_precision(const kdbgpu_index *);
+/* Quantizer.AbsMax of an int8 index (pkg/core/distance/quantizer.go:19-22), as trained by
+ * Quantizer.Train (:49-125) on the Go side.  Needed before float32 rows or queries are converted. */
+int kdbgpu_set_quantizer(kdbgpu_index *, float abs_max);
+/* Quantizer.Train (quantizer.go:49-125) itself, for hosts that would rather not sort on the CPU: n
+ * float32 rows [n][dim] (host memory, or device memory with row_stride in floats), the reference's
+ * stride sample, AbsMax = the 99.9th-percentile |value| (exact rank select on the device).  Sets the
+ * handle's quantizer and returns it in *abs_max (may be NULL).  This is what TrainQuantizer does in
+ * DB.Compress before the int8 rows are inserted (pkg/core/core.go:1224-1232). */
+int kdbgpu_train_quantizer(kdbgpu_index *, const float *rows, uint32_t n, float *abs_max);
+int kdbgpu_train_quantizer_device(kdbgpu_index *, const float *d_rows, size_t row_stride, uint32_t n, float *abs_max);
 
 /* ---- staging: the GPU mirror of Index.nodes / Node.vec (hnsw_node.go:13-39) ----------- */
 /* Rows exactly as the reference stores them (already unit-normalised for cosine,
  * hnsw_index.go:485-493); row i is internal id first_id + i.  Source of the bytes in the
  * reference: VectorArena.GetBytes (pkg/storage/mmap/arena.go:378). */
 int kdbgpu_upload_vectors(kdbgpu_index *, uint32_t first_id, uint32_t count, const float *rows);
+/* On a float16 / int8 handle the two calls above take float32 rows and convert them on the device as
+ * Add / AddBatch do (float16.Fromfloat32, Quantizer.Quantize + computeInt8Norm; hnsw_index.go:497-520,
+ * :1553-1577, :3371-3377).  kdbgpu_upload_rows_raw takes the rows already in stored form — the bytes of
+ * VectorArena.GetBytes for that precision ([count][dim] float32 / uint16 / int8, no padding). */
+int kdbgpu_upload_rows_raw(kdbgpu_index *, uint32_t first_id, uint32_t count, const void *rows);
+int kdbgpu_download_rows_raw(kdbgpu_index *, uint32_t first_id, uint32_t count, void *rows);
+/* int8: quantizedNorms[first_id .. first_id+count) (hnsw_index.go:87, :3371-3377) */
+int kdbgpu_download_norms(kdbgpu_index *, uint32_t first_id, uint32_t count, float *norms);
 /* Same, from device memory on the handle's device (row_stride in floats). */
 int kdbgpu_upload_vectors_device(kdbgpu_index *, uint32_t first_id, uint32_t count, const float *d_rows,
                                  size_t row_stride);

@@ -100,8 +100,12 @@ struct DevBuf {
 struct kdbgpu_index {
   int device = 0;
   int dim = 0, metric = 0, m = 0;
+  int precision = KDBGPU_PRECISION_F32;
+  int kind = KIND_L2_F32;
   uint32_t capacity = 0;
-  uint32_t stride = 0;
+  uint32_t stride = 0;     // 32-bit words per row slot / prepared query (multiple of 128)
+  uint32_t row_words = 0;  // 32-bit words between stored rows (= stride for float32)
+  float abs_max = 0.f;     // Quantizer.AbsMax (int8)
   uint32_t n = 0;
   uint32_t entry = 0;
   int max_level = -1;
@@ -118,7 +122,7 @@ struct kdbgpu_index {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;  // completion of the last launch that used this workspace
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    DevBuf<float> q_raw, q_prep;
+    DevBuf<float> q_raw, q_prep, qnorms;
     DevBuf<uint32_t> out_ids, out_counts, allow, visited, work_counter;
     DevBuf<double> out_scores;
     DevBuf<HeapEntry> cand_overflow;
@@ -135,7 +139,7 @@ struct kdbgpu_index {
       if (h_out) cudaFreeHost(h_out);
       h_out = nullptr;
       h_out_bytes = 0;
-      q_raw.release(); q_prep.release(); out_ids.release(); out_counts.release(); allow.release();
+      q_raw.release(); q_prep.release(); qnorms.release(); out_ids.release(); out_counts.release(); allow.release();
       visited.release(); work_counter.release(); out_scores.release(); cand_overflow.release();
       stats.release(); err_flag.release();
     }
@@ -147,7 +151,7 @@ struct kdbgpu_index {
   unsigned ws_next = 0;
   int last_ws = -1;
 
-  DevBuf<float> vecs;
+  DevBuf<float> vecs, norms, conv_tmp, qnorm1;
   DevBuf<uint32_t> adj0, upper_adj, upper_first, deleted;
   DevBuf<int8_t> levels;
   bool has_deleted = false;
@@ -185,6 +189,9 @@ struct kdbgpu_index {
   DevIndex dev() const {
     DevIndex d;
     d.vecs = vecs.p;
+    d.norms = norms.p;
+    d.row_words = row_words;
+    d.kind = kind;
     d.adj0 = adj0.p;
     d.upper_adj = upper_adj.p;
     d.upper_first = upper_first.p;
@@ -305,6 +312,7 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
   }
   SearchArgs a;
   a.queries = d_q_prepared;
+  a.qnorms = w.qnorms.p;
   a.nq = nq;
   a.k = k;
   a.ef = ef;
@@ -322,6 +330,22 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
   a.work_counter = w.work_counter.p;
   a.err_flag = d_err;
   CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
+  return KDBGPU_OK;
+}
+
+// query preparation of searchInternal (hnsw_index.go:401-434) into w.q_prep (+ w.qnorms for int8)
+int prepare_queries(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_raw, uint32_t nq, cudaStream_t s) {
+  CUDA_TRY(w.q_prep.reserve((size_t)nq * h->stride));
+  if (h->precision == KDBGPU_PRECISION_F32) {
+    CUDA_TRY(launch_prep_queries(d_q_raw, (size_t)h->dim, w.q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
+    return KDBGPU_OK;
+  }
+  if (h->precision == KDBGPU_PRECISION_INT8) {
+    if (h->abs_max == 0.f) return fail(KDBGPU_ERR_STATE, "int8 index without a trained quantizer (kdbgpu_set_quantizer)");
+    CUDA_TRY(w.qnorms.reserve(nq));
+  }
+  CUDA_TRY(launch_convert_rows(d_q_raw, (size_t)h->dim, w.q_prep.p, h->stride, nq, (uint32_t)h->dim, h->kind,
+                               h->metric == KDBGPU_METRIC_COSINE, h->abs_max, w.qnorms.p, true, s));
   return KDBGPU_OK;
 }
 
@@ -601,8 +625,20 @@ const char *kdbgpu_last_error(void) { return g_last_error.c_str(); }
 const char *kdbgpu_version(void) { return "kektordb_gpu 0.1.0 sm_100a"; }
 
 int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacity, kdbgpu_index **out) {
+  return kdbgpu_index_create_ex(device, dim, metric, KDBGPU_PRECISION_F32, m, capacity, out);
+}
+
+int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m, uint32_t capacity,
+                           kdbgpu_index **out) {
   if (!out) return fail(KDBGPU_ERR_INVALID, "out is NULL");
   *out = nullptr;
+  // GetFloat16Func / GetInt8Func (distance_go.go:159-177): float16 is Euclidean only, int8 Cosine only
+  if (precision != KDBGPU_PRECISION_F32 && precision != KDBGPU_PRECISION_F16 && precision != KDBGPU_PRECISION_INT8)
+    return fail(KDBGPU_ERR_INVALID, "unknown precision %d", precision);
+  if (precision == KDBGPU_PRECISION_F16 && metric != KDBGPU_METRIC_L2)
+    return fail(KDBGPU_ERR_INVALID, "metric 'cosine' not supported for float16 precision");
+  if (precision == KDBGPU_PRECISION_INT8 && metric != KDBGPU_METRIC_COSINE)
+    return fail(KDBGPU_ERR_INVALID, "metric 'euclidean' not supported for int8 precision");
   if (dim <= 0 || dim > 8192) return fail(KDBGPU_ERR_INVALID, "dim %d out of range (1..8192)", dim);
   if (metric != KDBGPU_METRIC_L2 && metric != KDBGPU_METRIC_COSINE)
     return fail(KDBGPU_ERR_INVALID, "unknown metric %d", metric);
@@ -631,7 +667,17 @@ int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacit
   h->metric = metric;
   h->m = m;
   h->capacity = capacity;
-  h->stride = ((uint32_t)dim + 127u) & ~127u;  // whole float4 columns for every lane (searcher.cuh)
+  h->precision = precision;
+  if (precision == KDBGPU_PRECISION_F32) {
+    h->kind = metric == KDBGPU_METRIC_COSINE ? KIND_COS_F32 : KIND_L2_F32;
+    h->stride = ((uint32_t)dim + 127u) & ~127u;  // whole float4 columns for every lane (searcher.cuh)
+    h->row_words = h->stride;
+  } else {
+    const uint32_t esize = precision == KDBGPU_PRECISION_F16 ? 2u : 1u;
+    h->kind = precision == KDBGPU_PRECISION_F16 ? KIND_L2_F16 : KIND_COS_I8;
+    h->row_words = (((uint32_t)dim * esize + 127u) & ~127u) / 4u;  // row pitch: whole 128-byte lines
+    h->stride = (h->row_words + 127u) & ~127u;                     // shared-memory slot: whole 16-byte columns per lane
+  }
   h->num_sms = prop.multiProcessorCount;
   const char *env;
   if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
@@ -649,7 +695,8 @@ int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacit
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&w.ev[i]);
   }
   const size_t n1 = (size_t)capacity + 1;
-  if (e == cudaSuccess) e = h->vecs.reserve(n1 * h->stride, true);
+  if (e == cudaSuccess) e = h->vecs.reserve(n1 * h->row_words + 128, true);
+  if (e == cudaSuccess && precision == KDBGPU_PRECISION_INT8) e = h->norms.reserve(n1, true);
   if (e == cudaSuccess) e = h->adj0.reserve(n1 * (size_t)(2 * m), true);
   if (e == cudaSuccess) e = h->levels.reserve(n1);
   if (e == cudaSuccess) e = cudaMemset(h->levels.p, 0xff, n1);
@@ -682,6 +729,9 @@ int kdbgpu_index_destroy(kdbgpu_index *h) {
     if (w.stream) cudaStreamDestroy(w.stream);
   }
   h->vecs.release();
+  h->norms.release();
+  h->conv_tmp.release();
+  h->qnorm1.release();
   h->adj0.release();
   h->upper_adj.release();
   h->upper_first.release();
@@ -736,6 +786,24 @@ int kdbgpu_upload_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, co
   DeviceGuard g(h->device);
   CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   h->tc_valid = false;
+  if (h->precision != KDBGPU_PRECISION_F32) {
+    // float32 in, stored form out: what Add / AddBatch do before the row reaches the arena
+    // (hnsw_index.go:497-520, :1553-1577); chunked through a device staging buffer
+    if (h->precision == KDBGPU_PRECISION_INT8 && h->abs_max == 0.f)
+      return fail(KDBGPU_ERR_STATE, "int8 index without a trained quantizer (kdbgpu_set_quantizer)");
+    const uint32_t chunk = 1u << 16;
+    CUDA_TRY(h->conv_tmp.reserve((size_t)(count < chunk ? count : chunk) * h->dim));
+    for (uint32_t i = 0; i < count; i += chunk) {
+      const uint32_t c = count - i < chunk ? count - i : chunk;
+      CUDA_TRY(cudaMemcpyAsync(h->conv_tmp.p, rows + (size_t)i * h->dim, (size_t)c * h->dim * sizeof(float),
+                               cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(launch_convert_rows(h->conv_tmp.p, (size_t)h->dim, h->vecs.p + (size_t)(first_id + i) * h->row_words,
+                                   h->row_words, c, (uint32_t)h->dim, h->kind, false, h->abs_max,
+                                   h->norms.p ? h->norms.p + first_id + i : nullptr, false, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return KDBGPU_OK;
+  }
   // padded columns were zeroed at creation and are never written
   CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), rows,
                              (size_t)h->dim * sizeof(float), (size_t)h->dim * sizeof(float), count,
@@ -743,6 +811,166 @@ int kdbgpu_upload_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, co
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return KDBGPU_OK;
 }
+
+int kdbgpu_upload_rows_raw(kdbgpu_index *h, uint32_t first_id, uint32_t count, const void *rows) {
+  if (!h || (!rows && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (first_id == 0 || (uint64_t)first_id + count - 1 > h->capacity)
+    return fail(KDBGPU_ERR_INVALID, "ids %u..%llu outside 1..%u", first_id, (unsigned long long)first_id + count - 1,
+                h->capacity);
+  if (count == 0) return KDBGPU_OK;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->tc_valid = false;
+  const size_t esize = h->precision == KDBGPU_PRECISION_F32 ? 4 : (h->precision == KDBGPU_PRECISION_F16 ? 2 : 1);
+  const size_t row_bytes = (size_t)h->dim * esize;
+  CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->row_words, (size_t)h->row_words * sizeof(float), rows,
+                             row_bytes, row_bytes, count, cudaMemcpyHostToDevice, h->stream));
+  if (h->precision == KDBGPU_PRECISION_INT8)
+    CUDA_TRY(launch_int8_norms(h->vecs.p + (size_t)first_id * h->row_words, h->row_words, count, (uint32_t)h->dim,
+                               h->norms.p + first_id, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_download_rows_raw(kdbgpu_index *h, uint32_t first_id, uint32_t count, void *rows) {
+  if (!h || (!rows && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (first_id == 0 || (uint64_t)first_id + count - 1 > h->capacity)
+    return fail(KDBGPU_ERR_INVALID, "ids outside 1..%u", h->capacity);
+  if (count == 0) return KDBGPU_OK;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t esize = h->precision == KDBGPU_PRECISION_F32 ? 4 : (h->precision == KDBGPU_PRECISION_F16 ? 2 : 1);
+  const size_t row_bytes = (size_t)h->dim * esize;
+  CUDA_TRY(cudaMemcpy2D(rows, row_bytes, h->vecs.p + (size_t)first_id * h->row_words,
+                        (size_t)h->row_words * sizeof(float), row_bytes, count, cudaMemcpyDeviceToHost));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_download_norms(kdbgpu_index *h, uint32_t first_id, uint32_t count, float *norms) {
+  if (!h || (!norms && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (h->precision != KDBGPU_PRECISION_INT8) return fail(KDBGPU_ERR_INVALID, "norms exist for int8 indexes only");
+  if (first_id == 0 || (uint64_t)first_id + count - 1 > h->capacity)
+    return fail(KDBGPU_ERR_INVALID, "ids outside 1..%u", h->capacity);
+  if (count == 0) return KDBGPU_OK;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(norms, h->norms.p + first_id, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_set_quantizer(kdbgpu_index *h, float abs_max) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (h->precision != KDBGPU_PRECISION_INT8) return fail(KDBGPU_ERR_INVALID, "the quantizer belongs to int8 indexes");
+  if (!(abs_max >= 0.f)) return fail(KDBGPU_ERR_INVALID, "AbsMax must be >= 0");
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  h->abs_max = abs_max;
+  return KDBGPU_OK;
+}
+
+namespace {
+// The sample of Quantizer.Train (pkg/core/distance/quantizer.go:62-94): everything up to 10 000 rows,
+// above that every step-th row (10 % of the rows, capped at 25 000, floor 10 000).
+void train_sample(uint32_t n, uint32_t *step, uint32_t *count) {
+  *step = 1;
+  *count = n;
+  if (n > 10000u) {
+    uint32_t target = n / 10u;
+    if (target > 25000u) target = 25000u;
+    if (target < 10000u) target = 10000u;
+    uint32_t st = n / target;
+    if (st < 1) st = 1;
+    uint32_t c = 0;
+    for (uint64_t i = 0; i < n; i += st) {
+      ++c;
+      if (c >= target) break;
+    }
+    *step = st;
+    *count = c;
+  }
+}
+// AbsMax = the value at index int(len * 0.999) of the ascending |values| of the sample (:96-125) —
+// an exact 3-pass radix select on the device instead of the reference's sort.  Sampled row i is
+// d_rows[i * step * row_stride ..].
+int train_select(kdbgpu_index *h, const float *d_rows, size_t row_stride, uint32_t count, uint32_t step,
+                 float *abs_max) {
+  const uint64_t total = (uint64_t)count * (uint64_t)h->dim;
+  long long qi = (long long)((double)total * 0.999);
+  if (qi >= (long long)total) qi = (long long)total - 1;
+  if (qi < 0) qi = 0;
+  DevBuf<unsigned long long> hist;
+  CUDA_TRY(hist.reserve(2048));
+  std::vector<unsigned long long> hh(2048);
+  uint64_t rem = (uint64_t)qi + 1;  // 1-based rank of the wanted value
+  uint32_t prefix = 0;
+  int shift = 32, rc = KDBGPU_OK;
+  cudaStream_t s = h->stream;
+  for (int pass = 0; pass < 3 && rc == KDBGPU_OK; ++pass) {
+    const int bits = pass < 2 ? 11 : 10;
+    const int hi_shift = shift;
+    shift -= bits;
+    cudaError_t e = cudaMemsetAsync(hist.p, 0, 2048 * sizeof(unsigned long long), s);
+    if (e == cudaSuccess)
+      e = launch_abs_hist(d_rows, row_stride, count, step, (uint32_t)h->dim, prefix, hi_shift, shift, bits, hist.p, s);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(hh.data(), hist.p, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      rc = fail(KDBGPU_ERR_CUDA, "quantizer training: %s", cudaGetErrorString(e));
+      break;
+    }
+    uint32_t b = 0;
+    for (; b < (1u << bits); ++b) {
+      if (hh[b] >= rem) break;
+      rem -= hh[b];
+    }
+    if (b == (1u << bits)) {
+      rc = fail(KDBGPU_ERR_INVALID, "quantizer training saw non-finite values");
+      break;
+    }
+    prefix |= b << shift;
+  }
+  hist.release();
+  if (rc != KDBGPU_OK) return rc;
+  float v;
+  memcpy(&v, &prefix, sizeof v);
+  h->abs_max = v;
+  if (abs_max) *abs_max = v;
+  return KDBGPU_OK;
+}
+}  // namespace
+
+int kdbgpu_train_quantizer(kdbgpu_index *h, const float *rows, uint32_t n, float *abs_max) {
+  if (!h || (!rows && n)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (h->precision != KDBGPU_PRECISION_INT8) return fail(KDBGPU_ERR_INVALID, "the quantizer belongs to int8 indexes");
+  if (n == 0) return KDBGPU_OK;  // "Empty dataset provided for training. Skipping." (:52-55)
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  uint32_t step, count;
+  train_sample(n, &step, &count);
+  // only the sampled rows travel; they land densely, so the select runs over them with step 1
+  CUDA_TRY(h->conv_tmp.reserve((size_t)count * h->dim));
+  CUDA_TRY(cudaMemcpy2DAsync(h->conv_tmp.p, (size_t)h->dim * sizeof(float), rows, (size_t)step * h->dim * sizeof(float),
+                             (size_t)h->dim * sizeof(float), count, cudaMemcpyHostToDevice, h->stream));
+  return train_select(h, h->conv_tmp.p, (size_t)h->dim, count, 1, abs_max);
+}
+
+int kdbgpu_train_quantizer_device(kdbgpu_index *h, const float *d_rows, size_t row_stride, uint32_t n, float *abs_max) {
+  if (!h || (!d_rows && n)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (h->precision != KDBGPU_PRECISION_INT8) return fail(KDBGPU_ERR_INVALID, "the quantizer belongs to int8 indexes");
+  if (row_stride < (size_t)h->dim) return fail(KDBGPU_ERR_INVALID, "bad stride");
+  if (n == 0) return KDBGPU_OK;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  uint32_t step, count;
+  train_sample(n, &step, &count);
+  return train_select(h, d_rows, row_stride, count, step, abs_max);
+}
+
+int kdbgpu_index_precision(const kdbgpu_index *h) { return h ? h->precision : -1; }
 
 int kdbgpu_upload_vectors_device(kdbgpu_index *h, uint32_t first_id, uint32_t count, const float *d_rows,
                                  size_t row_stride) {
@@ -754,6 +982,15 @@ int kdbgpu_upload_vectors_device(kdbgpu_index *h, uint32_t first_id, uint32_t co
   DeviceGuard g(h->device);
   CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
   h->tc_valid = false;
+  if (h->precision != KDBGPU_PRECISION_F32) {
+    if (h->precision == KDBGPU_PRECISION_INT8 && h->abs_max == 0.f)
+      return fail(KDBGPU_ERR_STATE, "int8 index without a trained quantizer (kdbgpu_set_quantizer)");
+    CUDA_TRY(launch_convert_rows(d_rows, row_stride, h->vecs.p + (size_t)first_id * h->row_words, h->row_words, count,
+                                 (uint32_t)h->dim, h->kind, false, h->abs_max,
+                                 h->norms.p ? h->norms.p + first_id : nullptr, false, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return KDBGPU_OK;
+  }
   CUDA_TRY(cudaMemcpy2DAsync(h->vecs.p + (size_t)first_id * h->stride, (size_t)h->stride * sizeof(float), d_rows,
                              row_stride * sizeof(float), (size_t)h->dim * sizeof(float), count,
                              cudaMemcpyDeviceToDevice, h->stream));
@@ -900,7 +1137,6 @@ int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int 
   cudaStream_t s = w.stream;
   CUDA_TRY(cudaStreamWaitEvent(s, w.done, 0));
   CUDA_TRY(w.q_raw.reserve((size_t)nq * h->dim));
-  CUDA_TRY(w.q_prep.reserve((size_t)nq * h->stride));
   // results, counters and the error flag live in one device blob -> a single D2H copy
   const size_t nk = (size_t)nq * k;
   const size_t o_ids = nk * sizeof(double);
@@ -925,7 +1161,10 @@ int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     if (rc) return rc;
     d_allow = w.allow.p;
   }
-  CUDA_TRY(launch_prep_queries(w.q_raw.p, (size_t)h->dim, w.q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
+  {
+    int prc = prepare_queries(h, w, w.q_raw.p, nq, s);
+    if (prc) return prc;
+  }
   CUDA_TRY(cudaEventRecord(w.ev[1], s));
   int rc = enqueue_search(h, w, w.q_prep.p, nq, k, ef, d_allow, allow_first, reinterpret_cast<uint32_t *>(blob + o_ids),
                           reinterpret_cast<double *>(blob), reinterpret_cast<uint32_t *>(blob + o_counts), s,
@@ -986,9 +1225,9 @@ int kdbgpu_search_batch_device(kdbgpu_index *h, const float *d_queries, uint32_t
     return KDBGPU_OK;
   }
   CUDA_TRY(cudaStreamWaitEvent(s, w.done, 0));
-  CUDA_TRY(w.q_prep.reserve((size_t)nq * h->stride));
-  CUDA_TRY(launch_prep_queries(d_queries, (size_t)h->dim, w.q_prep.p, nq, (uint32_t)h->dim, h->stride, h->metric, s));
-  int rc = enqueue_search(h, w, w.q_prep.p, nq, k, ef, reinterpret_cast<const uint32_t *>(d_allow), allow_first_id,
+  int rc = prepare_queries(h, w, d_queries, nq, s);
+  if (rc) return rc;
+  rc = enqueue_search(h, w, w.q_prep.p, nq, k, ef, reinterpret_cast<const uint32_t *>(d_allow), allow_first_id,
                           d_out_ids, d_out_scores, d_out_counts, s);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(w.done, s));
@@ -1006,11 +1245,22 @@ int kdbgpu_distance_batch(kdbgpu_index *h, const float *query, const uint32_t *i
   CUDA_TRY(h->ids_tmp.reserve(n));
   CUDA_TRY(h->dist_tmp.reserve(n));
   CUDA_TRY(cudaMemsetAsync(h->q_prep.p, 0, (size_t)h->stride * sizeof(float), s));
-  CUDA_TRY(cudaMemcpyAsync(h->q_prep.p, query, (size_t)h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (h->precision == KDBGPU_PRECISION_F32) {
+    CUDA_TRY(cudaMemcpyAsync(h->q_prep.p, query, (size_t)h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  } else {
+    // the prepared float32 query goes through the precision adaptation of searchInternal (:417-434)
+    if (h->precision == KDBGPU_PRECISION_INT8 && h->abs_max == 0.f)
+      return fail(KDBGPU_ERR_STATE, "int8 index without a trained quantizer (kdbgpu_set_quantizer)");
+    CUDA_TRY(h->q_raw.reserve((size_t)h->dim));
+    CUDA_TRY(h->qnorm1.reserve(1));
+    CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, query, (size_t)h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_convert_rows(h->q_raw.p, (size_t)h->dim, h->q_prep.p, h->stride, 1, (uint32_t)h->dim, h->kind, false,
+                                 h->abs_max, h->qnorm1.p, true, s));
+  }
   CUDA_TRY(cudaMemcpyAsync(h->ids_tmp.p, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   DevIndex ix = h->dev();
   ix.n = h->capacity;  // any staged row may be addressed, graph or not
-  CUDA_TRY(launch_distance_batch(ix, h->q_prep.p, h->ids_tmp.p, n, h->dist_tmp.p, s));
+  CUDA_TRY(launch_distance_batch(ix, h->q_prep.p, h->qnorm1.p, h->ids_tmp.p, n, h->dist_tmp.p, s));
   CUDA_TRY(cudaMemcpyAsync(out, h->dist_tmp.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return KDBGPU_OK;
@@ -1024,6 +1274,8 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
   if (nq == 0) return KDBGPU_OK;
   if (!queries || !out_ids || !out_scores || !out_counts) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (k <= 0 || k > 1024) return fail(KDBGPU_ERR_INVALID, "flat k %d outside 1..1024", k);
+  if (h->precision != KDBGPU_PRECISION_F32)  // BruteForceIndex holds []float32 only (vector_index.go:104-162)
+    return fail(KDBGPU_ERR_INVALID, "the flat scan exists for float32 indexes only");
   const bool prefilter = (mode & KDBGPU_FLAT_PREFILTER) != 0;
   mode &= ~KDBGPU_FLAT_PREFILTER;
   if (mode != 0 && mode != 1) return fail(KDBGPU_ERR_INVALID, "mode %d", mode);
@@ -1078,6 +1330,7 @@ int kdbgpu_flat_prefilter_scores(kdbgpu_index *h, const float *queries, uint32_t
                                  float *out_bound) {
   if (!h || !queries || !out_scores) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (mode != 0 && mode != 1) return fail(KDBGPU_ERR_INVALID, "mode %d", mode);
+  if (h->precision != KDBGPU_PRECISION_F32) return fail(KDBGPU_ERR_INVALID, "the flat scan exists for float32 indexes only");
   if (!h->has_graph || h->n == 0) return fail(KDBGPU_ERR_STATE, "no rows staged");
   if (nq == 0) return KDBGPU_OK;
   if ((uint64_t)nq * h->n > (1ull << 30)) return fail(KDBGPU_ERR_INVALID, "validation hook: nq * n too large");
@@ -1214,6 +1467,8 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   if (ef_const <= 0) ef_const = 200;  // hnsw.New default (hnsw_index.go:143-145)
   if (ef_const > 2048) return fail(KDBGPU_ERR_INVALID, "ef_const %d too large (max 2048)", ef_const);
   if (h->m < 2) return fail(KDBGPU_ERR_INVALID, "construction needs m >= 2");
+  if (h->precision != KDBGPU_PRECISION_F32)
+    return fail(KDBGPU_ERR_INVALID, "device-side construction exists for float32 indexes only (stage the graph with kdbgpu_set_graph)");
   std::unique_lock<std::shared_mutex> lk(h->mu);
   if ((uint64_t)h->n + count > h->capacity)
     return fail(KDBGPU_ERR_INVALID, "batch of %u does not fit: %u of %u ids used", count, h->n, h->capacity);
@@ -1471,6 +1726,8 @@ int kdbgpu_get_graph(kdbgpu_index *h, int32_t *levels, uint64_t *node_row, uint6
 int kdbgpu_download_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, float *rows) {
   if (!h || (!rows && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if ((uint64_t)first_id + count - 1 > h->capacity) return fail(KDBGPU_ERR_INVALID, "id range outside capacity");
+  if (h->precision != KDBGPU_PRECISION_F32)
+    return fail(KDBGPU_ERR_INVALID, "float32 rows exist for float32 indexes only (use kdbgpu_download_rows_raw)");
   if (count == 0) return KDBGPU_OK;
   std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);

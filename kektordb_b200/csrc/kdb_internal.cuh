@@ -8,7 +8,12 @@
 //   upper_adj  [rows][degu]      u32, degu = M; node i, level l>=1 -> row upper_first[i] + l-1
 //   levels     [(cap+1)]         i8,  -1 = nil node
 //   deleted    bitset over ids (u32 words)
+// float16 / int8 indexes (distance.Float16 / distance.Int8, reference distance_go.go:41-46) keep the
+// same arrays; `vecs` then holds the rows in their stored form (float16 bits / int8) with a pitch of
+// row_words 32-bit words (row bytes rounded up to 128), and int8 indexes add norms[(cap+1)] f32
+// (quantizedNorms, hnsw_index.go:87).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -16,14 +21,21 @@
 
 namespace kdb {
 
+// distance kind = (metric, precision) pair the reference offers (float32Funcs / float16Funcs /
+// int8Funcs, distance_go.go:133-146).  The first two values equal KDBGPU_METRIC_*.
+enum : int { KIND_L2_F32 = 0, KIND_COS_F32 = 1, KIND_L2_F16 = 2, KIND_COS_I8 = 3 };
+
 struct DevIndex {
-  const float *vecs;
+  const float *vecs;        // rows as 32-bit words (f32 values, or packed float16 bits / int8)
+  const float *norms;       // int8 only: computeInt8Norm of every stored row (hnsw_index.go:3371)
+  uint32_t row_words;       // 32-bit words between consecutive rows (= stride for float32)
+  int kind;                 // KIND_*
   const uint32_t *adj0;
   const uint32_t *upper_adj;
   const uint32_t *upper_first;
   const int8_t *levels;
   const uint32_t *deleted;  // may be nullptr
-  uint32_t stride;          // floats per row
+  uint32_t stride;          // 32-bit words per shared-memory row slot / prepared query (multiple of 128)
   uint32_t dim;
   uint32_t n;  // highest id
   uint32_t deg0, degu;
@@ -41,7 +53,8 @@ struct __align__(16) HeapEntry {
 };
 
 struct SearchArgs {
-  const float *queries;  // prepared [nq][stride]
+  const float *queries;  // prepared [nq][stride] (32-bit words: f32, or packed float16 / int8)
+  const float *qnorms;   // int8 only: query-side norm per query (hnsw_index.go:2405-2413)
   uint32_t nq;
   int k, ef;
   const uint32_t *allow;  // nullptr = nil allow-list
@@ -73,8 +86,23 @@ cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchT
                           cudaStream_t stream);
 cudaError_t launch_prep_queries(const float *in, size_t in_stride, float *out, uint32_t nq, uint32_t dim,
                                 uint32_t stride, int metric, cudaStream_t stream);
-cudaError_t launch_distance_batch(const DevIndex &ix, const float *query_prepared, const uint32_t *ids,
-                                  uint32_t n, double *out, cudaStream_t stream);
+cudaError_t launch_distance_batch(const DevIndex &ix, const float *query_prepared, const float *qnorm,
+                                  const uint32_t *ids, uint32_t n, double *out, cudaStream_t stream);
+// float16 / int8 indexes: f32 rows -> stored form.  normalise = the cosine query preparation of
+// searchInternal (hnsw_index.go:406-414); conversion = float16.Fromfloat32 (:427-430) or
+// Quantizer.Quantize (quantizer.go:135-160).  out rows have a pitch of out_words 32-bit words and are
+// zero padded; norms (int8, may be nullptr) receives computeInt8Norm per row, with 0 mapped to 1 when
+// query_side is set (:2410-2413).
+cudaError_t launch_convert_rows(const float *in, size_t in_stride, float *out, size_t out_words, uint32_t rows,
+                                uint32_t dim, int kind, bool normalise, float abs_max, float *norms,
+                                bool query_side, cudaStream_t stream);
+// one radix-select pass of Quantizer.Train's quantile (see abs_hist_kernel)
+cudaError_t launch_abs_hist(const float *rows, size_t row_stride, uint32_t n_sample, uint32_t step, uint32_t dim,
+                            uint32_t prefix, int hi_shift, int shift, int bits, unsigned long long *hist,
+                            cudaStream_t stream);
+// int8 rows already in stored form -> norms[row] = computeInt8Norm
+cudaError_t launch_int8_norms(const float *rows, size_t row_words, uint32_t count, uint32_t dim, float *norms,
+                              cudaStream_t stream);
 cudaError_t launch_merge_topk(int n_shards, uint32_t nq, int k, const uint32_t *ids, const double *scores,
                               const uint32_t *counts, uint32_t *out_ids, double *out_scores,
                               uint32_t *out_counts, cudaStream_t stream);
@@ -180,21 +208,23 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// The distance arithmetic ("kernel order"; oracle KDBO_ARITH_KERNEL restates it):
-// lane l owns the float4 columns c = l, l+32, ...; component j of column c feeds accumulator
-// (4l + j) by FMA in increasing c; lane partial (a0+a1)+(a2+a3); xor-butterfly 16,8,4,2,1.
-// Replaces dotProductAsDistanceGonum / squaredEuclideanDistanceGo
-// (pkg/core/distance/distance_go.go:122-128, :57-68) and the Rust kernels behind
-// native/compute/include/kektordb_compute.h:8-9.
-template <int METRIC>
-__device__ __forceinline__ float warp_reduce_row(const float4 *__restrict__ q4, const float4 *__restrict__ r4,
-                                                 uint32_t nchunks, int lane) {
+// The distance arithmetic ("kernel order"; oracle KDBO_ARITH_KERNEL restates it).
+// A lane owns the 16-byte columns c = l, l+32, ... of the row.
+//   float32: column = 4 elements; component j of column c feeds accumulator (4l + j) by FMA in
+//            increasing c; lane partial (a0+a1)+(a2+a3).
+//   float16: column = 8 elements (4 words x {lo, hi}); element i of the column feeds accumulator
+//            (8l + i); lane partial ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7)).  Differences are taken in
+//            f32 on the widened halves, as squaredEuclideanGoFloat16 does (distance_go.go:93-105).
+//   int8:    column = 16 elements; exact int32 dot (dotProductGoInt8, distance_go.go:108-118) — any
+//            order gives the same bits; the partial travels bit-cast in a float.
+// Then the xor-butterfly 16,8,4,2,1 (integer add for int8).
+// Replaces dotProductAsDistanceGonum / squaredEuclideanDistanceGo / squaredEuclideanGoFloat16 /
+// dotProductGoInt8 and the Rust kernels behind native/compute/include/kektordb_compute.h:8-11.
+template <int KIND>
+struct LaneAcc {
   float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
-#pragma unroll 4
-  for (uint32_t c = lane; c < nchunks; c += 32) {
-    const float4 a = q4[c];
-    const float4 b = r4[c];
-    if (METRIC == KDBGPU_METRIC_COSINE) {
+  __device__ __forceinline__ void add(const float4 &a, const float4 &b) {
+    if (KIND == KIND_COS_F32) {
       ax = __fmaf_rn(a.x, b.x, ax);
       ay = __fmaf_rn(a.y, b.y, ay);
       az = __fmaf_rn(a.z, b.z, az);
@@ -208,15 +238,74 @@ __device__ __forceinline__ float warp_reduce_row(const float4 *__restrict__ q4, 
       aw = __fmaf_rn(dw, dw, aw);
     }
   }
-  float s = __fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw));
+  __device__ __forceinline__ float lane_sum() const { return __fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw)); }
+};
+__device__ __forceinline__ float2 f16x2_widen(float word) {
+  const uint32_t u = __float_as_uint(word);
+  const __half2 h = *reinterpret_cast<const __half2 *>(&u);
+  return __half22float2(h);  // .x = low half = even element
+}
+template <>
+struct LaneAcc<KIND_L2_F16> {
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  __device__ __forceinline__ void add2(float qa, float xb, int w) {
+    const float2 q = f16x2_widen(qa), x = f16x2_widen(xb);
+    const float d0 = __fsub_rn(q.x, x.x), d1 = __fsub_rn(q.y, x.y);
+    a[2 * w] = __fmaf_rn(d0, d0, a[2 * w]);
+    a[2 * w + 1] = __fmaf_rn(d1, d1, a[2 * w + 1]);
+  }
+  __device__ __forceinline__ void add(const float4 &q, const float4 &b) {
+    add2(q.x, b.x, 0);
+    add2(q.y, b.y, 1);
+    add2(q.z, b.z, 2);
+    add2(q.w, b.w, 3);
+  }
+  __device__ __forceinline__ float lane_sum() const {
+    return __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])),
+                     __fadd_rn(__fadd_rn(a[4], a[5]), __fadd_rn(a[6], a[7])));
+  }
+};
+template <>
+struct LaneAcc<KIND_COS_I8> {
+  int a0 = 0, a1 = 0;
+  __device__ __forceinline__ void add(const float4 &q, const float4 &b) {
+    a0 = __dp4a(__float_as_int(q.x), __float_as_int(b.x), a0);
+    a1 = __dp4a(__float_as_int(q.y), __float_as_int(b.y), a1);
+    a0 = __dp4a(__float_as_int(q.z), __float_as_int(b.z), a0);
+    a1 = __dp4a(__float_as_int(q.w), __float_as_int(b.w), a1);
+  }
+  __device__ __forceinline__ float lane_sum() const { return __int_as_float(a0 + a1); }
+};
+template <int KIND>
+__device__ __forceinline__ float warp_sum(float s) {
+  if (KIND == KIND_COS_I8) return __int_as_float(__reduce_add_sync(0xffffffffu, __float_as_int(s)));
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
   return s;
 }
-// DistanceFuncF32 result: float64(sum) for L2 (distance_go.go:67), 1.0 - float64(dot) for cosine (:127)
-template <int METRIC>
-__device__ __forceinline__ double to_distance(float s) {
-  return METRIC == KDBGPU_METRIC_COSINE ? 1.0 - static_cast<double>(s) : static_cast<double>(s);
+template <int KIND>
+__device__ __forceinline__ float warp_reduce_row(const float4 *__restrict__ q4, const float4 *__restrict__ r4,
+                                                 uint32_t nchunks, int lane) {
+  LaneAcc<KIND> acc;
+#pragma unroll 4
+  for (uint32_t c = lane; c < nchunks; c += 32) acc.add(q4[c], r4[c]);
+  return warp_sum<KIND>(acc.lane_sum());
+}
+// int8 cosine distance from the exact dot and the two norms (searchLayerUnlocked distFn,
+// hnsw_index.go:2421-2449; distanceBetweenNodes :319-336): float64 divide, clamp, 1 - similarity
+__device__ __forceinline__ double int8_distance(int dot, float qnorm, float stored_norm) {
+  if (stored_norm == 0.f) return 1.0;
+  double sim = __ddiv_rn(static_cast<double>(dot), __dmul_rn(static_cast<double>(qnorm), static_cast<double>(stored_norm)));
+  if (sim > 1.0) sim = 1.0;
+  if (sim < -1.0) sim = -1.0;
+  return __dsub_rn(1.0, sim);
+}
+// DistanceFunc result from the reduced value `s`: float64(sum) for L2 (distance_go.go:67, :104),
+// 1.0 - float64(dot) for cosine f32 (:127), the norm-scaled form for int8
+template <int KIND>
+__device__ __forceinline__ double to_distance(float s, float qnorm = 0.f, float stored_norm = 0.f) {
+  if (KIND == KIND_COS_I8) return int8_distance(__float_as_int(s), qnorm, stored_norm);
+  return KIND == KIND_COS_F32 ? 1.0 - static_cast<double>(s) : static_cast<double>(s);
 }
 #endif  // __CUDACC__
 

@@ -65,28 +65,131 @@ __global__ void prep_queries_kernel(const float *__restrict__ in, size_t in_stri
   }
 }
 
-// The literal inner-loop hook: out[i] = distFn(query, ids[i]) (hnsw_index.go:2393-2396) — one warp
+// The literal inner-loop hook: out[i] = distFn(query, ids[i]) (hnsw_index.go:2388-2454) — one warp
 // per candidate row, 128-bit loads straight from HBM, same kernel-order reduction.
-template <int METRIC>
-__global__ void distance_batch_kernel(const DevIndex ix, const float *__restrict__ query,
+template <int KIND>
+__global__ void distance_batch_kernel(const DevIndex ix, const float *__restrict__ query, const float *__restrict__ qnorm,
                                       const uint32_t *__restrict__ ids, uint32_t n, double *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
   float4 *q4 = reinterpret_cast<float4 *>(smem);
-  const uint32_t nchunks = ix.stride >> 2;
+  const uint32_t nchunks = ix.row_words >> 2;
   for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) q4[c] = reinterpret_cast<const float4 *>(query)[c];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t wpb = blockDim.x >> 5;
+  const float qn = KIND == KIND_COS_I8 ? qnorm[0] : 0.f;
   for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
     const uint32_t id = ids[i];
     if (id == 0 || id > ix.n) {
       if (lane == 0) out[i] = __longlong_as_double(0x7ff8000000000000LL);  // nil node: NaN
       continue;
     }
-    const float s = warp_reduce_row<METRIC>(q4, reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.stride),
-                                            nchunks, lane);
-    if (lane == 0) out[i] = to_distance<METRIC>(s);
+    const float s = warp_reduce_row<KIND>(q4, reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.row_words),
+                                          nchunks, lane);
+    if (lane == 0) out[i] = to_distance<KIND>(s, qn, KIND == KIND_COS_I8 ? ix.norms[id] : 0.f);
   }
+}
+
+// f32 rows -> stored form of a float16 / int8 index (one warp per row), optionally after the cosine
+// query normalisation of searchInternal (hnsw_index.go:406-414, same arithmetic as
+// prep_queries_kernel).  float16: float16.Fromfloat32 = IEEE round-to-nearest-even (:427-430,
+// :501-505).  int8: Quantizer.Quantize (quantizer.go:135-160): f32 divide, f32 multiply by 127,
+// clip, round half away from zero in float64; norm = f32(sqrt(f64(sum of squares))) (:3371-3377).
+__global__ void convert_rows_kernel(const float *__restrict__ in, size_t in_stride, float *__restrict__ out,
+                                    size_t out_words, uint32_t rows, uint32_t dim, int kind, int normalise,
+                                    float abs_max, float *__restrict__ norms, int query_side) {
+  const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float *src = in + (size_t)r * in_stride;
+  uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)r * out_words);
+  float inv = 1.0f;
+  bool scale = false;
+  if (normalise) {
+    float norm_sq = 0.f;
+    if (lane == 0) {
+#pragma unroll 16
+      for (uint32_t i = 0; i < dim; ++i) {
+        const float v = __ldg(src + i);
+        norm_sq = __fadd_rn(norm_sq, __fmul_rn(v, v));
+      }
+    }
+    norm_sq = __shfl_sync(0xffffffffu, norm_sq, 0);
+    if (norm_sq > 0.f) {
+      inv = __fdiv_rn(1.0f, static_cast<float>(sqrt(static_cast<double>(norm_sq))));
+      scale = true;
+    }
+  }
+  int sumsq = 0;  // <= 127^2 * 8192 fits int32
+  for (uint32_t w = lane; w < (uint32_t)out_words; w += 32) {
+    uint32_t word = 0u;
+    if (kind == KIND_L2_F16) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t e = 2 * w + j;
+        float v = e < dim ? src[e] : 0.f;
+        if (scale) v = __fmul_rn(v, inv);
+        word |= (uint32_t)__half_as_ushort(__float2half_rn(v)) << (16 * j);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t e = 4 * w + j;
+        int qv = 0;
+        if (e < dim && abs_max != 0.f) {
+          float v = src[e];
+          if (scale) v = __fmul_rn(v, inv);
+          float scaled = __fmul_rn(__fdiv_rn(v, abs_max), 127.0f);
+          if (scaled > 127.0f)
+            scaled = 127.0f;
+          else if (scaled < -127.0f)
+            scaled = -127.0f;
+          qv = static_cast<int>(round(static_cast<double>(scaled)));
+        }
+        sumsq += qv * qv;
+        word |= ((uint32_t)qv & 0xffu) << (8 * j);
+      }
+    }
+    dst[w] = word;
+  }
+  if (kind == KIND_COS_I8 && norms != nullptr) {
+    sumsq = __reduce_add_sync(0xffffffffu, sumsq);
+    if (lane == 0) {
+      float nrm = static_cast<float>(sqrt(static_cast<double>(sumsq)));
+      if (query_side && nrm == 0.f) nrm = 1.f;
+      norms[r] = nrm;
+    }
+  }
+}
+
+// Quantizer.Train (quantizer.go:49-125) needs the value at a fixed rank of |x| over a stride sample
+// of the rows; the sort + index of the reference becomes an exact 3-pass radix select over the f32 bit
+// patterns (non-negative floats order like their bits).  One pass: histogram of `bits` bits at `shift`
+// over the sampled values whose higher bits equal `prefix`.
+__global__ void abs_hist_kernel(const float *__restrict__ rows, size_t row_stride, uint32_t n_sample, uint32_t step,
+                                uint32_t dim, uint32_t prefix, int hi_shift, int shift, int bits,
+                                unsigned long long *__restrict__ hist) {
+  const uint64_t total = (uint64_t)n_sample * dim;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = i / dim;
+    const uint32_t c = (uint32_t)(i - r * dim);
+    const uint32_t key = __float_as_uint(fabsf(rows[r * step * row_stride + c]));
+    if (hi_shift >= 32 || (key >> hi_shift) == (prefix >> hi_shift))
+      atomicAdd(&hist[(key >> shift) & ((1u << bits) - 1u)], 1ull);
+  }
+}
+
+// computeInt8Norm (hnsw_index.go:3371-3377) of rows already in stored form, one warp per row
+__global__ void int8_norms_kernel(const float *__restrict__ rows, size_t row_words, uint32_t count, uint32_t dim,
+                                  float *__restrict__ norms) {
+  const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= count) return;
+  const int *src = reinterpret_cast<const int *>(rows + (size_t)r * row_words);
+  int sumsq = 0;
+  for (uint32_t w = lane; w < (dim + 3) / 4; w += 32) sumsq = __dp4a(src[w], src[w], sumsq);  // padding is zero
+  sumsq = __reduce_add_sync(0xffffffffu, sumsq);
+  if (lane == 0) norms[r] = static_cast<float>(sqrt(static_cast<double>(sumsq)));
 }
 
 // CPL (float4 columns per lane) instantiated at compile time; other row lengths use the generic path
@@ -139,11 +242,12 @@ int occupancy_one(size_t smem) {
       EXPR;                                \
     } break;                               \
   }
-#define KDB_SWITCH_METRIC(SLv, EXPR)                   \
-  if (ix.metric == KDBGPU_METRIC_COSINE) {             \
-    KDB_SWITCH_CPL(SLv, KDBGPU_METRIC_COSINE, EXPR)    \
-  } else {                                             \
-    KDB_SWITCH_CPL(SLv, KDBGPU_METRIC_L2, EXPR)        \
+#define KDB_SWITCH_METRIC(SLv, EXPR)                                                        \
+  switch (ix.kind) {                                                                        \
+    case KIND_COS_F32: { KDB_SWITCH_CPL(SLv, KIND_COS_F32, EXPR) } break;                   \
+    case KIND_L2_F16: { KDB_SWITCH_CPL(SLv, KIND_L2_F16, EXPR) } break;                     \
+    case KIND_COS_I8: { KDB_SWITCH_CPL(SLv, KIND_COS_I8, EXPR) } break;                     \
+    default: { KDB_SWITCH_CPL(SLv, KIND_L2_F32, EXPR) } break;                              \
   }
 #define KDB_DISPATCH(EXPR)                       \
   switch (t.slots) {                             \
@@ -191,18 +295,54 @@ cudaError_t launch_prep_queries(const float *in, size_t in_stride, float *out, u
   return cudaGetLastError();
 }
 
-cudaError_t launch_distance_batch(const DevIndex &ix, const float *query_prepared, const uint32_t *ids,
-                                  uint32_t n, double *out, cudaStream_t stream) {
+cudaError_t launch_distance_batch(const DevIndex &ix, const float *query_prepared, const float *qnorm,
+                                  const uint32_t *ids, uint32_t n, double *out, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   const int threads = 256;
   const uint32_t wpb = threads / 32;
   int grid = (int)((n + wpb - 1) / wpb);
   if (grid > 148 * 8) grid = 148 * 8;
   const size_t smem = (size_t)ix.stride * sizeof(float);
-  if (ix.metric == KDBGPU_METRIC_COSINE)
-    distance_batch_kernel<KDBGPU_METRIC_COSINE><<<grid, threads, smem, stream>>>(ix, query_prepared, ids, n, out);
-  else
-    distance_batch_kernel<KDBGPU_METRIC_L2><<<grid, threads, smem, stream>>>(ix, query_prepared, ids, n, out);
+  switch (ix.kind) {
+    case KIND_COS_F32:
+      distance_batch_kernel<KIND_COS_F32><<<grid, threads, smem, stream>>>(ix, query_prepared, qnorm, ids, n, out);
+      break;
+    case KIND_L2_F16:
+      distance_batch_kernel<KIND_L2_F16><<<grid, threads, smem, stream>>>(ix, query_prepared, qnorm, ids, n, out);
+      break;
+    case KIND_COS_I8:
+      distance_batch_kernel<KIND_COS_I8><<<grid, threads, smem, stream>>>(ix, query_prepared, qnorm, ids, n, out);
+      break;
+    default:
+      distance_batch_kernel<KIND_L2_F32><<<grid, threads, smem, stream>>>(ix, query_prepared, qnorm, ids, n, out);
+      break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_rows(const float *in, size_t in_stride, float *out, size_t out_words, uint32_t rows,
+                                uint32_t dim, int kind, bool normalise, float abs_max, float *norms,
+                                bool query_side, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  const int wpb = 4;
+  convert_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(in, in_stride, out, out_words, rows, dim, kind,
+                                                                       normalise ? 1 : 0, abs_max, norms,
+                                                                       query_side ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_abs_hist(const float *rows, size_t row_stride, uint32_t n_sample, uint32_t step, uint32_t dim,
+                            uint32_t prefix, int hi_shift, int shift, int bits, unsigned long long *hist,
+                            cudaStream_t stream) {
+  abs_hist_kernel<<<148 * 4, 256, 0, stream>>>(rows, row_stride, n_sample, step, dim, prefix, hi_shift, shift, bits, hist);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_int8_norms(const float *rows, size_t row_words, uint32_t count, uint32_t dim, float *norms,
+                              cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  const int wpb = 4;
+  int8_norms_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, stream>>>(rows, row_words, count, dim, norms);
   return cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ struct SmemPtrs {
   HeapEntry *cand;
   uint32_t *eval_id;
   uint32_t *eval_del;
+  float *eval_norm;  // int8: stored norm of every neighbour to evaluate (quantizedNorms[id])
   uint32_t *marked;
   Ctl *ctl;
 };
@@ -64,6 +65,8 @@ __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots
   off += (size_t)dm * sizeof(uint32_t);
   const size_t o_evaldel = off;
   off += (size_t)dm * sizeof(uint32_t);
+  const size_t o_evalnorm = off;
+  off += (size_t)dm * sizeof(float);
   const size_t o_marked = off;
   off += (size_t)kMarkCap * sizeof(uint32_t);
   const size_t o_ctl = off;
@@ -77,6 +80,7 @@ __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots
     p->bars = reinterpret_cast<uint64_t *>(base + o_bars);
     p->eval_id = reinterpret_cast<uint32_t *>(base + o_evalid);
     p->eval_del = reinterpret_cast<uint32_t *>(base + o_evaldel);
+    p->eval_norm = reinterpret_cast<float *>(base + o_evalnorm);
     p->marked = reinterpret_cast<uint32_t *>(base + o_marked);
     p->ctl = reinterpret_cast<Ctl *>(base + o_ctl);
   }
@@ -199,10 +203,11 @@ struct Searcher {
   ResHeap res;          // meaningful on lane 0
   unsigned long long st_e, st_h, st_h0;
   bool overflow;
+  float qnorm;  // int8: query-side norm (hnsw_index.go:2405-2413)
   float4 qreg[CPL > 0 ? CPL : 1];
 
   __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem)
-      : ix(ix_), a(a_), lane(threadIdx.x & 31), phase_bits(0), st_e(0), st_h(0), st_h0(0), overflow(false) {
+      : ix(ix_), a(a_), lane(threadIdx.x & 31), phase_bits(0), st_e(0), st_h(0), st_h0(0), overflow(false), qnorm(1.f) {
     smem_layout(ix.stride, a.ef, SLOTS, a.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, CPL == 0, smem, &sm);
     vis = a.visited + (size_t)blockIdx.x * a.vis_words;
     cand.s = sm.cand;
@@ -215,6 +220,13 @@ struct Searcher {
   }
 
   __device__ __forceinline__ void init_barriers() {
+    // rows shorter than a slot (row_words < stride, float16 / int8 pitches) never overwrite the slot
+    // tail: zero it once so the padded columns contribute nothing
+    if (ix.row_words < ix.stride) {
+      for (int sl = 0; sl < SLOTS; ++sl)
+        for (uint32_t w = ix.row_words + lane; w < ix.stride; w += 32) sm.slots[(size_t)sl * ix.stride + w] = 0.f;
+      fence_proxy_async();
+    }
     if (lane == 0) {
       for (int i = 0; i < SLOTS; ++i) mbar_init(&sm.bars[i], 1);
       mbar_fence_init();
@@ -235,9 +247,9 @@ struct Searcher {
 
   __device__ __forceinline__ void issue_row(uint32_t j, uint32_t id) {  // lane 0
     const uint32_t slot = j & (SLOTS - 1);
-    const uint32_t row_bytes = ix.stride * sizeof(float);
+    const uint32_t row_bytes = ix.row_words * sizeof(float);
     mbar_expect_tx(&sm.bars[slot], row_bytes);
-    bulk_g2s(sm.slots + (size_t)slot * ix.stride, ix.vecs + (size_t)id * ix.stride, row_bytes, &sm.bars[slot]);
+    bulk_g2s(sm.slots + (size_t)slot * ix.stride, ix.vecs + (size_t)id * ix.row_words, row_bytes, &sm.bars[slot]);
   }
 
   __device__ __forceinline__ void wait_slot(uint32_t j) {
@@ -246,57 +258,25 @@ struct Searcher {
     phase_bits ^= 1u << slot;
   }
 
-  // lane partial of query x row held in slot (j mod SLOTS): (a0 + a1) + (a2 + a3), kernel order
+  // lane partial of query x row held in slot (j mod SLOTS), kernel order (LaneAcc, kdb_internal.cuh)
   __device__ __forceinline__ float lane_partial(uint32_t j) const {
     const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots + (size_t)(j & (SLOTS - 1)) * ix.stride);
-    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+    LaneAcc<METRIC> acc;
     if (CPL > 0) {
 #pragma unroll
-      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) {
-        const float4 q = qreg[t];
-        const float4 b = r4[lane + 32 * t];
-        if (METRIC == KDBGPU_METRIC_COSINE) {
-          ax = __fmaf_rn(q.x, b.x, ax);
-          ay = __fmaf_rn(q.y, b.y, ay);
-          az = __fmaf_rn(q.z, b.z, az);
-          aw = __fmaf_rn(q.w, b.w, aw);
-        } else {
-          const float dx = __fsub_rn(q.x, b.x), dy = __fsub_rn(q.y, b.y), dz = __fsub_rn(q.z, b.z),
-                      dw = __fsub_rn(q.w, b.w);
-          ax = __fmaf_rn(dx, dx, ax);
-          ay = __fmaf_rn(dy, dy, ay);
-          az = __fmaf_rn(dz, dz, az);
-          aw = __fmaf_rn(dw, dw, aw);
-        }
-      }
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) acc.add(qreg[t], r4[lane + 32 * t]);
     } else {
       const uint32_t nchunks = ix.stride >> 2;
 #pragma unroll 4
-      for (uint32_t c = lane; c < nchunks; c += 32) {
-        const float4 q = sm.q4[c];
-        const float4 b = r4[c];
-        if (METRIC == KDBGPU_METRIC_COSINE) {
-          ax = __fmaf_rn(q.x, b.x, ax);
-          ay = __fmaf_rn(q.y, b.y, ay);
-          az = __fmaf_rn(q.z, b.z, az);
-          aw = __fmaf_rn(q.w, b.w, aw);
-        } else {
-          const float dx = __fsub_rn(q.x, b.x), dy = __fsub_rn(q.y, b.y), dz = __fsub_rn(q.z, b.z),
-                      dw = __fsub_rn(q.w, b.w);
-          ax = __fmaf_rn(dx, dx, ax);
-          ay = __fmaf_rn(dy, dy, ay);
-          az = __fmaf_rn(dz, dz, az);
-          aw = __fmaf_rn(dw, dw, aw);
-        }
-      }
+      for (uint32_t c = lane; c < nchunks; c += 32) acc.add(sm.q4[c], r4[c]);
     }
-    return __fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw));
+    return acc.lane_sum();
   }
 
   // lane 0: the reference's per-neighbour result update (:2571-2591)
   __device__ __forceinline__ void heap_update(float s, uint32_t j, int ef) {
     HeapEntry e;
-    e.d = to_distance<METRIC>(s);
+    e.d = to_distance<METRIC>(s, qnorm, METRIC == KIND_COS_I8 ? sm.eval_norm[j] : 0.f);
     e.id = sm.eval_id[j];
     e.pad = 0;
     bool admit = res.n < ef;  // worstDist = MaxFloat64 while results is empty
@@ -345,15 +325,13 @@ struct Searcher {
     }
     __syncwarp();
     wait_slot(0);
-    float s0 = lane_partial(0);
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) s0 = __fadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, o));
+    const float s0 = warp_sum<METRIC>(lane_partial(0));
     __syncwarp();  // all lanes are done reading the slot
     if (lane == 0) {
       cand.n = 0;
       res.n = 0;
       HeapEntry e;
-      e.d = to_distance<METRIC>(s0);
+      e.d = to_distance<METRIC>(s0, qnorm, METRIC == KIND_COS_I8 ? ix.norms[ep] : 0.f);
       e.id = ep;
       e.pad = 0;
       cand.push(e);                // :2478
@@ -422,6 +400,7 @@ struct Searcher {
             const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
             sm.eval_id[pos] = id;
             sm.eval_del[pos] = del;
+            if (METRIC == KIND_COS_I8) sm.eval_norm[pos] = ix.norms[id];
           }
           n_eval += __popc(km);
         }
@@ -439,10 +418,15 @@ struct Searcher {
         if (two) wait_slot(j + 1);
         float sa = lane_partial(j);  // :2566
         float sb = two ? lane_partial(j + 1) : 0.f;
+        if (METRIC == KIND_COS_I8) {
+          sa = warp_sum<METRIC>(sa);
+          sb = warp_sum<METRIC>(sb);
+        } else {
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
-          sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
+          for (int o = 16; o >= 1; o >>= 1) {
+            sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
+            sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
+          }
         }
         __syncwarp();  // all lanes are done reading both slots
         if (lane == 0) {
@@ -473,6 +457,7 @@ struct Searcher {
   // searchInternal (hnsw_index.go:369-468) for query q
   __device__ void run_query(uint32_t q) {
     load_query(a.queries + (size_t)q * ix.stride);
+    if (METRIC == KIND_COS_I8) qnorm = a.qnorms[q];
     uint32_t ep = ix.entry;
     if (a.allow != nullptr && !bit_test(a.allow, ep)) ep = a.allow_entry;  // :436-447
     bool failed = ix.max_level < 0;

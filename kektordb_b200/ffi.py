@@ -15,6 +15,7 @@ LIB_PATH = _build.LIB
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_OVERFLOW = -1, -2, -3, -4, -5
 METRIC_L2, METRIC_COSINE = 0, 1
+PRECISION_F32, PRECISION_F16, PRECISION_INT8 = 0, 1, 2
 FLAT_PREFILTER = 0x10
 
 
@@ -36,7 +37,15 @@ SIGNATURES = {
     "kdbgpu_last_error": (C.c_char_p, []),
     "kdbgpu_version": (C.c_char_p, []),
     "kdbgpu_index_create": (_i32, [_i32, _i32, _i32, _i32, _u32, C.POINTER(_vp)]),
+    "kdbgpu_index_create_ex": (_i32, [_i32, _i32, _i32, _i32, _i32, _u32, C.POINTER(_vp)]),
     "kdbgpu_index_destroy": (_i32, [_vp]),
+    "kdbgpu_index_precision": (_i32, [_vp]),
+    "kdbgpu_set_quantizer": (_i32, [_vp, C.c_float]),
+    "kdbgpu_train_quantizer": (_i32, [_vp, _vp, _u32, C.POINTER(C.c_float)]),
+    "kdbgpu_train_quantizer_device": (_i32, [_vp, _vp, _sz, _u32, C.POINTER(C.c_float)]),
+    "kdbgpu_upload_rows_raw": (_i32, [_vp, _u32, _u32, _vp]),
+    "kdbgpu_download_rows_raw": (_i32, [_vp, _u32, _u32, _vp]),
+    "kdbgpu_download_norms": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_upload_vectors": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_upload_vectors_device": (_i32, [_vp, _u32, _u32, _vp, _sz]),
     "kdbgpu_set_graph": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _i32]),

@@ -24,6 +24,14 @@ _METRICS = {Euclidean: ffi.METRIC_L2, Cosine: ffi.METRIC_COSINE, "l2": ffi.METRI
             ffi.METRIC_L2: ffi.METRIC_L2, ffi.METRIC_COSINE: ffi.METRIC_COSINE}
 
 
+Float32, Float16, Int8 = "float32", "float16", "int8"  # distance.PrecisionType (distance_go.go:41-46)
+_PRECISIONS = {Float32: ffi.PRECISION_F32, Float16: ffi.PRECISION_F16, Int8: ffi.PRECISION_INT8,
+               ffi.PRECISION_F32: ffi.PRECISION_F32, ffi.PRECISION_F16: ffi.PRECISION_F16,
+               ffi.PRECISION_INT8: ffi.PRECISION_INT8}
+_PRECISION_NAMES = {ffi.PRECISION_F32: Float32, ffi.PRECISION_F16: Float16, ffi.PRECISION_INT8: Int8}
+_RAW_DTYPES = {ffi.PRECISION_F32: np.float32, ffi.PRECISION_F16: np.uint16, ffi.PRECISION_INT8: np.int8}
+
+
 @dataclass
 class SearchStats:
     dist_evals: int = 0
@@ -61,15 +69,19 @@ def dense_allow_list(ids, n: int) -> np.ndarray:
 class GpuIndex:
     """GPU mirror of one hnsw.Index: corpus rows + adjacency staged in HBM, searched on device."""
 
-    def __init__(self, dim: int, metric, m: int = 16, capacity: int = 1 << 20, device: int = 0):
-        if metric not in _METRICS:
-            raise ValueError(f"metric '{metric}' not supported for float32 precision")  # distance_go.go:155-157
+    def __init__(self, dim: int, metric, m: int = 16, capacity: int = 1 << 20, device: int = 0,
+                 precision=Float32):
+        if precision not in _PRECISIONS:
+            raise ValueError(f"unknown precision '{precision}'")
+        if metric not in _METRICS:  # distance_go.go:155-157
+            raise ValueError(f"metric '{metric}' not supported for {_PRECISION_NAMES[_PRECISIONS[precision]]} precision")
         self._lib = ffi.lib()
         self.dim, self.m, self.capacity, self.device = int(dim), int(m) if m > 0 else 16, int(capacity), int(device)
         self.metric = _METRICS[metric]
+        self.precision = _PRECISIONS[precision]
         self.needs_refine = False
         h = C.c_void_p()
-        ffi.check(self._lib.kdbgpu_index_create(device, dim, self.metric, m, capacity, C.byref(h)))
+        ffi.check(self._lib.kdbgpu_index_create_ex(device, dim, self.metric, self.precision, m, capacity, C.byref(h)))
         self._h = h
 
     # -- lifecycle -------------------------------------------------------------------------
@@ -97,6 +109,46 @@ class GpuIndex:
         if rows.ndim != 2 or rows.shape[1] != self.dim:
             raise ValueError(f"rows must be [count, {self.dim}]")
         ffi.check(self._lib.kdbgpu_upload_vectors(self._handle(), first_id, rows.shape[0], _ptr(rows)))
+
+    def upload_rows_raw(self, first_id: int, rows: np.ndarray) -> None:
+        """Rows already in stored form (float32 / float16 bits as uint16 / int8), as the arena holds them."""
+        rows = np.ascontiguousarray(rows, dtype=_RAW_DTYPES[self.precision])
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"rows must be [count, {self.dim}]")
+        ffi.check(self._lib.kdbgpu_upload_rows_raw(self._handle(), first_id, rows.shape[0], _ptr(rows)))
+
+    def download_rows_raw(self, first_id: int, count: int) -> np.ndarray:
+        out = np.zeros((count, self.dim), dtype=_RAW_DTYPES[self.precision])
+        ffi.check(self._lib.kdbgpu_download_rows_raw(self._handle(), first_id, count, _ptr(out)))
+        return out
+
+    def download_norms(self, first_id: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=np.float32)
+        ffi.check(self._lib.kdbgpu_download_norms(self._handle(), first_id, count, _ptr(out)))
+        return out
+
+    def set_quantizer(self, abs_max: float) -> None:
+        """Quantizer.AbsMax of an int8 index (pkg/core/distance/quantizer.go:19-22)."""
+        ffi.check(self._lib.kdbgpu_set_quantizer(self._handle(), float(abs_max)))
+
+    def TrainQuantizer(self, vectors) -> float:
+        """(*Index).TrainQuantizer (hnsw_index.go:2962-2966) -> Quantizer.Train; returns AbsMax."""
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        if v.ndim != 2 or v.shape[1] != self.dim:
+            raise ValueError(f"vectors must be [n, {self.dim}]")
+        am = C.c_float(0.0)
+        ffi.check(self._lib.kdbgpu_train_quantizer(self._handle(), _ptr(v), v.shape[0], C.byref(am)))
+        return float(am.value)
+
+    def train_quantizer_device(self, d_rows_ptr: int, row_stride: int, n: int) -> float:
+        am = C.c_float(0.0)
+        ffi.check(self._lib.kdbgpu_train_quantizer_device(self._handle(), C.c_void_p(d_rows_ptr), row_stride, n,
+                                                          C.byref(am)))
+        return float(am.value)
+
+    def upload_vectors_device(self, first_id: int, d_rows_ptr: int, count: int, row_stride: int) -> None:
+        ffi.check(self._lib.kdbgpu_upload_vectors_device(self._handle(), first_id, count, C.c_void_p(d_rows_ptr),
+                                                         row_stride))
 
     def set_graph(self, n: int, levels, node_row, row_off, nbrs, entry: int, max_level: int) -> None:
         levels = np.ascontiguousarray(levels, dtype=np.int32)
@@ -241,7 +293,7 @@ class GpuIndex:
         return Cosine if self.metric == ffi.METRIC_COSINE else Euclidean
 
     def Precision(self) -> str:
-        return "float32"
+        return _PRECISION_NAMES[self.precision]
 
     def GetDimension(self) -> int:
         return self.dim

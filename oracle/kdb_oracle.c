@@ -210,6 +210,216 @@ double kdbo_distance_generic(int metric, int arith, const float *a, const float 
   return dist_fn(metric, arith, a, b, n, 1);
 }
 
+/* ---- float16 / int8 precisions ----------------------------------------
+ * float16.Fromfloat32(v).Bits() (hnsw_index.go:427-430, :501-505, :1562-1566): the conversion lives
+ * in github.com/x448/float16 v0.8.4 (go.mod:19, not vendored) and is the IEEE 754 binary32 ->
+ * binary16 round-to-nearest-even conversion (subnormals kept, overflow to infinity); restated here
+ * and pinned against numpy's float16 cast and the F16C instruction in tests/test_oracle_quantized.py. */
+uint16_t kdbo_f32_to_f16(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const uint32_t e = (x >> 23) & 0xffu;
+  uint32_t m = x & 0x7fffffu;
+  if (e == 0xffu) return (uint16_t)(sign | (m ? 0x7e00u : 0x7c00u));
+  const int32_t exp = (int32_t)e - 127 + 15;
+  if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+  if (exp <= 0) {
+    if (exp < -10) return (uint16_t)sign;
+    m |= 0x800000u;
+    const uint32_t shift = (uint32_t)(14 - exp);
+    uint32_t half = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (half & 1u))) half++;
+    return (uint16_t)(sign | half);
+  }
+  uint32_t half = ((uint32_t)exp << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (half & 1u))) half++; /* a carry may reach 0x7c00 = +inf */
+  return (uint16_t)(sign | half);
+}
+/* float16.Frombits(b).Float32(): exact */
+float kdbo_f16_to_f32(uint16_t h) {
+  const uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
+  uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu, x;
+  if (e == 0) {
+    if (m == 0) {
+      x = sign;
+    } else { /* subnormal: renormalise */
+      int sh = 0;
+      while (!(m & 0x400u)) {
+        m <<= 1;
+        sh++;
+      }
+      m &= 0x3ffu;
+      x = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | (m << 13);
+    }
+  } else if (e == 31) {
+    x = sign | 0x7f800000u | (m << 13);
+  } else {
+    x = sign | ((e - 15 + 127) << 23) | (m << 13);
+  }
+  float f;
+  memcpy(&f, &x, 4);
+  return f;
+}
+
+/* squaredEuclideanGoFloat16 (distance_go.go:93-105): f32 difference of the widened halves,
+ * sequential f32 sum, separate multiply and add. */
+static float l2_f16_seq(const uint16_t *a, const uint16_t *b, size_t n) {
+  float sum = 0.0f;
+  for (size_t i = 0; i < n; i++) {
+    float diff = kdbo_f16_to_f32(a[i]) - kdbo_f16_to_f32(b[i]);
+    sum += diff * diff;
+  }
+  return sum;
+}
+/* Rust squared_euclidean_f16_fma (native/compute/src/lib.rs:101-141): 8-lane FMA accumulator,
+ * reduce_sum_ps, scalar remainder with separate multiply and add. */
+static float l2_f16_avx2(const uint16_t *a, const uint16_t *b, size_t n) {
+  size_t i = 0;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#if defined(KDBO_HAVE_AVX2) && defined(__F16C__)
+  __m256 s = _mm256_setzero_ps();
+  for (; i + 8 <= n; i += 8) {
+    __m256 x = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *)(a + i)));
+    __m256 y = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *)(b + i)));
+    __m256 d = _mm256_sub_ps(x, y);
+    s = _mm256_fmadd_ps(d, d, s);
+  }
+  _mm256_storeu_ps(acc, s);
+#else
+  for (; i + 8 <= n; i += 8)
+    for (int j = 0; j < 8; j++) {
+      float d = kdbo_f16_to_f32(a[i + j]) - kdbo_f16_to_f32(b[i + j]);
+      acc[j] = fmaf(d, d, acc[j]);
+    }
+#endif
+  float total = hsum8_rust(acc);
+  for (; i < n; i++) {
+    float d = kdbo_f16_to_f32(a[i]) - kdbo_f16_to_f32(b[i]);
+    total += d * d;
+  }
+  return total;
+}
+/* Kernel order for 16-bit rows: a lane's 16-byte column holds 8 elements, so there
+ * are 256 independent f32 accumulators; element e feeds accumulator e mod 256 by FMA in increasing
+ * e; lane l owns accumulators 8l..8l+7 and sums them ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7)); then the
+ * same xor-butterfly as the f32 rows. */
+static float l2_f16_kernel(const uint16_t *a, const uint16_t *b, size_t n) {
+  float acc[256];
+  memset(acc, 0, sizeof acc);
+  size_t e = 0;
+#if defined(KDBO_HAVE_AVX2) && defined(__F16C__)
+  const size_t full = n & ~(size_t)255;
+  if (full) {
+    __m256 s[32];
+    for (int j = 0; j < 32; j++) s[j] = _mm256_setzero_ps();
+    for (size_t t = 0; t < full; t += 256)
+      for (int j = 0; j < 32; j++) {
+        __m256 x = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *)(a + t + 8 * j)));
+        __m256 y = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *)(b + t + 8 * j)));
+        __m256 d = _mm256_sub_ps(x, y);
+        s[j] = _mm256_fmadd_ps(d, d, s[j]);
+      }
+    for (int j = 0; j < 32; j++) _mm256_storeu_ps(acc + 8 * j, s[j]);
+    e = full;
+  }
+#endif
+  for (; e < n; e++) {
+    float d = kdbo_f16_to_f32(a[e]) - kdbo_f16_to_f32(b[e]);
+    acc[e & 255] = fmaf(d, d, acc[e & 255]);
+  }
+  float lane[32];
+  for (int l = 0; l < 32; l++) {
+    const float *p = acc + 8 * l;
+    lane[l] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+  }
+  for (int w = 16; w >= 1; w >>= 1)
+    for (int l = 0; l < w; l++) lane[l] = lane[l] + lane[l + w];
+  return lane[0];
+}
+float kdbo_sq_euclid_f16(int arith, const uint16_t *a, const uint16_t *b, size_t n) {
+  switch (arith) {
+    case KDBO_ARITH_AVX2: return l2_f16_avx2(a, b, n);
+    case KDBO_ARITH_KERNEL: return l2_f16_kernel(a, b, n);
+    default: return l2_f16_seq(a, b, n);
+  }
+}
+/* dotProductGoInt8 (distance_go.go:108-118): exact int32 sum of int32 products — integer
+ * arithmetic, so every summation order gives the same bits.  (The reference's optional Rust AVX2
+ * kernel drops two of its four 32-bit partial sums in its horizontal reduction,
+ * native/compute/src/lib.rs:165-170 — `(hi64 + lo64) as i32`; the default pure-Go build is what
+ * this follows.) */
+int32_t kdbo_dot_i8(const int8_t *a, const int8_t *b, size_t n) {
+  int32_t sum = 0;
+  for (size_t i = 0; i < n; i++) sum += (int32_t)a[i] * (int32_t)b[i];
+  return sum;
+}
+/* computeInt8Norm, hnsw_index.go:3371-3377 */
+float kdbo_int8_norm(const int8_t *v, size_t n) {
+  int64_t sum = 0;
+  for (size_t i = 0; i < n; i++) sum += (int64_t)v[i] * (int64_t)v[i];
+  return (float)sqrt((double)sum);
+}
+/* int8 cosine distance from the integer dot and the two f32 norms
+ * (searchLayerUnlocked distFn hnsw_index.go:2421-2449, distanceBetweenNodes :319-336) */
+double kdbo_int8_cosine_distance(int32_t dot, float qnorm, float stored_norm) {
+  if (stored_norm == 0.0f) return 1.0;
+  double sim = (double)dot / ((double)qnorm * (double)stored_norm);
+  if (sim > 1.0) sim = 1.0;
+  if (sim < -1.0) sim = -1.0;
+  return 1.0 - sim;
+}
+/* Quantizer.Quantize, pkg/core/distance/quantizer.go:135-160 */
+void kdbo_quantize(float abs_max, const float *v, int8_t *out, size_t n) {
+  if (abs_max == 0.0f) {
+    memset(out, 0, n);
+    return;
+  }
+  for (size_t i = 0; i < n; i++) {
+    float scaled = (v[i] / abs_max) * 127.0f;
+    if (scaled > 127.0f)
+      scaled = 127.0f;
+    else if (scaled < -127.0f)
+      scaled = -127.0f;
+    out[i] = (int8_t)round((double)scaled); /* math.Round: half away from zero */
+  }
+}
+/* Quantizer.Train, quantizer.go:49-125: stride sample above 10 000 vectors (10 %, capped at
+ * 25 000, floor 10 000), 99.9th percentile of |value|.  Returns AbsMax (0 = nothing to train on). */
+static int f32_cmp(const void *a, const void *b) {
+  float x = *(const float *)a, y = *(const float *)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+float kdbo_train_quantizer(const float *vecs, size_t n, size_t dim) {
+  if (n == 0 || dim == 0) return 0.0f;
+  size_t step = 1, count = n;
+  if (n > 10000) {
+    size_t target = n / 10;
+    if (target > 25000) target = 25000;
+    if (target < 10000) target = 10000;
+    step = n / target;
+    if (step < 1) step = 1;
+    count = 0;
+    for (size_t i = 0; i < n; i += step) {
+      count++;
+      if (count >= target) break;
+    }
+  }
+  float *all = (float *)malloc(count * dim * sizeof(float));
+  size_t w = 0, taken = 0;
+  for (size_t i = 0; i < n && taken < count; i += step, taken++)
+    for (size_t j = 0; j < dim; j++) all[w++] = fabsf(vecs[i * dim + j]);
+  qsort(all, w, sizeof(float), f32_cmp);
+  long long qi = (long long)((double)w * 0.999);
+  if (qi >= (long long)w) qi = (long long)w - 1;
+  if (qi < 0) qi = 0;
+  float r = all[qi];
+  free(all);
+  return r;
+}
+
 /* normalize / invSqrt, hnsw_index.go:3030-3045: f32 sequential sum of squares, one f64 sqrt,
  * f32 reciprocal, f32 scale; a zero vector is left untouched. */
 void kdbo_normalize(float *v, size_t n) {
@@ -361,6 +571,13 @@ struct kdbo_index {
   uint32_t **upper;    /* per node: [level][m+1], slot 0 = count                         */
   volatile char *lock; /* per-node spin lock (stands in for the 128 shard RWMutexes)      */
   volatile char meta_lock;
+  /* float16 / int8 precisions: rows in stored form, int8 norms, quantizer */
+  int precision;    /* KDBO_PREC_* */
+  size_t qstride;   /* elements per quantized row (dim rounded up to 32) */
+  uint16_t *rows16; /* [(cap+1)][qstride] float16 bits */
+  int8_t *rows8;    /* [(cap+1)][qstride] */
+  float *norms;     /* quantizedNorms: computeInt8Norm of every stored row */
+  float abs_max;    /* Quantizer.AbsMax */
 };
 
 static inline void spin_lock(volatile char *l) {
@@ -375,8 +592,16 @@ static inline void spin_lock(volatile char *l) {
 static inline void spin_unlock(volatile char *l) { __atomic_store_n(l, 0, __ATOMIC_RELEASE); }
 
 kdbo_index *kdbo_new(int dim, int metric, int m, int efc, int arith, uint32_t capacity) {
+  return kdbo_new_ex(dim, metric, KDBO_PREC_F32, m, efc, arith, capacity);
+}
+kdbo_index *kdbo_new_ex(int dim, int metric, int precision, int m, int efc, int arith, uint32_t capacity) {
   if (dim <= 0 || capacity == 0) return NULL;
+  /* float16Funcs holds Euclidean only, int8Funcs Cosine only (distance_go.go:139-146) */
+  if (precision == KDBO_PREC_F16 && metric != KDBO_METRIC_L2) return NULL;
+  if (precision == KDBO_PREC_I8 && metric != KDBO_METRIC_COSINE) return NULL;
+  if (precision < KDBO_PREC_F32 || precision > KDBO_PREC_I8) return NULL;
   kdbo_index *h = (kdbo_index *)calloc(1, sizeof *h);
+  h->precision = precision;
   if (m <= 0) m = 16;       /* hnsw_index.go:140-142 */
   if (efc <= 0) efc = 200;  /* :143-145 */
   h->dim = dim;
@@ -389,11 +614,19 @@ kdbo_index *kdbo_new(int dim, int metric, int m, int efc, int arith, uint32_t ca
   h->cap = capacity;
   h->max_level = -1;
   size_t n1 = (size_t)capacity + 1;
-  if (posix_memalign((void **)&h->vecs, 64, n1 * h->stride * sizeof(float))) {
-    free(h);
-    return NULL;
+  h->qstride = ((size_t)dim + 31) & ~(size_t)31;
+  if (precision == KDBO_PREC_F32) {
+    if (posix_memalign((void **)&h->vecs, 64, n1 * h->stride * sizeof(float))) {
+      free(h);
+      return NULL;
+    }
+    memset(h->vecs, 0, n1 * h->stride * sizeof(float));
+  } else if (precision == KDBO_PREC_F16) {
+    h->rows16 = (uint16_t *)calloc(n1 * h->qstride, sizeof(uint16_t));
+  } else {
+    h->rows8 = (int8_t *)calloc(n1 * h->qstride, 1);
+    h->norms = (float *)calloc(n1, sizeof(float));
   }
-  memset(h->vecs, 0, n1 * h->stride * sizeof(float));
   h->level = (int8_t *)malloc(n1);
   memset(h->level, -1, n1);
   h->deleted = (uint8_t *)calloc(n1, 1);
@@ -407,6 +640,9 @@ void kdbo_free(kdbo_index *h) {
   for (size_t i = 0; i <= h->cap; i++) free(h->upper[i]);
   free(h->upper);
   free(h->vecs);
+  free(h->rows16);
+  free(h->rows8);
+  free(h->norms);
   free(h->level);
   free(h->deleted);
   free(h->l0);
@@ -426,8 +662,66 @@ static inline uint32_t *conn_row(const kdbo_index *h, uint32_t id, int level) {
   if (level == 0) return h->l0 + (size_t)id * (size_t)(h->mmax0 + 1);
   return h->upper[id] + (size_t)(level - 1) * (size_t)(h->m + 1);
 }
+int kdbo_precision(const kdbo_index *h) { return h->precision; }
+float kdbo_abs_max(const kdbo_index *h) { return h->abs_max; }
+void kdbo_set_quantizer(kdbo_index *h, float abs_max) { h->abs_max = abs_max; }
+const float *kdbo_norms(const kdbo_index *h) { return h->norms; }
+/* stored row in the index precision (node.GetVectorF32 / F16 / I8, hnsw_node.go:13-39) */
+static inline const void *row_ptr(const kdbo_index *h, uint32_t id) {
+  switch (h->precision) {
+    case KDBO_PREC_F16: return h->rows16 + (size_t)id * h->qstride;
+    case KDBO_PREC_I8: return h->rows8 + (size_t)id * h->qstride;
+    default: return h->vecs + (size_t)id * h->stride;
+  }
+}
+const void *kdbo_row_raw(const kdbo_index *h, uint32_t id) { return row_ptr(h, id); }
+size_t kdbo_row_raw_stride(const kdbo_index *h) { return h->precision == KDBO_PREC_F32 ? h->stride : h->qstride; }
+/* the query-side int8 norm of searchLayerUnlocked (hnsw_index.go:2405-2413): 0 -> 1 */
+static inline float query_norm_i8(const int8_t *q, size_t n) {
+  float qn = kdbo_int8_norm(q, n);
+  return qn == 0.0f ? 1.0f : qn;
+}
+/* distFn(node) of searchLayerUnlocked (hnsw_index.go:2388-2454): q is the prepared query in the
+ * index precision, qnorm its int8 norm */
+static inline double query_dist(const kdbo_index *h, const void *q, float qnorm, uint32_t id) {
+  const size_t dim = (size_t)h->dim;
+  switch (h->precision) {
+    case KDBO_PREC_F16:
+      return (double)kdbo_sq_euclid_f16(h->arith, (const uint16_t *)q, (const uint16_t *)row_ptr(h, id), dim);
+    case KDBO_PREC_I8:
+      return kdbo_int8_cosine_distance(kdbo_dot_i8((const int8_t *)q, (const int8_t *)row_ptr(h, id), dim), qnorm,
+                                       h->norms[id]);
+    default:
+      return dist_fn(h->metric, h->arith, (const float *)q, kdbo_vector(h, id), dim, 0);
+  }
+}
+/* distanceBetweenNodes, hnsw_index.go:297-341 */
 static inline double node_dist(const kdbo_index *h, uint32_t a, uint32_t b) {
-  return dist_fn(h->metric, h->arith, kdbo_vector(h, a), kdbo_vector(h, b), (size_t)h->dim, 0);
+  if (h->precision == KDBO_PREC_I8) {
+    if (h->norms[a] == 0.0f || h->norms[b] == 0.0f) return 1.0; /* :325-327 */
+    return query_dist(h, row_ptr(h, a), h->norms[a], b);
+  }
+  return query_dist(h, row_ptr(h, a), 0.0f, b);
+}
+/* converts one incoming f32 vector into the stored form of row `id`
+ * (Add :484-520, AddBatch :1553-1577; only cosine + float32 is normalised) */
+static void store_row(kdbo_index *h, uint32_t id, const float *vec) {
+  const size_t dim = (size_t)h->dim;
+  if (h->precision == KDBO_PREC_F16) {
+    uint16_t *dst = h->rows16 + (size_t)id * h->qstride;
+    memset(dst, 0, h->qstride * sizeof(uint16_t));
+    for (size_t i = 0; i < dim; i++) dst[i] = kdbo_f32_to_f16(vec[i]);
+  } else if (h->precision == KDBO_PREC_I8) {
+    int8_t *dst = h->rows8 + (size_t)id * h->qstride;
+    memset(dst, 0, h->qstride);
+    kdbo_quantize(h->abs_max, vec, dst, dim);
+    h->norms[id] = kdbo_int8_norm(dst, dim); /* :593-597, :1679-1683 */
+  } else {
+    float *dst = h->vecs + (size_t)id * h->stride;
+    memset(dst, 0, h->stride * sizeof(float));
+    memcpy(dst, vec, dim * sizeof(float));
+    if (h->metric == KDBO_METRIC_COSINE) kdbo_normalize(dst, dim);
+  }
 }
 
 /* ---- per-thread scratch (the reference's sync.Pool objects, hnsw_index.go:2358-2374) ---- */
@@ -494,7 +788,7 @@ static int allow_is_empty(const uint64_t *allow, size_t words) {
 
 /* searchLayerUnlocked, hnsw_index.go:2351-2611.  Returns the result count (<= k) written to
  * s->out ascending, or -1 when the entry node is nil (:2466-2468). */
-static int search_layer(const kdbo_index *h, scratch *s, const float *q, uint32_t entry, int k, int level,
+static int search_layer(const kdbo_index *h, scratch *s, const void *q, uint32_t entry, int k, int level,
                         const uint64_t *allow, size_t allow_words, int ef_search, int concurrent,
                         kdbo_stats *st) {
   heap *cands = &s->cands, *results = &s->results;
@@ -502,12 +796,12 @@ static int search_layer(const kdbo_index *h, scratch *s, const float *q, uint32_
   results->n = 0;
   int ef = ef_search; /* :2377-2380 */
   if (ef < k) ef = k;
-  const size_t dim = (size_t)h->dim;
+  const float qnorm = h->precision == KDBO_PREC_I8 ? query_norm_i8((const int8_t *)q, (size_t)h->dim) : 0.0f;
   const int allow_active = allow != NULL && !allow_is_empty(allow, allow_words); /* :2481, :2545 */
   const uint32_t n_nodes = h->counter + 1; /* len(nodes) after growNodes */
 
   if (entry >= n_nodes || h->level[entry] < 0) return -1; /* :2463-2468 */
-  double dist = dist_fn(h->metric, h->arith, q, kdbo_vector(h, entry), dim, 0);
+  double dist = query_dist(h, q, qnorm, entry);
   if (st) st->dist_evals++;
   cand ep = {entry, dist};
   min_push(cands, ep); /* :2478 */
@@ -540,7 +834,7 @@ static int search_layer(const kdbo_index *h, scratch *s, const float *q, uint32_
       if (allow_active && !allow_has(allow, allow_words, nb)) continue; /* :2545-2549 */
       if (nb >= n_nodes) continue;                                      /* :2553-2556 */
       if (__atomic_load_n(&h->level[nb], __ATOMIC_ACQUIRE) < 0) continue; /* nil node :2559-2561 */
-      double d = dist_fn(h->metric, h->arith, q, kdbo_vector(h, nb), dim, 0); /* :2566 */
+      double d = query_dist(h, q, qnorm, nb); /* :2566 */
       if (st) st->dist_evals++;
       int admit = (int)results->n < ef; /* :2572-2577: worstDist = MaxFloat64 when empty */
       if (!admit) admit = d < results->a[0].d;
@@ -618,22 +912,16 @@ int kdbo_select_neighbors(const kdbo_index *h, const uint32_t *ids, const double
 
 /* Index.Add, hnsw_index.go:472-809 */
 static uint32_t add_one(kdbo_index *h, scratch *s, const float *vec, double u, int concurrent) {
-  const size_t dim = (size_t)h->dim;
-  float *tmp = (float *)malloc(h->stride * sizeof(float));
-  memset(tmp, 0, h->stride * sizeof(float));
-  memcpy(tmp, vec, dim * sizeof(float));
-  if (h->metric == KDBO_METRIC_COSINE) kdbo_normalize(tmp, dim); /* :485-493 */
-
+  /* int8: the first Add trains the quantizer on its own vector (ensureQuantizerTrained, :510-517) */
+  if (h->precision == KDBO_PREC_I8 && h->abs_max == 0.0f) h->abs_max = kdbo_train_quantizer(vec, 1, (size_t)h->dim);
   /* PHASE 1 under metaMu (:559-676) */
   spin_lock(&h->meta_lock);
   if (h->counter >= h->cap) {
     spin_unlock(&h->meta_lock);
-    free(tmp);
     return 0;
   }
   uint32_t id = h->counter + 1; /* ids start at 1, :590 */
-  memcpy(h->vecs + (size_t)id * h->stride, tmp, h->stride * sizeof(float));
-  free(tmp);
+  store_row(h, id, vec);      /* :485-520 (normalise / convert / quantise) */
   int level = kdbo_random_level(u, h->m, h->max_level); /* :647 */
   if (level > 120) level = 120;
   if (level > 0) h->upper[id] = (uint32_t *)calloc((size_t)level * (size_t)(h->m + 1), sizeof(uint32_t));
@@ -650,7 +938,7 @@ static uint32_t add_one(kdbo_index *h, scratch *s, const float *vec, double u, i
   uint32_t ep = h->entry;
   spin_unlock(&h->meta_lock);
 
-  const float *q = kdbo_vector(h, id);
+  const void *q = row_ptr(h, id); /* currObj := storedVector (:674) */
   const int efc = h->efc;
   /* zoom in, :685-690 */
   for (int l = cur_max; l > level; l--) {
@@ -816,10 +1104,7 @@ int kdbo_add_batch(kdbo_index *h, const float *vecs, size_t n, const double *u, 
   const uint32_t pre_entry = h->entry;
   for (size_t i = 0; i < n; i++) {
     uint32_t id = start_id + (uint32_t)i;
-    float *dst = h->vecs + (size_t)id * h->stride;
-    memset(dst, 0, h->stride * sizeof(float));
-    memcpy(dst, vecs + i * dim, dim * sizeof(float));
-    if (h->metric == KDBO_METRIC_COSINE) kdbo_normalize(dst, dim); /* :1557-1559 */
+    store_row(h, id, vecs + i * dim); /* :1553-1577 */
     int level = kdbo_random_level(u[i], h->m, pre_max);              /* :1738 */
     if (level > 120) level = 120;
     if (level > 0) h->upper[id] = (uint32_t *)calloc((size_t)level * (size_t)(h->m + 1), sizeof(uint32_t));
@@ -847,7 +1132,7 @@ int kdbo_add_batch(kdbo_index *h, const float *vecs, size_t n, const double *u, 
 #endif
     for (long long i = 0; i < (long long)n; i++) {
       uint32_t id = start_id + (uint32_t)i;
-      const float *q = kdbo_vector(h, id);
+      const void *q = row_ptr(h, id);
       int node_level = h->level[id];
       uint32_t ep = pre_entry;
       size_t nl = 0;
@@ -969,11 +1254,22 @@ static int search_internal(const kdbo_index *h, scratch *s, const float *query, 
   int max_level = h->max_level;
   if (max_level == -1) return 0;                           /* :383-385 */
   int actual_ef = kdbo_effective_ef(ef_search, needs_refine); /* :387-399 */
-  const float *q = query;
+  const void *q = query;
   if (h->metric == KDBO_METRIC_COSINE) { /* :406-414 */
     memcpy(qbuf, query, (size_t)h->dim * sizeof(float));
     kdbo_normalize(qbuf, (size_t)h->dim);
     q = qbuf;
+  }
+  /* adapt to the precision (:417-434); the converted query lives behind the f32 copy in qbuf */
+  if (h->precision == KDBO_PREC_F16) {
+    const float *src = (const float *)q;
+    uint16_t *q16 = (uint16_t *)(qbuf + h->stride);
+    for (int i = 0; i < h->dim; i++) q16[i] = kdbo_f32_to_f16(src[i]);
+    q = q16;
+  } else if (h->precision == KDBO_PREC_I8) {
+    int8_t *q8 = (int8_t *)(qbuf + h->stride);
+    kdbo_quantize(h->abs_max, (const float *)q, q8, (size_t)h->dim);
+    q = q8;
   }
   if (allow != NULL) { /* :436-447 smart entry point */
     if (!allow_has(allow, allow_words, entry)) {
@@ -1002,7 +1298,7 @@ int kdbo_search(const kdbo_index *h, const float *query, int k, int ef_search, i
                 const uint64_t *allow, size_t allow_words, uint32_t *out_ids, double *out_scores,
                 kdbo_stats *stats) {
   scratch *s = scratch_new(h);
-  float *qbuf = (float *)malloc(h->stride * sizeof(float));
+  float *qbuf = (float *)malloc(2 * h->stride * sizeof(float));
   int n = search_internal(h, s, query, k, ef_search, needs_refine, allow, allow_words, qbuf, stats);
   for (int i = 0; i < n; i++) { /* SearchWithScores :361-364: Score = raw distance */
     out_ids[i] = s->out[i].id;
@@ -1023,7 +1319,7 @@ int kdbo_search_batch(const kdbo_index *h, const float *queries, size_t nq, int 
 #endif
   {
     scratch *s = scratch_new(h);
-    float *qbuf = (float *)malloc(h->stride * sizeof(float));
+    float *qbuf = (float *)malloc(2 * h->stride * sizeof(float));
     kdbo_stats local = {0, 0, 0};
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 4)
@@ -1052,7 +1348,7 @@ int kdbo_search_batch(const kdbo_index *h, const float *queries, size_t nq, int 
   return 0;
 }
 
-int kdbo_search_layer(const kdbo_index *h, const float *q, uint32_t entry, int k, int level,
+int kdbo_search_layer(const kdbo_index *h, const void *q, uint32_t entry, int k, int level,
                       const uint64_t *allow, size_t allow_words, int ef_search, uint32_t *out_ids,
                       double *out_scores, kdbo_stats *stats) {
   scratch *s = scratch_new(h);
@@ -1108,6 +1404,7 @@ int kdbo_flat_search_batch(const kdbo_index *h, const float *queries, size_t nq,
                            const uint64_t *allow, size_t allow_words, uint32_t *out_ids,
                            double *out_scores, int32_t *out_counts, int threads) {
   if (threads < 1) threads = 1;
+  if (h->precision != KDBO_PREC_F32) return -1; /* BruteForceIndex holds []float32 only */
   const size_t dim = (size_t)h->dim;
   /* BruteForceIndex treats an empty allow-list as unfiltered (vector_index.go:132) */
   const int allow_active = allow != NULL && !allow_is_empty(allow, allow_words);
@@ -1210,7 +1507,7 @@ void kdbo_export_graph(const kdbo_index *h, int32_t *levels, uint64_t *node_row,
   node_row[h->counter + 1] = r;
   row_off[r] = e;
 }
-int kdbo_import_graph(kdbo_index *h, uint32_t n, const float *rows, size_t row_stride, const int32_t *levels,
+int kdbo_import_graph(kdbo_index *h, uint32_t n, const void *rows_any, size_t row_stride, const int32_t *levels,
                       const uint64_t *node_row, const uint64_t *row_off, const uint32_t *nbrs,
                       const uint8_t *deleted, uint32_t entry, int max_level) {
   if (n > h->cap) return -1;
@@ -1221,8 +1518,20 @@ int kdbo_import_graph(kdbo_index *h, uint32_t n, const float *rows, size_t row_s
     h->deleted[id] = 0;
   }
   for (uint32_t id = 1; id <= n; id++) {
-    memset(h->vecs + (size_t)id * h->stride, 0, h->stride * sizeof(float));
-    memcpy(h->vecs + (size_t)id * h->stride, rows + (size_t)id * row_stride, (size_t)h->dim * sizeof(float));
+    if (h->precision == KDBO_PREC_F16) { /* rows in stored form: float16 bits */
+      uint16_t *dst = h->rows16 + (size_t)id * h->qstride;
+      memset(dst, 0, h->qstride * sizeof(uint16_t));
+      memcpy(dst, (const uint16_t *)rows_any + (size_t)id * row_stride, (size_t)h->dim * sizeof(uint16_t));
+    } else if (h->precision == KDBO_PREC_I8) { /* int8 rows; norms follow from them (computeInt8Norm) */
+      int8_t *dst = h->rows8 + (size_t)id * h->qstride;
+      memset(dst, 0, h->qstride);
+      memcpy(dst, (const int8_t *)rows_any + (size_t)id * row_stride, (size_t)h->dim);
+      h->norms[id] = kdbo_int8_norm(dst, (size_t)h->dim);
+    } else {
+      const float *rows = (const float *)rows_any;
+      memset(h->vecs + (size_t)id * h->stride, 0, h->stride * sizeof(float));
+      memcpy(h->vecs + (size_t)id * h->stride, rows + (size_t)id * row_stride, (size_t)h->dim * sizeof(float));
+    }
     int L = levels[id];
     if (L > 120) return -1;
     h->level[id] = (int8_t)L;

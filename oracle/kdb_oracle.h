@@ -37,6 +37,12 @@ extern "C" {
 #define KDBO_ARITH_AVX2 1   /* 8-lane FMA + hadd + scalar tail (native/compute/src/lib.rs:22-99)   */
 #define KDBO_ARITH_KERNEL 2 /* the exact lane/tree order of the sm_100a kernel      */
 
+/* PrecisionType (distance_go.go:41-46).  float16 exists for Euclidean only, int8 for Cosine only
+ * (float16Funcs / int8Funcs, distance_go.go:139-146). */
+#define KDBO_PREC_F32 0
+#define KDBO_PREC_F16 1
+#define KDBO_PREC_I8 2
+
 typedef struct kdbo_index kdbo_index;
 
 typedef struct {
@@ -48,7 +54,15 @@ typedef struct {
 /* ---- lifecycle ------------------------------------------------------------------ */
 /* hnsw.New defaults: m<=0 -> 16, efc<=0 -> 200, mMax0 = 2m, ml = 1/ln m (hnsw_index.go:138-151) */
 kdbo_index *kdbo_new(int dim, int metric, int m, int ef_construction, int arith, uint32_t capacity);
+/* hnsw.New with a precision; NULL for a (metric, precision) pair the reference does not offer */
+kdbo_index *kdbo_new_ex(int dim, int metric, int precision, int m, int ef_construction, int arith,
+                        uint32_t capacity);
 void kdbo_free(kdbo_index *);
+int kdbo_precision(const kdbo_index *);
+/* Quantizer.AbsMax (pkg/core/distance/quantizer.go:19-22); set before adding int8 rows, as
+ * DB.Compress does through TrainQuantizer (pkg/core/core.go:1224-1232) */
+void kdbo_set_quantizer(kdbo_index *, float abs_max);
+float kdbo_abs_max(const kdbo_index *);
 void kdbo_set_arith(kdbo_index *, int arith);
 
 /* ---- build (graph construction stays CPU in the product; restated to obtain graphs) -- */
@@ -81,7 +95,7 @@ int kdbo_search_batch(const kdbo_index *, const float *queries, size_t nq, int k
                       double *out_scores, int32_t *out_counts, kdbo_stats *stats, int threads);
 /* searchLayerUnlocked (hnsw_index.go:2351-2611) on one level, exposed for tests. The query
  * must already be prepared (normalised for cosine). */
-int kdbo_search_layer(const kdbo_index *, const float *prepared_query, uint32_t entry, int k,
+int kdbo_search_layer(const kdbo_index *, const void *prepared_query, uint32_t entry, int k,
                       int level, const uint64_t *allow, size_t allow_words, int ef_search,
                       uint32_t *out_ids, double *out_scores, kdbo_stats *stats);
 
@@ -103,6 +117,15 @@ double kdbo_distance_generic(int metric, int arith, const float *a, const float 
 float kdbo_sq_euclid_f32(int arith, const float *a, const float *b, size_t n);
 float kdbo_dot_f32(int arith, const float *a, const float *b, size_t n);
 void kdbo_normalize(float *v, size_t n);      /* hnsw_index.go:3030-3045 */
+/* float16 / int8 precisions */
+uint16_t kdbo_f32_to_f16(float f);             /* float16.Fromfloat32(f).Bits(), IEEE RNE        */
+float kdbo_f16_to_f32(uint16_t h);             /* float16.Frombits(h).Float32(), exact           */
+float kdbo_sq_euclid_f16(int arith, const uint16_t *a, const uint16_t *b, size_t n); /* distance_go.go:93-105, lib.rs:101-141 */
+int32_t kdbo_dot_i8(const int8_t *a, const int8_t *b, size_t n);                     /* distance_go.go:108-118 */
+float kdbo_int8_norm(const int8_t *v, size_t n);                                     /* hnsw_index.go:3371-3377 */
+double kdbo_int8_cosine_distance(int32_t dot, float qnorm, float stored_norm);       /* hnsw_index.go:2421-2449 */
+void kdbo_quantize(float abs_max, const float *v, int8_t *out, size_t n);            /* quantizer.go:135-160 */
+float kdbo_train_quantizer(const float *vecs, size_t n, size_t dim);                 /* quantizer.go:49-125 */
 int kdbo_random_level(double u, int m, int current_max); /* hnsw_index.go:2616-2625 */
 double kdbo_score_from_distance(double d);    /* 1/(1+d), pkg/engine/search_utils.go:48-52 */
 int kdbo_effective_ef(int ef_search, int needs_refine); /* hnsw_index.go:387-399 */
@@ -119,7 +142,10 @@ uint32_t kdbo_entry(const kdbo_index *);
 int kdbo_max_level(const kdbo_index *);
 int kdbo_dim(const kdbo_index *);
 int kdbo_m(const kdbo_index *);
-const float *kdbo_vector(const kdbo_index *, uint32_t id); /* stored (normalised) row */
+const float *kdbo_vector(const kdbo_index *, uint32_t id); /* stored (normalised) row; float32 indexes only */
+const void *kdbo_row_raw(const kdbo_index *, uint32_t id);  /* stored row in the index precision  */
+size_t kdbo_row_raw_stride(const kdbo_index *);             /* elements between stored rows       */
+const float *kdbo_norms(const kdbo_index *);                /* int8: quantizedNorms, else NULL    */
 size_t kdbo_row_stride(const kdbo_index *);                 /* floats between rows      */
 /* Flattened adjacency: node i owns rows node_row[i]..node_row[i+1]-1 (one per level 0..L_i),
  * row r holds nbrs[row_off[r]..row_off[r+1]-1] in reference order. */
@@ -127,8 +153,9 @@ void kdbo_export_sizes(const kdbo_index *, uint64_t *n_rows, uint64_t *n_edges);
 void kdbo_export_graph(const kdbo_index *, int32_t *levels /*[n+1]*/, uint64_t *node_row /*[n+2]*/,
                        uint64_t *row_off /*[rows+1]*/, uint32_t *nbrs /*[edges]*/,
                        uint8_t *deleted /*[n+1]*/);
-/* Load vectors (already in stored form) + a graph produced elsewhere; replaces the content. */
-int kdbo_import_graph(kdbo_index *, uint32_t n, const float *rows, size_t row_stride,
+/* Load vectors (already in stored form: f32 / float16 bits / int8 by the index precision; row_stride
+ * in elements) + a graph produced elsewhere; replaces the content. */
+int kdbo_import_graph(kdbo_index *, uint32_t n, const void *rows, size_t row_stride,
                       const int32_t *levels, const uint64_t *node_row, const uint64_t *row_off,
                       const uint32_t *nbrs, const uint8_t *deleted, uint32_t entry, int max_level);
 

@@ -25,6 +25,10 @@ METRIC_COSINE = 1
 ARITH_SEQ = 0      # pure-Go sequential f32 loops (distance_go.go:57-89)
 ARITH_AVX2 = 1     # Rust AVX2/FMA order (native/compute/src/lib.rs:22-99)
 ARITH_KERNEL = 2   # summation order of the sm_100a kernel
+PREC_F32 = 0       # distance.Float32 (distance_go.go:41-46)
+PREC_F16 = 1       # distance.Float16 — Euclidean only
+PREC_I8 = 2        # distance.Int8 — Cosine only
+_RAW_DTYPE = {PREC_F32: np.float32, PREC_F16: np.uint16, PREC_I8: np.int8}
 
 
 def build(force: bool = False) -> str:
@@ -64,7 +68,35 @@ def lib():
     vp, u32p, f32p, f64p = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_double)
     L.kdbo_new.restype = vp
     L.kdbo_new.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
+    L.kdbo_new_ex.restype = vp
+    L.kdbo_new_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
     L.kdbo_free.argtypes = [vp]
+    L.kdbo_precision.restype = C.c_int
+    L.kdbo_precision.argtypes = [vp]
+    L.kdbo_set_quantizer.argtypes = [vp, C.c_float]
+    L.kdbo_abs_max.restype = C.c_float
+    L.kdbo_abs_max.argtypes = [vp]
+    L.kdbo_f32_to_f16.restype = C.c_uint16
+    L.kdbo_f32_to_f16.argtypes = [C.c_float]
+    L.kdbo_f16_to_f32.restype = C.c_float
+    L.kdbo_f16_to_f32.argtypes = [C.c_uint16]
+    L.kdbo_sq_euclid_f16.restype = C.c_float
+    L.kdbo_sq_euclid_f16.argtypes = [C.c_int, vp, vp, C.c_size_t]
+    L.kdbo_dot_i8.restype = C.c_int32
+    L.kdbo_dot_i8.argtypes = [vp, vp, C.c_size_t]
+    L.kdbo_int8_norm.restype = C.c_float
+    L.kdbo_int8_norm.argtypes = [vp, C.c_size_t]
+    L.kdbo_int8_cosine_distance.restype = C.c_double
+    L.kdbo_int8_cosine_distance.argtypes = [C.c_int32, C.c_float, C.c_float]
+    L.kdbo_quantize.argtypes = [C.c_float, vp, vp, C.c_size_t]
+    L.kdbo_train_quantizer.restype = C.c_float
+    L.kdbo_train_quantizer.argtypes = [vp, C.c_size_t, C.c_size_t]
+    L.kdbo_row_raw.restype = vp
+    L.kdbo_row_raw.argtypes = [vp, C.c_uint32]
+    L.kdbo_row_raw_stride.restype = C.c_size_t
+    L.kdbo_row_raw_stride.argtypes = [vp]
+    L.kdbo_norms.restype = C.POINTER(C.c_float)
+    L.kdbo_norms.argtypes = [vp]
     L.kdbo_set_arith.argtypes = [vp, C.c_int]
     L.kdbo_add.restype = C.c_uint32
     L.kdbo_add.argtypes = [vp, vp, C.c_double]
@@ -159,6 +191,53 @@ def normalize_rows(m) -> np.ndarray:
     return out
 
 
+def f32_to_f16_bits(v) -> np.ndarray:
+    """float16.Fromfloat32(x).Bits() elementwise (IEEE round-to-nearest-even)."""
+    a = _f32(v)
+    L = lib()
+    return np.array([L.kdbo_f32_to_f16(float(x)) for x in a.ravel()], dtype=np.uint16).reshape(a.shape)
+
+
+def f16_bits_to_f32(v) -> np.ndarray:
+    a = np.ascontiguousarray(v, dtype=np.uint16)
+    L = lib()
+    return np.array([L.kdbo_f16_to_f32(int(x)) for x in a.ravel()], dtype=np.float32).reshape(a.shape)
+
+
+def sq_euclid_f16(arith: int, a, b) -> np.float32:
+    a, b = np.ascontiguousarray(a, np.uint16), np.ascontiguousarray(b, np.uint16)
+    return np.float32(lib().kdbo_sq_euclid_f16(arith, _p(a), _p(b), a.size))
+
+
+def dot_i8(a, b) -> int:
+    a, b = np.ascontiguousarray(a, np.int8), np.ascontiguousarray(b, np.int8)
+    return int(lib().kdbo_dot_i8(_p(a), _p(b), a.size))
+
+
+def int8_norm(v) -> np.float32:
+    a = np.ascontiguousarray(v, np.int8)
+    return np.float32(lib().kdbo_int8_norm(_p(a), a.size))
+
+
+def int8_cosine_distance(dot: int, qnorm: float, stored_norm: float) -> float:
+    return float(lib().kdbo_int8_cosine_distance(int(dot), float(qnorm), float(stored_norm)))
+
+
+def quantize(abs_max: float, v) -> np.ndarray:
+    """Quantizer.Quantize (pkg/core/distance/quantizer.go:135-160), row-wise for 2-D input."""
+    a = _f32(v)
+    out = np.zeros(a.shape, dtype=np.int8)
+    lib().kdbo_quantize(float(abs_max), _p(a), _p(out), a.size)
+    return out
+
+
+def train_quantizer(vecs) -> np.float32:
+    """Quantizer.Train (quantizer.go:49-125): AbsMax = 99.9th percentile of |value| over a stride sample."""
+    a = _f32(vecs)
+    assert a.ndim == 2
+    return np.float32(lib().kdbo_train_quantizer(_p(a), a.shape[0], a.shape[1]))
+
+
 def random_level(u: float, m: int, current_max: int) -> int:
     return int(lib().kdbo_random_level(u, m, current_max))
 
@@ -220,12 +299,12 @@ class OracleIndex:
     """Mirror of hnsw.Index (reference pkg/core/hnsw/hnsw_index.go) restricted to the hot path."""
 
     def __init__(self, dim: int, metric: int, m: int = 16, ef_construction: int = 200,
-                 arith: int = ARITH_SEQ, capacity: int = 1 << 16):
+                 arith: int = ARITH_SEQ, capacity: int = 1 << 16, precision: int = PREC_F32):
         self._L = lib()
-        self._h = self._L.kdbo_new(dim, metric, m, ef_construction, arith, capacity)
+        self._h = self._L.kdbo_new_ex(dim, metric, precision, m, ef_construction, arith, capacity)
         if not self._h:
-            raise MemoryError("kdbo_new failed")
-        self.dim, self.metric, self.capacity = dim, metric, capacity
+            raise ValueError("kdbo_new_ex failed (unsupported metric/precision pair, or out of memory)")
+        self.dim, self.metric, self.capacity, self.precision = dim, metric, capacity, precision
         self.m = m if m > 0 else 16
         self.ef_construction = ef_construction if ef_construction > 0 else 200
         self.needs_refine = False
@@ -238,6 +317,13 @@ class OracleIndex:
     # -- build ---------------------------------------------------------------------------
     def set_arith(self, arith: int) -> None:
         self._L.kdbo_set_arith(self._h, arith)
+
+    def set_quantizer(self, abs_max: float) -> None:
+        self._L.kdbo_set_quantizer(self._h, float(abs_max))
+
+    @property
+    def abs_max(self) -> float:
+        return float(self._L.kdbo_abs_max(self._h))
 
     def add(self, vec, u: float) -> int:
         v = _f32(vec)
@@ -295,7 +381,7 @@ class OracleIndex:
 
     def search_layer(self, prepared_query, entry: int, k: int, level: int, ef_search: int,
                      allow: np.ndarray | None = None):
-        q = _f32(prepared_query)
+        q = np.ascontiguousarray(prepared_query, dtype=_RAW_DTYPE[self.precision])
         cap = max(k, ef_search, 1)
         ids = np.zeros(cap, dtype=np.uint32)
         sc = np.zeros(cap, dtype=np.float64)
@@ -347,6 +433,21 @@ class OracleIndex:
         arr = np.ctypeslib.as_array(base, shape=((n + 1) * stride,)).reshape(n + 1, stride)
         return np.ascontiguousarray(arr[:, : self.dim])
 
+    def rows_raw(self) -> np.ndarray:
+        """Stored rows [count+1, dim] in the index precision: float32, float16 bits (uint16) or int8."""
+        n = self.count
+        stride = int(self._L.kdbo_row_raw_stride(self._h))
+        dt = np.dtype(_RAW_DTYPE[self.precision])
+        base = self._L.kdbo_row_raw(self._h, 0)
+        buf = (C.c_char * ((n + 1) * stride * dt.itemsize)).from_address(base)
+        arr = np.frombuffer(buf, dtype=dt).reshape(n + 1, stride)
+        return np.ascontiguousarray(arr[:, : self.dim])
+
+    def norms(self) -> np.ndarray:
+        """int8 indexes: quantizedNorms[0..count] (computeInt8Norm of every stored row)."""
+        assert self.precision == PREC_I8
+        return np.ctypeslib.as_array(self._L.kdbo_norms(self._h), shape=(self.count + 1,)).copy()
+
     def export_graph(self) -> Graph:
         n = self.count
         rows, edges = C.c_uint64(), C.c_uint64()
@@ -360,8 +461,8 @@ class OracleIndex:
         return Graph(n, levels, node_row, row_off, nbrs[: edges.value], deleted, self.entry, self.max_level)
 
     def import_graph(self, vectors: np.ndarray, g: Graph) -> None:
-        """vectors: [n+1, dim] stored rows (row 0 unused)."""
-        v = _f32(vectors)
+        """vectors: [n+1, dim] stored rows (row 0 unused) in the index precision."""
+        v = np.ascontiguousarray(vectors, dtype=_RAW_DTYPE[self.precision])
         assert v.shape == (g.n + 1, self.dim)
         nbrs = g.nbrs if g.nbrs.size else np.zeros(1, dtype=np.uint32)
         rc = self._L.kdbo_import_graph(self._h, g.n, _p(v), self.dim, _p(np.ascontiguousarray(g.levels, np.int32)),
