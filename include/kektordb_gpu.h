@@ -200,6 +200,7 @@ int kdbgpu_download_vectors(kdbgpu_index *, uint32_t first_id, uint32_t count, f
  * synchronises the device.  For callers of the *_device entry points. */
 int kdbgpu_last_search_stats(kdbgpu_index *, kdbgpu_stats *stats);
 int kdbgpu_index_device(const kdbgpu_index *);
+int kdbgpu_index_dim(const kdbgpu_index *);
 uint32_t kdbgpu_index_count(const kdbgpu_index *);   /* n of the last kdbgpu_set_graph        */
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *);
 /* Resident CTAs the traversal kernel runs with for (k, ef) — queries in flight per launch. */
@@ -210,6 +211,37 @@ int kdbgpu_search_concurrency(kdbgpu_index *, int k, int ef_search);
  * entries kept in shared memory, cap on resident query-warps per SM (0 = no cap).  A value <= 0
  * (< 0 for the cap) keeps the current setting.  Results never depend on the shape. */
 int kdbgpu_set_tuning(kdbgpu_index *, int slots, int cand_smem, int max_ctas_per_sm);
+
+/* ---- micro-batcher: the reference's call shape on top of the batched entry point ----------------
+ * Every search in the reference is one blocking call per query from its own goroutine
+ * (idx.SearchWithScores(query, k, allowList, efSearch), pkg/engine/ops.go:1006, :1296).  A batcher keeps
+ * exactly that shape for the cgo shim — kdbgpu_batcher_search takes ONE query, blocks, returns its
+ * result — and forms device batches underneath: callers with the same (k, ef_search, allow-list) are
+ * grouped; a group is dispatched at once while the device is idle, and otherwise when it reaches
+ * max_batch queries or max_wait_us has passed since its first query.  Any number of threads may call.
+ * A failed search returns the error code and an empty result (hnsw_index.go:355-359).  Results are the
+ * ones kdbgpu_search_batch gives for that query alone: queries of a batch are independent. */
+typedef struct kdbgpu_batcher kdbgpu_batcher;
+/* The batch executor a batcher fronts; kdbgpu_batcher_create uses kdbgpu_search_batch on one handle,
+ * kdbgpu_batcher_create_fn takes any function of that shape (a sharded multi-GPU search, a test double). */
+typedef int (*kdbgpu_batch_fn)(void *ctx, const float *queries, uint32_t nq, int k, int ef_search,
+                               const uint64_t *allow, size_t allow_words, uint32_t *out_ids, double *out_scores,
+                               uint32_t *out_counts);
+typedef struct {
+  uint64_t queries, batches, max_batch_seen;
+  uint64_t dispatched_idle;     /* batches sent at once because nothing was in flight */
+  uint64_t dispatched_full;     /* batches sent because they reached max_batch         */
+  uint64_t dispatched_deadline; /* batches sent because max_wait_us passed             */
+} kdbgpu_batcher_stats_t;
+int kdbgpu_batcher_create(kdbgpu_index *, uint32_t max_batch, uint32_t max_wait_us, kdbgpu_batcher **out);
+int kdbgpu_batcher_create_fn(kdbgpu_batch_fn fn, void *ctx, int dim, uint32_t max_batch, uint32_t max_wait_us,
+                             kdbgpu_batcher **out);
+/* Waits for the callers inside to finish, then frees the batcher (not the index). */
+int kdbgpu_batcher_destroy(kdbgpu_batcher *);
+/* (*Index).SearchWithScores for one query: out_ids / out_scores hold k entries, *out_count <= k. */
+int kdbgpu_batcher_search(kdbgpu_batcher *, const float *query, int k, int ef_search, const uint64_t *allow,
+                          size_t allow_words, uint32_t *out_ids, double *out_scores, uint32_t *out_count);
+int kdbgpu_batcher_stats(kdbgpu_batcher *, kdbgpu_batcher_stats_t *out);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkektordb_gpu.so")
-SOURCES = ["api.cu", "search.cu", "flat.cu", "flat_tc.cu", "build.cu"]
+SOURCES = ["api.cu", "search.cu", "flat.cu", "flat_tc.cu", "build.cu", "batcher.cpp"]
 HEADERS = ["kdb_internal.cuh", "searcher.cuh", os.path.join("..", "..", "include", "kektordb_gpu.h")]
 
 
@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:  # one nvcc per translation unit, in parallel
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = common + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs, failed = [], False

@@ -1399,6 +1399,7 @@ int kdbgpu_last_search_stats(kdbgpu_index *h, kdbgpu_stats *stats) {
 }
 
 int kdbgpu_index_device(const kdbgpu_index *h) { return h ? h->device : -1; }
+int kdbgpu_index_dim(const kdbgpu_index *h) { return h ? h->dim : -1; }
 uint32_t kdbgpu_index_count(const kdbgpu_index *h) { return h ? h->n : 0; }
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *h) {
   if (!h) return 0;

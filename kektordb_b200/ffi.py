@@ -25,6 +25,16 @@ class GpuError(RuntimeError):
         self.code = code
 
 
+class BatcherStats(C.Structure):
+    _fields_ = [("queries", C.c_uint64), ("batches", C.c_uint64), ("max_batch_seen", C.c_uint64),
+                ("dispatched_idle", C.c_uint64), ("dispatched_full", C.c_uint64), ("dispatched_deadline", C.c_uint64)]
+
+
+# kdbgpu_batch_fn: the batch executor a micro-batcher fronts
+BATCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                       C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint32))
+
+
 class Stats(C.Structure):
     _fields_ = [("dist_evals", C.c_uint64), ("hops", C.c_uint64), ("hops_l0", C.c_uint64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float)]
@@ -64,6 +74,12 @@ SIGNATURES = {
     "kdbgpu_download_vectors": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_last_search_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "kdbgpu_index_device": (_i32, [_vp]),
+    "kdbgpu_index_dim": (_i32, [_vp]),
+    "kdbgpu_batcher_create": (_i32, [_vp, _u32, _u32, C.POINTER(_vp)]),
+    "kdbgpu_batcher_create_fn": (_i32, [BATCH_FN, _vp, _i32, _u32, _u32, C.POINTER(_vp)]),
+    "kdbgpu_batcher_destroy": (_i32, [_vp]),
+    "kdbgpu_batcher_search": (_i32, [_vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, C.POINTER(_u32)]),
+    "kdbgpu_batcher_stats": (_i32, [_vp, C.POINTER(BatcherStats)]),
     "kdbgpu_index_count": (_u32, [_vp]),
     "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),
     "kdbgpu_search_concurrency": (_i32, [_vp, _i32, _i32]),
