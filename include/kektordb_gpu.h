@@ -103,6 +103,21 @@ int kdbgpu_upload_rows_raw(kdbgpu_index *, uint32_t first_id, uint32_t count, co
 int kdbgpu_download_rows_raw(kdbgpu_index *, uint32_t first_id, uint32_t count, void *rows);
 /* int8: quantizedNorms[first_id .. first_id+count) (hnsw_index.go:87, :3371-3377) */
 int kdbgpu_download_norms(kdbgpu_index *, uint32_t first_id, uint32_t count, float *norms);
+/* Arena -> HBM staging: the reference keeps the stored rows in memory-mapped chunk files
+ * (pkg/storage/mmap/arena.go: <dir>/arena_%04d.bin, 64 MiB each, 64-byte header {magic 0x4B414F4E,
+ * version 1, dim, precision}, then (64 MiB - 64) / vectorSize rows; logical id -> physical slot through
+ * ArenaState.SlotTable, 0xFFFFFFFF = unallocated; :14-19, :121-152, :307-376, :378-444).  These calls
+ * move whole chunks to the device at DMA rate and place every row at its logical id there, instead of
+ * VectorArena.GetBytes + a copy per row.  slot_table is ArenaState.SlotTable (indexed by internal id,
+ * table_len entries; NULL = sequential slots, id i in slot i-1, with table_len = highest id + 1).
+ * Header magic / version / dim / precision are validated as addChunk does (:346-364).
+ *   kdbgpu_arena_load_dir     reads the chunk files of `dir` itself (cold start);
+ *   kdbgpu_arena_stage_chunk  takes one chunk the host already has mapped (header included).
+ * *rows_staged (may be NULL) receives the number of rows placed. */
+int kdbgpu_arena_load_dir(kdbgpu_index *, const char *dir, const uint32_t *slot_table, uint32_t table_len,
+                          uint64_t *rows_staged);
+int kdbgpu_arena_stage_chunk(kdbgpu_index *, uint32_t chunk_id, const void *chunk, size_t chunk_bytes,
+                             const uint32_t *slot_table, uint32_t table_len, uint32_t *rows_staged);
 /* Same, from device memory on the handle's device (row_stride in floats). */
 int kdbgpu_upload_vectors_device(kdbgpu_index *, uint32_t first_id, uint32_t count, const float *d_rows,
                                  size_t row_stride);

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkektordb_gpu.so")
-SOURCES = ["api.cu", "search.cu", "flat.cu", "flat_tc.cu", "build.cu", "batcher.cpp"]
+SOURCES = ["api.cu", "search.cu", "flat.cu", "flat_tc.cu", "build.cu", "arena.cu", "batcher.cpp"]
 HEADERS = ["kdb_internal.cuh", "searcher.cuh", os.path.join("..", "..", "include", "kektordb_gpu.h")]
 
 

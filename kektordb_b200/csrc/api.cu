@@ -48,6 +48,15 @@ cudaError_t launch_seq_add(const DevIndex &ix, const SearchArgs &a, uint32_t sta
                            uint32_t *adj0, uint32_t *upper_adj, uint32_t *entry_io, cudaStream_t stream);
 }  // namespace kdb
 
+namespace kdb {
+int arena_check_header(const unsigned char *hdr, uint32_t dim, int precision, const char *what);
+size_t arena_chunk_size();
+size_t arena_header_size();
+uint32_t arena_vecs_per_chunk(uint32_t vector_bytes);
+int arena_max_chunk(const char *dir, std::string *err);
+long arena_read_chunk(const char *dir, int id, unsigned char *hdr, unsigned char *dst, size_t want, std::string *err);
+}  // namespace kdb
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -61,6 +70,20 @@ int fail(int code, const char *fmt, ...) {
   g_last_error = buf;
   return code;
 }
+
+}  // namespace
+namespace kdb {
+int arena_fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+}  // namespace kdb
+namespace {
 
 #define CUDA_TRY(expr)                                                                              \
   do {                                                                                              \
@@ -968,6 +991,157 @@ int kdbgpu_train_quantizer_device(kdbgpu_index *h, const float *d_rows, size_t r
   uint32_t step, count;
   train_sample(n, &step, &count);
   return train_select(h, d_rows, row_stride, count, step, abs_max);
+}
+
+namespace {
+uint32_t elem_bytes(const kdbgpu_index *h) {
+  return h->precision == KDBGPU_PRECISION_F32 ? 4u : (h->precision == KDBGPU_PRECISION_F16 ? 2u : 1u);
+}
+// which chunks hold a slot of ids 1..last_id (host scan of the slot table; NULL = sequential slots)
+std::vector<char> chunks_in_use(const uint32_t *slot_table, uint32_t last_id, uint32_t vpc) {
+  std::vector<char> used;
+  auto mark = [&](uint32_t p) {
+    const uint32_t c = p / vpc;
+    if (c >= used.size()) used.resize((size_t)c + 1, 0);
+    used[c] = 1;
+  };
+  if (!slot_table) {
+    if (last_id >= 1) {
+      mark(0);
+      mark(last_id - 1);
+      for (size_t c = 0; c < used.size(); ++c) used[c] = 1;
+    }
+  } else {
+    for (uint32_t id = 1; id <= last_id; ++id)
+      if (slot_table[id] != 0xffffffffu) mark(slot_table[id]);
+  }
+  return used;
+}
+}  // namespace
+
+int kdbgpu_arena_stage_chunk(kdbgpu_index *h, uint32_t chunk_id, const void *chunk, size_t chunk_bytes,
+                             const uint32_t *slot_table, uint32_t table_len, uint32_t *rows_staged) {
+  if (rows_staged) *rows_staged = 0;
+  if (!h || !chunk) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (chunk_bytes < arena_header_size()) return fail(KDBGPU_ERR_INVALID, "chunk shorter than its header");
+  if (table_len < 2) return KDBGPU_OK;
+  const unsigned char *bytes = static_cast<const unsigned char *>(chunk);
+  int rc = arena_check_header(bytes, (uint32_t)h->dim, h->precision, "chunk");
+  if (rc) return rc;
+  const uint32_t vb = (uint32_t)h->dim * elem_bytes(h), vpc = arena_vecs_per_chunk(vb);
+  if (vpc == 0) return fail(KDBGPU_ERR_INVALID, "vector size %u exceeds chunk payload capacity", vb);
+  const size_t payload = (size_t)vpc * vb;
+  size_t have = chunk_bytes - arena_header_size();  // a short buffer: the rest reads as zero pages, as in the mmap
+  if (have > payload) have = payload;
+  uint32_t last_id = table_len - 1;
+  if (last_id > h->capacity) last_id = h->capacity;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->tc_valid = false;
+  DevBuf<unsigned char> d_stage;
+  DevBuf<uint32_t> d_slot;
+  DevBuf<unsigned int> d_cnt;
+  struct Free {
+    DevBuf<unsigned char> &a;
+    DevBuf<uint32_t> &b;
+    DevBuf<unsigned int> &c;
+    ~Free() { a.release(); b.release(); c.release(); }
+  } freer{d_stage, d_slot, d_cnt};
+  CUDA_TRY(d_stage.reserve(payload + 16));
+  CUDA_TRY(d_cnt.reserve(1, true));
+  cudaStream_t s = h->stream;
+  if (slot_table) {
+    CUDA_TRY(d_slot.reserve(table_len));
+    CUDA_TRY(cudaMemcpyAsync(d_slot.p, slot_table, (size_t)table_len * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  }
+  if (have < payload) CUDA_TRY(cudaMemsetAsync(d_stage.p + have, 0, payload - have, s));
+  CUDA_TRY(cudaMemcpyAsync(d_stage.p, bytes + arena_header_size(), have, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(launch_arena_scatter(d_stage.p, chunk_id, vpc, vb, slot_table ? d_slot.p : nullptr, 1, last_id, h->vecs.p,
+                                h->row_words, d_cnt.p, s));
+  if (h->precision == KDBGPU_PRECISION_INT8)
+    CUDA_TRY(launch_int8_norms(h->vecs.p + (size_t)h->row_words, h->row_words, last_id, (uint32_t)h->dim, h->norms.p + 1, s));
+  unsigned int cnt = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (rows_staged) *rows_staged = cnt;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_arena_load_dir(kdbgpu_index *h, const char *dir, const uint32_t *slot_table, uint32_t table_len,
+                          uint64_t *rows_staged) {
+  if (rows_staged) *rows_staged = 0;
+  if (!h || !dir) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (table_len < 2) return KDBGPU_OK;
+  const uint32_t vb = (uint32_t)h->dim * elem_bytes(h), vpc = arena_vecs_per_chunk(vb);
+  if (vpc == 0) return fail(KDBGPU_ERR_INVALID, "vector size %u exceeds chunk payload capacity", vb);
+  const size_t payload = (size_t)vpc * vb;
+  uint32_t last_id = table_len - 1;
+  if (last_id > h->capacity) last_id = h->capacity;
+  std::string err;
+  const int max_chunk = arena_max_chunk(dir, &err);
+  if (max_chunk < 0) return fail(KDBGPU_ERR_INVALID, "no arena_%%04d.bin chunk in %s", dir);
+  const std::vector<char> used = chunks_in_use(slot_table, last_id, vpc);
+  for (size_t c = 0; c < used.size(); ++c)
+    if (used[c] && (int)c > max_chunk)
+      return fail(KDBGPU_ERR_INVALID, "slot table refers to chunk %zu but %s holds chunks 0..%d", c, dir, max_chunk);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->tc_valid = false;
+  DevBuf<unsigned char> d_stage[2];
+  DevBuf<uint32_t> d_slot;
+  DevBuf<unsigned int> d_cnt;
+  unsigned char *pinned[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  struct Free {
+    DevBuf<unsigned char> *st;
+    DevBuf<uint32_t> &b;
+    DevBuf<unsigned int> &c;
+    unsigned char **pin;
+    cudaEvent_t *ev;
+    ~Free() {
+      st[0].release(); st[1].release(); b.release(); c.release();
+      for (int i = 0; i < 2; ++i) {
+        if (pin[i]) cudaFreeHost(pin[i]);
+        if (ev[i]) cudaEventDestroy(ev[i]);
+      }
+    }
+  } freer{d_stage, d_slot, d_cnt, pinned, ev};
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(d_stage[i].reserve(payload + 16));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pinned[i]), payload, cudaHostAllocDefault));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(d_cnt.reserve(1, true));
+  cudaStream_t s = h->stream;
+  if (slot_table) {
+    CUDA_TRY(d_slot.reserve(table_len));
+    CUDA_TRY(cudaMemcpyAsync(d_slot.p, slot_table, (size_t)table_len * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  }
+  int nb = 0;
+  for (size_t c = 0; c < used.size(); ++c) {
+    if (!used[c]) continue;
+    const int b = nb++ & 1;
+    CUDA_TRY(cudaEventSynchronize(ev[b]));  // the copy that last read this pinned buffer is done
+    unsigned char hdr[64];
+    if (arena_read_chunk(dir, (int)c, hdr, pinned[b], payload, &err) < 0) return fail(KDBGPU_ERR_INVALID, "%s", err.c_str());
+    char what[64];
+    snprintf(what, sizeof what, "file arena_%04d.bin", (int)c);
+    int rc = arena_check_header(hdr, (uint32_t)h->dim, h->precision, what);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_stage[b].p, pinned[b], payload, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(ev[b], s));
+    CUDA_TRY(launch_arena_scatter(d_stage[b].p, (uint32_t)c, vpc, vb, slot_table ? d_slot.p : nullptr, 1, last_id,
+                                  h->vecs.p, h->row_words, d_cnt.p, s));
+  }
+  if (h->precision == KDBGPU_PRECISION_INT8)
+    CUDA_TRY(launch_int8_norms(h->vecs.p + (size_t)h->row_words, h->row_words, last_id, (uint32_t)h->dim, h->norms.p + 1, s));
+  unsigned int cnt = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (rows_staged) *rows_staged = cnt;
+  return KDBGPU_OK;
 }
 
 int kdbgpu_index_precision(const kdbgpu_index *h) { return h ? h->precision : -1; }

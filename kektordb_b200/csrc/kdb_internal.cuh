@@ -100,6 +100,10 @@ cudaError_t launch_convert_rows(const float *in, size_t in_stride, float *out, s
 cudaError_t launch_abs_hist(const float *rows, size_t row_stride, uint32_t n_sample, uint32_t step, uint32_t dim,
                             uint32_t prefix, int hi_shift, int shift, int bits, unsigned long long *hist,
                             cudaStream_t stream);
+// arena chunk payload (device) -> mirror rows of the ids whose physical slot lives in that chunk
+cudaError_t launch_arena_scatter(const unsigned char *chunk, uint32_t chunk_id, uint32_t vecs_per_chunk,
+                                 uint32_t vector_bytes, const uint32_t *slot_table, uint32_t first_id, uint32_t last_id,
+                                 float *vecs, size_t row_words, unsigned int *n_staged, cudaStream_t stream);
 // int8 rows already in stored form -> norms[row] = computeInt8Norm
 cudaError_t launch_int8_norms(const float *rows, size_t row_words, uint32_t count, uint32_t dim, float *norms,
                               cudaStream_t stream);

@@ -179,6 +179,31 @@ __global__ void abs_hist_kernel(const float *__restrict__ rows, size_t row_strid
   }
 }
 
+// Arena chunk -> logical rows (VectorArena.GetBytes, pkg/storage/mmap/arena.go:378-444): physical slot
+// p of logical id i lives in chunk p / vecs_per_chunk at payload offset (p % vecs_per_chunk) *
+// vector_bytes.  `chunk` is the chunk's payload (header stripped) already in device memory; one warp
+// moves one row into the mirror (pitch row_words, padding untouched = zero).
+__global__ void arena_scatter_kernel(const unsigned char *__restrict__ chunk, uint32_t chunk_id, uint32_t vecs_per_chunk,
+                                     uint32_t vector_bytes, const uint32_t *__restrict__ slot_table, uint32_t first_id,
+                                     uint32_t last_id, float *__restrict__ vecs, size_t row_words,
+                                     unsigned int *__restrict__ n_staged) {
+  const uint32_t id = first_id + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (id > last_id) return;
+  const uint32_t p = slot_table ? slot_table[id] : id - 1u;  // sequential Adds: AllocSlot hands out 0, 1, 2, ... (:121-152)
+  if (p == 0xffffffffu || p / vecs_per_chunk != chunk_id) return;
+  const unsigned char *src = chunk + (size_t)(p % vecs_per_chunk) * vector_bytes;
+  unsigned char *dst = reinterpret_cast<unsigned char *>(vecs + (size_t)id * row_words);
+  if ((vector_bytes & 3u) == 0u && (reinterpret_cast<uintptr_t>(src) & 3u) == 0u) {
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t w = lane; w < (vector_bytes >> 2); w += 32) d4[w] = s4[w];
+  } else {
+    for (uint32_t b = lane; b < vector_bytes; b += 32) dst[b] = src[b];
+  }
+  if (lane == 0) atomicAdd(n_staged, 1u);
+}
+
 // computeInt8Norm (hnsw_index.go:3371-3377) of rows already in stored form, one warp per row
 __global__ void int8_norms_kernel(const float *__restrict__ rows, size_t row_words, uint32_t count, uint32_t dim,
                                   float *__restrict__ norms) {
@@ -335,6 +360,17 @@ cudaError_t launch_abs_hist(const float *rows, size_t row_stride, uint32_t n_sam
                             uint32_t prefix, int hi_shift, int shift, int bits, unsigned long long *hist,
                             cudaStream_t stream) {
   abs_hist_kernel<<<148 * 4, 256, 0, stream>>>(rows, row_stride, n_sample, step, dim, prefix, hi_shift, shift, bits, hist);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_arena_scatter(const unsigned char *chunk, uint32_t chunk_id, uint32_t vecs_per_chunk,
+                                 uint32_t vector_bytes, const uint32_t *slot_table, uint32_t first_id, uint32_t last_id,
+                                 float *vecs, size_t row_words, unsigned int *n_staged, cudaStream_t stream) {
+  if (last_id < first_id) return cudaSuccess;
+  const uint32_t count = last_id - first_id + 1, wpb = 8;
+  arena_scatter_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, stream>>>(chunk, chunk_id, vecs_per_chunk, vector_bytes,
+                                                                      slot_table, first_id, last_id, vecs, row_words,
+                                                                      n_staged);
   return cudaGetLastError();
 }
 

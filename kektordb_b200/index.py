@@ -127,6 +127,29 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_download_norms(self._handle(), first_id, count, _ptr(out)))
         return out
 
+    def load_arena(self, arena_dir: str, slot_table: np.ndarray | None = None, n: int | None = None) -> int:
+        """Stage the rows of a reference vector arena (pkg/storage/mmap/arena.go) from its chunk files.
+        slot_table = ArenaState.SlotTable (uint32, indexed by internal id) or None for sequential slots
+        of ids 1..n.  Returns the number of rows staged."""
+        staged = C.c_uint64(0)
+        if slot_table is None:
+            if n is None:
+                raise ValueError("n is needed without a slot table")
+            ffi.check(self._lib.kdbgpu_arena_load_dir(self._handle(), arena_dir.encode(), None, n + 1, C.byref(staged)))
+        else:
+            st = np.ascontiguousarray(slot_table, dtype=np.uint32)
+            ffi.check(self._lib.kdbgpu_arena_load_dir(self._handle(), arena_dir.encode(), _ptr(st), st.size, C.byref(staged)))
+        return int(staged.value)
+
+    def stage_arena_chunk(self, chunk_id: int, chunk: np.ndarray, slot_table: np.ndarray | None, table_len: int) -> int:
+        """One chunk the host already holds (header included), e.g. the Go side's mmap of arena_%04d.bin."""
+        buf = np.ascontiguousarray(chunk, dtype=np.uint8)
+        st = None if slot_table is None else np.ascontiguousarray(slot_table, dtype=np.uint32)
+        staged = C.c_uint32(0)
+        ffi.check(self._lib.kdbgpu_arena_stage_chunk(self._handle(), chunk_id, _ptr(buf), buf.size, _ptr(st), table_len,
+                                                     C.byref(staged)))
+        return int(staged.value)
+
     def set_quantizer(self, abs_max: float) -> None:
         """Quantizer.AbsMax of an int8 index (pkg/core/distance/quantizer.go:19-22)."""
         ffi.check(self._lib.kdbgpu_set_quantizer(self._handle(), float(abs_max)))
