@@ -74,7 +74,8 @@ int kdbgpu_index_create(int device, int dim, int metric, int m, uint32_t capacit
 /* hnsw.New with its precision argument (hnsw_index.go:138).  A float16 / int8 handle keeps the rows
  * in their stored form (2 / 1 bytes per element: the traversal kernel is HBM-bound, so bytes per row
  * are what it pays for) and answers kdbgpu_search_batch / kdbgpu_distance_batch with the reference's
- * arithmetic for that precision; the flat scan and device-side construction are float32-only. */
+ * arithmetic for that precision, kdbgpu_add_batch builds with that precision's distances (as DB.Compress
+ * does through AddBatch, pkg/core/core.go:1210-1270); the flat scan is float32-only (BruteForceIndex). */
 int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m, uint32_t capacity,
                            kdbgpu_index **out);
 int kdbgpu_index_destroy(kdbgpu_index *);

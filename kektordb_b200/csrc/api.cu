@@ -703,6 +703,9 @@ int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m
   }
   h->num_sms = prop.multiProcessorCount;
   const char *env;
+  // float16 / int8 rows: the traversal is latency-bound, so resident query-warps matter more than
+  // shared-memory heap capacity (measured: profiles/README.md, quantized sweep)
+  if (precision != KDBGPU_PRECISION_F32) h->tuning.cand_smem = 64;
   if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
   if ((env = getenv("KDBGPU_CAND_SMEM"))) h->tuning.cand_smem = atoi(env);
   if ((env = getenv("KDBGPU_MAX_CTAS_PER_SM"))) h->tuning.max_ctas_per_sm = atoi(env);
@@ -1642,8 +1645,8 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   if (ef_const <= 0) ef_const = 200;  // hnsw.New default (hnsw_index.go:143-145)
   if (ef_const > 2048) return fail(KDBGPU_ERR_INVALID, "ef_const %d too large (max 2048)", ef_const);
   if (h->m < 2) return fail(KDBGPU_ERR_INVALID, "construction needs m >= 2");
-  if (h->precision != KDBGPU_PRECISION_F32)
-    return fail(KDBGPU_ERR_INVALID, "device-side construction exists for float32 indexes only (stage the graph with kdbgpu_set_graph)");
+  if (h->precision == KDBGPU_PRECISION_INT8 && h->abs_max == 0.f)
+    return fail(KDBGPU_ERR_STATE, "int8 index without a trained quantizer (kdbgpu_set_quantizer / kdbgpu_train_quantizer)");
   std::unique_lock<std::shared_mutex> lk(h->mu);
   if ((uint64_t)h->n + count > h->capacity)
     return fail(KDBGPU_ERR_INVALID, "batch of %u does not fit: %u of %u ids used", count, h->n, h->capacity);
@@ -1661,8 +1664,15 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
     d_src = h->q_raw.p;
     row_stride = (size_t)h->dim;
   }
-  CUDA_TRY(launch_prep_queries(d_src, row_stride, h->vecs.p + (size_t)start_id * h->stride, count, (uint32_t)h->dim,
-                               h->stride, h->metric, s));
+  if (h->precision == KDBGPU_PRECISION_F32) {
+    CUDA_TRY(launch_prep_queries(d_src, row_stride, h->vecs.p + (size_t)start_id * h->stride, count, (uint32_t)h->dim,
+                                 h->stride, h->metric, s));
+  } else {
+    // float16 / int8 rows are converted, never normalised (:497-520, :1553-1577); int8 norms alongside
+    CUDA_TRY(launch_convert_rows(d_src, row_stride, h->vecs.p + (size_t)start_id * h->row_words, h->row_words, count,
+                                 (uint32_t)h->dim, h->kind, false, h->abs_max,
+                                 h->norms.p ? h->norms.p + start_id : nullptr, false, s));
+  }
   // levels (:647, :1738) and upper-row allocation
   const int pre_max = h->max_level;
   const uint32_t pre_entry = h->entry;

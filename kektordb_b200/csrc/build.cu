@@ -29,17 +29,27 @@ __device__ __forceinline__ uint32_t *row_ptr(uint32_t *adj0, uint32_t *upper_adj
   return upper_adj + ((size_t)ix.upper_first[id] + (uint32_t)(level - 1)) * ix.degu;
 }
 
-// distance between a vector staged in shared memory (q4) and stored node `id`
+// distanceBetweenNodes (hnsw_index.go:297-341): a stored row staged in shared memory (q4, int8 norm
+// qnorm) against stored node `id`; int8 returns 1.0 when either norm is 0 (:325-327)
 template <int METRIC>
-__device__ __forceinline__ double dist_to_node(const DevIndex &ix, const float4 *q4, uint32_t id, int lane) {
-  const float s = warp_reduce_row<METRIC>(q4, reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.stride),
-                                          ix.stride >> 2, lane);
+__device__ __forceinline__ double dist_to_node(const DevIndex &ix, const float4 *q4, float qnorm, uint32_t id,
+                                               int lane) {
+  const float s = warp_reduce_row<METRIC>(q4, reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.row_words),
+                                          ix.row_words >> 2, lane);
+  if (METRIC == KIND_COS_I8) {
+    if (qnorm == 0.f) return 1.0;
+    return to_distance<METRIC>(s, qnorm, ix.norms[id]);
+  }
   return to_distance<METRIC>(s);
+}
+template <int METRIC>
+__device__ __forceinline__ float node_norm(const DevIndex &ix, uint32_t id) {
+  return METRIC == KIND_COS_I8 ? ix.norms[id] : 0.f;
 }
 
 __device__ __forceinline__ void stage_vector(const DevIndex &ix, float4 *q4, uint32_t id, int tid, int nthreads) {
-  const float4 *src = reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.stride);
-  for (uint32_t c = tid; c < (ix.stride >> 2); c += nthreads) q4[c] = src[c];
+  const float4 *src = reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.row_words);
+  for (uint32_t c = tid; c < (ix.row_words >> 2); c += nthreads) q4[c] = src[c];
 }
 
 // In-place bitonic sort of n2 (power of two) pairs by (d, id) or by id only.
@@ -98,8 +108,9 @@ __device__ int select_neighbors_dev(const DevIndex &ix, const double *d, const u
     if (tid == 0) *flag = 0;
     __syncthreads();
     const double de = d[w];
+    const float qn = node_norm<METRIC>(ix, ids[w]);
     for (int r = warp; r < nr; r += nwarps) {  // :2652-2679 (any closer kept neighbour discards e)
-      const double dd = dist_to_node<METRIC>(ix, q4, ids[sel[r]], lane);
+      const double dd = dist_to_node<METRIC>(ix, q4, qn, ids[sel[r]], lane);
       if (lane == 0 && dd < de) *flag = 1;
     }
     __syncthreads();
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(32)
     if (i >= b.count) break;
     const uint32_t id = b.start_id + i;
     const int node_level = ix.levels[id];
-    s.load_query(ix.vecs + (size_t)id * ix.stride);
+    s.load_row_as_query(id);  // currObj := storedVector (:674, :1806)
     uint32_t ep = b.pre_entry;
     for (int l = b.pre_max; l > node_level; --l) {  // zoom in (:1819-1824)
       const int n = s.search_layer(l, 1, ep);
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(kCommitThreads) commit_kernel(const DevIndex i
         const uint32_t e = ids[i];
         const bool dead = ix.levels[e] < 0 || (ix.deleted && bit_test(ix.deleted, e));  // :2024-2026
         if (!dead)
-          dv = dist_to_node<METRIC>(ix, q4, e, lane);
+          dv = dist_to_node<METRIC>(ix, q4, node_norm<METRIC>(ix, t), e, lane);
         else if (lane == 0)
           ids[i] = 0xffffffffu;
       } else if (lane == 0) {
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(32) seq_add_kernel(const DevIndex ix_in, const
       continue;
     }
     __syncthreads();
-    s.load_query(ix.vecs + (size_t)id * ix.stride);
+    s.load_row_as_query(id);
     uint32_t ep = entry;
     for (int l = cur_max; l > level; --l) {  // :685-690
       const int n = s.search_layer(l, 1, ep);
@@ -488,7 +499,7 @@ __global__ void __launch_bounds__(32) seq_add_kernel(const DevIndex ix_in, const
         na++;
         __syncthreads();
         for (uint32_t j = warp; j < na; j += 1) {
-          const double dv = dist_to_node<METRIC>(ix, q2, aid[j], lane);
+          const double dv = dist_to_node<METRIC>(ix, q2, node_norm<METRIC>(ix, nb), aid[j], lane);
           if (lane == 0) ad[j] = dv;
         }
         __syncthreads();
@@ -519,7 +530,7 @@ constexpr int kBuildSlots = 8;
 
 __host__ inline int build_cpl_of(const DevIndex &ix) {
   const uint32_t c = ix.stride / 128;
-  return (c == 1 || c == 2 || c == 4 || c == 6 || c == 8 || c == 12) ? (int)c : 0;
+  return (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8 || c == 12) ? (int)c : 0;
 }
 
 template <int METRIC, int CPL>
@@ -543,30 +554,49 @@ int build_search_occ_one(size_t smem) {
   }
   return nb;
 }
-#define KDB_BUILD_DISPATCH(EXPR)                                  \
-  if (ix.metric == KDBGPU_METRIC_COSINE) {                        \
-    constexpr int MT = KDBGPU_METRIC_COSINE;                      \
+#define KDB_BUILD_CPL(EXPR)                                       \
     switch (build_cpl_of(ix)) {                                   \
       case 1: { constexpr int CP = 1; EXPR; } break;              \
       case 2: { constexpr int CP = 2; EXPR; } break;              \
+      case 3: { constexpr int CP = 3; EXPR; } break;              \
       case 4: { constexpr int CP = 4; EXPR; } break;              \
       case 6: { constexpr int CP = 6; EXPR; } break;              \
       case 8: { constexpr int CP = 8; EXPR; } break;              \
       case 12: { constexpr int CP = 12; EXPR; } break;            \
       default: { constexpr int CP = 0; EXPR; } break;             \
-    }                                                             \
-  } else {                                                        \
-    constexpr int MT = KDBGPU_METRIC_L2;                          \
-    switch (build_cpl_of(ix)) {                                   \
-      case 1: { constexpr int CP = 1; EXPR; } break;              \
-      case 2: { constexpr int CP = 2; EXPR; } break;              \
-      case 4: { constexpr int CP = 4; EXPR; } break;              \
-      case 6: { constexpr int CP = 6; EXPR; } break;              \
-      case 8: { constexpr int CP = 8; EXPR; } break;              \
-      case 12: { constexpr int CP = 12; EXPR; } break;            \
-      default: { constexpr int CP = 0; EXPR; } break;             \
-    }                                                             \
+    }
+#define KDB_BUILD_DISPATCH(EXPR)                                                   \
+  switch (ix.kind) {                                                               \
+    case KIND_COS_F32: { constexpr int MT = KIND_COS_F32; KDB_BUILD_CPL(EXPR) } break; \
+    case KIND_L2_F16: { constexpr int MT = KIND_L2_F16; KDB_BUILD_CPL(EXPR) } break;   \
+    case KIND_COS_I8: { constexpr int MT = KIND_COS_I8; KDB_BUILD_CPL(EXPR) } break;   \
+    default: { constexpr int MT = KIND_L2_F32; KDB_BUILD_CPL(EXPR) } break;            \
   }
+#define KDB_KIND_DISPATCH(EXPR)                                          \
+  switch (ix.kind) {                                                     \
+    case KIND_COS_F32: { constexpr int MT = KIND_COS_F32; EXPR; } break; \
+    case KIND_L2_F16: { constexpr int MT = KIND_L2_F16; EXPR; } break;   \
+    case KIND_COS_I8: { constexpr int MT = KIND_COS_I8; EXPR; } break;   \
+    default: { constexpr int MT = KIND_L2_F32; EXPR; } break;            \
+  }
+
+template <int MT>
+cudaError_t launch_commit_kind(const DevIndex &ix, const CommitArgs &c, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = commit_kernel<MT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kCommitThreads, smem, stream>>>(ix, c);
+  return cudaGetLastError();
+}
+template <int MT>
+cudaError_t launch_seq_kind(const DevIndex &ix, const SearchArgs &a, const SeqAddArgs &b, size_t smem,
+                            cudaStream_t stream) {
+  auto kern = seq_add_kernel<MT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<1, 32, smem, stream>>>(ix, a, b);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_build_search_cfg(const DevIndex &ix, const SearchArgs &a, const BuildSearchArgs &b, int grid,
                                     size_t smem, cudaStream_t stream) {
@@ -677,16 +707,9 @@ cudaError_t launch_add_batch(const DevIndex &ix, const SearchArgs &a, const Buil
   c.scratch_cap = L.scratch_cap;
   c.err_flag = a.err_flag;
   const size_t csmem = commit_smem_bytes(ix);
-  if (ix.metric == KDBGPU_METRIC_COSINE) {
-    auto kern = commit_kernel<KDBGPU_METRIC_COSINE>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)) != cudaSuccess) return e;
-    kern<<<L.commit_grid, kCommitThreads, csmem, stream>>>(ix, c);
-  } else {
-    auto kern = commit_kernel<KDBGPU_METRIC_L2>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)) != cudaSuccess) return e;
-    kern<<<L.commit_grid, kCommitThreads, csmem, stream>>>(ix, c);
-  }
-  return cudaGetLastError();
+  e = cudaSuccess;
+  KDB_KIND_DISPATCH(e = (launch_commit_kind<MT>(ix, c, L.commit_grid, csmem, stream)))
+  return e;
 }
 
 // the single-Add fallback: `count` sequential Adds by one CTA
@@ -700,17 +723,9 @@ cudaError_t launch_seq_add(const DevIndex &ix, const SearchArgs &a, uint32_t sta
   b.upper_adj = upper_adj;
   b.entry_io = entry_io;
   const size_t smem = seq_add_smem_bytes(ix, efc, a.cand_smem);
-  cudaError_t e;
-  if (ix.metric == KDBGPU_METRIC_COSINE) {
-    auto kern = seq_add_kernel<KDBGPU_METRIC_COSINE>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    kern<<<1, 32, smem, stream>>>(ix, a, b);
-  } else {
-    auto kern = seq_add_kernel<KDBGPU_METRIC_L2>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    kern<<<1, 32, smem, stream>>>(ix, a, b);
-  }
-  return cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  KDB_KIND_DISPATCH(e = (launch_seq_kind<MT>(ix, a, b, smem, stream)))
+  return e;
 }
 
 }  // namespace kdb

@@ -203,7 +203,10 @@ struct Searcher {
   ResHeap res;          // meaningful on lane 0
   unsigned long long st_e, st_h, st_h0;
   bool overflow;
-  float qnorm;  // int8: query-side norm (hnsw_index.go:2405-2413)
+  double worst;  // lane 0: results.Peek().Distance while the result heap is non-empty (kept in a register)
+  float qnorm;   // int8: query-side norm (hnsw_index.go:2405-2413)
+  uint32_t slots_u32, bars_u32, slot_bytes, row_bytes;  // shared-window addresses of the row slots / barriers
+  const unsigned char *vec_bytes;
   float4 qreg[CPL > 0 ? CPL : 1];
 
   __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem)
@@ -217,6 +220,11 @@ struct Searcher {
     cand.n = 0;
     res.a = sm.res;
     res.n = 0;
+    slots_u32 = smem_u32(sm.slots);
+    bars_u32 = smem_u32(sm.bars);
+    slot_bytes = ix.stride * (uint32_t)sizeof(float);
+    row_bytes = ix.row_words * (uint32_t)sizeof(float);
+    vec_bytes = reinterpret_cast<const unsigned char *>(ix.vecs);
   }
 
   __device__ __forceinline__ void init_barriers() {
@@ -245,16 +253,37 @@ struct Searcher {
     __syncwarp();
   }
 
+  // a stored row as the query (construction: currObj := storedVector, hnsw_index.go:674, :1806): the
+  // row's own bytes, zero beyond its pitch, and for int8 the query-side norm of :2405-2413 (0 -> 1)
+  __device__ __forceinline__ void load_row_as_query(uint32_t id) {
+    const float4 *src = reinterpret_cast<const float4 *>(ix.vecs + (size_t)id * ix.row_words);
+    const uint32_t valid = ix.row_words >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (CPL > 0) {
+#pragma unroll
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) qreg[t] = (uint32_t)(lane + 32 * t) < valid ? src[lane + 32 * t] : z;
+    } else {
+      for (uint32_t c = lane; c < (ix.stride >> 2); c += 32) sm.q4[c] = c < valid ? src[c] : z;
+    }
+    if (METRIC == KIND_COS_I8) {
+      const float nrm = ix.norms[id];
+      qnorm = nrm == 0.f ? 1.f : nrm;
+    }
+    __syncwarp();
+  }
+
   __device__ __forceinline__ void issue_row(uint32_t j, uint32_t id) {  // lane 0
     const uint32_t slot = j & (SLOTS - 1);
-    const uint32_t row_bytes = ix.row_words * sizeof(float);
-    mbar_expect_tx(&sm.bars[slot], row_bytes);
-    bulk_g2s(sm.slots + (size_t)slot * ix.stride, ix.vecs + (size_t)id * ix.row_words, row_bytes, &sm.bars[slot]);
+    const uint32_t bar = bars_u32 + slot * 8u;
+    mbar_expect_tx_u32(bar, row_bytes);
+    bulk_g2s_u32(slots_u32 + slot * slot_bytes, vec_bytes + (size_t)id * row_bytes, row_bytes, bar);
   }
 
   __device__ __forceinline__ void wait_slot(uint32_t j) {
     const uint32_t slot = j & (SLOTS - 1);
-    mbar_wait(&sm.bars[slot], (phase_bits >> slot) & 1u);
+    const uint32_t bar = bars_u32 + slot * 8u, parity = (phase_bits >> slot) & 1u;
+    while (!mbar_try_wait_u32(bar, parity)) {
+    }
     phase_bits ^= 1u << slot;
   }
 
@@ -276,16 +305,31 @@ struct Searcher {
   // lane 0: the reference's per-neighbour result update (:2571-2591)
   __device__ __forceinline__ void heap_update(float s, uint32_t j, int ef) {
     HeapEntry e;
-    e.d = to_distance<METRIC>(s, qnorm, METRIC == KIND_COS_I8 ? sm.eval_norm[j] : 0.f);
+    if (METRIC == KIND_COS_I8) {
+      // Once the result heap is full most neighbours are turned away (:2577).  That verdict does not
+      // need the float64 divide: with P = qNorm * storedNorm > 0 and w = the worst kept distance,
+      //   dot <= ((1 - w) - 1e-12) * P   ==>   1 - dot / P >= w + 1e-12   ==>   the reference's rounded
+      // distance (three roundings, <= 1e-15 off; the clamp only ever yields 2 >= w) is >= w: not admitted.
+      const float sn = sm.eval_norm[j];
+      if (res.n >= ef && sn != 0.f) {
+        const double P = __dmul_rn(static_cast<double>(qnorm), static_cast<double>(sn));
+        const double t = __dmul_rn(__dsub_rn(__dsub_rn(1.0, worst), 1e-12), P);
+        if (static_cast<double>(__float_as_int(s)) <= t) return;
+      }
+      e.d = int8_distance(__float_as_int(s), qnorm, sn);
+    } else {
+      e.d = to_distance<METRIC>(s);
+    }
     e.id = sm.eval_id[j];
     e.pad = 0;
     bool admit = res.n < ef;  // worstDist = MaxFloat64 while results is empty
-    if (!admit) admit = e.d < res.a[0].d;
+    if (!admit) admit = e.d < worst;
     if (admit) {
       if (!cand.push(e)) overflow = true;  // :2581
       if (!sm.eval_del[j]) {              // :2584
         res.push(e);
         if (res.n > ef) (void)res.pop();  // :2587-2589
+        worst = res.a[0].d;
       }
     }
   }
@@ -339,7 +383,10 @@ struct Searcher {
       bool ep_valid = true;        // :2481-2485 (an empty allow-list never reaches the kernel)
       if (a.allow != nullptr && !bit_test(a.allow, ep)) ep_valid = false;
       const bool del = ix.deleted != nullptr && bit_test(ix.deleted, ep);
-      if (ep_valid && !del) res.push(e);  // :2487-2489
+      if (ep_valid && !del) {  // :2487-2489
+        res.push(e);
+        worst = e.d;
+      }
       st_e += 1;
     }
     __syncwarp();
@@ -348,7 +395,7 @@ struct Searcher {
       uint32_t cur = 0xffffffffu;
       if (lane == 0 && cand.n > 0 && !overflow) {
         const HeapEntry c = cand.pop();
-        if (!(res.n >= ef && c.d > res.a[0].d)) cur = c.id;  // :2501-2506
+        if (!(res.n >= ef && c.d > worst)) cur = c.id;  // :2501-2506
       }
       cur = __shfl_sync(0xffffffffu, cur, 0);
       if (cur == 0xffffffffu) break;

@@ -97,3 +97,65 @@ def test_capacity_is_enforced():
         gi.AddBatch(rng.standard_normal((20, 8)).astype(np.float32), rng.random(20), 10)
     assert gi.count == 40
     gi.close()
+
+
+# ---- float16 / int8 indexes: construction with the precision's own distances (what DB.Compress does:
+# ---- TrainQuantizer, then AddBatch into a new index of that precision, pkg/core/core.go:1210-1270)
+def _compare_quantized(prec, n, dim, m, efc, batches, seed, data="normal"):
+    from kektordb_b200 import GpuIndex
+    rng = np.random.default_rng(seed)
+    X = (rng.standard_normal((n, dim)) if data == "normal" else rng.integers(-2, 3, (n, dim))).astype(np.float32)
+    u = rng.random(n)
+    oprec, metric, om = (O.PREC_F16, "euclidean", O.METRIC_L2) if prec == "float16" else (O.PREC_I8, "cosine", O.METRIC_COSINE)
+    oi = O.OracleIndex(dim, om, m, efc, O.ARITH_KERNEL, n, precision=oprec)
+    gi = GpuIndex(dim, metric, m, n, precision=prec)
+    if prec == "int8":
+        am = gi.TrainQuantizer(X)                       # on the device
+        assert np.float32(am) == O.train_quantizer(X)
+        oi.set_quantizer(am)
+    pos = 0
+    for b in batches:
+        b = min(b, n - pos)
+        if b <= 0:
+            break
+        gi.AddBatch(X[pos:pos + b], u[pos:pos + b], efc)
+        oi.add_batch(X[pos:pos + b], u[pos:pos + b], efc, threads=8)
+        pos += b
+        g = oi.export_graph()
+        gn, levels, node_row, row_off, nbrs, entry, max_level = gi.get_graph()
+        assert (gn, entry, max_level) == (g.n, g.entry, g.max_level)
+        assert np.array_equal(levels, g.levels)
+        assert np.array_equal(row_off, g.row_off)
+        assert np.array_equal(nbrs, g.nbrs)
+    assert np.array_equal(gi.download_rows_raw(1, n), oi.rows_raw()[1:])
+    if prec == "int8":
+        assert np.array_equal(gi.download_norms(1, n), oi.norms()[1:])
+    Q = rng.standard_normal((48, dim)).astype(np.float32)
+    ids, sc, cnt, st = gi.SearchWithScores(Q, 10, None, 50)
+    oids, osc, ocnt, ost = oi.search_batch(Q, 10, 50, threads=8)
+    assert np.array_equal(ids, oids) and np.array_equal(sc, osc) and st.dist_evals == ost.dist_evals
+    gi.close()
+
+
+@pytest.mark.parametrize("prec", ["float16", "int8"])
+def test_quantized_sequential_fallback_and_batches(prec):
+    _compare_quantized(prec, 400, 24, 4, 20, [10, 5, 5, 30, 50, 300], 11)
+
+
+@pytest.mark.parametrize("prec,dim", [("float16", 128), ("int8", 128), ("float16", 768), ("int8", 768), ("int8", 200)])
+def test_quantized_batches(prec, dim):
+    _compare_quantized(prec, 2000 if dim < 768 else 1200, dim, 8, 40, [40, 60, 100, 300, 2000], 12 + dim)
+
+
+@pytest.mark.parametrize("prec", ["float16", "int8"])
+def test_quantized_exact_ties(prec):
+    _compare_quantized(prec, 1000, 12, 6, 30, [30, 70, 300, 600], 13, data="grid")
+
+
+def test_int8_construction_needs_a_trained_quantizer():
+    from kektordb_b200 import GpuIndex, ffi
+    gi = GpuIndex(8, "cosine", 4, 50, precision="int8")
+    rng = np.random.default_rng(7)
+    with pytest.raises(ffi.GpuError):
+        gi.AddBatch(rng.standard_normal((10, 8)).astype(np.float32), rng.random(10), 10)
+    gi.close()

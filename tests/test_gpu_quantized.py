@@ -197,14 +197,12 @@ def test_float32_upload_equals_raw_upload(prec):
         gi.close()
 
 
-def test_quantized_handles_refuse_float32_only_paths():
+def test_quantized_handles_refuse_the_flat_scan():
     from kektordb_b200 import ffi
     oi, X, rng = _oracle_index(O.PREC_I8, 300, 16, 4, 20, 5)
     gi, _ = _mirror(oi, O.PREC_I8, 4)
     with pytest.raises(ffi.GpuError):
         gi.flat_search(X[:2], 3, 0)
-    with pytest.raises(ffi.GpuError):
-        gi.AddBatch(X[:4], rng.random(4))
     gi.close()
     GpuIndex = _gpu()
     g2 = GpuIndex(16, "cosine", 4, 8, precision="int8")     # no quantizer yet
