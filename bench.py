@@ -299,6 +299,7 @@ def main():
 
     # ---- ground truth + recall (untimed) ---------------------------------------------------------
     n_gt = min(256, B)
+    gi.prepare_search(B, k, ef)  # every launch workspace allocated up front (no allocation inside a timed region)
     ids0, sc0, cnt0, st0 = gi.SearchWithScores(Qh_np[:B], k, None, ef)  # also the first warm-up
     gt_ids, gt_sc, _, _ = gi.flat_search(Qh_np[:n_gt], k, 1)
     recall_local = recall_at_k(ids0[:n_gt], gt_ids)

@@ -257,6 +257,7 @@ def run_hybrid(args, torch, bench):
                           "gpu_launches": 0}), flush=True)
         return 0
 
+    gi.prepare_search(B, k, ef)
     ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, allow, ef)
     n_gt = min(256, B)
     gt_ids, _, gt_cnt, _ = gi.flat_search(Q[:n_gt], k, 1, allow, prefilter=True)
@@ -328,8 +329,8 @@ def run_quantized(args, torch, bench):
     """the HNSW traversal over int8 (cosine) / float16 (euclidean) rows.  Distances follow
     the reference's arithmetic for the precision (hnsw_index.go:2398-2449, distance_go.go:93-118); int8
     results are bit-identical to the CPU path in any summation order (integer dot), float16 ones in
-    kernel order.  The graph is the float32 GPU build over the same rows (device-side construction is
-    float32-only; DB.Compress would rebuild with the quantized distances) — both arms search the same graph."""
+    kernel order.  The graph is built on the device with the precision's own distances (TrainQuantizer +
+    AddBatch, as DB.Compress does) and is bit-identical to the oracle's build; both arms search the same graph."""
     import threading
     from kektordb_b200 import GpuIndex, ffi
     from oracle import oracle as O
@@ -341,29 +342,36 @@ def run_quantized(args, torch, bench):
     ncores = len(os.sched_getaffinity(0))
     n_total = args.warmup + args.steps
     X = bench.make_data(torch, N, D, args.latent, args.noise, 42, dev)
-    gf, build_s = bench.build_index(torch, GpuIndex, X, args.m, args.efc, args.build_batch, 1, local_rank, metric)
-    del X
+    if metric == "cosine":  # DB.Compress feeds the new index the stored (unit-norm) float32 rows (core.go:1150-1165)
+        X /= X.norm(dim=1, keepdim=True).clamp_min(1e-30)
     Qd = bench.make_data(torch, n_total * B, D, args.latent, args.noise, 4242, dev)
     Qh = torch.empty((n_total * B, D), dtype=torch.float32, pin_memory=True)
     Qh.copy_(Qd)
     torch.cuda.synchronize()
     Q = Qh.numpy()
-    # exact float32 ground truth for recall, from the float32 index
+    # exact float32 ground truth for recall: flat scan over the float32 rows
     n_gt = min(256, B)
+    gf = GpuIndex(D, metric, 8, N, device=local_rank)
+    gf.upload_vectors_device(1, X.data_ptr(), N, D)
+    _rows_only_graph(gf, N)
     gt_ids, _, _, _ = gf.flat_search(Q[:n_gt], k, 1, prefilter=True)
-    # the quantized mirror: stored float32 rows -> TrainQuantizer -> converted on the device; same topology
-    V = _download_rows(gf, N)
-    graph = gf.get_graph()
     gf.close()
+    # the quantized index, built on the device with its own distances: TrainQuantizer, then AddBatch
+    # (what DB.Compress does, core.go:1224-1270)
     gi = GpuIndex(D, metric, args.m, N, device=local_rank, precision=prec)
     t0 = time.time()
-    abs_max = gi.TrainQuantizer(V[1:]) if prec == "int8" else None
+    abs_max = gi.train_quantizer_device(X.data_ptr(), D, N) if prec == "int8" else None
+    u = np.random.default_rng(1).random(N)
+    pos = 0
+    for b in bench.build_schedule(N, args.efc, args.build_batch):
+        gi.add_batch_device(X[pos:pos + b].data_ptr(), b, D, u[pos:pos + b], args.efc)
+        pos += b
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    stage_s = 0.0
+    del X
+    graph = gi.get_graph()
     step = 1 << 17
-    for i in range(1, N + 1, step):
-        gi.upload_vectors(i, V[i:i + step])
-    gi.set_graph(*graph)
-    stage_s = time.time() - t0
-    del V
     oprec = O.PREC_I8 if prec == "int8" else O.PREC_F16
 
     def oracle_index(arith):
@@ -401,6 +409,7 @@ def run_quantized(args, torch, bench):
                           "gpu_launches": 0}), flush=True)
         return 0
 
+    gi.prepare_search(B, k, ef)
     ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, None, ef)
     recall = bench.recall_at_k(ids0[:n_gt], gt_ids)
     # ---- device-resident timing: consecutive batches alternate over n_ov streams (as bench.py's headline)
@@ -498,7 +507,8 @@ def run_quantized(args, torch, bench):
         "data": "synthetic", "recall_at_10": round(recall, 4),
         "config": {"workload": f"{N}x{D} {metric}, HNSW M={args.m} efC={args.efc} efSearch={ef}, top-{k}, batch={B}, rows held as "
                                f"{prec} ({row_bytes} B per row); recall is against the exact float32 scan",
-                   "graph": "float32 GPU build over the same rows (kdbgpu_add_batch); same graph for both arms",
+                   "graph": f"built on the GPU over the {prec} rows with {prec} distances (kdbgpu_train_quantizer + "
+                            "kdbgpu_add_batch); same graph for both arms",
                    "quantizer_abs_max": abs_max, "l2_policy": "inputs larger than L2, new query batch every step",
                    "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "stage_seconds": round(stage_s, 2),
                    "host_cores": ncores},

@@ -128,6 +128,22 @@ int kdbgpu_upload_vectors_device(kdbgpu_index *, uint32_t first_id, uint32_t cou
  * in the reference's order.  entry / max_level = entrypointID / maxLevel. */
 int kdbgpu_set_graph(kdbgpu_index *, uint32_t n, const int32_t *levels, const uint64_t *node_row,
                      const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level);
+/* Incremental refresh — follow the CPU index without re-staging everything:
+ *   kdbgpu_register_nodes  ids first_id .. first_id+count-1 (= nodeCounter+1 onwards) come to exist with
+ *                          levels[i] = len(Connections)-1 and empty rows (Add phase 1, hnsw_index.go:559-655;
+ *                          -1 = an id that stays nil); their vectors go through kdbgpu_upload_vectors / _rows_raw;
+ *   kdbgpu_patch_rows      node ids[i]'s Connections[row_levels[i]] := nbrs[row_off[i] .. row_off[i+1]) — the rows
+ *                          Add's forward / reverse links (:717-783), Vacuum's reconnectNode and Refine's commits
+ *                          (optimizer.go:195-222, :288-468) rewrite;
+ *   kdbgpu_remove_nodes    nodes[id] = nil (Vacuum's physical cleanup, optimizer.go:252-274; it has already
+ *                          rewired every live row that pointed at them);
+ *   kdbgpu_set_entry       entrypointID / maxLevel (:793-801, optimizer.go:231-249; max_level -1 = empty graph).
+ * Each call takes the handle exclusively and lets the searches in flight finish on the old state first. */
+int kdbgpu_register_nodes(kdbgpu_index *, uint32_t first_id, uint32_t count, const int32_t *levels);
+int kdbgpu_patch_rows(kdbgpu_index *, uint32_t count, const uint32_t *ids, const int32_t *row_levels,
+                      const uint64_t *row_off, const uint32_t *nbrs);
+int kdbgpu_remove_nodes(kdbgpu_index *, uint32_t count, const uint32_t *ids);
+int kdbgpu_set_entry(kdbgpu_index *, uint32_t entry, int max_level);
 /* Node.Deleted flags as a dense bitset over ids (bit i of word i/64); NULL clears all. */
 int kdbgpu_set_deleted(kdbgpu_index *, const uint64_t *bitset, size_t words);
 
@@ -221,6 +237,9 @@ uint32_t kdbgpu_index_count(const kdbgpu_index *);   /* n of the last kdbgpu_set
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *);
 /* Resident CTAs the traversal kernel runs with for (k, ef) — queries in flight per launch. */
 int kdbgpu_search_concurrency(kdbgpu_index *, int k, int ef_search);
+/* Reserves every launch workspace (visited bitsets, staging, pinned result buffers) for batches of up
+ * to nq queries of this (k, ef_search) shape, so the first searches do not allocate.  Optional. */
+int kdbgpu_prepare_search(kdbgpu_index *, uint32_t nq, int k, int ef_search);
 
 /* ---- tuning hook (tests / benchmarks only; not bound by the Go shim) --------------------- */
 /* Shape of the traversal kernel (one warp per query): bulk-copy row slots per query, candidate-heap

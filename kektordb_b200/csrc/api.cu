@@ -1372,6 +1372,40 @@ int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int 
   return KDBGPU_OK;
 }
 
+// Reserve every launch workspace for batches of up to nq queries now, so that no search pays a
+// cudaMalloc / cudaHostAlloc (both synchronise the device) on its first trip through a workspace.
+int kdbgpu_prepare_search(kdbgpu_index *h, uint32_t nq, int k, int ef_search) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (nq == 0 || k <= 0 || k > 10000) return fail(KDBGPU_ERR_INVALID, "bad shape");
+  const int ef = ef_search < k ? k : ef_search;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  DevIndex ix = h->dev();
+  const int occ = search_occupancy(ix, ef, h->tuning);
+  if (occ <= 0) return fail(KDBGPU_ERR_INVALID, "search configuration does not fit shared memory (dim=%d ef=%d)", h->dim, ef);
+  const size_t nk = (size_t)nq * k;
+  const size_t blob_bytes = ((nk * (sizeof(double) + sizeof(uint32_t)) + (size_t)nq * sizeof(uint32_t) + 7) & ~(size_t)7) +
+                            4 * sizeof(unsigned long long) + sizeof(long long);
+  for (auto &w : h->sws) {
+    int rc = ensure_ws(h, w, occ * h->num_sms);
+    if (rc) return rc;
+    CUDA_TRY(w.q_raw.reserve((size_t)nq * h->dim));
+    CUDA_TRY(w.q_prep.reserve((size_t)nq * h->stride));
+    if (h->precision == KDBGPU_PRECISION_INT8) CUDA_TRY(w.qnorms.reserve(nq));
+    CUDA_TRY(w.allow.reserve(((size_t)h->capacity + 1 + 31) / 32 + 2));
+    CUDA_TRY(w.out_blob.reserve(blob_bytes));
+    if (w.h_out_bytes < blob_bytes) {
+      if (w.h_out) cudaFreeHost(w.h_out);
+      w.h_out = nullptr;
+      w.h_out_bytes = 0;
+      CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&w.h_out), blob_bytes + blob_bytes / 4, cudaHostAllocDefault));
+      w.h_out_bytes = blob_bytes + blob_bytes / 4;
+    }
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  return KDBGPU_OK;
+}
+
 int kdbgpu_search_batch_device(kdbgpu_index *h, const float *d_queries, uint32_t nq, int k, int ef_search,
                                const uint64_t *d_allow, size_t allow_words, uint32_t allow_first_id,
                                uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream) {
@@ -1851,6 +1885,146 @@ int kdbgpu_add_batch_device(kdbgpu_index *h, uint32_t count, const float *d_rows
                             const double *level_draws, int ef_const) {
   if (h && row_stride < (size_t)h->dim) return fail(KDBGPU_ERR_INVALID, "row_stride smaller than dim");
   return add_batch_impl(h, count, d_rows, row_stride, true, level_draws, ef_const);
+}
+
+// ---- incremental mirror refresh: follow the CPU index's Add / Delete / Vacuum /
+// ---- Refine without re-staging the whole topology ------------------------------------------------
+int kdbgpu_register_nodes(kdbgpu_index *h, uint32_t first_id, uint32_t count, const int32_t *levels) {
+  if (!h || (!levels && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (count == 0) return KDBGPU_OK;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  if (first_id != h->n + 1) return fail(KDBGPU_ERR_INVALID, "nodes are registered in id order: expected %u, got %u", h->n + 1, first_id);
+  if ((uint64_t)h->n + count > h->capacity)
+    return fail(KDBGPU_ERR_INVALID, "%u more nodes do not fit: %u of %u ids used", count, h->n, h->capacity);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaStream_t s = h->stream;
+  std::vector<int8_t> lv(count);
+  std::vector<uint32_t> uf(count, 0u), up_node;
+  std::vector<uint8_t> up_level;
+  uint32_t cursor = h->upper_rows_used;
+  for (uint32_t i = 0; i < count; ++i) {
+    const int32_t L = levels[i];
+    if (L < -1 || L > 120) return fail(KDBGPU_ERR_INVALID, "node %u has level %d", first_id + i, L);
+    lv[i] = (int8_t)L;  // -1 registers a nil slot (an id the reference burnt, e.g. a failed insert)
+    uf[i] = cursor;
+    for (int l = 1; l <= L; ++l) {
+      up_node.push_back(first_id + i);
+      up_level.push_back((uint8_t)l);
+    }
+    if (L > 0) cursor += (uint32_t)L;
+  }
+  int rc = grow_upper(h, (size_t)cursor + 1, s);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->levels.p + first_id, lv.data(), count, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->upper_first.p + first_id, uf.data(), (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(h->adj0.p + (size_t)first_id * 2 * h->m, 0, (size_t)count * 2 * h->m * sizeof(uint32_t), s));
+  const uint32_t n_new_upper = cursor - h->upper_rows_used;
+  if (n_new_upper) {
+    CUDA_TRY(cudaMemsetAsync(h->upper_adj.p + (size_t)h->upper_rows_used * h->m, 0,
+                             (size_t)n_new_upper * h->m * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemcpyAsync(h->upper_node.p + h->upper_rows_used, up_node.data(), (size_t)n_new_upper * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->upper_level.p + h->upper_rows_used, up_level.data(), n_new_upper, cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (uint32_t i = 0; i < count; ++i) {
+    h->h_levels[first_id + i] = lv[i];
+    h->h_upper_first[first_id + i] = uf[i];
+  }
+  h->upper_rows_used = cursor;
+  h->n = first_id + count - 1;
+  h->has_graph = true;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_patch_rows(kdbgpu_index *h, uint32_t count, const uint32_t *ids, const int32_t *row_levels,
+                      const uint64_t *row_off, const uint32_t *nbrs) {
+  if (!h || (count && (!ids || !row_levels || !row_off))) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (count == 0) return KDBGPU_OK;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "no topology staged yet");
+  const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
+  // two groups (level-0 rows / upper rows); nil and out-of-range neighbours are dropped exactly as
+  // kdbgpu_set_graph does (the reference skips them with no side effect, hnsw_index.go:2553-2561)
+  std::vector<uint32_t> dst[2], off[2], cnt[2], src;
+  for (uint32_t i = 0; i < count; ++i) {
+    const uint32_t id = ids[i];
+    const int32_t l = row_levels[i];
+    if (id == 0 || id > h->n || h->h_levels[id] < 0) return fail(KDBGPU_ERR_INVALID, "patch %u: node %u is not a live node", i, id);
+    if (l < 0 || l > h->h_levels[id]) return fail(KDBGPU_ERR_INVALID, "patch %u: node %u has no level %d", i, id, l);
+    const uint32_t cap = l == 0 ? deg0 : degu;
+    const int gsel = l == 0 ? 0 : 1;
+    const uint32_t start = (uint32_t)src.size();
+    for (uint64_t e = row_off[i]; e < row_off[i + 1]; ++e) {
+      const uint32_t nb = nbrs[e];
+      if (nb == 0 || nb > h->n || h->h_levels[nb] < 0) continue;
+      if (src.size() - start >= cap) return fail(KDBGPU_ERR_INVALID, "node %u level %d has more than %u neighbours", id, l, cap);
+      src.push_back(nb);
+    }
+    dst[gsel].push_back(l == 0 ? id : h->h_upper_first[id] + (uint32_t)(l - 1));
+    off[gsel].push_back(start);
+    cnt[gsel].push_back((uint32_t)src.size() - start);
+  }
+  if (src.empty()) src.push_back(0u);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());  // searches in flight finish on the old rows
+  cudaStream_t s = h->stream;
+  DevBuf<uint32_t> d_src, d_meta;
+  struct Free {
+    DevBuf<uint32_t> &a, &b;
+    ~Free() { a.release(); b.release(); }
+  } freer{d_src, d_meta};
+  CUDA_TRY(d_src.reserve(src.size()));
+  CUDA_TRY(cudaMemcpyAsync(d_src.p, src.data(), src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  const size_t n0 = dst[0].size(), n1 = dst[1].size();
+  CUDA_TRY(d_meta.reserve(3 * (n0 + n1) + 1));
+  uint32_t *m = d_meta.p;
+  for (int gsel = 0; gsel < 2; ++gsel) {
+    const size_t n = dst[gsel].size();
+    if (!n) continue;
+    CUDA_TRY(cudaMemcpyAsync(m, dst[gsel].data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m + n, off[gsel].data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m + 2 * n, cnt[gsel].data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_patch_rows(gsel == 0 ? h->adj0.p : h->upper_adj.p, gsel == 0 ? deg0 : degu, m, m + n, m + 2 * n,
+                               d_src.p, (uint32_t)n, s));
+    m += 3 * n;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_remove_nodes(kdbgpu_index *h, uint32_t count, const uint32_t *ids) {
+  if (!h || (count && !ids)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (count == 0) return KDBGPU_OK;
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  for (uint32_t i = 0; i < count; ++i)
+    if (ids[i] == 0 || ids[i] > h->n) return fail(KDBGPU_ERR_INVALID, "node %u outside 1..%u", ids[i], h->n);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaStream_t s = h->stream;
+  const int8_t nil = -1;
+  for (uint32_t i = 0; i < count; ++i) {  // nodes[deadID] = nil (optimizer.go:270)
+    h->h_levels[ids[i]] = -1;
+    CUDA_TRY(cudaMemcpyAsync(h->levels.p + ids[i], &nil, 1, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(h->adj0.p + (size_t)ids[i] * 2 * h->m, 0, (size_t)2 * h->m * sizeof(uint32_t), s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return KDBGPU_OK;
+}
+
+int kdbgpu_set_entry(kdbgpu_index *h, uint32_t entry, int max_level) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  if (max_level >= 0 && (entry == 0 || entry > h->n || h->h_levels[entry] < 0))
+    return fail(KDBGPU_ERR_INVALID, "entry point %u is not a live node", entry);
+  if (max_level >= 0 && max_level > h->h_levels[entry])
+    return fail(KDBGPU_ERR_INVALID, "entry point %u has level %d, not %d", entry, (int)h->h_levels[entry], max_level);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->entry = max_level >= 0 ? entry : 0;
+  h->max_level = max_level;
+  return KDBGPU_OK;
 }
 
 int kdbgpu_get_graph_sizes(kdbgpu_index *h, uint32_t *n, uint64_t *n_rows, uint64_t *n_edges, uint32_t *entry,

@@ -96,6 +96,9 @@ cudaError_t launch_distance_batch(const DevIndex &ix, const float *query_prepare
 cudaError_t launch_convert_rows(const float *in, size_t in_stride, float *out, size_t out_words, uint32_t rows,
                                 uint32_t dim, int kind, bool normalise, float abs_max, float *norms,
                                 bool query_side, cudaStream_t stream);
+// adjacency rows rewritten in place (incremental mirror refresh)
+cudaError_t launch_patch_rows(uint32_t *base, uint32_t deg, const uint32_t *dst_row, const uint32_t *src_off,
+                              const uint32_t *src_cnt, const uint32_t *src, uint32_t n_patches, cudaStream_t stream);
 // one radix-select pass of Quantizer.Train's quantile (see abs_hist_kernel)
 cudaError_t launch_abs_hist(const float *rows, size_t row_stride, uint32_t n_sample, uint32_t step, uint32_t dim,
                             uint32_t prefix, int hi_shift, int shift, int bits, unsigned long long *hist,

@@ -204,6 +204,20 @@ __global__ void arena_scatter_kernel(const unsigned char *__restrict__ chunk, ui
   if (lane == 0) atomicAdd(n_staged, 1u);
 }
 
+// Incremental topology refresh: adjacency row dst_row[i] of `base` (deg slots) := src[src_off[i] ..
+// +src_cnt[i]), zero padded — the rewritten node.Connections[level] of Add's forward / reverse links
+// (hnsw_index.go:717-783), Vacuum's reconnectNode and Refine's commits (optimizer.go).
+__global__ void patch_rows_kernel(uint32_t *__restrict__ base, uint32_t deg, const uint32_t *__restrict__ dst_row,
+                                  const uint32_t *__restrict__ src_off, const uint32_t *__restrict__ src_cnt,
+                                  const uint32_t *__restrict__ src, uint32_t n_patches) {
+  const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= n_patches) return;
+  uint32_t *row = base + (size_t)dst_row[p] * deg;
+  const uint32_t off = src_off[p], cnt = src_cnt[p];
+  for (uint32_t t = lane; t < deg; t += 32) row[t] = t < cnt ? src[off + t] : 0u;
+}
+
 // computeInt8Norm (hnsw_index.go:3371-3377) of rows already in stored form, one warp per row
 __global__ void int8_norms_kernel(const float *__restrict__ rows, size_t row_words, uint32_t count, uint32_t dim,
                                   float *__restrict__ norms) {
@@ -353,6 +367,15 @@ cudaError_t launch_convert_rows(const float *in, size_t in_stride, float *out, s
   convert_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(in, in_stride, out, out_words, rows, dim, kind,
                                                                        normalise ? 1 : 0, abs_max, norms,
                                                                        query_side ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_patch_rows(uint32_t *base, uint32_t deg, const uint32_t *dst_row, const uint32_t *src_off,
+                              const uint32_t *src_cnt, const uint32_t *src, uint32_t n_patches, cudaStream_t stream) {
+  if (n_patches == 0) return cudaSuccess;
+  const uint32_t wpb = 8;
+  patch_rows_kernel<<<(n_patches + wpb - 1) / wpb, wpb * 32, 0, stream>>>(base, deg, dst_row, src_off, src_cnt, src,
+                                                                       n_patches);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,10 @@ SIGNATURES = {
     "kdbgpu_upload_vectors": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_upload_vectors_device": (_i32, [_vp, _u32, _u32, _vp, _sz]),
     "kdbgpu_set_graph": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _i32]),
+    "kdbgpu_register_nodes": (_i32, [_vp, _u32, _u32, _vp]),
+    "kdbgpu_patch_rows": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp]),
+    "kdbgpu_remove_nodes": (_i32, [_vp, _u32, _vp]),
+    "kdbgpu_set_entry": (_i32, [_vp, _u32, _i32]),
     "kdbgpu_set_deleted": (_i32, [_vp, _vp, _sz]),
     "kdbgpu_search_batch": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, C.POINTER(Stats)]),
     "kdbgpu_search_batch_device": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _u32, _vp, _vp, _vp, _vp]),
@@ -85,6 +89,7 @@ SIGNATURES = {
     "kdbgpu_index_count": (_u32, [_vp]),
     "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),
     "kdbgpu_search_concurrency": (_i32, [_vp, _i32, _i32]),
+    "kdbgpu_prepare_search": (_i32, [_vp, _u32, _i32, _i32]),
     "kdbgpu_set_tuning": (_i32, [_vp, _i32, _i32, _i32]),
 }
 

@@ -185,6 +185,28 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_set_graph(self._handle(), n, _ptr(levels), _ptr(node_row), _ptr(row_off),
                                              _ptr(nbrs), entry, max_level))
 
+    # -- incremental refresh (follow the CPU index's Add / Vacuum / Refine) ----------------------------
+    def register_nodes(self, first_id: int, levels) -> None:
+        lv = np.ascontiguousarray(levels, dtype=np.int32)
+        ffi.check(self._lib.kdbgpu_register_nodes(self._handle(), first_id, lv.size, _ptr(lv)))
+
+    def patch_rows(self, ids, row_levels, rows) -> None:
+        """rows: list of neighbour-id sequences, one per (ids[i], row_levels[i])."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        lv = np.ascontiguousarray(row_levels, dtype=np.int32)
+        off = np.zeros(len(rows) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(r) for r in rows])
+        flat = np.concatenate([np.asarray(r, dtype=np.uint32) for r in rows]) if len(rows) and off[-1] else np.zeros(1, np.uint32)
+        flat = np.ascontiguousarray(flat, dtype=np.uint32)
+        ffi.check(self._lib.kdbgpu_patch_rows(self._handle(), ids.size, _ptr(ids), _ptr(lv), _ptr(off), _ptr(flat)))
+
+    def remove_nodes(self, ids) -> None:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        ffi.check(self._lib.kdbgpu_remove_nodes(self._handle(), ids.size, _ptr(ids)))
+
+    def set_entry(self, entry: int, max_level: int) -> None:
+        ffi.check(self._lib.kdbgpu_set_entry(self._handle(), entry, max_level))
+
     def set_deleted(self, bitset: np.ndarray | None) -> None:
         if bitset is None:
             ffi.check(self._lib.kdbgpu_set_deleted(self._handle(), None, 0))
@@ -328,6 +350,9 @@ class GpuIndex:
     @property
     def device_bytes(self) -> int:
         return int(self._lib.kdbgpu_index_device_bytes(self._handle()))
+
+    def prepare_search(self, nq: int, k: int, ef_search: int) -> None:
+        ffi.check(self._lib.kdbgpu_prepare_search(self._handle(), nq, k, effective_ef(int(ef_search), self.needs_refine)))
 
     def search_concurrency(self, k: int, ef_search: int) -> int:
         return int(self._lib.kdbgpu_search_concurrency(self._handle(), k, ef_search))
