@@ -267,6 +267,7 @@ def main():
         return fn[args.workload](args, torch, sys.modules[__name__])
     dist = None
     if world > 1 and args.impl == "ours":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
