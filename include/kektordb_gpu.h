@@ -246,6 +246,12 @@ int kdbgpu_prepare_search(kdbgpu_index *, uint32_t nq, int k, int ef_search);
  * entries kept in shared memory, cap on resident query-warps per SM (0 = no cap).  A value <= 0
  * (< 0 for the cap) keeps the current setting.  Results never depend on the shape. */
 int kdbgpu_set_tuning(kdbgpu_index *, int slots, int cand_smem, int max_ctas_per_sm);
+/* The traversal answers a batch in two passes: a fast pass that keeps the candidate / result queues as one
+ * sorted list in registers (valid while all distances a query meets are distinct — any priority queue then
+ * pops what the reference's binary heaps pop), and the heap pass (hnsw_heap.go restated exactly) over the
+ * queries that met two equal distances, over everything when soft-deleted nodes exist or ef > 128.
+ * Results are identical either way; on = 0 sends every query through the heap pass (default on = 1). */
+int kdbgpu_set_fast_path(kdbgpu_index *, int on);
 
 /* ---- micro-batcher: the reference's call shape on top of the batched entry point ----------------
  * Every search in the reference is one blocking call per query from its own goroutine

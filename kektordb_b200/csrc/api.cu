@@ -146,7 +146,7 @@ struct kdbgpu_index {
     cudaEvent_t done = nullptr;  // completion of the last launch that used this workspace
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<float> q_raw, q_prep, qnorms;
-    DevBuf<uint32_t> out_ids, out_counts, allow, visited, work_counter;
+    DevBuf<uint32_t> out_ids, out_counts, allow, visited, work_counter, redo;
     DevBuf<double> out_scores;
     DevBuf<HeapEntry> cand_overflow;
     DevBuf<unsigned long long> stats;
@@ -163,7 +163,7 @@ struct kdbgpu_index {
       h_out = nullptr;
       h_out_bytes = 0;
       q_raw.release(); q_prep.release(); qnorms.release(); out_ids.release(); out_counts.release(); allow.release();
-      visited.release(); work_counter.release(); out_scores.release(); cand_overflow.release();
+      visited.release(); work_counter.release(); redo.release(); out_scores.release(); cand_overflow.release();
       stats.release(); err_flag.release();
     }
   };
@@ -281,7 +281,7 @@ int ensure_ws(kdbgpu_index *h, kdbgpu_index::SearchWs &w, int grid) {
     w.grid = grid;
   }
   CUDA_TRY(w.stats.reserve(4, true));
-  CUDA_TRY(w.work_counter.reserve(1, true));
+  CUDA_TRY(w.work_counter.reserve(4, true));  // [0] fast kernel, [1] exact kernel, [2] queries handed over
   CUDA_TRY(w.err_flag.reserve(1, true));
   return KDBGPU_OK;
 }
@@ -320,11 +320,12 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
   if (occ <= 0)
     return fail(KDBGPU_ERR_INVALID, "search configuration does not fit shared memory (dim=%d ef=%d smem=%zu)", h->dim,
                 ef, search_smem_bytes(ix, ef, h->tuning));
-  int grid = occ * h->num_sms;
-  if ((uint32_t)grid > nq) grid = (int)nq;
-  int rc = ensure_ws(h, w, occ * h->num_sms);
+  const bool fast = search_fast_eligible(ix, ef, h->tuning);
+  const int occ_fast = fast ? search_fast_occupancy(ix, h->tuning) : 0;
+  const int occ_max = occ_fast > occ ? occ_fast : occ;
+  int rc = ensure_ws(h, w, occ_max * h->num_sms);
   if (rc) return rc;
-  CUDA_TRY(cudaMemsetAsync(w.work_counter.p, 0, sizeof(uint32_t), stream));
+  CUDA_TRY(cudaMemsetAsync(w.work_counter.p, 0, 4 * sizeof(uint32_t), stream));
   if (d_stats && d_err) {  // contiguous in the caller's blob: stats[4] then err
     CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long) + sizeof(long long), stream));
   } else {
@@ -333,7 +334,7 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
     CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), stream));
     CUDA_TRY(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
   }
-  SearchArgs a;
+  SearchArgs a{};
   a.queries = d_q_prepared;
   a.qnorms = w.qnorms.p;
   a.nq = nq;
@@ -352,6 +353,22 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
   a.stats = d_stats;
   a.work_counter = w.work_counter.p;
   a.err_flag = d_err;
+  int grid = occ * h->num_sms;
+  if ((uint32_t)grid > nq) grid = (int)nq;
+  if (fast && occ_fast > 0) {
+    // pass 1: sorted-list fast path; pass 2: the heap path over whatever met a distance tie
+    CUDA_TRY(w.redo.reserve(nq));
+    int gfast = occ_fast * h->num_sms;
+    if ((uint32_t)gfast > nq) gfast = (int)nq;
+    a.redo_list = w.redo.p;
+    a.redo_count = w.work_counter.p + 2;
+    CUDA_TRY(launch_search_fast(ix, a, h->tuning, gfast, stream));
+    a.work_counter = w.work_counter.p + 1;
+    a.query_list = w.redo.p;
+    a.query_count = w.work_counter.p + 2;
+    a.redo_list = nullptr;
+    a.redo_count = nullptr;
+  }
   CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
   return KDBGPU_OK;
 }
@@ -706,6 +723,7 @@ int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m
   // float16 / int8 rows: the traversal is latency-bound, so resident query-warps matter more than
   // shared-memory heap capacity (measured: profiles/README.md, quantized sweep)
   if (precision != KDBGPU_PRECISION_F32) h->tuning.cand_smem = 64;
+  if ((env = getenv("KDBGPU_FAST"))) h->tuning.fast = atoi(env);
   if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
   if ((env = getenv("KDBGPU_CAND_SMEM"))) h->tuning.cand_smem = atoi(env);
   if ((env = getenv("KDBGPU_MAX_CTAS_PER_SM"))) h->tuning.max_ctas_per_sm = atoi(env);
@@ -1386,9 +1404,11 @@ int kdbgpu_prepare_search(kdbgpu_index *h, uint32_t nq, int k, int ef_search) {
   const size_t nk = (size_t)nq * k;
   const size_t blob_bytes = ((nk * (sizeof(double) + sizeof(uint32_t)) + (size_t)nq * sizeof(uint32_t) + 7) & ~(size_t)7) +
                             4 * sizeof(unsigned long long) + sizeof(long long);
+  const int occ_fast = search_fast_eligible(ix, ef, h->tuning) ? search_fast_occupancy(ix, h->tuning) : 0;
   for (auto &w : h->sws) {
-    int rc = ensure_ws(h, w, occ * h->num_sms);
+    int rc = ensure_ws(h, w, (occ_fast > occ ? occ_fast : occ) * h->num_sms);
     if (rc) return rc;
+    CUDA_TRY(w.redo.reserve(nq));
     CUDA_TRY(w.q_raw.reserve((size_t)nq * h->dim));
     CUDA_TRY(w.q_prep.reserve((size_t)nq * h->stride));
     if (h->precision == KDBGPU_PRECISION_INT8) CUDA_TRY(w.qnorms.reserve(nq));
@@ -1764,7 +1784,7 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   CUDA_TRY(cudaMemsetAsync(h->work_counter.p, 0, sizeof(uint32_t), s));
   CUDA_TRY(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
-  SearchArgs a;
+  SearchArgs a{};
   a.queries = nullptr;
   a.nq = count;
   a.k = ef_const;
@@ -2100,6 +2120,13 @@ int kdbgpu_download_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, 
 
 extern "C" {
 // test/tuning hook (not part of the reference-facing surface): CTA shape of the traversal kernel
+int kdbgpu_set_fast_path(kdbgpu_index *h, int on) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  h->tuning.fast = on ? 1 : 0;
+  return KDBGPU_OK;
+}
+
 int kdbgpu_set_tuning(kdbgpu_index *h, int slots, int cand_smem, int max_ctas_per_sm) {
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
   SearchTuning t = h->tuning;

@@ -70,9 +70,16 @@ struct SearchArgs {
   unsigned long long *stats;  // [3] E, H, H0
   uint32_t *work_counter;
   int *err_flag;
+  // fast kernel: queries that met a distance tie are appended here for the exact kernel, which then
+  // runs over query_list[0 .. *query_count) instead of 0 .. nq
+  uint32_t *redo_list;
+  uint32_t *redo_count;
+  const uint32_t *query_list;
+  const uint32_t *query_count;
 };
 
 struct SearchTuning {
+  int fast = 1;             // sorted-list fast path with exact re-run on ties (searcher.cuh); 0 = heaps only
   int slots = 4;            // row slots per query-warp (bulk copies in flight per query), power of two
   int cand_smem = 192;      // candidate-heap entries held in shared memory (the rest spills to HBM)
   int max_ctas_per_sm = 0;  // 0 = whatever fits
@@ -84,6 +91,11 @@ size_t search_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t);
 int search_occupancy(const DevIndex &ix, int ef, const SearchTuning &t);
 cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
                           cudaStream_t stream);
+// fast path (ef <= 128, no soft-deleted nodes): shape, occupancy, launch
+bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t);
+int search_fast_occupancy(const DevIndex &ix, const SearchTuning &t);
+cudaError_t launch_search_fast(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
+                               cudaStream_t stream);
 cudaError_t launch_prep_queries(const float *in, size_t in_stride, float *out, uint32_t nq, uint32_t dim,
                                 uint32_t stride, int metric, cudaStream_t stream);
 cudaError_t launch_distance_batch(const DevIndex &ix, const float *query_prepared, const float *qnorm,

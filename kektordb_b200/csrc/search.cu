@@ -17,12 +17,37 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const DevIndex ix, cons
   extern __shared__ __align__(128) unsigned char smem[];
   Searcher<SLOTS, METRIC, CPL> s(ix, a, smem);
   s.init_barriers();
+  // all of 0 .. nq, or the queries the fast kernel handed over (distance ties)
+  const uint32_t limit = a.query_count ? *a.query_count : a.nq;
+  for (;;) {
+    uint32_t i = 0;
+    if (s.lane == 0) i = atomicAdd(a.work_counter, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= limit) break;
+    s.run_query(a.query_list ? a.query_list[i] : i);
+  }
+  if (s.lane == 0) {
+    atomicAdd(&a.stats[0], s.st_e);
+    atomicAdd(&a.stats[1], s.st_h);
+    atomicAdd(&a.stats[2], s.st_h0);
+  }
+}
+
+// The fast path of the same search (searcher.cuh, "Fast path"): sorted list in registers, whole-warp
+// maintenance; a query that meets two equal distances is appended to redo_list and answered by
+// hnsw_search_kernel afterwards, so the output is always the reference's.
+template <int SLOTS, int METRIC, int CPL>
+__global__ void __launch_bounds__(32) hnsw_search_fast_kernel(const DevIndex ix, const SearchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  Searcher<SLOTS, METRIC, CPL> s(ix, a, smem, false);
+  s.init_barriers();
   for (;;) {
     uint32_t q = 0;
     if (s.lane == 0) q = atomicAdd(a.work_counter, 1u);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= a.nq) break;
-    s.run_query(q);
+    if (!s.run_query_fast(q) && s.lane == 0) a.redo_list[atomicAdd(a.redo_count, 1u)] = q;
+    __syncwarp();
   }
   if (s.lane == 0) {
     atomicAdd(&a.stats[0], s.st_e);
@@ -258,6 +283,27 @@ int occupancy_one(size_t smem) {
   return nb;
 }
 
+template <int METRIC, int CPL>
+cudaError_t launch_fast_one(const DevIndex &ix, const SearchArgs &a, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = hnsw_search_fast_kernel<4, METRIC, CPL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, 32, smem, stream>>>(ix, a);
+  return cudaGetLastError();
+}
+template <int METRIC, int CPL>
+int occupancy_fast_one(size_t smem) {
+  auto kern = hnsw_search_fast_kernel<4, METRIC, CPL>;
+  int nb = 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return nb;
+}
+
 #define KDB_CASE_CPL(SLv, METRICv, CPLv, EXPR) \
   case CPLv: {                                 \
     constexpr int SL = SLv;                    \
@@ -323,6 +369,54 @@ cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchT
   const int cpl = cpl_of(ix);
   cudaError_t e = cudaErrorInvalidConfiguration;
   KDB_DISPATCH(e = (launch_one<SL, MT, CP>(ix, a, grid, smem, stream)))
+  return e;
+}
+
+// ---- fast path: 4 slots, no heaps in shared memory ------------------------------------------------
+#define KDB_FAST_CPL(METRICv, EXPR)                                   \
+  switch (cpl) {                                                      \
+    case 1: { constexpr int MT = METRICv; constexpr int CP = 1; EXPR; } break;   \
+    case 2: { constexpr int MT = METRICv; constexpr int CP = 2; EXPR; } break;   \
+    case 3: { constexpr int MT = METRICv; constexpr int CP = 3; EXPR; } break;   \
+    case 4: { constexpr int MT = METRICv; constexpr int CP = 4; EXPR; } break;   \
+    case 6: { constexpr int MT = METRICv; constexpr int CP = 6; EXPR; } break;   \
+    case 8: { constexpr int MT = METRICv; constexpr int CP = 8; EXPR; } break;   \
+    case 12: { constexpr int MT = METRICv; constexpr int CP = 12; EXPR; } break; \
+    default: { constexpr int MT = METRICv; constexpr int CP = 0; EXPR; } break;  \
+  }
+#define KDB_FAST_DISPATCH(EXPR)                                         \
+  switch (ix.kind) {                                                    \
+    case KIND_COS_F32: { KDB_FAST_CPL(KIND_COS_F32, EXPR) } break;      \
+    case KIND_L2_F16: { KDB_FAST_CPL(KIND_L2_F16, EXPR) } break;        \
+    case KIND_COS_I8: { KDB_FAST_CPL(KIND_COS_I8, EXPR) } break;        \
+    default: { KDB_FAST_CPL(KIND_L2_F32, EXPR) } break;                 \
+  }
+
+static size_t search_fast_smem_bytes(const DevIndex &ix) {
+  return smem_layout(ix.stride, 0, 4, 0, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, cpl_of(ix) == 0, nullptr, nullptr);
+}
+
+bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t) {
+  // soft-deleted nodes are traversed but never kept (hnsw_index.go:2584): they need the two separate queues
+  return t.fast != 0 && t.slots == 4 && ef <= 128 && ix.deleted == nullptr && search_fast_smem_bytes(ix) <= 227 * 1024;
+}
+
+int search_fast_occupancy(const DevIndex &ix, const SearchTuning &t) {
+  const size_t smem = search_fast_smem_bytes(ix);
+  const int cpl = cpl_of(ix);
+  int nb = 0;
+  KDB_FAST_DISPATCH(nb = (occupancy_fast_one<MT, CP>(smem)))
+  if (t.max_ctas_per_sm > 0 && nb > t.max_ctas_per_sm) nb = t.max_ctas_per_sm;
+  return nb;
+}
+
+cudaError_t launch_search_fast(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
+                               cudaStream_t stream) {
+  (void)t;
+  const size_t smem = search_fast_smem_bytes(ix);
+  const int cpl = cpl_of(ix);
+  cudaError_t e = cudaErrorInvalidConfiguration;
+  KDB_FAST_DISPATCH(e = (launch_fast_one<MT, CP>(ix, a, grid, smem, stream)))
   return e;
 }
 

@@ -205,13 +205,22 @@ struct Searcher {
   bool overflow;
   double worst;  // lane 0: results.Peek().Distance while the result heap is non-empty (kept in a register)
   float qnorm;   // int8: query-side norm (hnsw_index.go:2405-2413)
+  // fast path (search_layer_fast): the candidate / result queues as ONE sorted list in registers,
+  // entry i in lane i >> 2, slot i & 3, ascending by distance, +inf beyond the live entries
+  double ld[4];
+  uint32_t lid[4];
+  uint32_t lexp;  // bit r: entry r of this lane has been expanded (popped from the candidate queue)
+  int ln;         // live entries (uniform)
+  bool tie;       // two equal distances met: the heaps' tie order is needed, the exact kernel re-runs the query
   uint32_t slots_u32, bars_u32, slot_bytes, row_bytes;  // shared-window addresses of the row slots / barriers
   const unsigned char *vec_bytes;
   float4 qreg[CPL > 0 ? CPL : 1];
 
-  __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem)
-      : ix(ix_), a(a_), lane(threadIdx.x & 31), phase_bits(0), st_e(0), st_h(0), st_h0(0), overflow(false), qnorm(1.f) {
-    smem_layout(ix.stride, a.ef, SLOTS, a.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, CPL == 0, smem, &sm);
+  // heaps_in_smem = false: the fast kernel's carve-up (no result / candidate heap arrays)
+  __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem, bool heaps_in_smem = true)
+      : ix(ix_), a(a_), lane(threadIdx.x & 31), phase_bits(0), st_e(0), st_h(0), st_h0(0), overflow(false), qnorm(1.f), lexp(0), ln(0), tie(false) {
+    smem_layout(ix.stride, heaps_in_smem ? a.ef : 0, SLOTS, heaps_in_smem ? a.cand_smem : 0u,
+                ix.deg0 > ix.degu ? ix.deg0 : ix.degu, CPL == 0, smem, &sm);
     vis = a.visited + (size_t)blockIdx.x * a.vis_words;
     cand.s = sm.cand;
     cand.g = a.cand_overflow + (size_t)blockIdx.x * a.ovf_cap;
@@ -357,6 +366,65 @@ struct Searcher {
     __syncwarp();
   }
 
+  // Phase B of a hop: the adjacency row of `cur` -> the ordered list of neighbours to evaluate
+  // (sm.eval_id / eval_del / eval_norm).  Returns their number (on every lane).
+  __device__ __forceinline__ uint32_t collect_neighbours(uint32_t cur, int level, bool log_marks, bool &expand) {
+    uint32_t n_eval = 0;
+    // "level >= len(currentNode.Connections)" -> continue (:2521-2524)
+    expand = (level == 0) || (ix.levels[cur] >= level);
+    if (expand) {
+      const uint32_t *row;
+      uint32_t deg;
+      if (level == 0) {
+        deg = ix.deg0;
+        row = ix.adj0 + (size_t)cur * deg;
+      } else {
+        deg = ix.degu;
+        row = ix.upper_adj + ((size_t)ix.upper_first[cur] + (uint32_t)(level - 1)) * deg;
+      }
+      for (uint32_t base = 0; base < deg; base += 32) {  // :2537
+        const uint32_t idx = base + lane;
+        const uint32_t id = idx < deg ? row[idx] : 0u;  // plain load: build kernels mutate rows
+        const bool act = id != 0u;                      // rows are compacted at upload; 0 = padding
+        if (__ballot_sync(0xffffffffu, act) == 0u) break;
+        // a repeated id inside the row is visited by its first occurrence (:2539-2542)
+        const uint32_t same = __match_any_sync(0xffffffffu, id);
+        const bool leader = act && ((__ffs(same) - 1) == lane);
+        bool fresh = false;
+        if (leader) {
+          const uint32_t bit = 1u << (id & 31);
+          const uint32_t old = atomicOr(&vis[id >> 5], bit);  // visited.Has + visited.Add
+          fresh = (old & bit) == 0u;
+        }
+        if (log_marks) {
+          const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
+          const uint32_t m0 = sm.ctl->n_marked;
+          if (fresh) {
+            const uint32_t pos = m0 + __popc(fm & ((1u << lane) - 1u));
+            if (pos < (uint32_t)kMarkCap) sm.marked[pos] = id;
+          }
+          __syncwarp();
+          if (lane == 0) sm.ctl->n_marked = m0 + __popc(fm);
+          __syncwarp();
+        }
+        // allow-list before any distance work (:2545-2549)
+        const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id));
+        uint32_t del = 0u;
+        if (keep && ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
+          sm.eval_id[pos] = id;
+          sm.eval_del[pos] = del;
+          if (METRIC == KIND_COS_I8) sm.eval_norm[pos] = ix.norms[id];
+        }
+        n_eval += __popc(km);
+      }
+      __syncwarp();
+    }
+    return n_eval;
+  }
+
   // searchLayerUnlocked (hnsw_index.go:2351-2611).  Returns (on every lane) the number of results
   // left in the max-heap `res` (not yet drained), or -1 if the entry node is nil (:2466-2468).
   __device__ int search_layer(const int level, const int ef, const uint32_t ep) {
@@ -400,59 +468,8 @@ struct Searcher {
       cur = __shfl_sync(0xffffffffu, cur, 0);
       if (cur == 0xffffffffu) break;
       // ---- B: adjacency row -> ordered list of neighbours to evaluate
-      uint32_t n_eval = 0;
-      // "level >= len(currentNode.Connections)" -> continue (:2521-2524)
-      const bool expand = (level == 0) || (ix.levels[cur] >= level);
-      if (expand) {
-        const uint32_t *row;
-        uint32_t deg;
-        if (level == 0) {
-          deg = ix.deg0;
-          row = ix.adj0 + (size_t)cur * deg;
-        } else {
-          deg = ix.degu;
-          row = ix.upper_adj + ((size_t)ix.upper_first[cur] + (uint32_t)(level - 1)) * deg;
-        }
-        for (uint32_t base = 0; base < deg; base += 32) {  // :2537
-          const uint32_t idx = base + lane;
-          const uint32_t id = idx < deg ? row[idx] : 0u;  // plain load: build kernels mutate rows
-          const bool act = id != 0u;                      // rows are compacted at upload; 0 = padding
-          if (__ballot_sync(0xffffffffu, act) == 0u) break;
-          // a repeated id inside the row is visited by its first occurrence (:2539-2542)
-          const uint32_t same = __match_any_sync(0xffffffffu, id);
-          const bool leader = act && ((__ffs(same) - 1) == lane);
-          bool fresh = false;
-          if (leader) {
-            const uint32_t bit = 1u << (id & 31);
-            const uint32_t old = atomicOr(&vis[id >> 5], bit);  // visited.Has + visited.Add
-            fresh = (old & bit) == 0u;
-          }
-          if (log_marks) {
-            const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
-            const uint32_t m0 = sm.ctl->n_marked;
-            if (fresh) {
-              const uint32_t pos = m0 + __popc(fm & ((1u << lane) - 1u));
-              if (pos < (uint32_t)kMarkCap) sm.marked[pos] = id;
-            }
-            __syncwarp();
-            if (lane == 0) sm.ctl->n_marked = m0 + __popc(fm);
-            __syncwarp();
-          }
-          // allow-list before any distance work (:2545-2549)
-          const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id));
-          uint32_t del = 0u;
-          if (keep && ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
-          const uint32_t km = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
-            sm.eval_id[pos] = id;
-            sm.eval_del[pos] = del;
-            if (METRIC == KIND_COS_I8) sm.eval_norm[pos] = ix.norms[id];
-          }
-          n_eval += __popc(km);
-        }
-        __syncwarp();
-      }
+      bool expand;
+      const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand);
       // ---- C + D: stream the rows, two per iteration (independent reductions interleave), and
       // apply each heap update as soon as its distance exists
       if (lane == 0) {
@@ -499,6 +516,224 @@ struct Searcher {
     const int n = __shfl_sync(0xffffffffu, res.n, 0);
     __syncwarp();
     return n;
+  }
+
+
+  // ================================================================================================
+  // Fast path.  While every distance a query meets is distinct, ANY correct priority queue pops the
+  // same sequence as the reference's binary heaps (hnsw_heap.go): the minimum / maximum is unique at
+  // every pop, so the expansions, admissions, evictions and the final ascending order are all forced.
+  // Then the two heaps collapse into one sorted list of the ef best admitted entries with an
+  // "expanded" bit: an admitted entry that is not among the ef best can never be expanded (it is
+  // farther than the worst kept one, which is what stops the search, :2501-2506).  The list lives in
+  // registers (4 entries per lane, ef <= 128) and is maintained by the whole warp — ~40 instructions
+  // per admission instead of ~150 dependent ones on lane 0.  The first equal pair of distances sets
+  // `tie` and the query is re-run by the exact heap path; results are therefore always the reference's.
+  // Not used when soft-deleted nodes exist (they are traversed but not kept, :2584) or ef > 128.
+  // ================================================================================================
+  __device__ __forceinline__ void sl_clear() {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      ld[r] = inf;
+      lid[r] = 0u;
+    }
+    lexp = 0u;
+    ln = 0;
+  }
+  __device__ __forceinline__ double sl_key(int slot) const {
+    return slot == 0 ? ld[0] : (slot == 1 ? ld[1] : (slot == 2 ? ld[2] : ld[3]));
+  }
+  // all lanes; the caller has decided admission.  cap = ef.
+  __device__ __forceinline__ void sl_insert(double xd, uint32_t xid, int cap) {
+    int c = 0;
+    bool eq = false;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      c += ld[r] < xd ? 1 : 0;
+      eq = eq || (ld[r] == xd);
+    }
+    const int p = __reduce_add_sync(0xffffffffu, c);  // keys strictly smaller than x
+    if (__any_sync(0xffffffffu, eq)) tie = true;
+    const double pd = __shfl_up_sync(0xffffffffu, ld[3], 1);
+    const uint32_t pid = __shfl_up_sync(0xffffffffu, lid[3], 1);
+    const uint32_t pe = __shfl_up_sync(0xffffffffu, lexp >> 3, 1) & 1u;
+    const int base = lane << 2;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    uint32_t ne = 0u;
+#pragma unroll
+    for (int r = 3; r >= 0; --r) {  // top slot first: each slot reads the still-old value below it
+      const int idx = base + r;
+      const double sd = r > 0 ? ld[r > 0 ? r - 1 : 0] : pd;
+      const uint32_t sid = r > 0 ? lid[r > 0 ? r - 1 : 0] : pid;
+      const uint32_t se = r > 0 ? ((lexp >> (r > 0 ? r - 1 : 0)) & 1u) : pe;
+      const bool here = idx == p, shift = idx > p, gone = idx >= cap;
+      double nd = here ? xd : (shift ? sd : ld[r]);
+      uint32_t nid = here ? xid : (shift ? sid : lid[r]);
+      uint32_t nb = here ? 0u : (shift ? se : ((lexp >> r) & 1u));
+      if (gone) {  // what moved past the capacity is the evicted worst entry
+        nd = inf;
+        nid = 0u;
+        nb = 0u;
+      }
+      ld[r] = nd;
+      lid[r] = nid;
+      ne |= nb << r;
+    }
+    lexp = ne;
+    ln = ln < cap ? ln + 1 : cap;
+  }
+  // worst kept distance = key of entry ef - 1 (valid once ln == ef)
+  __device__ __forceinline__ double sl_worst(int cap) const {
+    return __shfl_sync(0xffffffffu, sl_key((cap - 1) & 3), (cap - 1) >> 2);
+  }
+  // nearest entry not expanded yet -> its id (and marks it), or 0xffffffff
+  __device__ __forceinline__ uint32_t sl_pop_nearest() {
+    const int base = lane << 2;
+    uint32_t live = 0u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) live |= (base + r < ln ? 1u : 0u) << r;
+    const uint32_t m = live & ~lexp;
+    const uint32_t b = __ballot_sync(0xffffffffu, m != 0u);
+    if (b == 0u) return 0xffffffffu;
+    const int L = __ffs(b) - 1;
+    const int r0 = m ? __ffs(m) - 1 : 0;
+    const uint32_t mine = r0 == 0 ? lid[0] : (r0 == 1 ? lid[1] : (r0 == 2 ? lid[2] : lid[3]));
+    const uint32_t id = __shfl_sync(0xffffffffu, mine, L);
+    if (lane == L) lexp |= 1u << r0;
+    return id;
+  }
+  // the per-neighbour result update (:2571-2591) on the sorted list; all lanes
+  __device__ __forceinline__ void list_update(float s, uint32_t j, int ef) {
+    double d;
+    if (METRIC == KIND_COS_I8) {
+      const float sn = sm.eval_norm[j];
+      if (ln >= ef && sn != 0.f) {  // certain reject without the float64 divide (see heap_update)
+        const double P = __dmul_rn(static_cast<double>(qnorm), static_cast<double>(sn));
+        const double t = __dmul_rn(__dsub_rn(__dsub_rn(1.0, worst), 1e-12), P);
+        if (static_cast<double>(__float_as_int(s)) <= t) return;
+      }
+      d = int8_distance(__float_as_int(s), qnorm, sn);
+    } else {
+      d = to_distance<METRIC>(s);
+    }
+    if (ln < ef || d < worst) {
+      sl_insert(d, sm.eval_id[j], ef);
+      if (ln >= ef) worst = sl_worst(ef);
+    }
+  }
+
+  // searchLayerUnlocked on the sorted list.  Returns the number of kept entries (they stay in the
+  // list, ascending), or -1 if the entry node is nil.  `tie` may be set: the result is then void.
+  __device__ int search_layer_fast(const int level, const int ef, const uint32_t ep) {
+    const bool log_marks = level > 0;
+    if (ep == 0 || ep > ix.n || ix.levels[ep] < 0) return -1;
+    if (lane == 0) {
+      sm.ctl->n_marked = 0;
+      issue_row(0, ep);
+    }
+    __syncwarp();
+    wait_slot(0);
+    const float s0 = warp_sum<METRIC>(lane_partial(0));
+    __syncwarp();
+    sl_clear();
+    sl_insert(to_distance<METRIC>(s0, qnorm, METRIC == KIND_COS_I8 ? ix.norms[ep] : 0.f), ep, ef);  // :2478, :2487
+    if (ln >= ef) worst = sl_worst(ef);
+    if (lane == 0) {
+      mark_logged(ep, log_marks);  // :2479
+      st_e += 1;
+    }
+    __syncwarp();
+    for (;;) {
+      const uint32_t cur = tie ? 0xffffffffu : sl_pop_nearest();  // :2496-2506
+      if (cur == 0xffffffffu) break;
+      bool expand;
+      const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand);
+      if (lane == 0) {
+        const uint32_t pro = n_eval < (uint32_t)SLOTS ? n_eval : (uint32_t)SLOTS;
+        for (uint32_t j = 0; j < pro; ++j) issue_row(j, sm.eval_id[j]);
+      }
+      for (uint32_t j = 0; j < n_eval; j += 2) {
+        const bool two = j + 1 < n_eval;
+        wait_slot(j);
+        if (two) wait_slot(j + 1);
+        float sa = lane_partial(j);
+        float sb = two ? lane_partial(j + 1) : 0.f;
+        if (METRIC == KIND_COS_I8) {
+          sa = warp_sum<METRIC>(sa);
+          sb = warp_sum<METRIC>(sb);
+        } else {
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
+            sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && j + SLOTS < n_eval) {
+          fence_proxy_async();
+          issue_row(j + SLOTS, sm.eval_id[j + SLOTS]);
+          if (j + 1 + SLOTS < n_eval) issue_row(j + 1 + SLOTS, sm.eval_id[j + 1 + SLOTS]);
+        }
+        list_update(sa, j, ef);
+        if (two) list_update(sb, j + 1, ef);
+      }
+      if (lane == 0) {
+        st_e += n_eval;
+        if (expand) {
+          st_h += 1;
+          if (level == 0) st_h0 += 1;
+        }
+      }
+      __syncwarp();
+    }
+    return ln;
+  }
+
+  // searchInternal on the fast path.  Returns false when a tie was met (nothing written; the exact
+  // path must answer the query).  Counters are only kept for queries answered here.
+  __device__ bool run_query_fast(uint32_t q) {
+    const unsigned long long e0 = st_e, h0 = st_h, h00 = st_h0;
+    tie = false;
+    load_query(a.queries + (size_t)q * ix.stride);
+    if (METRIC == KIND_COS_I8) qnorm = a.qnorms[q];
+    uint32_t ep = ix.entry;
+    if (a.allow != nullptr && !bit_test(a.allow, ep)) ep = a.allow_entry;
+    bool failed = ix.max_level < 0;
+    for (int l = ix.max_level; l > 0 && !failed && !tie; --l) {
+      const int n = search_layer_fast(l, 1, ep);
+      if (n > 0) ep = __shfl_sync(0xffffffffu, lid[0], 0);
+      clear_visited(true);
+      if (n <= 0) failed = true;
+    }
+    int count = 0;
+    if (!failed && !tie) {
+      const int n = search_layer_fast(0, a.ef, ep);
+      clear_visited(false);
+      if (n > 0 && !tie) {
+        count = n < a.k ? n : a.k;
+        const int base = lane << 2;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (base + r < count) {  // already ascending (:2596-2610)
+            a.out_ids[(size_t)q * a.k + base + r] = lid[r];
+            a.out_scores[(size_t)q * a.k + base + r] = ld[r];
+          }
+      }
+    }
+    if (tie) {
+      st_e = e0;
+      st_h = h0;
+      st_h0 = h00;
+      return false;
+    }
+    for (int i = count + lane; i < a.k; i += 32) {
+      a.out_ids[(size_t)q * a.k + i] = 0u;
+      a.out_scores[(size_t)q * a.k + i] = 0.0;
+    }
+    if (lane == 0) a.out_counts[q] = (uint32_t)count;
+    __syncwarp();
+    return true;
   }
 
   // searchInternal (hnsw_index.go:369-468) for query q

@@ -90,6 +90,7 @@ SIGNATURES = {
     "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),
     "kdbgpu_search_concurrency": (_i32, [_vp, _i32, _i32]),
     "kdbgpu_prepare_search": (_i32, [_vp, _u32, _i32, _i32]),
+    "kdbgpu_set_fast_path": (_i32, [_vp, _i32]),
     "kdbgpu_set_tuning": (_i32, [_vp, _i32, _i32, _i32]),
 }
 

@@ -387,3 +387,25 @@ def test_merge_topk_kernel_matches_numpy():
         assert o_ids[q, :n].cpu().numpy().astype(np.uint32).tolist() == [w[1] for w in want]
         assert o_sc[q, :n].cpu().numpy().tolist() == [w[0] for w in want]
     gi.close()
+
+
+# ---- the sorted-list fast pass and the heap pass answer identically ------------------------------
+@pytest.mark.parametrize("data,metric,dim,ef", [("normal", O.METRIC_COSINE, 96, 64), ("grid", O.METRIC_L2, 12, 40),
+                                               ("normal", O.METRIC_L2, 200, 128), ("uniform", O.METRIC_COSINE, 33, 10)])
+def test_fast_pass_equals_heap_pass(data, metric, dim, ef):
+    """kdbgpu_set_fast_path: with distinct distances any priority queue pops what the reference's heaps pop;
+    queries that meet a tie (the integer-grid data is full of them) are re-run by the heap pass.  Same ids,
+    scores, counts and counters either way — and both equal the oracle."""
+    oi, X, rng = _build(3000, dim, metric, 8, 60, 4321 + dim, data=data)
+    gi, g = _mirror(oi, metric, 8)
+    Q = (rng.standard_normal((200, dim)) if data != "grid" else rng.integers(-2, 3, (200, dim))).astype(np.float32)
+    members = np.where(rng.random(g.n + 1) < 0.3)[0]
+    allow = O.dense_bitset(members[members > 0], g.n)
+    for al in (None, allow):
+        gi.set_fast_path(True)
+        fast = gi.SearchWithScores(Q, 10, al, ef)
+        gi.set_fast_path(False)
+        heap = gi.SearchWithScores(Q, 10, al, ef)
+        _assert_same(fast, oi.search_batch(Q, 10, ef, allow=al, threads=8))
+        _assert_same(heap, oi.search_batch(Q, 10, ef, allow=al, threads=8))
+    gi.close()
