@@ -250,7 +250,10 @@ int kdbgpu_set_tuning(kdbgpu_index *, int slots, int cand_smem, int max_ctas_per
  * sorted list in registers (valid while all distances a query meets are distinct — any priority queue then
  * pops what the reference's binary heaps pop), and the heap pass (hnsw_heap.go restated exactly) over the
  * queries that met two equal distances, over everything when soft-deleted nodes exist or ef > 128.
- * Results are identical either way; on = 0 sends every query through the heap pass (default on = 1). */
+ * Results are identical either way.  on = 0: heap pass only; 1 (default): the fast pass where ties are
+ * practically absent (int8: distances are full-precision float64 ratios); 2: the fast pass for every
+ * precision (float32 / float16 distances are float32 sums, coarse enough that a large share of the
+ * queries meets a tie and is answered twice — slower, kept for testing). */
 int kdbgpu_set_fast_path(kdbgpu_index *, int on);
 
 /* ---- micro-batcher: the reference's call shape on top of the batched entry point ----------------

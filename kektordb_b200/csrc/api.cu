@@ -2123,7 +2123,7 @@ extern "C" {
 int kdbgpu_set_fast_path(kdbgpu_index *h, int on) {
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
   std::unique_lock<std::shared_mutex> lk(h->mu);
-  h->tuning.fast = on ? 1 : 0;
+  h->tuning.fast = on < 0 ? 0 : (on > 2 ? 2 : on);
   return KDBGPU_OK;
 }
 

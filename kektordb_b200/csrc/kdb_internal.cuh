@@ -79,7 +79,8 @@ struct SearchArgs {
 };
 
 struct SearchTuning {
-  int fast = 1;             // sorted-list fast path with exact re-run on ties (searcher.cuh); 0 = heaps only
+  int fast = 1;             // sorted-list fast pass with exact re-run on ties (searcher.cuh): 0 = heaps only,
+                            // 1 = where ties are practically absent (int8), 2 = every kind
   int slots = 4;            // row slots per query-warp (bulk copies in flight per query), power of two
   int cand_smem = 192;      // candidate-heap entries held in shared memory (the rest spills to HBM)
   int max_ctas_per_sm = 0;  // 0 = whatever fits

@@ -351,8 +351,9 @@ class GpuIndex:
     def device_bytes(self) -> int:
         return int(self._lib.kdbgpu_index_device_bytes(self._handle()))
 
-    def set_fast_path(self, on: bool) -> None:
-        ffi.check(self._lib.kdbgpu_set_fast_path(self._handle(), 1 if on else 0))
+    def set_fast_path(self, mode) -> None:
+        """0 / False: heap pass only; 1 / True: default (fast pass for int8); 2: fast pass for every precision."""
+        ffi.check(self._lib.kdbgpu_set_fast_path(self._handle(), int(mode)))
 
     def prepare_search(self, nq: int, k: int, ef_search: int) -> None:
         ffi.check(self._lib.kdbgpu_prepare_search(self._handle(), nq, k, effective_ef(int(ef_search), self.needs_refine)))

@@ -402,9 +402,9 @@ def test_fast_pass_equals_heap_pass(data, metric, dim, ef):
     members = np.where(rng.random(g.n + 1) < 0.3)[0]
     allow = O.dense_bitset(members[members > 0], g.n)
     for al in (None, allow):
-        gi.set_fast_path(True)
+        gi.set_fast_path(2)
         fast = gi.SearchWithScores(Q, 10, al, ef)
-        gi.set_fast_path(False)
+        gi.set_fast_path(0)
         heap = gi.SearchWithScores(Q, 10, al, ef)
         _assert_same(fast, oi.search_batch(Q, 10, ef, allow=al, threads=8))
         _assert_same(heap, oi.search_batch(Q, 10, ef, allow=al, threads=8))

@@ -224,3 +224,16 @@ def test_train_quantizer_on_the_device_equals_quantizer_train(n, dim):
     gi.upload_vectors(1, X[:8])
     assert np.array_equal(gi.download_rows_raw(1, 8), O.quantize(am, X[:8]))
     gi.close()
+
+
+@pytest.mark.parametrize("prec", [O.PREC_F16, O.PREC_I8])
+def test_fast_pass_equals_heap_pass_on_quantized_rows(prec):
+    """The sorted-list fast pass (default for int8) and the heap pass give the same bits, ties included."""
+    oi, X, rng = _oracle_index(prec, 2500, 64, 8, 60, 555, "grid")
+    gi, g = _mirror(oi, prec, 8)
+    Q = rng.integers(-2, 3, (128, 64)).astype(np.float32)
+    want = oi.search_batch(Q, 10, 64, threads=8)
+    for mode in (2, 1, 0):
+        gi.set_fast_path(mode)
+        _assert_same(gi.SearchWithScores(Q, 10, None, 64), want)
+    gi.close()
