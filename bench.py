@@ -57,6 +57,7 @@ def parse_args():
     p.add_argument("--build-batch", type=int, default=16384)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-single-call", action="store_true", help="skip the one-query-per-call (micro-batcher) measurement")
     p.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"])
     p.add_argument("--workload", default="hnsw", choices=["hnsw", "flat", "hybrid", "quantized"],
                    help="hnsw = BASELINE configs[1] (the headline); flat = configs[2] (tensor-core flat top-100); "
@@ -418,6 +419,27 @@ def main():
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e_d2h = B * k * 12 + B * 4
+    # ---- the reference's own call shape: one blocking single-query call per caller thread, batched by the
+    # ---- library's micro-batcher; native caller threads, rank 0, single GPU only
+    one_call = None
+    if mode == "single" and not args.no_single_call:
+        try:
+            from kektordb_b200 import Batcher
+            from tests.native import driver
+            bt = Batcher(gi, max_batch=B, max_wait_us=200)
+            n_callers = n_ov * B
+            driver.run_callers(bt, Qh_np[:args.warmup * B], k, ef, n_callers)  # warm-up
+            st_w = bt.stats()
+            ids1, sc1, cnt1, secs1 = driver.run_callers(bt, Qh_np[args.warmup * B:], k, ef, n_callers)
+            st_b = bt.stats()
+            nb = st_b.batches - st_w.batches
+            one_call = {"value": round(args.steps * B / secs1, 1), "unit": "queries/s", "caller_threads": n_callers,
+                        "mean_batch": round((st_b.queries - st_w.queries) / max(1, nb), 1), "batches": nb,
+                        "max_wait_us": 200, "first_batch_equal_to_batched_call": bool(
+                            np.array_equal(ids1[:B], gi.SearchWithScores(Qh_np[args.warmup * B:(args.warmup + 1) * B], k, None, ef)[0]))}
+            bt.close()
+        except Exception as ex:  # the main line must still print
+            one_call = {"error": repr(ex)}
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -509,7 +531,7 @@ def main():
                        "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "host_cores": ncores},
             "e2e": {"value": round(e2e_value, 1), "unit": "queries/s",
                     "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": e2e_d2h,
-                    "ms_per_step": round(e2e_ms / args.steps, 4)},
+                    "ms_per_step": round(e2e_ms / args.steps, 4), "one_query_per_call": one_call},
             "gpu_launches": 2 * args.steps + (args.steps if mode == "shard" else 0),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
         }

@@ -16,7 +16,9 @@
 //
 // Errors follow the reference: a failed search yields an empty result for that caller
 // (hnsw_index.go:355-359) and the error code is returned.
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <condition_variable>
 #include <cstring>
 #include <list>
@@ -43,9 +45,13 @@ struct Group {
   size_t allow_words;
   std::vector<Request *> reqs;
   std::chrono::steady_clock::time_point deadline;
-  bool open = true;   // still accepting members
-  bool done = false;  // results scattered
-  std::condition_variable cv;
+  bool open = true;  // still accepting members (guarded by the batcher mutex)
+  std::condition_variable cv;  // leader: "full / device idle / deadline" (waits with the batcher mutex)
+  // completion is signalled under the group's own mutex, so that a thousand followers waking up contend
+  // with each other only — not with the callers that are forming the next groups
+  std::mutex done_mu;
+  std::condition_variable done_cv;
+  bool done = false;
 };
 
 }  // namespace
@@ -59,9 +65,8 @@ struct kdbgpu_batcher {
   std::mutex mu;
   std::list<std::shared_ptr<Group>> open_groups;
   uint32_t inflight = 0;  // batch calls currently executing
-  uint32_t callers = 0;   // threads inside kdbgpu_batcher_search
-  bool closing = false;
-  std::condition_variable idle_cv;
+  std::atomic<uint32_t> callers{0};  // threads inside kdbgpu_batcher_search
+  std::atomic<bool> closing{false};
   // counters
   uint64_t n_queries = 0, n_batches = 0, max_seen = 0, n_immediate = 0, n_full = 0, n_timeout = 0;
 };
@@ -108,10 +113,10 @@ int kdbgpu_batcher_create(kdbgpu_index *index, uint32_t max_batch, uint32_t max_
 
 int kdbgpu_batcher_destroy(kdbgpu_batcher *b) {
   if (!b) return KDBGPU_OK;
+  b->closing.store(true);  // new callers are refused; the ones inside finish
+  while (b->callers.load() != 0) std::this_thread::yield();
   {
-    std::unique_lock<std::mutex> lk(b->mu);
-    b->closing = true;  // new callers are refused; the ones inside finish
-    b->idle_cv.wait(lk, [&] { return b->callers == 0; });
+    std::unique_lock<std::mutex> lk(b->mu);  // the last leader has left its critical section
   }
   delete b;
   return KDBGPU_OK;
@@ -127,15 +132,13 @@ int kdbgpu_batcher_search(kdbgpu_batcher *b, const float *query, int k, int ef_s
   req.out_scores = out_scores;
   req.out_count = out_count;
 
-  std::unique_lock<std::mutex> lk(b->mu);
-  if (b->closing) return KDBGPU_ERR_STATE;
-  b->callers++;
-  struct Leave {
+  struct Inside {  // counts the caller for kdbgpu_batcher_destroy
     kdbgpu_batcher *b;
-    ~Leave() {  // runs with b->mu held
-      if (--b->callers == 0) b->idle_cv.notify_all();
-    }
-  };
+    explicit Inside(kdbgpu_batcher *bb) : b(bb) { b->callers.fetch_add(1); }
+    ~Inside() { b->callers.fetch_sub(1); }
+  } inside(b);
+  if (b->closing.load()) return KDBGPU_ERR_STATE;
+  std::unique_lock<std::mutex> lk(b->mu);
   // ---- join an open group with the same (k, ef, filter), or open one and lead it
   std::shared_ptr<Group> g;
   for (auto &og : b->open_groups)
@@ -157,10 +160,10 @@ int kdbgpu_batcher_search(kdbgpu_batcher *b, const float *query, int k, int ef_s
   g->reqs.push_back(&req);
   if (!leader) {
     if (g->reqs.size() >= b->max_batch) g->cv.notify_all();  // full: wake the leader
-    g->cv.wait(lk, [&] { return g->done; });
-    const int rc = req.rc;
-    Leave leave{b};
-    return rc;
+    lk.unlock();
+    std::unique_lock<std::mutex> dl(g->done_mu);
+    g->done_cv.wait(dl, [&] { return g->done; });
+    return req.rc;
   }
   // ---- leader: collect while the device is busy, then run the batch
   int why = 0;  // 0 immediate, 1 full, 2 deadline
@@ -212,13 +215,15 @@ int kdbgpu_batcher_search(kdbgpu_batcher *b, const float *query, int k, int ef_s
       }
     }
   }
+  {
+    std::lock_guard<std::mutex> dl(g->done_mu);
+    g->done = true;
+  }
+  g->done_cv.notify_all();
   lk.lock();
   b->inflight--;
-  g->done = true;
-  g->cv.notify_all();
   // a batch finished: leaders that were collecting may go now
   for (auto &og : b->open_groups) og->cv.notify_all();
-  Leave leave{b};
   return rc;
 }
 
