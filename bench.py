@@ -58,7 +58,7 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-single-call", action="store_true", help="skip the one-query-per-call (micro-batcher) measurement")
-    p.add_argument("--batcher-wait-us", type=int, default=3000,
+    p.add_argument("--batcher-wait-us", type=int, default=1000,
                    help="micro-batcher deadline; a query's own service time is ~4 ms, and waking 1024 blocked OS "
                         "threads spreads their next requests over ~1-2 ms, so shorter deadlines form small batches")
     p.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"])

@@ -237,3 +237,26 @@ def test_fast_pass_equals_heap_pass_on_quantized_rows(prec):
         gi.set_fast_path(mode)
         _assert_same(gi.SearchWithScores(Q, 10, None, 64), want)
     gi.close()
+
+
+@pytest.mark.parametrize("prec", [O.PREC_F16, O.PREC_I8])
+def test_wide_beams_small_indexes_and_empty_filters(prec):
+    """ef > 128 (heap pass only), k larger than the index, efSearch = 0, an empty and a non-matching allow-list."""
+    oi, X, rng = _oracle_index(prec, 60, 40, 4, 30, 31)
+    gi, g = _mirror(oi, prec, 4)
+    Q = rng.standard_normal((17, 40)).astype(np.float32)
+    for k, ef in ((100, 300), (10, 200), (3, 0), (1, 1)):
+        _assert_same(gi.SearchWithScores(Q, k, None, ef), oi.search_batch(Q, k, ef, threads=4))
+    empty = O.dense_bitset([], g.n)                      # searchInternal returns [] (:443-445)
+    ids, sc, cnt, _ = gi.SearchWithScores(Q, 5, empty, 20)
+    assert not cnt.any() and not ids.any()
+    one = O.dense_bitset([7], g.n)
+    _assert_same(gi.SearchWithScores(Q, 5, one, 20), oi.search_batch(Q, 5, 20, allow=one, threads=4))
+    ids, sc, cnt, _ = gi.SearchWithScores(Q[:0], 5, None, 20)
+    assert ids.shape == (0, 5)
+    gi.close()
+    big, X2, rng2 = _oracle_index(prec, 3000, 64, 8, 60, 32)
+    gb, _ = _mirror(big, prec, 8)
+    Q2 = rng2.standard_normal((64, 64)).astype(np.float32)
+    _assert_same(gb.SearchWithScores(Q2, 20, None, 250), big.search_batch(Q2, 20, 250, threads=8))
+    gb.close()
