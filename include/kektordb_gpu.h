@@ -115,6 +115,9 @@ int kdbgpu_download_norms(kdbgpu_index *, uint32_t first_id, uint32_t count, flo
  *   kdbgpu_arena_load_dir     reads the chunk files of `dir` itself (cold start);
  *   kdbgpu_arena_stage_chunk  takes one chunk the host already has mapped (header included).
  * *rows_staged (may be NULL) receives the number of rows placed. */
+/* Host-only look at an arena directory: dim / precision (0 f32, 1 f16, 2 int8, = KDBGPU_PRECISION_*) from the
+ * chunk headers, number of chunk files, rows per chunk.  Any out pointer may be NULL.  Needs no device. */
+int kdbgpu_arena_probe(const char *dir, uint32_t *dim, int *precision, uint32_t *n_chunks, uint32_t *vecs_per_chunk);
 int kdbgpu_arena_load_dir(kdbgpu_index *, const char *dir, const uint32_t *slot_table, uint32_t table_len,
                           uint64_t *rows_staged);
 int kdbgpu_arena_stage_chunk(kdbgpu_index *, uint32_t chunk_id, const void *chunk, size_t chunk_bytes,

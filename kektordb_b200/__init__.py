@@ -4,8 +4,8 @@ Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C ABI of
 include/kektordb_gpu.h), `ffi.py` (ctypes binding of that ABI), `index.py` (host-side mirror
 of hnsw.Index's search surface), `batcher.py` (one-query-per-call micro-batcher over the same ABI) and `build.py` (nvcc build, in-tree).
 """
-from .index import Cosine, Euclidean, Float16, Float32, Int8, GpuIndex, SearchStats, dense_allow_list, effective_ef  # noqa: F401
+from .index import Cosine, Euclidean, Float16, Float32, Int8, GpuIndex, SearchStats, arena_probe, dense_allow_list, effective_ef  # noqa: F401
 
 from .batcher import Batcher, BatcherStats  # noqa: E402,F401
 
-__all__ = ["Batcher", "BatcherStats", "GpuIndex", "SearchStats", "Cosine", "Euclidean", "Float32", "Float16", "Int8", "dense_allow_list", "effective_ef"]
+__all__ = ["Batcher", "BatcherStats", "GpuIndex", "SearchStats", "arena_probe", "Cosine", "Euclidean", "Float32", "Float16", "Int8", "dense_allow_list", "effective_ef"]

@@ -1040,6 +1040,39 @@ std::vector<char> chunks_in_use(const uint32_t *slot_table, uint32_t last_id, ui
 }
 }  // namespace
 
+// Host-only: what a directory of arena chunks holds (loadExistingChunks + the header fields addChunk
+// validates, arena.go:283-305, :346-364).  No device needed.
+int kdbgpu_arena_probe(const char *dir, uint32_t *dim, int *precision, uint32_t *n_chunks, uint32_t *vecs_per_chunk) {
+  if (!dir) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  std::string err;
+  const int max_chunk = arena_max_chunk(dir, &err);
+  if (max_chunk < 0) return fail(KDBGPU_ERR_INVALID, "no arena_%%04d.bin chunk in %s", dir);
+  unsigned char hdr[64], dummy[16];
+  uint32_t d0 = 0;
+  int p0 = -1;
+  for (int c = 0; c <= max_chunk; ++c) {
+    if (arena_read_chunk(dir, c, hdr, dummy, 0, &err) < 0) continue;  // a dropped chunk (DeferDropChunk) leaves a hole
+    const uint32_t magic = (uint32_t)hdr[0] | ((uint32_t)hdr[1] << 8) | ((uint32_t)hdr[2] << 16) | ((uint32_t)hdr[3] << 24);
+    const uint32_t version = (uint32_t)hdr[4] | ((uint32_t)hdr[5] << 8) | ((uint32_t)hdr[6] << 16) | ((uint32_t)hdr[7] << 24);
+    const uint32_t fdim = (uint32_t)hdr[8] | ((uint32_t)hdr[9] << 8) | ((uint32_t)hdr[10] << 16) | ((uint32_t)hdr[11] << 24);
+    if (magic != 0x4B414F4Eu) return fail(KDBGPU_ERR_INVALID, "file arena_%04d.bin is not a valid arena (magic mismatch)", c);
+    if (version != 1u) return fail(KDBGPU_ERR_INVALID, "file arena_%04d.bin unsupported version %u", c, version);
+    if (p0 < 0) {
+      d0 = fdim;
+      p0 = (int)hdr[12];
+    } else if (fdim != d0 || (int)hdr[12] != p0) {
+      return fail(KDBGPU_ERR_INVALID, "file arena_%04d.bin disagrees with chunk 0 on dimension / precision", c);
+    }
+  }
+  if (p0 < 0 || p0 > 2 || d0 == 0) return fail(KDBGPU_ERR_INVALID, "no readable chunk header in %s", dir);
+  const uint32_t vb = d0 * (p0 == 0 ? 4u : (p0 == 1 ? 2u : 1u));
+  if (dim) *dim = d0;
+  if (precision) *precision = p0;
+  if (n_chunks) *n_chunks = (uint32_t)max_chunk + 1;
+  if (vecs_per_chunk) *vecs_per_chunk = arena_vecs_per_chunk(vb);
+  return KDBGPU_OK;
+}
+
 int kdbgpu_arena_stage_chunk(kdbgpu_index *h, uint32_t chunk_id, const void *chunk, size_t chunk_bytes,
                              const uint32_t *slot_table, uint32_t table_len, uint32_t *rows_staged) {
   if (rows_staged) *rows_staged = 0;

@@ -53,6 +53,7 @@ SIGNATURES = {
     "kdbgpu_set_quantizer": (_i32, [_vp, C.c_float]),
     "kdbgpu_train_quantizer": (_i32, [_vp, _vp, _u32, C.POINTER(C.c_float)]),
     "kdbgpu_train_quantizer_device": (_i32, [_vp, _vp, _sz, _u32, C.POINTER(C.c_float)]),
+    "kdbgpu_arena_probe": (_i32, [C.c_char_p, C.POINTER(_u32), C.POINTER(_i32), C.POINTER(_u32), C.POINTER(_u32)]),
     "kdbgpu_arena_load_dir": (_i32, [_vp, C.c_char_p, _vp, _u32, C.POINTER(C.c_uint64)]),
     "kdbgpu_arena_stage_chunk": (_i32, [_vp, _u32, _vp, _sz, _vp, _u32, C.POINTER(_u32)]),
     "kdbgpu_upload_rows_raw": (_i32, [_vp, _u32, _u32, _vp]),

@@ -66,6 +66,13 @@ def dense_allow_list(ids, n: int) -> np.ndarray:
     return words
 
 
+def arena_probe(arena_dir: str):
+    """(dim, precision name, n_chunks, vecs_per_chunk) of a reference vector arena directory; host-only."""
+    dim, prec, nch, vpc = C.c_uint32(0), C.c_int(0), C.c_uint32(0), C.c_uint32(0)
+    ffi.check(ffi.lib().kdbgpu_arena_probe(arena_dir.encode(), C.byref(dim), C.byref(prec), C.byref(nch), C.byref(vpc)))
+    return dim.value, _PRECISION_NAMES[prec.value], nch.value, vpc.value
+
+
 class GpuIndex:
     """GPU mirror of one hnsw.Index: corpus rows + adjacency staged in HBM, searched on device."""
 

@@ -48,3 +48,22 @@ def test_header_validation(tmp_path):
         A.write_arena(d, rows, 0, st, truncate=True, header_override=bad)
         with pytest.raises(ValueError):
             A.read_arena(d, 4, 0, st)
+
+
+def test_library_probe_reads_the_same_headers_without_a_device(tmp_path):
+    """kdbgpu_arena_probe (host-only): dim / precision / chunk count / rows per chunk, and addChunk's header checks."""
+    from kektordb_b200 import arena_probe, ffi
+    rng = np.random.default_rng(5)
+    n, dim = 90000, 768
+    rows = rng.integers(-100, 100, (n + 1, dim)).astype(np.int8)
+    d = str(tmp_path / "arena")
+    n_chunks = A.write_arena(d, rows, 2, A.sequential_slot_table(n), truncate=True)
+    assert n_chunks == 2
+    assert arena_probe(d) == (dim, "int8", 2, A.vecs_per_chunk(dim, 2))
+    for bad, msg in (({"magic": 9}, "magic mismatch"), ({"version": 4}, "unsupported version")):
+        b = str(tmp_path / next(iter(bad)))
+        A.write_arena(b, rows[:10], 2, A.sequential_slot_table(9), truncate=True, header_override=bad)
+        with pytest.raises(ffi.GpuError, match=msg):
+            arena_probe(b)
+    with pytest.raises(ffi.GpuError):
+        arena_probe(str(tmp_path / "missing"))
