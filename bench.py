@@ -43,7 +43,8 @@ def parse_args():
     p.add_argument("--mode", default="replica", choices=["replica", "shard"],
                    help="N>1: replica = full corpus per GPU, queries split (no collective); "
                         "shard = corpus split by id range, NCCL all-gather of per-shard top-k + merge")
-    p.add_argument("--n", type=int, default=1_000_000)
+    p.add_argument("--n", "--corpus-size", dest="n", type=int, default=1_000_000,
+                   help="rows in the corpus (under torchrun spell it --corpus-size: torchrun's own parser chokes on --n)")
     p.add_argument("--dim", type=int, default=768)
     p.add_argument("--m", type=int, default=32)
     p.add_argument("--efc", type=int, default=200)
