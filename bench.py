@@ -272,7 +272,9 @@ def main():
         return fn[args.workload](args, torch, sys.modules[__name__])
     dist = None
     if world > 1 and args.impl == "ours":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
+        # keep stdout to the one JSON line: NCCL's version banner / warnings go to stderr
+        os.environ.pop("NCCL_DEBUG", None) if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION" else None
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
