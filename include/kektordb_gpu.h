@@ -58,6 +58,8 @@ typedef struct {
   uint64_t hops_l0;    /* of which on level 0 (rows of 2M ids; the rest M ids)      */
   float kernel_ms;     /* device time of the traversal kernel(s), CUDA events      */
   float total_ms;      /* device time of the whole call incl. H2D / D2H copies     */
+  uint32_t heap_pass_queries; /* queries re-answered by the heap pass after a distance tie in the
+                                 fast pass (kdbgpu_set_fast_path); 0 when the fast pass is off */
 } kdbgpu_stats;
 
 /* ---- library ---------------------------------------------------------------------- */

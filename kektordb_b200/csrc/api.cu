@@ -370,6 +370,8 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
     a.redo_count = nullptr;
   }
   CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
+  if (fast && occ_fast > 0)  // stats[3] = queries the heap pass answered after a tie in the fast pass
+    CUDA_TRY(cudaMemcpyAsync(d_stats + 3, w.work_counter.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
   return KDBGPU_OK;
 }
 
@@ -1414,6 +1416,7 @@ int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     stats->dist_evals = st[0];
     stats->hops = st[1];
     stats->hops_l0 = st[2];
+    stats->heap_pass_queries = (uint32_t)st[3];
     cudaEventElapsedTime(&stats->kernel_ms, w.ev[1], w.ev[2]);
     cudaEventElapsedTime(&stats->total_ms, w.ev[0], w.ev[3]);
   }

@@ -527,8 +527,13 @@ struct Searcher {
   // "expanded" bit: an admitted entry that is not among the ef best can never be expanded (it is
   // farther than the worst kept one, which is what stops the search, :2501-2506).  The list lives in
   // registers (4 entries per lane, ef <= 128) and is maintained by the whole warp — ~40 instructions
-  // per admission instead of ~150 dependent ones on lane 0.  The first equal pair of distances sets
-  // `tie` and the query is re-run by the exact heap path; results are therefore always the reference's.
+  // per admission instead of ~150 dependent ones on lane 0.  A tie only matters where it makes an
+  // extreme ambiguous, so `tie` is set (and the query re-run by the exact heap path) exactly when
+  //   * the nearest unexpanded entry and the next candidate in order are equally far (pop, :2496),
+  //   * an evicted entry is as far as the new worst kept one (eviction :2587-2589; such an entry would
+  //     also still pass the strict early-exit test :2501-2506 and be expanded by the reference),
+  //   * two of the first k (+1) entries of the final list are equally far (output order, :2596-2610);
+  // equal pairs that never reach one of those positions cannot change anything the caller can observe.
   // Not used when soft-deleted nodes exist (they are traversed but not kept, :2584) or ef > 128.
   // ================================================================================================
   __device__ __forceinline__ void sl_clear() {
@@ -547,14 +552,9 @@ struct Searcher {
   // all lanes; the caller has decided admission.  cap = ef.
   __device__ __forceinline__ void sl_insert(double xd, uint32_t xid, int cap) {
     int c = 0;
-    bool eq = false;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      c += ld[r] < xd ? 1 : 0;
-      eq = eq || (ld[r] == xd);
-    }
+    for (int r = 0; r < 4; ++r) c += ld[r] < xd ? 1 : 0;
     const int p = __reduce_add_sync(0xffffffffu, c);  // keys strictly smaller than x
-    if (__any_sync(0xffffffffu, eq)) tie = true;
     const double pd = __shfl_up_sync(0xffffffffu, ld[3], 1);
     const uint32_t pid = __shfl_up_sync(0xffffffffu, lid[3], 1);
     const uint32_t pe = __shfl_up_sync(0xffffffffu, lexp >> 3, 1) & 1u;
@@ -600,6 +600,15 @@ struct Searcher {
     const int r0 = m ? __ffs(m) - 1 : 0;
     const uint32_t mine = r0 == 0 ? lid[0] : (r0 == 1 ? lid[1] : (r0 == 2 ? lid[2] : lid[3]));
     const uint32_t id = __shfl_sync(0xffffffffu, mine, L);
+    // the candidate queue's minimum must be unique: the next entry in order, if it is still a
+    // candidate, must be strictly farther (otherwise the heap's tie order decides who is expanded first)
+    const double nd0 = __shfl_down_sync(0xffffffffu, ld[0], 1);
+    const uint32_t ne0 = __shfl_down_sync(0xffffffffu, lexp, 1) & 1u;
+    const double succ_d = r0 == 0 ? ld[1] : (r0 == 1 ? ld[2] : (r0 == 2 ? ld[3] : nd0));
+    const uint32_t succ_exp = r0 < 3 ? ((lexp >> (r0 + 1)) & 1u) : ne0;
+    const bool succ_live = base + r0 + 1 < ln;
+    const bool bad = lane == L && succ_live && succ_exp == 0u && succ_d == sl_key(r0);
+    if (__any_sync(0xffffffffu, bad)) tie = true;
     if (lane == L) lexp |= 1u << r0;
     return id;
   }
@@ -618,8 +627,15 @@ struct Searcher {
       d = to_distance<METRIC>(s);
     }
     if (ln < ef || d < worst) {
+      const bool evicts = ln >= ef;
+      const double evicted = worst;
       sl_insert(d, sm.eval_id[j], ef);
-      if (ln >= ef) worst = sl_worst(ef);
+      if (ln >= ef) {
+        worst = sl_worst(ef);
+        // the result queue's maximum must be unique when it is evicted; an evicted entry as far as the
+        // new worst one would also still be expanded by the reference (:2501-2506 is a strict test)
+        if (evicts && worst == evicted) tie = true;
+      }
     }
   }
 
@@ -710,6 +726,18 @@ struct Searcher {
     if (!failed && !tie) {
       const int n = search_layer_fast(0, a.ef, ep);
       clear_visited(false);
+      if (n > 0) {  // equal distances among the first k (+1) entries: their order is the heap's
+        const int base = lane << 2;
+        const double nd0 = __shfl_down_sync(0xffffffffu, ld[0], 1);
+        const int last_pair = (n - 2 < a.k - 1) ? n - 2 : a.k - 1;  // pairs (i, i+1), i <= last_pair
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double nxt = r < 3 ? ld[r < 3 ? r + 1 : 3] : nd0;
+          bad = bad || (base + r <= last_pair && ld[r] == nxt);
+        }
+        if (__any_sync(0xffffffffu, bad)) tie = true;
+      }
       if (n > 0 && !tie) {
         count = n < a.k ? n : a.k;
         const int base = lane << 2;

@@ -37,7 +37,7 @@ BATCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint32, C.
 
 class Stats(C.Structure):
     _fields_ = [("dist_evals", C.c_uint64), ("hops", C.c_uint64), ("hops_l0", C.c_uint64),
-                ("kernel_ms", C.c_float), ("total_ms", C.c_float)]
+                ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("heap_pass_queries", C.c_uint32)]
 
 
 # every symbol include/kektordb_gpu.h declares: name -> (restype, argtypes)

@@ -39,6 +39,7 @@ class SearchStats:
     hops_l0: int = 0
     kernel_ms: float = 0.0
     total_ms: float = 0.0
+    heap_pass_queries: int = 0
 
 
 def _ptr(a):
@@ -279,7 +280,7 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_search_batch(self._handle(), _ptr(q), nq, k, ef, _ptr(allow),
                                                 0 if allow is None else allow.size, _ptr(ids), _ptr(scores),
                                                 _ptr(counts), C.byref(st)))
-        stats = SearchStats(st.dist_evals, st.hops, st.hops_l0, st.kernel_ms, st.total_ms)
+        stats = SearchStats(st.dist_evals, st.hops, st.hops_l0, st.kernel_ms, st.total_ms, st.heap_pass_queries)
         return ids, scores, counts, stats
 
     search_with_scores = SearchWithScores
