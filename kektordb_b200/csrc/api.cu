@@ -321,7 +321,7 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
     return fail(KDBGPU_ERR_INVALID, "search configuration does not fit shared memory (dim=%d ef=%d smem=%zu)", h->dim,
                 ef, search_smem_bytes(ix, ef, h->tuning));
   const bool fast = search_fast_eligible(ix, ef, h->tuning);
-  const int occ_fast = fast ? search_fast_occupancy(ix, h->tuning) : 0;
+  const int occ_fast = fast ? search_fast_occupancy(ix, ef, h->tuning) : 0;
   const int occ_max = occ_fast > occ ? occ_fast : occ;
   int rc = ensure_ws(h, w, occ_max * h->num_sms);
   if (rc) return rc;
@@ -360,16 +360,23 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
     CUDA_TRY(w.redo.reserve(nq));
     int gfast = occ_fast * h->num_sms;
     if ((uint32_t)gfast > nq) gfast = (int)nq;
-    a.redo_list = w.redo.p;
     a.redo_count = w.work_counter.p + 2;
-    CUDA_TRY(launch_search_fast(ix, a, h->tuning, gfast, stream));
-    a.work_counter = w.work_counter.p + 1;
-    a.query_list = w.redo.p;
-    a.query_count = w.work_counter.p + 2;
-    a.redo_list = nullptr;
-    a.redo_count = nullptr;
+    if (search_fast_hands_over(ix)) {
+      a.redo_list = w.redo.p;
+      CUDA_TRY(launch_search_fast(ix, a, h->tuning, gfast, stream));
+      a.work_counter = w.work_counter.p + 1;
+      a.query_list = w.redo.p;
+      a.query_count = w.work_counter.p + 2;
+      a.redo_list = nullptr;
+      a.redo_count = nullptr;
+      CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
+    } else {  // tied queries are re-run by the heap path inside the same launch
+      a.redo_list = nullptr;
+      CUDA_TRY(launch_search_fast(ix, a, h->tuning, gfast, stream));
+    }
+  } else {
+    CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
   }
-  CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
   if (fast && occ_fast > 0)  // stats[3] = queries the heap pass answered after a tie in the fast pass
     CUDA_TRY(cudaMemcpyAsync(d_stats + 3, w.work_counter.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
   return KDBGPU_OK;
@@ -1440,7 +1447,7 @@ int kdbgpu_prepare_search(kdbgpu_index *h, uint32_t nq, int k, int ef_search) {
   const size_t nk = (size_t)nq * k;
   const size_t blob_bytes = ((nk * (sizeof(double) + sizeof(uint32_t)) + (size_t)nq * sizeof(uint32_t) + 7) & ~(size_t)7) +
                             4 * sizeof(unsigned long long) + sizeof(long long);
-  const int occ_fast = search_fast_eligible(ix, ef, h->tuning) ? search_fast_occupancy(ix, h->tuning) : 0;
+  const int occ_fast = search_fast_eligible(ix, ef, h->tuning) ? search_fast_occupancy(ix, ef, h->tuning) : 0;
   for (auto &w : h->sws) {
     int rc = ensure_ws(h, w, (occ_fast > occ ? occ_fast : occ) * h->num_sms);
     if (rc) return rc;

@@ -94,7 +94,8 @@ cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchT
                           cudaStream_t stream);
 // fast path (ef <= 128, no soft-deleted nodes): shape, occupancy, launch
 bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t);
-int search_fast_occupancy(const DevIndex &ix, const SearchTuning &t);
+int search_fast_occupancy(const DevIndex &ix, int ef, const SearchTuning &t);
+bool search_fast_hands_over(const DevIndex &ix);  // ties go to a second (heap) launch instead of being re-run in place
 cudaError_t launch_search_fast(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
                                cudaStream_t stream);
 cudaError_t launch_prep_queries(const float *in, size_t in_stride, float *out, uint32_t nq, uint32_t dim,

@@ -39,16 +39,30 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const DevIndex ix, cons
 template <int SLOTS, int METRIC, int CPL>
 __global__ void __launch_bounds__(32) hnsw_search_fast_kernel(const DevIndex ix, const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  Searcher<SLOTS, METRIC, CPL> s(ix, a, smem, false);
+  // two shapes: without heap arrays in shared memory (more resident query-warps; ties are handed to the
+  // heap kernel through redo_list — for rows whose distances practically never tie), or with them, the
+  // tied query being re-run by the heap path at once in this warp (a second launch would add a whole
+  // query's latency to the batch)
+  const bool hand_over = a.redo_list != nullptr;
+  Searcher<SLOTS, METRIC, CPL> s(ix, a, smem, !hand_over);
   s.init_barriers();
+  unsigned int n_tied = 0;
   for (;;) {
     uint32_t q = 0;
     if (s.lane == 0) q = atomicAdd(a.work_counter, 1u);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= a.nq) break;
-    if (!s.run_query_fast(q) && s.lane == 0) a.redo_list[atomicAdd(a.redo_count, 1u)] = q;
+    if (!s.run_query_fast(q)) {
+      if (hand_over) {
+        if (s.lane == 0) a.redo_list[atomicAdd(a.redo_count, 1u)] = q;
+      } else {
+        s.run_query(q);
+        n_tied++;
+      }
+    }
     __syncwarp();
   }
+  if (s.lane == 0 && n_tied) atomicAdd(a.redo_count, n_tied);
   if (s.lane == 0) {
     atomicAdd(&a.stats[0], s.st_e);
     atomicAdd(&a.stats[1], s.st_h);
@@ -392,9 +406,12 @@ cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchT
     default: { KDB_FAST_CPL(KIND_L2_F32, EXPR) } break;                 \
   }
 
-static size_t search_fast_smem_bytes(const DevIndex &ix) {
-  return smem_layout(ix.stride, 0, 4, 0, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, cpl_of(ix) == 0, nullptr, nullptr);
+// hand_over: no heap arrays (ties go to the heap kernel); otherwise the heap kernel's own carve-up
+static size_t search_fast_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t, bool hand_over) {
+  return smem_layout(ix.stride, hand_over ? 0 : ef, 4, hand_over ? 0u : (uint32_t)t.cand_smem,
+                     ix.deg0 > ix.degu ? ix.deg0 : ix.degu, cpl_of(ix) == 0, nullptr, nullptr);
 }
+bool search_fast_hands_over(const DevIndex &ix) { return ix.kind == KIND_COS_I8; }
 
 bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t) {
   // soft-deleted nodes are traversed but never kept (hnsw_index.go:2584): they need the two separate queues.
@@ -403,11 +420,12 @@ bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t) {
   // that ~40 % of the queries at 1 M x 768 meet an equal pair among their 128 kept entries and would be
   // answered twice (measured: 245 k instead of 282 k queries/s).  fast = 2 forces it for every kind.
   const bool kind_ok = t.fast >= 2 || (t.fast == 1 && ix.kind == KIND_COS_I8);
-  return kind_ok && t.slots == 4 && ef <= 128 && ix.deleted == nullptr && search_fast_smem_bytes(ix) <= 227 * 1024;
+  return kind_ok && t.slots == 4 && ef <= 128 && ix.deleted == nullptr &&
+         search_fast_smem_bytes(ix, ef, t, search_fast_hands_over(ix)) <= 227 * 1024;
 }
 
-int search_fast_occupancy(const DevIndex &ix, const SearchTuning &t) {
-  const size_t smem = search_fast_smem_bytes(ix);
+int search_fast_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
+  const size_t smem = search_fast_smem_bytes(ix, ef, t, search_fast_hands_over(ix));
   const int cpl = cpl_of(ix);
   int nb = 0;
   KDB_FAST_DISPATCH(nb = (occupancy_fast_one<MT, CP>(smem)))
@@ -417,8 +435,7 @@ int search_fast_occupancy(const DevIndex &ix, const SearchTuning &t) {
 
 cudaError_t launch_search_fast(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
                                cudaStream_t stream) {
-  (void)t;
-  const size_t smem = search_fast_smem_bytes(ix);
+  const size_t smem = search_fast_smem_bytes(ix, a.ef, t, a.redo_list != nullptr);
   const int cpl = cpl_of(ix);
   cudaError_t e = cudaErrorInvalidConfiguration;
   KDB_FAST_DISPATCH(e = (launch_fast_one<MT, CP>(ix, a, grid, smem, stream)))
