@@ -254,11 +254,12 @@ int kdbgpu_set_tuning(kdbgpu_index *, int slots, int cand_smem, int max_ctas_per
 /* The traversal answers a batch in two passes: a fast pass that keeps the candidate / result queues as one
  * sorted list in registers (valid while all distances a query meets are distinct — any priority queue then
  * pops what the reference's binary heaps pop), and the heap pass (hnsw_heap.go restated exactly) over the
- * queries that met two equal distances, over everything when soft-deleted nodes exist or ef > 128.
+ * queries where a distance tie made a pop / eviction / the final order ambiguous, and over everything when
+ * soft-deleted nodes exist or ef > 128.
  * Results are identical either way.  on = 0: heap pass only; 1 (default): the fast pass where ties are
  * practically absent (int8: distances are full-precision float64 ratios); 2: the fast pass for every
- * precision (float32 / float16 distances are float32 sums, coarse enough that a large share of the
- * queries meets a tie and is answered twice — slower, kept for testing). */
+ * precision (float32 / float16 distances are float32 sums: 2-3 % of the queries at 1 M x 768 meet a relevant
+ * tie and are re-run, and the pass measures slower than the heaps there — kept for testing). */
 int kdbgpu_set_fast_path(kdbgpu_index *, int on);
 
 /* ---- micro-batcher: the reference's call shape on top of the batched entry point ----------------

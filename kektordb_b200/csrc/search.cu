@@ -415,10 +415,9 @@ bool search_fast_hands_over(const DevIndex &ix) { return ix.kind == KIND_COS_I8;
 
 bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t) {
   // soft-deleted nodes are traversed but never kept (hnsw_index.go:2584): they need the two separate queues.
-  // fast = 1 (default) uses the pass where ties are practically absent: int8 distances are full-precision
-  // float64 ratios, while float32 / float16 distances are float32 sums widened to float64 — coarse enough
-  // that ~40 % of the queries at 1 M x 768 meet an equal pair among their 128 kept entries and would be
-  // answered twice (measured: 245 k instead of 282 k queries/s).  fast = 2 forces it for every kind.
+  // fast = 1 (default) uses the pass where it measures faster: int8 rows (distances are full-precision
+  // float64 ratios, no ties, +12 %).  On float32 / float16 rows (float32 sums: 2-3 % of the queries at
+  // 1 M x 768 meet a relevant tie) it measures slower than the heaps; fast = 2 forces it.
   const bool kind_ok = t.fast >= 2 || (t.fast == 1 && ix.kind == KIND_COS_I8);
   return kind_ok && t.slots == 4 && ef <= 128 && ix.deleted == nullptr &&
          search_fast_smem_bytes(ix, ef, t, search_fast_hands_over(ix)) <= 227 * 1024;
