@@ -1677,10 +1677,14 @@ int kdbgpu_index_dim(const kdbgpu_index *h) { return h ? h->dim : -1; }
 uint32_t kdbgpu_index_count(const kdbgpu_index *h) { return h ? h->n : 0; }
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *h) {
   if (!h) return 0;
-  return h->vecs.bytes() + h->adj0.bytes() + h->upper_adj.bytes() + h->upper_first.bytes() + h->deleted.bytes() +
-         h->levels.bytes() + h->visited.bytes() + h->cand_overflow.bytes() + h->sws[0].visited.bytes() * kdbgpu_index::kNumSearchWs +
-         h->sws[0].cand_overflow.bytes() * kdbgpu_index::kNumSearchWs + h->flat_dist.bytes() + h->q_raw.bytes() +
-         h->q_prep.bytes() + h->out_ids.bytes() + h->out_scores.bytes() + h->allow.bytes();
+  uint64_t ws = 0;
+  for (const auto &w : h->sws)
+    ws += w.visited.bytes() + w.cand_overflow.bytes() + w.q_raw.bytes() + w.q_prep.bytes() + w.qnorms.bytes() +
+          w.allow.bytes() + w.out_blob.bytes() + w.redo.bytes();
+  return h->vecs.bytes() + h->norms.bytes() + h->adj0.bytes() + h->upper_adj.bytes() + h->upper_first.bytes() +
+         h->upper_node.bytes() + h->upper_level.bytes() + h->deleted.bytes() + h->levels.bytes() + h->visited.bytes() +
+         h->cand_overflow.bytes() + ws + h->flat_dist.bytes() + h->q_raw.bytes() + h->q_prep.bytes() + h->out_ids.bytes() +
+         h->out_scores.bytes() + h->allow.bytes() + h->x_bf16.bytes() + h->conv_tmp.bytes();
 }
 int kdbgpu_search_concurrency(kdbgpu_index *h, int k, int ef_search) {
   if (!h) return 0;

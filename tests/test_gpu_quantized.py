@@ -260,3 +260,32 @@ def test_wide_beams_small_indexes_and_empty_filters(prec):
     Q2 = rng2.standard_normal((64, 64)).astype(np.float32)
     _assert_same(gb.SearchWithScores(Q2, 20, None, 250), big.search_batch(Q2, 20, 250, threads=8))
     gb.close()
+
+
+@pytest.mark.parametrize("name", ["int8_cosine_d40_m8", "f16_l2_d36_m6"])
+def test_quantized_golden_fixtures(name):
+    """Committed fixtures replayed through the C ABI: stored rows + topology -> the expected output; and the
+    float32 inputs converted on the device give the fixture's rows (and norms)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    GpuIndex = _gpu()
+    prec, dim, n, m = int(z["precision"]), int(z["dim"]), int(z["n"]), int(z["m"])
+    gi = GpuIndex(dim, "euclidean" if prec == O.PREC_F16 else "cosine", m, n, precision=_prec_name(prec))
+    if prec == O.PREC_I8:
+        assert np.float32(gi.TrainQuantizer(z["inputs"])) == np.float32(z["abs_max"])
+    gi.upload_vectors(1, z["inputs"])
+    assert np.array_equal(gi.download_rows_raw(1, n), z["rows"][1:])
+    if prec == O.PREC_I8:
+        assert np.array_equal(gi.download_norms(1, n), z["norms"][1:])
+    gi.upload_rows_raw(1, z["rows"][1:])
+    gi.set_graph(n, z["levels"], z["node_row"], z["row_off"], z["nbrs"], int(z["entry"]), int(z["max_level"]))
+    if z["deleted"].any():
+        gi.set_deleted(O.dense_bitset(np.where(z["deleted"])[0], n))
+    allow = z["allow"] if z["allow"].size else None
+    for mode in (1, 0, 2):
+        gi.set_fast_path(mode)
+        ids, sc, cnt, st = gi.SearchWithScores(z["queries"], int(z["k"]), allow, int(z["ef"]))
+        assert np.array_equal(ids, z["ids"]) and np.array_equal(sc, z["scores"])
+        assert np.array_equal(cnt, z["counts"].astype(np.uint32))
+        assert st.dist_evals == int(z["dist_evals"]) and st.hops == int(z["hops"])
+    gi.close()

@@ -227,3 +227,42 @@ def test_flat_scan_is_float32_only():
     oi.add_many(X, rng.random(50))
     ids, sc, cnt = oi.flat_search_batch(X[:2], 3, 0)
     assert not cnt.any()
+
+
+# ---- committed fixtures (tests/golden/make_golden.py) ------------------------------------------------
+import os  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["int8_cosine_d40_m8", "f16_l2_d36_m6"])
+def test_quantized_golden_fixtures_replay(name):
+    """The committed float16 / int8 fixtures: stored rows follow from the float32 inputs by an independent
+    numpy restatement of the conversions, and the oracle replays the expected output from rows + topology —
+    for int8 in the reference's pure-Go order as well (integer dot: every order gives the same bits)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    prec, dim, n = int(z["precision"]), int(z["dim"]), int(z["n"])
+    X = z["inputs"]
+    if prec == O.PREC_F16:
+        with np.errstate(over="ignore"):
+            assert np.array_equal(z["rows"][1:], X.astype(np.float16).view(np.uint16))
+    else:
+        am = np.float32(z["abs_max"])
+        s = np.sort(np.abs(X).ravel())
+        assert am == s[min(int(s.size * 0.999), s.size - 1)]                       # Quantizer.Train, n <= 10 000
+        scaled = np.clip((X / am).astype(np.float32) * np.float32(127.0), -127.0, 127.0).astype(np.float64)
+        want = (np.sign(scaled) * np.floor(np.abs(scaled) + 0.5)).astype(np.int8)  # math.Round
+        assert np.array_equal(z["rows"][1:], want)
+        assert np.array_equal(z["norms"][1:], np.sqrt((want.astype(np.int64) ** 2).sum(1).astype(np.float64)).astype(np.float32))
+    g = O.Graph(n, z["levels"], z["node_row"], z["row_off"], z["nbrs"], z["deleted"], int(z["entry"]), int(z["max_level"]))
+    allow = z["allow"] if z["allow"].size else None
+    for arith in ((O.ARITH_KERNEL, O.ARITH_SEQ, O.ARITH_AVX2) if prec == O.PREC_I8 else (O.ARITH_KERNEL,)):
+        oi = O.OracleIndex(dim, int(z["metric"]), int(z["m"]), 50, arith, n, precision=prec)
+        if prec == O.PREC_I8:
+            oi.set_quantizer(float(z["abs_max"]))
+        oi.import_graph(z["rows"], g)
+        for d in np.where(z["deleted"])[0]:
+            oi.delete(int(d))
+        ids, sc, cnt, st = oi.search_batch(z["queries"], int(z["k"]), int(z["ef"]), allow=allow, threads=4)
+        assert np.array_equal(ids, z["ids"]) and np.array_equal(sc, z["scores"]) and np.array_equal(cnt, z["counts"])
+        assert st.dist_evals == int(z["dist_evals"]) and st.hops == int(z["hops"])
