@@ -413,7 +413,8 @@ def run_quantized(args, torch, bench):
     ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, None, ef)
     recall = bench.recall_at_k(ids0[:n_gt], gt_ids)
     # ---- device-resident timing: consecutive batches alternate over n_ov streams (as bench.py's headline)
-    n_ov = max(1, min(4, args.overlap))
+    # these rows are latency / issue-bound: four batches in flight unless --overlap says otherwise
+    n_ov = max(1, min(4, args.overlap if "--overlap" in os.sys.argv else 4))
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_ov)]
     d_ids = [torch.zeros((B, k), dtype=torch.int32, device=dev) for _ in range(n_ov)]
     d_sc = [torch.zeros((B, k), dtype=torch.float64, device=dev) for _ in range(n_ov)]
