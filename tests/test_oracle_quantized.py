@@ -266,3 +266,49 @@ def test_quantized_golden_fixtures_replay(name):
         ids, sc, cnt, st = oi.search_batch(z["queries"], int(z["k"]), int(z["ef"]), allow=allow, threads=4)
         assert np.array_equal(ids, z["ids"]) and np.array_equal(sc, z["scores"]) and np.array_equal(cnt, z["counts"])
         assert st.dist_evals == int(z["dist_evals"]) and st.hops == int(z["hops"])
+
+
+# ---- randomized cross-check against the pure-Python restatement (ties, deletes, filters) -----------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(2, 90), m=st.sampled_from([2, 4, 8]),
+       prec=st.sampled_from([O.PREC_F16, O.PREC_I8]), k=st.integers(1, 10), ef=st.integers(0, 30),
+       grid=st.booleans(), use_allow=st.booleans(), n_del=st.integers(0, 8), batch=st.sampled_from([0, 12]))
+def test_quantized_oracle_equals_python_restatement(seed, n, m, prec, k, ef, grid, use_allow, n_del, batch):
+    rng = np.random.default_rng(seed)
+    dim = 6
+    X = (rng.integers(-3, 4, (n, dim)) if grid else rng.standard_normal((n, dim))).astype(np.float32)
+    metric = O.METRIC_L2 if prec == O.PREC_F16 else O.METRIC_COSINE
+    oi = O.OracleIndex(dim, metric, m, 10, O.ARITH_SEQ, n + 4, precision=prec)
+    if prec == O.PREC_I8:
+        oi.set_quantizer(max(float(O.train_quantizer(X)), 1e-3))
+    if batch:
+        oi.build_batched(X, rng.random(n), batch=batch, threads=2)
+    else:
+        oi.add_many(X, rng.random(n))
+    for d in rng.integers(1, n + 1, min(n_del, n)):
+        oi.delete(int(d))
+    g = oi.export_graph()
+    rows = oi.rows_raw()
+    levels = {i: int(g.levels[i]) for i in range(1, g.n + 1) if g.levels[i] >= 0}
+    deleted = {i for i in range(1, g.n + 1) if g.deleted[i]}
+    allow_set = allow = None
+    if use_allow:
+        allow_set = set(int(i) for i in np.where(rng.random(n + 1) < 0.4)[0] if i > 0)
+        allow = O.dense_bitset(sorted(allow_set), n)
+    norms = oi.norms() if prec == O.PREC_I8 else None
+    for _ in range(3):
+        q = (rng.integers(-3, 4, dim) if grid else rng.standard_normal(dim)).astype(np.float32)
+        if prec == O.PREC_F16:
+            qq = O.f32_to_f16_bits(q)
+            dist = lambda i: float(O.sq_euclid_f16(O.ARITH_SEQ, qq, rows[i]))
+        else:
+            qq = O.quantize(oi.abs_max, O.normalize(q))
+            qn = float(O.int8_norm(qq)) or 1.0
+            dist = lambda i: O.int8_cosine_distance(int(qq.astype(np.int32) @ rows[i].astype(np.int32)), qn, norms[i])
+        want = pyref.search(dist, lambda i, l: g.row(i, l).tolist(), levels, deleted, g.entry, g.max_level, k, ef, allow_set)
+        ids, sc = oi.search(q, k, ef, allow=allow)
+        assert [int(i) for i in ids] == [w[0] for w in want]
+        assert [float(s) for s in sc] == [w[1] for w in want]
