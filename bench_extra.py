@@ -209,6 +209,71 @@ def _flat_reference_arm(args, gi, X, Q, k, ncores):
     return 0
 
 
+
+def _measure(args, torch, bench, gi, Qd, Q, B, k, ef, local_rank, dev, n_ov, allow):
+    """Device-resident timing with consecutive batches alternating over n_ov streams (as bench.py's headline),
+    isolated launches, and end-to-end timing through the C ABI with host buffers from n_ov caller threads.
+    allow: dense uint64 bitset (numpy) shared by every batch, or None.  Returns (dev_ms, iso_ms, e2e_s, stats, clocks)."""
+    import threading
+    n_total = args.warmup + args.steps
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_ov)]
+    d_ids = [torch.zeros((B, k), dtype=torch.int32, device=dev) for _ in range(n_ov)]
+    d_sc = [torch.zeros((B, k), dtype=torch.float64, device=dev) for _ in range(n_ov)]
+    d_cnt = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(n_ov)]
+    d_allow, allow_words, allow_first = None, 0, 0
+    if allow is not None:
+        d_allow = torch.from_numpy(allow.view(np.int64)).to(dev)
+        allow_words = int(allow.size)
+        nz = np.flatnonzero(allow)
+        allow_first = int(nz[0] * 64 + (int(allow[nz[0]]) & -int(allow[nz[0]])).bit_length() - 1) if nz.size else 0
+
+    def launch(i, j):
+        gi.search_device(Qd[i * B:(i + 1) * B].data_ptr(), B, k, ef, d_ids[j].data_ptr(), d_sc[j].data_ptr(),
+                         d_cnt[j].data_ptr(), streams[j].cuda_stream, d_allow.data_ptr() if d_allow is not None else 0,
+                         allow_words, allow_first)
+
+    for i in range(args.warmup):
+        launch(i, i % n_ov)
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank, args.clock_sampler)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(streams[0])
+    for s_ in streams[1:]:
+        s_.wait_event(ev0)
+    for i in range(args.warmup, n_total):
+        launch(i, i % n_ov)
+    for s_ in streams[1:]:
+        streams[0].wait_stream(s_)
+    ev1.record(streams[0])
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    st = gi.last_search_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(streams[0])
+    for r in range(5):
+        launch(r, 0)
+    e1.record(streams[0])
+    torch.cuda.synchronize()
+    iso_ms = e0.elapsed_time(e1) / 5
+    for i in range(args.warmup):
+        gi.SearchWithScores(Q[i * B:(i + 1) * B], k, allow, ef)
+
+    def worker(j):
+        torch.cuda.set_device(local_rank)
+        for i in range(args.warmup + j, n_total, n_ov):
+            gi.SearchWithScores(Q[i * B:(i + 1) * B], k, allow, ef)
+
+    ws = [threading.Thread(target=worker, args=(j,)) for j in range(n_ov)]
+    t1 = time.perf_counter()
+    for t in ws:
+        t.start()
+    for t in ws:
+        t.join()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t1
+    return dev_ms, iso_ms, e2e_s, st, sampler.stop()
+
 # --------------------------------------------------------------------------------------------------
 def run_hybrid(args, torch, bench):
     """configs[4]: HNSW + allow-list (10 % selectivity).  Semantics of the reference: non-members are
@@ -263,20 +328,10 @@ def run_hybrid(args, torch, bench):
     gt_ids, _, gt_cnt, _ = gi.flat_search(Q[:n_gt], k, 1, allow, prefilter=True)
     recall = bench.recall_at_k(ids0[:n_gt], gt_ids)
     only_members = bool(member[ids0[ids0 > 0]].all())
-    for i in range(args.warmup):
-        gi.SearchWithScores(Q[i * B:(i + 1) * B], k, allow, ef)
-    torch.cuda.synchronize()
-    sampler = bench.ClockSampler(local_rank, args.clock_sampler)
-    sampler.start()
-    kern_ms, E, H, H0 = 0.0, 0, 0, 0
-    t0 = time.perf_counter()
-    for i in range(args.warmup, n_total):
-        _, _, _, st = gi.SearchWithScores(Q[i * B:(i + 1) * B], k, allow, ef)
-        kern_ms += st.kernel_ms
-        E, H, H0 = E + st.dist_evals, H + st.hops, H0 + st.hops_l0
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
+    n_ov = max(1, min(4, args.overlap))
+    dev_ms, iso_ms, e2e_s, st, clocks = _measure(args, torch, bench, gi, Qd, Q, B, k, ef, local_rank, dev, n_ov, allow)
+    kern_ms = dev_ms
+    E, H, H0 = st.dist_evals * args.steps, st.hops * args.steps, st.hops_l0 * args.steps
     pk = _peaks()
     stride = (D + 127) // 128 * 128
     byts = E * stride * 4 + H0 * 2 * args.m * 4 + (H - H0) * args.m * 4
@@ -310,7 +365,7 @@ def run_hybrid(args, torch, bench):
         "config": {"workload": f"{N}x{D} cosine, HNSW M={args.m} efC={args.efc} efSearch={ef}, top-{k}, allow-list "
                                f"Bernoulli({sel}) seed 7 shared by the batch, batch={B} (BASELINE configs[4])",
                    "l2_policy": "inputs larger than L2", "build_seconds": round(build_s, 2), "host_cores": ncores,
-                   "value_is": "device time of the traversal kernel (CUDA events inside the library), one batch in flight"},
+                   "batches_in_flight": n_ov},
         "e2e": {"value": round(B * args.steps / e2e_s, 1), "unit": "queries/s",
                 "h2d_bytes_per_step": B * D * 4 + allow.nbytes, "d2h_bytes_per_step": B * k * 12 + B * 4 + 40,
                 "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
@@ -412,63 +467,8 @@ def run_quantized(args, torch, bench):
     gi.prepare_search(B, k, ef)
     ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, None, ef)
     recall = bench.recall_at_k(ids0[:n_gt], gt_ids)
-    # ---- device-resident timing: consecutive batches alternate over n_ov streams (as bench.py's headline)
-    # these rows are latency / issue-bound: four batches in flight unless --overlap says otherwise
     n_ov = max(1, min(4, args.overlap if "--overlap" in os.sys.argv else 4))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_ov)]
-    d_ids = [torch.zeros((B, k), dtype=torch.int32, device=dev) for _ in range(n_ov)]
-    d_sc = [torch.zeros((B, k), dtype=torch.float64, device=dev) for _ in range(n_ov)]
-    d_cnt = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(n_ov)]
-
-    def step_device(i):
-        j = i % n_ov
-        gi.search_device(Qd[i * B:(i + 1) * B].data_ptr(), B, k, ef, d_ids[j].data_ptr(), d_sc[j].data_ptr(),
-                         d_cnt[j].data_ptr(), streams[j].cuda_stream)
-
-    for i in range(args.warmup):
-        step_device(i)
-    torch.cuda.synchronize()
-    sampler = bench.ClockSampler(local_rank, args.clock_sampler)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(streams[0])
-    for s_ in streams[1:]:
-        s_.wait_event(ev0)
-    for i in range(args.warmup, n_total):
-        step_device(i)
-    for s_ in streams[1:]:
-        streams[0].wait_stream(s_)
-    ev1.record(streams[0])
-    torch.cuda.synchronize()
-    dev_ms = ev0.elapsed_time(ev1)
-    st = gi.last_search_stats()
-    # isolated launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(streams[0])
-    for r in range(5):
-        gi.search_device(Qd[r * B:(r + 1) * B].data_ptr(), B, k, ef, d_ids[0].data_ptr(), d_sc[0].data_ptr(),
-                         d_cnt[0].data_ptr(), streams[0].cuda_stream)
-    e1.record(streams[0])
-    torch.cuda.synchronize()
-    iso_ms = e0.elapsed_time(e1) / 5
-    # ---- e2e through the C ABI with host buffers, n_ov caller threads
-    for i in range(args.warmup):
-        gi.SearchWithScores(Q[i * B:(i + 1) * B], k, None, ef)
-
-    def worker(j):
-        torch.cuda.set_device(local_rank)
-        for i in range(args.warmup + j, n_total, n_ov):
-            gi.SearchWithScores(Q[i * B:(i + 1) * B], k, None, ef)
-
-    ws = [threading.Thread(target=worker, args=(j,)) for j in range(n_ov)]
-    t1 = time.perf_counter()
-    for t in ws:
-        t.start()
-    for t in ws:
-        t.join()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t1
-    clocks = sampler.stop()
+    dev_ms, iso_ms, e2e_s, st, clocks = _measure(args, torch, bench, gi, Qd, Q, B, k, ef, local_rank, dev, n_ov, None)
     pk = _peaks()
     esize = 1 if prec == "int8" else 2
     row_bytes = (D * esize + 127) // 128 * 128
