@@ -131,3 +131,61 @@ def test_refresh_argument_checks():
     gi.register_nodes(41, [0, -1, 1])
     assert gi.count == 43
     gi.close()
+
+
+def test_searches_and_refresh_calls_from_concurrent_threads():
+    """Searches (shared lock, several in flight) race with patch / delete calls (exclusive lock): every search
+    must see one consistent state — its result equals the oracle's on the topology before or after the patch."""
+    import threading
+    from kektordb_b200 import GpuIndex
+    rng = np.random.default_rng(31)
+    n, dim, m = 2500, 40, 8
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    oi = O.OracleIndex(dim, O.METRIC_COSINE, m, 60, O.ARITH_KERNEL, n)
+    oi.build_batched(X, rng.random(n), batch=500, threads=8)
+    g = oi.export_graph()
+    rows = _rows(g)
+    # state B: 40 level-0 rows lose their last neighbour
+    victims = [key for key in list(rows)[::50] if key[1] == 0 and len(rows[key]) > 2][:40]
+    new_rows = dict(rows)
+    for key in victims:
+        new_rows[key] = rows[key][:-1]
+    node_row, row_off, nbrs = [0], [0], []
+    for i in range(1, n + 1):
+        node_row.append(len(row_off) - 1)
+        for l in range(int(g.levels[i]) + 1):
+            nbrs.extend(new_rows[(i, l)])
+            row_off.append(len(nbrs))
+    node_row.append(len(row_off) - 1)
+    gB = O.Graph(n, g.levels, np.array(node_row, np.uint64), np.array(row_off, np.uint64), np.array(nbrs, np.uint32),
+                 np.zeros(n + 1, np.uint8), g.entry, g.max_level)
+    oB = O.OracleIndex(dim, O.METRIC_COSINE, m, 60, O.ARITH_KERNEL, n)
+    oB.import_graph(oi.vectors(), gB)
+    Q = rng.standard_normal((96, dim)).astype(np.float32)
+    wantA = oi.search_batch(Q, 10, 64, threads=8)
+    wantB = oB.search_batch(Q, 10, 64, threads=8)
+    gi = GpuIndex(dim, "cosine", m, n)
+    gi.upload_vectors(1, oi.vectors()[1:])
+    gi.set_graph(g.n, g.levels, g.node_row, g.row_off, g.nbrs, g.entry, g.max_level)
+    bad, stop = [], threading.Event()
+
+    def searcher():
+        while not stop.is_set():
+            ids, sc, cnt, _ = gi.SearchWithScores(Q, 10, None, 64)
+            okA = np.array_equal(ids, wantA[0]) and np.array_equal(sc, wantA[1])
+            okB = np.array_equal(ids, wantB[0]) and np.array_equal(sc, wantB[1])
+            if not (okA or okB):
+                bad.append(1)
+
+    ts = [threading.Thread(target=searcher) for _ in range(4)]
+    for t in ts:
+        t.start()
+    for flip in range(6):   # A -> B -> A -> ...
+        src = new_rows if flip % 2 == 0 else rows
+        gi.patch_rows([v[0] for v in victims], [v[1] for v in victims], [src[v] for v in victims])
+        gi.set_deleted(None)
+    stop.set()
+    for t in ts:
+        t.join()
+    assert not bad
+    gi.close()
