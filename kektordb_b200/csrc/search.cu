@@ -3,72 +3,11 @@
 //
 // hnsw_search_kernel stands in for (*Index).searchInternal / searchLayerUnlocked (reference
 // pkg/core/hnsw/hnsw_index.go:369-468, :2351-2611).
-#include "searcher.cuh"
+#include "search_inst.cuh"
 
 namespace kdb {
 
-using namespace dev;
-
 namespace {
-
-// One warp per CTA, persistent over the batch: queries are claimed from a global counter.
-template <int SLOTS, int METRIC, int CPL>
-__global__ void __launch_bounds__(32) hnsw_search_kernel(const DevIndex ix, const SearchArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  Searcher<SLOTS, METRIC, CPL> s(ix, a, smem);
-  s.init_barriers();
-  // all of 0 .. nq, or the queries the fast kernel handed over (distance ties)
-  const uint32_t limit = a.query_count ? *a.query_count : a.nq;
-  for (;;) {
-    uint32_t i = 0;
-    if (s.lane == 0) i = atomicAdd(a.work_counter, 1u);
-    i = __shfl_sync(0xffffffffu, i, 0);
-    if (i >= limit) break;
-    s.run_query(a.query_list ? a.query_list[i] : i);
-  }
-  if (s.lane == 0) {
-    atomicAdd(&a.stats[0], s.st_e);
-    atomicAdd(&a.stats[1], s.st_h);
-    atomicAdd(&a.stats[2], s.st_h0);
-  }
-}
-
-// The fast path of the same search (searcher.cuh, "Fast path"): sorted list in registers, whole-warp
-// maintenance; a query that meets two equal distances is appended to redo_list and answered by
-// hnsw_search_kernel afterwards, so the output is always the reference's.
-template <int SLOTS, int METRIC, int CPL>
-__global__ void __launch_bounds__(32) hnsw_search_fast_kernel(const DevIndex ix, const SearchArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  // two shapes: without heap arrays in shared memory (more resident query-warps; ties are handed to the
-  // heap kernel through redo_list — for rows whose distances practically never tie), or with them, the
-  // tied query being re-run by the heap path at once in this warp (a second launch would add a whole
-  // query's latency to the batch)
-  const bool hand_over = a.redo_list != nullptr;
-  Searcher<SLOTS, METRIC, CPL> s(ix, a, smem, !hand_over);
-  s.init_barriers();
-  unsigned int n_tied = 0;
-  for (;;) {
-    uint32_t q = 0;
-    if (s.lane == 0) q = atomicAdd(a.work_counter, 1u);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= a.nq) break;
-    if (!s.run_query_fast(q)) {
-      if (hand_over) {
-        if (s.lane == 0) a.redo_list[atomicAdd(a.redo_count, 1u)] = q;
-      } else {
-        s.run_query(q);
-        n_tied++;
-      }
-    }
-    __syncwarp();
-  }
-  if (s.lane == 0 && n_tied) atomicAdd(a.redo_count, n_tied);
-  if (s.lane == 0) {
-    atomicAdd(&a.stats[0], s.st_e);
-    atomicAdd(&a.stats[1], s.st_h);
-    atomicAdd(&a.stats[2], s.st_h0);
-  }
-}
 
 // normalize() of hnsw_index.go:3030-3045, bit-exact: sequential f32 sum of squares without FMA,
 // one f64 sqrt, f32 reciprocal, f32 scale; zero vectors untouched.  One warp per query; also pads
@@ -276,87 +215,17 @@ __host__ inline int cpl_of(const DevIndex &ix) {
   return (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8 || c == 12) ? (int)c : 0;
 }
 
-template <int SL, int METRIC, int CPL>
-cudaError_t launch_one(const DevIndex &ix, const SearchArgs &a, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = hnsw_search_kernel<SL, METRIC, CPL>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, 32, smem, stream>>>(ix, a);
-  return cudaGetLastError();
-}
-template <int SL, int METRIC, int CPL>
-int occupancy_one(size_t smem) {
-  auto kern = hnsw_search_kernel<SL, METRIC, CPL>;
-  int nb = 0;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem);
-  if (e != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 0;
-  }
-  return nb;
-}
+}  // namespace
 
-template <int METRIC, int CPL>
-cudaError_t launch_fast_one(const DevIndex &ix, const SearchArgs &a, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = hnsw_search_fast_kernel<4, METRIC, CPL>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, 32, smem, stream>>>(ix, a);
-  return cudaGetLastError();
+namespace {
+search_kind_fn kind_fn(const DevIndex &ix) {
+  switch (ix.kind) {
+    case KIND_COS_F32: return search_dispatch_k1;
+    case KIND_L2_F16: return search_dispatch_k2;
+    case KIND_COS_I8: return search_dispatch_k3;
+    default: return search_dispatch_k0;
+  }
 }
-template <int METRIC, int CPL>
-int occupancy_fast_one(size_t smem) {
-  auto kern = hnsw_search_fast_kernel<4, METRIC, CPL>;
-  int nb = 0;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem);
-  if (e != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 0;
-  }
-  return nb;
-}
-
-#define KDB_CASE_CPL(SLv, METRICv, CPLv, EXPR) \
-  case CPLv: {                                 \
-    constexpr int SL = SLv;                    \
-    constexpr int MT = METRICv;                \
-    constexpr int CP = CPLv;                   \
-    EXPR;                                      \
-  } break;
-#define KDB_SWITCH_CPL(SLv, METRICv, EXPR) \
-  switch (cpl) {                           \
-    KDB_CASE_CPL(SLv, METRICv, 1, EXPR)    \
-    KDB_CASE_CPL(SLv, METRICv, 2, EXPR)    \
-    KDB_CASE_CPL(SLv, METRICv, 3, EXPR)    \
-    KDB_CASE_CPL(SLv, METRICv, 4, EXPR)    \
-    KDB_CASE_CPL(SLv, METRICv, 6, EXPR)    \
-    KDB_CASE_CPL(SLv, METRICv, 8, EXPR)    \
-    KDB_CASE_CPL(SLv, METRICv, 12, EXPR)   \
-    default: {                             \
-      constexpr int SL = SLv;              \
-      constexpr int MT = METRICv;          \
-      constexpr int CP = 0;                \
-      EXPR;                                \
-    } break;                               \
-  }
-#define KDB_SWITCH_METRIC(SLv, EXPR)                                                        \
-  switch (ix.kind) {                                                                        \
-    case KIND_COS_F32: { KDB_SWITCH_CPL(SLv, KIND_COS_F32, EXPR) } break;                   \
-    case KIND_L2_F16: { KDB_SWITCH_CPL(SLv, KIND_L2_F16, EXPR) } break;                     \
-    case KIND_COS_I8: { KDB_SWITCH_CPL(SLv, KIND_COS_I8, EXPR) } break;                     \
-    default: { KDB_SWITCH_CPL(SLv, KIND_L2_F32, EXPR) } break;                              \
-  }
-#define KDB_DISPATCH(EXPR)                       \
-  switch (t.slots) {                             \
-    case 2: { KDB_SWITCH_METRIC(2, EXPR) } break;   \
-    case 4: { KDB_SWITCH_METRIC(4, EXPR) } break;   \
-    case 8: { KDB_SWITCH_METRIC(8, EXPR) } break;   \
-    case 16: { KDB_SWITCH_METRIC(16, EXPR) } break; \
-    default: break;                              \
-  }
-
 }  // namespace
 
 bool search_slots_supported(int slots) { return slots == 2 || slots == 4 || slots == 8 || slots == 16; }
@@ -369,10 +238,11 @@ size_t search_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t) {
 int search_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
   const size_t smem = search_smem_bytes(ix, ef, t);
   if (smem > 227 * 1024) return 0;
-  const int cpl = cpl_of(ix);
-  int nb = -1;
-  KDB_DISPATCH(nb = (occupancy_one<SL, MT, CP>(smem)))
-  if (nb < 0) return 0;
+  int nb = 0;
+  if (kind_fn(ix)(SEARCH_OP_OCCUPANCY, ix, nullptr, t.slots, cpl_of(ix), 0, smem, nullptr, &nb) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
   if (t.max_ctas_per_sm > 0 && nb > t.max_ctas_per_sm) nb = t.max_ctas_per_sm;
   return nb;
 }
@@ -380,31 +250,8 @@ int search_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
 cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
                           cudaStream_t stream) {
   const size_t smem = search_smem_bytes(ix, a.ef, t);
-  const int cpl = cpl_of(ix);
-  cudaError_t e = cudaErrorInvalidConfiguration;
-  KDB_DISPATCH(e = (launch_one<SL, MT, CP>(ix, a, grid, smem, stream)))
-  return e;
+  return kind_fn(ix)(SEARCH_OP_LAUNCH, ix, &a, t.slots, cpl_of(ix), grid, smem, stream, nullptr);
 }
-
-// ---- fast path: 4 slots, no heaps in shared memory ------------------------------------------------
-#define KDB_FAST_CPL(METRICv, EXPR)                                   \
-  switch (cpl) {                                                      \
-    case 1: { constexpr int MT = METRICv; constexpr int CP = 1; EXPR; } break;   \
-    case 2: { constexpr int MT = METRICv; constexpr int CP = 2; EXPR; } break;   \
-    case 3: { constexpr int MT = METRICv; constexpr int CP = 3; EXPR; } break;   \
-    case 4: { constexpr int MT = METRICv; constexpr int CP = 4; EXPR; } break;   \
-    case 6: { constexpr int MT = METRICv; constexpr int CP = 6; EXPR; } break;   \
-    case 8: { constexpr int MT = METRICv; constexpr int CP = 8; EXPR; } break;   \
-    case 12: { constexpr int MT = METRICv; constexpr int CP = 12; EXPR; } break; \
-    default: { constexpr int MT = METRICv; constexpr int CP = 0; EXPR; } break;  \
-  }
-#define KDB_FAST_DISPATCH(EXPR)                                         \
-  switch (ix.kind) {                                                    \
-    case KIND_COS_F32: { KDB_FAST_CPL(KIND_COS_F32, EXPR) } break;      \
-    case KIND_L2_F16: { KDB_FAST_CPL(KIND_L2_F16, EXPR) } break;        \
-    case KIND_COS_I8: { KDB_FAST_CPL(KIND_COS_I8, EXPR) } break;        \
-    default: { KDB_FAST_CPL(KIND_L2_F32, EXPR) } break;                 \
-  }
 
 // hand_over: no heap arrays (ties go to the heap kernel); otherwise the heap kernel's own carve-up
 static size_t search_fast_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t, bool hand_over) {
@@ -425,9 +272,11 @@ bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t) {
 
 int search_fast_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
   const size_t smem = search_fast_smem_bytes(ix, ef, t, search_fast_hands_over(ix));
-  const int cpl = cpl_of(ix);
   int nb = 0;
-  KDB_FAST_DISPATCH(nb = (occupancy_fast_one<MT, CP>(smem)))
+  if (kind_fn(ix)(SEARCH_OP_OCCUPANCY_FAST, ix, nullptr, 4, cpl_of(ix), 0, smem, nullptr, &nb) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
   if (t.max_ctas_per_sm > 0 && nb > t.max_ctas_per_sm) nb = t.max_ctas_per_sm;
   return nb;
 }
@@ -435,10 +284,7 @@ int search_fast_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
 cudaError_t launch_search_fast(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
                                cudaStream_t stream) {
   const size_t smem = search_fast_smem_bytes(ix, a.ef, t, a.redo_list != nullptr);
-  const int cpl = cpl_of(ix);
-  cudaError_t e = cudaErrorInvalidConfiguration;
-  KDB_FAST_DISPATCH(e = (launch_fast_one<MT, CP>(ix, a, grid, smem, stream)))
-  return e;
+  return kind_fn(ix)(SEARCH_OP_LAUNCH_FAST, ix, &a, 4, cpl_of(ix), grid, smem, stream, nullptr);
 }
 
 cudaError_t launch_prep_queries(const float *in, size_t in_stride, float *out, uint32_t nq, uint32_t dim,
