@@ -59,6 +59,8 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-single-call", action="store_true", help="skip the one-query-per-call (micro-batcher) measurement")
+    p.add_argument("--single-call-threads", type=int, default=0,
+                   help="native caller threads of the one-query-per-call measurement (0 = batches in flight x batch)")
     p.add_argument("--batcher-wait-us", type=int, default=1000,
                    help="micro-batcher deadline; a query's own service time is ~4 ms, and waking 1024 blocked OS "
                         "threads spreads their next requests over ~1-2 ms, so shorter deadlines form small batches")
@@ -433,7 +435,7 @@ def main():
             from kektordb_b200 import Batcher
             from tests.native import driver
             bt = Batcher(gi, max_batch=B, max_wait_us=args.batcher_wait_us)
-            n_callers = n_ov * B
+            n_callers = args.single_call_threads or n_ov * B
             driver.run_callers(bt, Qh_np[:args.warmup * B], k, ef, n_callers)  # warm-up
             st_w = bt.stats()
             ids1, sc1, cnt1, secs1 = driver.run_callers(bt, Qh_np[args.warmup * B:], k, ef, n_callers)
