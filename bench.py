@@ -265,9 +265,13 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if args.workload != "hnsw":
-        if world > 1:
-            raise SystemExit("--workload flat/hybrid/quantized are single-GPU lines")
         import bench_extra
+        if world > 1 and args.workload == "flat" and args.impl == "ours":
+            if args.data_model == "lowrank" and "--data-model" not in sys.argv:
+                args.latent = 0
+            return bench_extra.run_flat_sharded(args, torch, sys.modules[__name__])
+        if world > 1:
+            raise SystemExit("--workload hybrid/quantized are single-GPU lines")
         if args.workload == "flat" and args.data_model == "lowrank" and "--data-model" not in sys.argv:
             args.latent = 0  # configs[2] is quoted on plain random-normal vectors; exact search has no recall issue
         fn = {"flat": bench_extra.run_flat, "hybrid": bench_extra.run_hybrid, "quantized": bench_extra.run_quantized}
