@@ -177,19 +177,22 @@ def run_flat_sharded(args, torch, bench):
     m_ids = torch.zeros((B, k), dtype=torch.int32, device=dev)
     m_sc = torch.zeros((B, k), dtype=torch.float64, device=dev)
     m_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(device=dev)  # an explicit stream: a NULL stream would mean the library's own
 
     def step(i):
         ids, sc, cnt, st = gi.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True)
-        l_ids = torch.from_numpy(np.where(ids > 0, ids + base, ids).astype(np.int32)).to(dev)
-        l_sc = torch.from_numpy(sc).to(dev)
-        l_cnt = torch.from_numpy(cnt.astype(np.int32)).to(dev)
-        dist.all_gather_into_tensor(g_ids.view(world * B, k), l_ids)   # the one exchange step
-        dist.all_gather_into_tensor(g_sc.view(world * B, k), l_sc)
-        dist.all_gather_into_tensor(g_cnt.view(world * B), l_cnt)
+        with torch.cuda.stream(stream):
+            l_ids = torch.from_numpy(np.where(ids > 0, ids.astype(np.int64) + base, 0).astype(np.int32)).to(dev)
+            l_sc = torch.from_numpy(sc).to(dev)
+            l_cnt = torch.from_numpy(cnt.astype(np.int32)).to(dev)
+            dist.all_gather_into_tensor(g_ids.view(world * B, k), l_ids)   # the one exchange step
+            dist.all_gather_into_tensor(g_sc.view(world * B, k), l_sc)
+            dist.all_gather_into_tensor(g_cnt.view(world * B), l_cnt)
         ffi.check(ffi.lib().kdbgpu_merge_topk_device(gi._h, world, B, k, g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(),
                                                      m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr(), stream.cuda_stream))
-        out = (m_ids.cpu().numpy(), m_sc.cpu().numpy(), m_cnt.cpu().numpy())
+        with torch.cuda.stream(stream):
+            out = (m_ids.cpu().numpy(), m_sc.cpu().numpy(), m_cnt.cpu().numpy())
+        stream.synchronize()
         return out, st
 
     for i in range(args.warmup):
