@@ -215,6 +215,76 @@ int kdbgpu_merge_topk_device(kdbgpu_index *, int n_shards, uint32_t nq, int k, c
                              const double *d_scores, const uint32_t *d_counts, uint32_t *d_out_ids,
                              double *d_out_scores, uint32_t *d_out_counts, void *stream);
 
+/* ---- multi-GPU: id-range shard groups -------------------------------------------
+ * The corpus is split by contiguous internal-id range over G GPUs; shard g is a self-contained hnsw.Index
+ * over its ids (an HNSW graph cannot be cut by id range), mirrored by one kdbgpu_index on its own GPU whose
+ * LOCAL ids 1..n stand for the GLOBAL ids id_base+1 .. id_base+n.  A group answers
+ * idx.SearchWithScores(query, k, allowList, efSearch) (pkg/engine/ops.go:1006) over the whole corpus: every
+ * shard runs the unchanged traversal (its epilogue writes global ids), ONE exchange moves the per-shard
+ * top-k — scores, ids, counts, counters and error flag packed in one buffer per shard — and a merge kernel
+ * keeps the k best by (distance, id).  The reference has no sharded mode; the parity oracle is "G reference
+ * indexes + exact merge" (tests/test_gpu_shard.py).
+ *
+ * Two ways to form a group:
+ *   kdbgpu_shard_group_create_local  every shard lives in THIS process (the Go host: one process, G GPUs).
+ *                                    The exchange is a peer copy of each shard's packed result into the merge
+ *                                    GPU's gather buffer over NVLink (cudaMemcpyPeerAsync); no NCCL.  Shards
+ *                                    may share a device (tests).
+ *   kdbgpu_shard_group_create_rank   one shard per process / rank (torchrun-style, one process per GPU).  The
+ *                                    exchange is one ncclAllGather of the packed results per batch; NCCL
+ *                                    (libnccl.so.2) is loaded on first use.  Rank 0 obtains the 128-byte id with
+ *                                    kdbgpu_shard_unique_id and hands it to the other ranks by any channel.
+ *                                    Calls on a rank group are COLLECTIVE: every rank issues the same searches
+ *                                    in the same order, and every rank receives the merged result.
+ * Up to 4 batches are in flight per group: the exchange + merge of batch i (on a high-priority stream) overlap the
+ * traversal of batch i+1. */
+typedef struct kdbgpu_shard_group kdbgpu_shard_group;
+#define KDBGPU_SHARD_ID_BYTES 128
+typedef struct {
+  uint64_t dist_evals, hops, hops_l0; /* summed over all shards                                       */
+  float traversal_ms;                 /* slowest local shard: H2D + prep + traversal (device time)    */
+  float exchange_ms;                  /* all-gather / peer copies                                     */
+  float merge_ms;                     /* merge kernel                                                 */
+  float total_ms;                     /* first H2D .. merged result on the host                       */
+  uint32_t n_shards;
+} kdbgpu_shard_stats;
+int kdbgpu_shard_unique_id(unsigned char id[KDBGPU_SHARD_ID_BYTES]);
+int kdbgpu_shard_group_create_rank(kdbgpu_index *local, int rank, int world, const unsigned char id[KDBGPU_SHARD_ID_BYTES],
+                                   uint32_t id_base, kdbgpu_shard_group **out);
+int kdbgpu_shard_group_create_local(kdbgpu_index *const *shards, int n_shards, const uint32_t *id_bases,
+                                    kdbgpu_shard_group **out);
+/* Waits for the batches in flight, then frees the group (not the indexes). */
+int kdbgpu_shard_group_destroy(kdbgpu_shard_group *);
+int kdbgpu_shard_group_size(const kdbgpu_shard_group *); /* G */
+/* SearchWithScores over the sharded corpus; arguments as kdbgpu_search_batch.  `allow` is a dense bitset over
+ * GLOBAL ids; each shard applies its own slice with the semantics of hnsw_index.go:436-447 (a shard whose slice
+ * is empty contributes nothing, as an index searched with an empty allow-list returns []).  out_ids are global. */
+int kdbgpu_shard_search_batch(kdbgpu_shard_group *, const float *queries, uint32_t nq, int k, int ef_search,
+                              const uint64_t *allow, size_t allow_words, uint32_t *out_ids, double *out_scores,
+                              uint32_t *out_counts, kdbgpu_shard_stats *stats);
+/* The same call split in two so that ONE thread can keep several batches in flight (collectives stay in issue
+ * order): submit queues the H2D copy, traversals, exchange, merge and D2H copy and returns a ticket; wait blocks
+ * until that batch's results are in the caller's buffers.  `queries` must stay valid until wait returns. */
+typedef struct kdbgpu_shard_ticket kdbgpu_shard_ticket;
+int kdbgpu_shard_search_submit(kdbgpu_shard_group *, const float *queries, uint32_t nq, int k, int ef_search,
+                               const uint64_t *allow, size_t allow_words, kdbgpu_shard_ticket **ticket);
+int kdbgpu_shard_search_wait(kdbgpu_shard_ticket *, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
+                             kdbgpu_shard_stats *stats);
+/* Device-resident form: queries and outputs on the device of the group's first local shard; everything is queued
+ * without host synchronisation and `stream` (a cudaStream_t, NULL = an internal one) is made to wait for the
+ * merged result.  Errors of the launch (candidate-heap overflow) surface in kdbgpu_shard_sync. */
+int kdbgpu_shard_search_batch_device(kdbgpu_shard_group *, const float *d_queries, uint32_t nq, int k, int ef_search,
+                                     uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream);
+/* Waits for every batch queued by the device-resident form; stats (may be NULL) = the last batch's counters and
+ * device times.  Returns KDBGPU_ERR_OVERFLOW if any shard's traversal overflowed since the last sync. */
+int kdbgpu_shard_sync(kdbgpu_shard_group *, kdbgpu_shard_stats *stats);
+/* BruteForceIndex.SearchWithScores (pkg/core/vector_index.go:104-162) over the sharded corpus: every shard scans
+ * its rows (mode as kdbgpu_flat_search_batch, KDBGPU_FLAT_PREFILTER included), same exchange and merge; the
+ * merged answer equals the unsharded scan bit for bit (ties by id).  No host round trip between scan and merge. */
+int kdbgpu_shard_flat_search_batch(kdbgpu_shard_group *, const float *queries, uint32_t nq, int k, int mode,
+                                   const uint64_t *allow, size_t allow_words, uint32_t *out_ids, double *out_scores,
+                                   uint32_t *out_counts, kdbgpu_shard_stats *stats);
+
 /* ---- graph construction on the device (extension; the reference builds on the CPU) --------- */
 /* (*Index).AddBatch (hnsw_index.go:1466, addBatchInternal :1479-2088) for `count` raw vectors that
  * receive ids n+1 .. n+count.  level_draws[i] is the rand.Float64() of randomLevel (:2616-2625).
@@ -234,7 +304,8 @@ int kdbgpu_download_vectors(kdbgpu_index *, uint32_t first_id, uint32_t count, f
 
 /* ---- introspection -------------------------------------------------------------------- */
 /* Counters (dist_evals, hops, hops_l0) of the most recent traversal launch on this handle;
- * synchronises the device.  For callers of the *_device entry points. */
+ * synchronises the device.  For callers of the *_device entry points: returns KDBGPU_ERR_OVERFLOW (counters
+ * still filled) when a query of that launch exceeded the candidate-heap bound and was answered with count 0. */
 int kdbgpu_last_search_stats(kdbgpu_index *, kdbgpu_stats *stats);
 int kdbgpu_index_device(const kdbgpu_index *);
 int kdbgpu_index_dim(const kdbgpu_index *);
@@ -251,6 +322,12 @@ int kdbgpu_prepare_search(kdbgpu_index *, uint32_t nq, int k, int ef_search);
  * entries kept in shared memory, cap on resident query-warps per SM (0 = no cap).  A value <= 0
  * (< 0 for the cap) keeps the current setting.  Results never depend on the shape. */
 int kdbgpu_set_tuning(kdbgpu_index *, int slots, int cand_smem, int max_ctas_per_sm);
+/* The reference's candidate heap is unbounded; ours holds cand_smem entries in shared memory and spills up to
+ * spill_entries (default 32768) to HBM per query.  A query that would need more returns count 0 and the call
+ * fails with KDBGPU_ERR_OVERFLOW (kdbgpu_search_batch: at once; the *_device forms: from
+ * kdbgpu_last_search_stats / kdbgpu_shard_sync).  This hook sets the spill bound (tests force the overflow with it;
+ * a host may raise it). */
+int kdbgpu_set_candidate_bound(kdbgpu_index *, uint32_t spill_entries);
 /* The traversal answers a batch in two passes: a fast pass that keeps the candidate / result queues as one
  * sorted list in registers (valid while all distances a query meets are distinct — any priority queue then
  * pops what the reference's binary heaps pop), and the heap pass (hnsw_heap.go restated exactly) over the
@@ -292,6 +369,35 @@ int kdbgpu_batcher_destroy(kdbgpu_batcher *);
 int kdbgpu_batcher_search(kdbgpu_batcher *, const float *query, int k, int ef_search, const uint64_t *allow,
                           size_t allow_words, uint32_t *out_ids, double *out_scores, uint32_t *out_count);
 int kdbgpu_batcher_stats(kdbgpu_batcher *, kdbgpu_batcher_stats_t *out);
+/* A batcher over a shard group (kdbgpu_shard_search_batch as the executor): one blocking / asynchronous call per
+ * query in front of G GPUs.  Local groups only (a rank group's calls are collective). */
+int kdbgpu_batcher_create_group(kdbgpu_shard_group *, int dim, uint32_t max_batch, uint32_t max_wait_us,
+                                kdbgpu_batcher **out);
+/* Asynchronous form — for hosts whose callers must not block inside the C call (a Go shim: a goroutine blocked in
+ * cgo pins an OS thread, so thousands of in-flight searches would pin thousands of threads):
+ *   kdbgpu_batcher_submit  copies the query into the batcher's staging (the caller's buffers are not retained: cgo
+ *                          pointer rules) and returns a ticket at once.  filter_id != 0 names an allow-list
+ *                          registered with kdbgpu_batcher_register_filter (no per-query hashing / copying of MBs of
+ *                          bitset); otherwise allow / allow_words as in kdbgpu_batcher_search.
+ *   kdbgpu_batcher_poll    blocks up to timeout_us for finished queries and returns up to max_tickets of their
+ *                          tickets — ONE dispatcher thread (goroutine) calls it in a loop and wakes the waiters.
+ *   kdbgpu_batcher_take    copies the result of a finished ticket into the caller's buffers (k entries each, the k of
+ *                          the submit) and releases the ticket; returns that query's error code.  Blocks until the
+ *                          query is finished if it is not yet.  Every ticket must be taken exactly once.
+ * The batches are run by the batcher's own worker threads (KDBGPU_BATCHER_WORKERS, default 4). */
+int kdbgpu_batcher_submit(kdbgpu_batcher *, const float *query, int k, int ef_search, const uint64_t *allow,
+                          size_t allow_words, uint64_t filter_id, uint64_t *ticket);
+int kdbgpu_batcher_poll(kdbgpu_batcher *, uint64_t *tickets, uint32_t max_tickets, uint32_t timeout_us, uint32_t *n_done);
+int kdbgpu_batcher_take(kdbgpu_batcher *, uint64_t ticket, uint32_t *out_ids, double *out_scores, uint32_t *out_count);
+int kdbgpu_batcher_register_filter(kdbgpu_batcher *, const uint64_t *allow, size_t allow_words, uint64_t *filter_id);
+int kdbgpu_batcher_release_filter(kdbgpu_batcher *, uint64_t filter_id);
+
+/* ---- host staging memory ------------------------------------------------------------------------- */
+/* Page-locked host memory (cudaHostAlloc) for buffers that cross the boundary often — query batches, result
+ * arrays: copies from / to it run at DMA rate and asynchronously.  Without a CUDA device the memory is ordinary
+ * (aligned) host memory.  Release with kdbgpu_host_free (NULL is fine). */
+int kdbgpu_host_alloc(void **out, size_t bytes);
+void kdbgpu_host_free(void *p);
 
 #ifdef __cplusplus
 }

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkektordb_gpu.so")
-SOURCES = ["api.cu", "search.cu", "search_k0.cu", "search_k1.cu", "search_k2.cu", "search_k3.cu", "flat.cu", "flat_tc.cu", "build.cu", "arena.cu", "batcher.cpp"]
-HEADERS = ["kdb_internal.cuh", "searcher.cuh", "search_inst.cuh", os.path.join("..", "..", "include", "kektordb_gpu.h")]
+SOURCES = ["api.cu", "search.cu", "search_k0.cu", "search_k1.cu", "search_k2.cu", "search_k3.cu", "flat.cu", "flat_tc.cu", "build.cu", "arena.cu", "shard.cu", "batcher.cpp"]
+HEADERS = ["kdb_internal.cuh", "handle.h", "searcher.cuh", "search_inst.cuh", os.path.join("..", "..", "include", "kektordb_gpu.h")]
 
 
 def nvcc_path() -> str:
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", host_cxx, "-o", LIB] + objs + ["-lcudart"]
+    link = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", host_cxx, "-o", LIB] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "kdb_internal.cuh"
+#include "handle.h"
 
 using namespace kdb;
 
@@ -57,11 +57,10 @@ int arena_max_chunk(const char *dir, std::string *err);
 long arena_read_chunk(const char *dir, int id, unsigned char *hdr, unsigned char *dst, size_t want, std::string *err);
 }  // namespace kdb
 
-namespace {
+static thread_local std::string g_last_error;
 
-thread_local std::string g_last_error;
-
-int fail(int code, const char *fmt, ...) {
+namespace kdb {
+int set_error(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -70,9 +69,6 @@ int fail(int code, const char *fmt, ...) {
   g_last_error = buf;
   return code;
 }
-
-}  // namespace
-namespace kdb {
 int arena_fail(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -83,175 +79,10 @@ int arena_fail(int code, const char *fmt, ...) {
   return code;
 }
 }  // namespace kdb
-namespace {
 
-#define CUDA_TRY(expr)                                                                              \
-  do {                                                                                              \
-    cudaError_t _e = (expr);                                                                        \
-    if (_e != cudaSuccess) {                                                                        \
-      (void)cudaGetLastError();                                                                     \
-      return fail(_e == cudaErrorMemoryAllocation ? KDBGPU_ERR_NOMEM : KDBGPU_ERR_CUDA, "%s: %s", #expr, \
-                  cudaGetErrorString(_e));                                                          \
-    }                                                                                               \
-  } while (0)
-
-template <typename T>
-struct DevBuf {
-  T *p = nullptr;
-  size_t n = 0;
-  cudaError_t reserve(size_t want, bool zero = false) {
-    if (want <= n) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T));
-    if (e != cudaSuccess) return e;
-    n = want;
-    if (zero) e = cudaMemset(p, 0, want * sizeof(T));
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-  }
-  size_t bytes() const { return n * sizeof(T); }
-};
-
-}  // namespace
-
-struct kdbgpu_index {
-  int device = 0;
-  int dim = 0, metric = 0, m = 0;
-  int precision = KDBGPU_PRECISION_F32;
-  int kind = KIND_L2_F32;
-  uint32_t capacity = 0;
-  uint32_t stride = 0;     // 32-bit words per row slot / prepared query (multiple of 128)
-  uint32_t row_words = 0;  // 32-bit words between stored rows (= stride for float32)
-  float abs_max = 0.f;     // Quantizer.AbsMax (int8)
-  uint32_t n = 0;
-  uint32_t entry = 0;
-  int max_level = -1;
-  bool has_graph = false;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int num_sms = 0;
-  SearchTuning tuning;
-  // searches hold `mu` shared (kNumSearchWs of them can be in flight, each on its own workspace and
-  // stream, so consecutive batches overlap on the device); everything that changes the mirror or
-  // uses the handle-level workspace holds it exclusively
-  std::shared_mutex mu;
-  struct SearchWs {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;  // completion of the last launch that used this workspace
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    DevBuf<float> q_raw, q_prep, qnorms;
-    DevBuf<uint32_t> out_ids, out_counts, allow, visited, work_counter, redo;
-    DevBuf<double> out_scores;
-    DevBuf<HeapEntry> cand_overflow;
-    DevBuf<unsigned long long> stats;
-    DevBuf<int> err_flag;
-    DevBuf<unsigned char> out_blob;  // host path: scores | ids | counts | stats | err, one D2H copy
-    unsigned char *h_out = nullptr;  // pinned staging for that copy
-    size_t h_out_bytes = 0;
-    int grid = 0;
-    uint32_t vis_words = 0;
-    bool busy = false;
-    void release() {
-      out_blob.release();
-      if (h_out) cudaFreeHost(h_out);
-      h_out = nullptr;
-      h_out_bytes = 0;
-      q_raw.release(); q_prep.release(); qnorms.release(); out_ids.release(); out_counts.release(); allow.release();
-      visited.release(); work_counter.release(); redo.release(); out_scores.release(); cand_overflow.release();
-      stats.release(); err_flag.release();
-    }
-  };
-  static constexpr int kNumSearchWs = 4;
-  SearchWs sws[kNumSearchWs];
-  std::mutex ws_mu;
-  std::condition_variable ws_cv;
-  unsigned ws_next = 0;
-  int last_ws = -1;
-
-  DevBuf<float> vecs, norms, conv_tmp, qnorm1;
-  DevBuf<uint32_t> adj0, upper_adj, upper_first, deleted;
-  DevBuf<int8_t> levels;
-  bool has_deleted = false;
-  // per-call workspace
-  DevBuf<float> q_raw, q_prep;
-  DevBuf<uint32_t> out_ids, out_counts, allow, visited, ids_tmp;
-  DevBuf<double> out_scores, flat_dist, dist_tmp;
-  DevBuf<HeapEntry> cand_overflow;
-  DevBuf<unsigned long long> stats;
-  DevBuf<uint32_t> work_counter;
-  DevBuf<int> err_flag;
-  int ws_grid = 0;
-  uint32_t vis_words = 0;
-  uint32_t ovf_cap = 1u << 15;
-  // construction state: host mirrors of levels / upper-row ownership, device build workspace
-  std::vector<int8_t> h_levels;
-  std::vector<uint32_t> h_upper_first;
-  uint32_t upper_rows_used = 0;
-  DevBuf<uint32_t> upper_node;
-  DevBuf<uint8_t> upper_level;
-  DevBuf<uint32_t> b_out_off, b_slot_node, b_cand_ids, b_cand_cnt, b_row_cnt, b_row_off, b_srcs, b_active,
-      b_scalars, b_scratch_ids;
-  DevBuf<uint8_t> b_slot_level;
-  DevBuf<double> b_scratch_d;
-  // tensor-core flat pre-filter: bf16 mirror of the rows (built lazily, dropped when rows change)
-  DevBuf<uint16_t> x_bf16, tq_bf16;
-  DevBuf<float> x_sumsq, x_resid2, x_max, tc_beta, tq_sumsq, tq_resid2, t_gmin, t_theta, t_bound;
-  DevBuf<uint32_t> t_cnt, t_subcnt, t_flags, t_fcnt, t_fid;
-  DevBuf<uint2> t_sub, t_ovf;
-  DevBuf<float> t_thf;
-  DevBuf<unsigned long long> t_nres;
-  bool tc_valid = false;
-  uint32_t tc_n = 0;
-
-  DevIndex dev() const {
-    DevIndex d;
-    d.vecs = vecs.p;
-    d.norms = norms.p;
-    d.row_words = row_words;
-    d.kind = kind;
-    d.adj0 = adj0.p;
-    d.upper_adj = upper_adj.p;
-    d.upper_first = upper_first.p;
-    d.levels = levels.p;
-    d.deleted = has_deleted ? deleted.p : nullptr;
-    d.stride = stride;
-    d.dim = (uint32_t)dim;
-    d.n = n;
-    d.deg0 = (uint32_t)(2 * m);
-    d.degu = (uint32_t)m;
-    d.entry = entry;
-    d.max_level = max_level;
-    d.metric = metric;
-    return d;
-  }
-};
+#define fail kdb::set_error
 
 namespace {
-
-// Makes the handle's device current for the calling thread.  It is deliberately NOT restored on
-// return: restoring a device the thread never used would create a primary context there (CUDA 12
-// cudaSetDevice semantics) — costly in multi-process, one-rank-per-GPU deployments.
-struct DeviceGuard {
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    int cur = -1;
-    if (cudaGetDevice(&cur) != cudaSuccess) {
-      ok = false;
-      (void)cudaGetLastError();
-      return;
-    }
-    if (cur != dev && cudaSetDevice(dev) != cudaSuccess) {
-      ok = false;
-      (void)cudaGetLastError();
-    }
-  }
-};
 
 int ensure_search_workspace(kdbgpu_index *h, int grid) {
   const uint32_t words = (((h->capacity + 1 + 31) / 32) + 3) & ~3u;
@@ -268,6 +99,10 @@ int ensure_search_workspace(kdbgpu_index *h, int grid) {
   CUDA_TRY(h->err_flag.reserve(1, true));
   return KDBGPU_OK;
 }
+
+}  // namespace
+
+namespace kdb {
 
 // ---- per-launch search workspaces ---------------------------------------------------------------
 int ensure_ws(kdbgpu_index *h, kdbgpu_index::SearchWs &w, int grid) {
@@ -313,8 +148,8 @@ void release_ws(kdbgpu_index *h, int j) {
 // launch waits for the previous user of the workspace and records its own completion on w.done.
 int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_prepared, uint32_t nq, int k, int ef,
                    const uint32_t *d_allow, uint32_t allow_entry, uint32_t *d_ids, double *d_scores,
-                   uint32_t *d_counts, cudaStream_t stream, unsigned long long *d_stats = nullptr,
-                   int *d_err = nullptr) {
+                   uint32_t *d_counts, cudaStream_t stream, unsigned long long *d_stats, int *d_err,
+                   uint32_t id_base) {
   DevIndex ix = h->dev();
   const int occ = search_occupancy(ix, ef, h->tuning);
   if (occ <= 0)
@@ -353,6 +188,7 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
   a.stats = d_stats;
   a.work_counter = w.work_counter.p;
   a.err_flag = d_err;
+  a.id_base = id_base;
   int grid = occ * h->num_sms;
   if ((uint32_t)grid > nq) grid = (int)nq;
   if (fast && occ_fast > 0) {
@@ -421,6 +257,10 @@ int stage_allow(kdbgpu_index *h, DevBuf<uint32_t> &dst, const uint64_t *allow, s
 }
 
 
+}  // namespace kdb
+
+namespace {
+
 // ---- flat scan -------------------------------------------------------------------------------------
 // exhaustive float64 scan (flat.cu); caller holds the handle exclusively
 int flat_scan_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, const uint32_t *d_allow,
@@ -441,16 +281,16 @@ int flat_scan_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int k, in
   for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
     const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
     CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries + (size_t)q0 * h->dim, (size_t)c * h->dim * sizeof(float),
-                             cudaMemcpyHostToDevice, s));
+                             cudaMemcpyDefault, s));
     CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
                                  mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
     CUDA_TRY(launch_flat_distances(ix, h->q_raw.p, h->q_prep.p, c, mode, h->flat_dist.p, s));
     CUDA_TRY(launch_flat_select(ix, h->flat_dist.p, c, k, d_allow, h->out_ids.p, h->out_scores.p, h->out_counts.p, s));
     CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
-                             cudaMemcpyDeviceToHost, s));
+                             cudaMemcpyDefault, s));
     CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
-                             cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                             cudaMemcpyDefault, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDefault, s));
     CUDA_TRY(cudaStreamSynchronize(s));
   }
   return KDBGPU_OK;
@@ -497,7 +337,7 @@ int tc_stage_queries(kdbgpu_index *h, const float *queries, uint32_t c, uint32_t
   CUDA_TRY(h->tq_bf16.reserve((size_t)c_pad * P.dp));
   CUDA_TRY(h->tq_sumsq.reserve(c_pad));
   CUDA_TRY(h->tq_resid2.reserve(c_pad));
-  CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries, (size_t)c * h->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries, (size_t)c * h->dim * sizeof(float), cudaMemcpyDefault, s));
   if (after_h2d) CUDA_TRY(cudaEventRecord(after_h2d, s));
   CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
                                mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
@@ -618,11 +458,11 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
                                h->out_ids.p, h->out_scores.p, h->out_counts.p, h->t_flags.p, h->t_nres.p, s));
     CUDA_TRY(cudaEventRecord(ev_c1, s));
     CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
-                             cudaMemcpyDeviceToHost, s));
+                             cudaMemcpyDefault, s));
     CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
-                             cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(flags.data() + q0, h->t_flags.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                             cudaMemcpyDefault, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDefault, s));
+    CUDA_TRY(cudaMemcpyAsync(flags.data() + q0, h->t_flags.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDefault, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
@@ -641,14 +481,16 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     std::vector<float> rq(r * (size_t)h->dim);
     std::vector<uint32_t> rid(r * (size_t)k), rcnt(r);
     std::vector<double> rsc(r * (size_t)k);
+    // `queries` / the outputs may live on either side (cudaMemcpyDefault); this path is rare
     for (size_t i = 0; i < r; ++i)
-      memcpy(&rq[i * h->dim], queries + (size_t)redo[i] * h->dim, (size_t)h->dim * sizeof(float));
+      CUDA_TRY(cudaMemcpy(&rq[i * h->dim], queries + (size_t)redo[i] * h->dim, (size_t)h->dim * sizeof(float),
+                          cudaMemcpyDefault));
     rc = flat_scan_impl(h, rq.data(), (uint32_t)r, k, mode, d_allow, rid.data(), rsc.data(), rcnt.data());
     if (rc) return rc;
     for (size_t i = 0; i < r; ++i) {
-      memcpy(out_ids + (size_t)redo[i] * k, &rid[i * k], (size_t)k * sizeof(uint32_t));
-      memcpy(out_scores + (size_t)redo[i] * k, &rsc[i * k], (size_t)k * sizeof(double));
-      out_counts[redo[i]] = rcnt[i];
+      CUDA_TRY(cudaMemcpy(out_ids + (size_t)redo[i] * k, &rid[i * k], (size_t)k * sizeof(uint32_t), cudaMemcpyDefault));
+      CUDA_TRY(cudaMemcpy(out_scores + (size_t)redo[i] * k, &rsc[i * k], (size_t)k * sizeof(double), cudaMemcpyDefault));
+      CUDA_TRY(cudaMemcpy(out_counts + redo[i], &rcnt[i], sizeof(uint32_t), cudaMemcpyDefault));
     }
   }
   *evals = nres + (uint64_t)redo.size() * h->n;
@@ -657,6 +499,38 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
 }
 
 }  // namespace
+
+namespace kdb {
+int flat_search_locked(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, bool prefilter,
+                       const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
+                       kdbgpu_stats *stats) {
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaEventRecord(h->ev[0], s));
+  uint64_t evals = 0, fallbacks = 0;
+  float gemm_ms = 0.f, compute_ms = 0.f;
+  int rc;
+  if (prefilter)
+    rc = flat_prefilter_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts, &evals, &fallbacks,
+                             &gemm_ms, &compute_ms);
+  else {
+    rc = flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
+    evals = (uint64_t)nq * h->n;
+  }
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->dist_evals = evals;
+    stats->hops = fallbacks;
+    cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
+    // pre-filter: kernel_ms = every kernel of the call (no copies); hops_l0 = the two tensor-core
+    // passes + threshold alone, in nanoseconds
+    stats->kernel_ms = prefilter && compute_ms > 0.f ? compute_ms : stats->total_ms;
+    stats->hops_l0 = prefilter ? (uint64_t)(gemm_ms * 1e6f) : 0;
+  }
+  return KDBGPU_OK;
+}
+}  // namespace kdb
 
 extern "C" {
 
@@ -1376,11 +1250,8 @@ int kdbgpu_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq, int 
   CUDA_TRY(w.q_raw.reserve((size_t)nq * h->dim));
   // results, counters and the error flag live in one device blob -> a single D2H copy
   const size_t nk = (size_t)nq * k;
-  const size_t o_ids = nk * sizeof(double);
-  const size_t o_counts = o_ids + nk * sizeof(uint32_t);
-  const size_t o_stats = (o_counts + (size_t)nq * sizeof(uint32_t) + 7) & ~(size_t)7;
-  const size_t o_err = o_stats + 4 * sizeof(unsigned long long);
-  const size_t blob_bytes = o_err + sizeof(long long);
+  const BlobLayout BL = blob_layout(nq, k);
+  const size_t o_ids = BL.o_ids, o_counts = BL.o_counts, o_stats = BL.o_stats, o_err = BL.o_err, blob_bytes = BL.bytes;
   CUDA_TRY(w.out_blob.reserve(blob_bytes));
   if (w.h_out_bytes < blob_bytes) {
     if (w.h_out) cudaFreeHost(w.h_out);
@@ -1444,9 +1315,7 @@ int kdbgpu_prepare_search(kdbgpu_index *h, uint32_t nq, int k, int ef_search) {
   DevIndex ix = h->dev();
   const int occ = search_occupancy(ix, ef, h->tuning);
   if (occ <= 0) return fail(KDBGPU_ERR_INVALID, "search configuration does not fit shared memory (dim=%d ef=%d)", h->dim, ef);
-  const size_t nk = (size_t)nq * k;
-  const size_t blob_bytes = ((nk * (sizeof(double) + sizeof(uint32_t)) + (size_t)nq * sizeof(uint32_t) + 7) & ~(size_t)7) +
-                            4 * sizeof(unsigned long long) + sizeof(long long);
+  const size_t blob_bytes = blob_layout(nq, k).bytes;
   const int occ_fast = search_fast_eligible(ix, ef, h->tuning) ? search_fast_occupancy(ix, ef, h->tuning) : 0;
   for (auto &w : h->sws) {
     int rc = ensure_ws(h, w, (occ_fast > occ ? occ_fast : occ) * h->num_sms);
@@ -1482,15 +1351,20 @@ int kdbgpu_search_batch_device(kdbgpu_index *h, const float *d_queries, uint32_t
   if (d_allow && allow_words * 64 < (size_t)h->n + 1)
     return fail(KDBGPU_ERR_INVALID, "device allow-list must cover ids 0..%u", h->n);
   DeviceGuard g(h->device);
-  // asynchronous path: workspaces rotate; reuse is ordered on the device through w.done
-  int wi;
+  // asynchronous path: the launch takes a free workspace under the same busy protocol as the host path (so
+  // that concurrent callers never share visited bitsets / counters), records w.done and hands the workspace
+  // back; the next user orders itself behind w.done on the device.
+  const int wi = acquire_ws(h);
+  kdbgpu_index::SearchWs &w = h->sws[wi];
+  struct Release {
+    kdbgpu_index *h;
+    int wi;
+    ~Release() { release_ws(h, wi); }
+  } releaser{h, wi};
   {
     std::lock_guard<std::mutex> wl(h->ws_mu);
-    wi = (int)(h->ws_next % kdbgpu_index::kNumSearchWs);
-    h->ws_next = (unsigned)wi + 1;
     h->last_ws = wi;
   }
-  kdbgpu_index::SearchWs &w = h->sws[wi];
   cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : w.stream;
   if (h->max_level < 0 || (d_allow && (allow_first_id == 0 || allow_first_id > h->n))) {
     CUDA_TRY(cudaMemsetAsync(d_out_ids, 0, (size_t)nq * k * sizeof(uint32_t), s));
@@ -1500,11 +1374,13 @@ int kdbgpu_search_batch_device(kdbgpu_index *h, const float *d_queries, uint32_t
   }
   CUDA_TRY(cudaStreamWaitEvent(s, w.done, 0));
   int rc = prepare_queries(h, w, d_queries, nq, s);
+  if (rc == KDBGPU_OK)
+    rc = enqueue_search(h, w, w.q_prep.p, nq, k, ef, reinterpret_cast<const uint32_t *>(d_allow), allow_first_id,
+                        d_out_ids, d_out_scores, d_out_counts, s);
+  // whatever was queued (possibly nothing) is what the next user of the workspace must wait for
+  cudaError_t re = cudaEventRecord(w.done, s);
   if (rc) return rc;
-  rc = enqueue_search(h, w, w.q_prep.p, nq, k, ef, reinterpret_cast<const uint32_t *>(d_allow), allow_first_id,
-                          d_out_ids, d_out_scores, d_out_counts, s);
-  if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(w.done, s));
+  CUDA_TRY(re);
   return KDBGPU_OK;
 }
 
@@ -1574,30 +1450,7 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
       d_allow = h->allow.p;
     }
   }
-  CUDA_TRY(cudaEventRecord(h->ev[0], s));
-  uint64_t evals = 0, fallbacks = 0;
-  float gemm_ms = 0.f, compute_ms = 0.f;
-  int rc;
-  if (prefilter)
-    rc = flat_prefilter_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts, &evals, &fallbacks,
-                             &gemm_ms, &compute_ms);
-  else {
-    rc = flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
-    evals = (uint64_t)nq * h->n;
-  }
-  if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(h->ev[3], s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  if (stats) {
-    stats->dist_evals = evals;
-    stats->hops = fallbacks;
-    cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
-    // pre-filter: kernel_ms = every kernel of the call (no copies); hops_l0 = the two tensor-core
-    // passes + threshold alone, in nanoseconds
-    stats->kernel_ms = prefilter && compute_ms > 0.f ? compute_ms : stats->total_ms;
-    stats->hops_l0 = prefilter ? (uint64_t)(gemm_ms * 1e6f) : 0;
-  }
-  return KDBGPU_OK;
+  return flat_search_locked(h, queries, nq, k, mode, prefilter, d_allow, out_ids, out_scores, out_counts, stats);
 }
 
 int kdbgpu_flat_prefilter_scores(kdbgpu_index *h, const float *queries, uint32_t nq, int mode, float *out_scores,
@@ -1666,9 +1519,16 @@ int kdbgpu_last_search_stats(kdbgpu_index *h, kdbgpu_stats *stats) {
   unsigned long long st[4] = {0, 0, 0, 0};
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(st, h->sws[h->last_ws].stats.p, sizeof st, cudaMemcpyDeviceToHost));
+  int err = 0;
+  if (h->sws[h->last_ws].err_flag.p)
+    CUDA_TRY(cudaMemcpy(&err, h->sws[h->last_ws].err_flag.p, sizeof err, cudaMemcpyDeviceToHost));
   stats->dist_evals = st[0];
   stats->hops = st[1];
   stats->hops_l0 = st[2];
+  stats->heap_pass_queries = (uint32_t)st[3];
+  if (err == KDBGPU_ERR_OVERFLOW)  // such a query returned count 0; the reference's candidate heap is unbounded
+    return fail(KDBGPU_ERR_OVERFLOW, "candidate heap exceeded %u entries for at least one query of the last launch",
+                h->ovf_cap + (uint32_t)h->tuning.cand_smem);
   return KDBGPU_OK;
 }
 
@@ -2072,6 +1932,10 @@ int kdbgpu_remove_nodes(kdbgpu_index *h, uint32_t count, const uint32_t *ids) {
   cudaStream_t s = h->stream;
   const int8_t nil = -1;
   for (uint32_t i = 0; i < count; ++i) {  // nodes[deadID] = nil (optimizer.go:270)
+    const int old_level = h->h_levels[ids[i]];
+    if (old_level > 0 && h->upper_adj.p && ids[i] < h->h_upper_first.size())  // its upper rows go with it
+      CUDA_TRY(cudaMemsetAsync(h->upper_adj.p + (size_t)h->h_upper_first[ids[i]] * h->m, 0,
+                               (size_t)old_level * h->m * sizeof(uint32_t), s));
     h->h_levels[ids[i]] = -1;
     CUDA_TRY(cudaMemcpyAsync(h->levels.p + ids[i], &nil, 1, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(h->adj0.p + (size_t)ids[i] * 2 * h->m, 0, (size_t)2 * h->m * sizeof(uint32_t), s));
@@ -2174,6 +2038,18 @@ int kdbgpu_set_fast_path(kdbgpu_index *h, int on) {
   return KDBGPU_OK;
 }
 
+int kdbgpu_set_candidate_bound(kdbgpu_index *h, uint32_t spill_entries) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (spill_entries == 0 || spill_entries > (1u << 24)) return fail(KDBGPU_ERR_INVALID, "spill_entries outside 1..2^24");
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->ovf_cap = spill_entries;
+  h->ws_grid = 0;  // every workspace re-sizes its spill area on next use
+  for (auto &w : h->sws) w.grid = 0;
+  return KDBGPU_OK;
+}
+
 int kdbgpu_set_tuning(kdbgpu_index *h, int slots, int cand_smem, int max_ctas_per_sm) {
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
   SearchTuning t = h->tuning;
@@ -2187,3 +2063,50 @@ int kdbgpu_set_tuning(kdbgpu_index *h, int slots, int cand_smem, int max_ctas_pe
 }
 
 }  // extern "C"
+
+// ---- host staging memory --------------------------------------------------------------------------
+namespace {
+std::mutex g_pinned_mu;
+std::vector<void *> g_pinned;  // pointers handed out by cudaHostAlloc (the rest came from aligned_alloc)
+}  // namespace
+
+extern "C" {
+
+int kdbgpu_host_alloc(void **out, size_t bytes) {
+  if (!out) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (bytes == 0) bytes = 1;
+  void *p = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 &&
+      cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess && p) {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned.push_back(p);
+    *out = p;
+    return KDBGPU_OK;
+  }
+  (void)cudaGetLastError();
+  p = aligned_alloc(64, (bytes + 63) & ~(size_t)63);
+  if (!p) return fail(KDBGPU_ERR_NOMEM, "host allocation of %zu bytes failed", bytes);
+  *out = p;
+  return KDBGPU_OK;
+}
+
+void kdbgpu_host_free(void *p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+      if (g_pinned[i] == p) {
+        g_pinned[i] = g_pinned.back();
+        g_pinned.pop_back();
+        cudaFreeHost(p);
+        (void)cudaGetLastError();
+        return;
+      }
+  }
+  free(p);
+}
+
+}  // extern "C"
+

@@ -301,7 +301,116 @@ __global__ void __launch_bounds__(128)
   if (threadIdx.x == 0) out_counts[q] = m;
 }
 
+// The same merge over per-shard result blobs (BlobLayout) as they arrive from the all-gather / the peer copies:
+// one CTA per query; CTA 0 also folds the shards' counters and error flags.
+__global__ void __launch_bounds__(128)
+    merge_packed_kernel(int n_shards, uint32_t nq, int k, const unsigned char *__restrict__ gather, size_t shard_stride,
+                        BlobLayout L, unsigned char *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  const uint32_t q = blockIdx.x;
+  const int total_cap = n_shards * k;
+  double *s_d = reinterpret_cast<double *>(merge_smem);
+  uint32_t *s_id = reinterpret_cast<uint32_t *>(s_d + total_cap);
+  __shared__ uint32_t s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < total_cap; i += blockDim.x) {
+    const int s = i / k, j = i % k;
+    const unsigned char *b = gather + (size_t)s * shard_stride;
+    uint32_t c = reinterpret_cast<const uint32_t *>(b + L.o_counts)[q];
+    if (c > (uint32_t)k) c = (uint32_t)k;
+    if ((uint32_t)j < c) {
+      const size_t o = (size_t)q * k + j;
+      const uint32_t pos = atomicAdd(&s_n, 1u);
+      s_d[pos] = reinterpret_cast<const double *>(b + L.o_scores)[o];
+      s_id[pos] = reinterpret_cast<const uint32_t *>(b + L.o_ids)[o];
+    }
+  }
+  __syncthreads();
+  const uint32_t n = s_n;
+  double *o_sc = reinterpret_cast<double *>(out + L.o_scores) + (size_t)q * k;
+  uint32_t *o_id = reinterpret_cast<uint32_t *>(out + L.o_ids) + (size_t)q * k;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = s_d[i];
+    const uint32_t id = s_id[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+      const double dj = s_d[j];
+      rank += (dj < d || (dj == d && s_id[j] < id)) ? 1u : 0u;
+    }
+    if (rank < (uint32_t)k) {
+      o_id[rank] = id;
+      o_sc[rank] = d;
+    }
+  }
+  const uint32_t m = n < (uint32_t)k ? n : (uint32_t)k;
+  for (uint32_t i = m + threadIdx.x; i < (uint32_t)k; i += blockDim.x) {
+    o_id[i] = 0;
+    o_sc[i] = 0.0;
+  }
+  if (threadIdx.x == 0) reinterpret_cast<uint32_t *>(out + L.o_counts)[q] = m;
+  if (q == 0 && threadIdx.x < 5) {
+    if (threadIdx.x < 4) {
+      unsigned long long t = 0;
+      for (int s = 0; s < n_shards; ++s)
+        t += reinterpret_cast<const unsigned long long *>(gather + (size_t)s * shard_stride + L.o_stats)[threadIdx.x];
+      reinterpret_cast<unsigned long long *>(out + L.o_stats)[threadIdx.x] = t;
+    } else {
+      int e = 0;
+      for (int s = 0; s < n_shards; ++s) {
+        const int es = *reinterpret_cast<const int *>(gather + (size_t)s * shard_stride + L.o_err);
+        if (e == 0) e = es;
+      }
+      *reinterpret_cast<int *>(out + L.o_err) = e;
+    }
+  }
+}
+
+__global__ void slice_bits_kernel(const uint32_t *__restrict__ src, size_t src_words, uint32_t base,
+                                  uint32_t *__restrict__ dst, size_t n_words) {
+  const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  const uint64_t bit0 = (uint64_t)base + (uint64_t)w * 32u;  // global bit of local bit 32w
+  const size_t sw = (size_t)(bit0 >> 5);
+  const uint32_t sh = (uint32_t)(bit0 & 31u);
+  const uint32_t lo = sw < src_words ? src[sw] : 0u;
+  const uint32_t hi = sw + 1 < src_words ? src[sw + 1] : 0u;
+  uint32_t v = __funnelshift_r(lo, hi, sh);
+  if (w == 0) v &= ~1u;  // local id 0 is the nil slot
+  dst[w] = v;
+}
+
+// local ids -> global ids of an id-range shard (empty slots, id 0, stay 0)
+__global__ void add_id_base_kernel(uint32_t *ids, size_t n, uint32_t base) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] != 0u) ids[i] += base;
+}
+
 }  // namespace
+
+cudaError_t launch_add_id_base(uint32_t *ids, size_t n, uint32_t base, cudaStream_t stream) {
+  if (n == 0 || base == 0) return cudaSuccess;
+  add_id_base_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ids, n, base);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_packed(int n_shards, uint32_t nq, int k, const unsigned char *gather, size_t shard_stride,
+                                const BlobLayout &L, unsigned char *out, cudaStream_t stream) {
+  if (nq == 0) return cudaSuccess;
+  const size_t smem = (size_t)n_shards * k * (sizeof(double) + sizeof(uint32_t));
+  if (n_shards > 64 || smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  merge_packed_kernel<<<nq, 128, smem, stream>>>(n_shards, nq, k, gather, shard_stride, L, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_slice_bits(const uint32_t *src, size_t src_words, uint32_t base, uint32_t *dst, size_t n_words,
+                              cudaStream_t stream) {
+  if (n_words == 0) return cudaSuccess;
+  slice_bits_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, stream>>>(src, src_words, base, dst, n_words);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_flat_distances(const DevIndex &ix, const float *queries_raw, const float *queries_prepared,
                                   uint32_t nq, int mode, double *dist, cudaStream_t stream) {

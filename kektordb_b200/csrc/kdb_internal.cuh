@@ -76,6 +76,9 @@ struct SearchArgs {
   uint32_t *redo_count;
   const uint32_t *query_list;
   const uint32_t *query_count;
+  // id-range shards: returned ids are local id + id_base, so that the per-shard results can be
+  // gathered and merged without another pass (empty slots stay 0)
+  uint32_t id_base;
 };
 
 struct SearchTuning {
@@ -127,6 +130,34 @@ cudaError_t launch_int8_norms(const float *rows, size_t row_words, uint32_t coun
 cudaError_t launch_merge_topk(int n_shards, uint32_t nq, int k, const uint32_t *ids, const double *scores,
                               const uint32_t *counts, uint32_t *out_ids, double *out_scores,
                               uint32_t *out_counts, cudaStream_t stream);
+// One batch's results as ONE device blob, so that a single copy (D2H) or a single collective (all-gather of
+// per-shard results) moves everything: scores [nq][k] f64 | ids [nq][k] u32 | counts [nq] u32 | stats [4] u64 |
+// err i32 (+ pad).  `bytes` is a multiple of 16.
+struct BlobLayout {
+  size_t o_scores, o_ids, o_counts, o_stats, o_err, bytes;
+};
+inline BlobLayout blob_layout(uint32_t nq, int k) {
+  BlobLayout L;
+  const size_t nk = (size_t)nq * (size_t)k;
+  L.o_scores = 0;
+  L.o_ids = nk * sizeof(double);
+  L.o_counts = L.o_ids + nk * sizeof(uint32_t);
+  L.o_stats = (L.o_counts + (size_t)nq * sizeof(uint32_t) + 7) & ~(size_t)7;
+  L.o_err = L.o_stats + 4 * sizeof(unsigned long long);
+  L.bytes = (L.o_err + sizeof(long long) + 15) & ~(size_t)15;
+  return L;
+}
+// merge of per-shard blobs `gather` [n_shards] x shard_stride bytes (each laid out as L) into `out` (same
+// layout): per query the k best by (distance, id); stats summed, err = first non-zero.  ids are global already.
+cudaError_t launch_merge_packed(int n_shards, uint32_t nq, int k, const unsigned char *gather, size_t shard_stride,
+                                const BlobLayout &L, unsigned char *out, cudaStream_t stream);
+// local ids -> global ids of an id-range shard (empty slots stay 0); the traversal does this in its epilogue
+// (SearchArgs.id_base), the flat scan's results go through this kernel
+cudaError_t launch_add_id_base(uint32_t *ids, size_t n, uint32_t base, cudaStream_t stream);
+// local bit i of dst (words [0, n_words)) = global bit (base + i) of src (src_words 32-bit words; bits beyond are 0);
+// local bit 0 (the nil id) is cleared.  Slices a global allow-list for the shard owning ids base+1 ..
+cudaError_t launch_slice_bits(const uint32_t *src, size_t src_words, uint32_t base, uint32_t *dst, size_t n_words,
+                              cudaStream_t stream);
 // flat scan: dist [nq][n_rows] f64 (row r = id r+1), then exact top-k per query
 cudaError_t launch_flat_distances(const DevIndex &ix, const float *queries_raw, const float *queries_prepared,
                                   uint32_t nq, int mode, double *dist, cudaStream_t stream);

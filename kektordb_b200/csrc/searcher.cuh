@@ -390,6 +390,9 @@ struct Searcher {
         // a repeated id inside the row is visited by its first occurrence (:2539-2542)
         const uint32_t same = __match_any_sync(0xffffffffu, id);
         const bool leader = act && ((__ffs(same) - 1) == lane);
+        // nodes[neighborID] == nil is tested at search time (:2553-2561): a row the host has not re-patched yet
+        // may still name a node Vacuum removed.  Loaded before the atomic so that the two latencies overlap.
+        const bool is_node = leader && id <= ix.n && ix.levels[id] >= 0;
         bool fresh = false;
         if (leader) {
           const uint32_t bit = 1u << (id & 31);
@@ -408,7 +411,7 @@ struct Searcher {
           __syncwarp();
         }
         // allow-list before any distance work (:2545-2549)
-        const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id));
+        const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id)) && is_node;
         uint32_t del = 0u;
         if (keep && ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
         const uint32_t km = __ballot_sync(0xffffffffu, keep);
@@ -744,7 +747,7 @@ struct Searcher {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
           if (base + r < count) {  // already ascending (:2596-2610)
-            a.out_ids[(size_t)q * a.k + base + r] = lid[r];
+            a.out_ids[(size_t)q * a.k + base + r] = lid[r] + a.id_base;
             a.out_scores[(size_t)q * a.k + base + r] = ld[r];
           }
       }
@@ -785,7 +788,7 @@ struct Searcher {
           for (int i = n - 1; i >= 0; --i) {
             const HeapEntry e = res.pop();
             if (i < a.k) {
-              a.out_ids[(size_t)q * a.k + i] = e.id;
+              a.out_ids[(size_t)q * a.k + i] = e.id + a.id_base;
               a.out_scores[(size_t)q * a.k + i] = e.d;
             }
           }

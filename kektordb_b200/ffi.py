@@ -40,6 +40,14 @@ class Stats(C.Structure):
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("heap_pass_queries", C.c_uint32)]
 
 
+class ShardStats(C.Structure):
+    _fields_ = [("dist_evals", C.c_uint64), ("hops", C.c_uint64), ("hops_l0", C.c_uint64),
+                ("traversal_ms", C.c_float), ("exchange_ms", C.c_float), ("merge_ms", C.c_float),
+                ("total_ms", C.c_float), ("n_shards", C.c_uint32)]
+
+
+SHARD_ID_BYTES = 128
+
 # every symbol include/kektordb_gpu.h declares: name -> (restype, argtypes)
 _vp, _u32, _i32, _sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
 SIGNATURES = {
@@ -87,12 +95,32 @@ SIGNATURES = {
     "kdbgpu_batcher_destroy": (_i32, [_vp]),
     "kdbgpu_batcher_search": (_i32, [_vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, C.POINTER(_u32)]),
     "kdbgpu_batcher_stats": (_i32, [_vp, C.POINTER(BatcherStats)]),
+    "kdbgpu_batcher_create_group": (_i32, [_vp, _i32, _u32, _u32, C.POINTER(_vp)]),
+    "kdbgpu_batcher_submit": (_i32, [_vp, _vp, _i32, _i32, _vp, _sz, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "kdbgpu_batcher_poll": (_i32, [_vp, _vp, _u32, _u32, C.POINTER(_u32)]),
+    "kdbgpu_batcher_take": (_i32, [_vp, C.c_uint64, _vp, _vp, C.POINTER(_u32)]),
+    "kdbgpu_batcher_register_filter": (_i32, [_vp, _vp, _sz, C.POINTER(C.c_uint64)]),
+    "kdbgpu_batcher_release_filter": (_i32, [_vp, C.c_uint64]),
+    "kdbgpu_host_alloc": (_i32, [C.POINTER(_vp), _sz]),
+    "kdbgpu_host_free": (None, [_vp]),
     "kdbgpu_index_count": (_u32, [_vp]),
     "kdbgpu_index_device_bytes": (C.c_uint64, [_vp]),
     "kdbgpu_search_concurrency": (_i32, [_vp, _i32, _i32]),
     "kdbgpu_prepare_search": (_i32, [_vp, _u32, _i32, _i32]),
     "kdbgpu_set_fast_path": (_i32, [_vp, _i32]),
     "kdbgpu_set_tuning": (_i32, [_vp, _i32, _i32, _i32]),
+    "kdbgpu_set_candidate_bound": (_i32, [_vp, _u32]),
+    "kdbgpu_shard_unique_id": (_i32, [_vp]),
+    "kdbgpu_shard_group_create_rank": (_i32, [_vp, _i32, _i32, _vp, _u32, C.POINTER(_vp)]),
+    "kdbgpu_shard_group_create_local": (_i32, [C.POINTER(_vp), _i32, _vp, C.POINTER(_vp)]),
+    "kdbgpu_shard_group_destroy": (_i32, [_vp]),
+    "kdbgpu_shard_group_size": (_i32, [_vp]),
+    "kdbgpu_shard_search_batch": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, C.POINTER(ShardStats)]),
+    "kdbgpu_shard_search_submit": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, C.POINTER(_vp)]),
+    "kdbgpu_shard_search_wait": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(ShardStats)]),
+    "kdbgpu_shard_search_batch_device": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "kdbgpu_shard_sync": (_i32, [_vp, C.POINTER(ShardStats)]),
+    "kdbgpu_shard_flat_search_batch": (_i32, [_vp, _vp, _u32, _i32, _i32, _vp, _sz, _vp, _vp, _vp, C.POINTER(ShardStats)]),
 }
 
 _lib = None

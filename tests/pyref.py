@@ -118,3 +118,21 @@ def search(dist, rows, node_levels, deleted, entry, max_level, k, ef_search, all
     except KeyError:
         return []
     return res
+
+
+def merge_reference(ids, scores, counts, k):
+    """What the merge kernels compute (kdbgpu_merge_topk_device, the shard group's merge), in numpy: per
+    query the k smallest of the union by (distance, id).  ids/scores [S][Q][k], counts [S][Q]."""
+    import numpy as np
+    S, Q, kk = ids.shape
+    out_ids = np.zeros((Q, k), dtype=np.uint32)
+    out_sc = np.zeros((Q, k), dtype=np.float64)
+    out_cnt = np.zeros(Q, dtype=np.uint32)
+    for q in range(Q):
+        pool = [(float(scores[s, q, i]), int(ids[s, q, i])) for s in range(S) for i in range(min(int(counts[s, q]), kk))]
+        pool.sort()
+        pool = pool[:k]
+        out_cnt[q] = len(pool)
+        for i, (d, idx) in enumerate(pool):
+            out_ids[q, i], out_sc[q, i] = idx, d
+    return out_ids, out_sc, out_cnt

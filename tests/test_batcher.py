@@ -151,3 +151,90 @@ def test_argument_validation_and_shutdown():
     assert lib.kdbgpu_batcher_search(b._h, None, 3, 3, None, 0, None, None, None) == ffi.ERR_INVALID
     b.close()
     b.close()
+
+
+# ---- asynchronous form: submit / poll / take (the Go shim's shape: no caller blocks inside the C call) --------
+def test_submit_poll_take_routes_every_result_and_needs_no_caller_thread():
+    log = []
+    b = Batcher(fn=_executor(log, delay=0.01), dim=DIM, max_batch=64, max_wait_us=20_000)
+    n, k = 300, 4
+    t0 = time.perf_counter()
+    tickets = {b.submit(_q(i), k, 32): i for i in range(n)}   # returns at once: nothing has been answered yet
+    assert time.perf_counter() - t0 < 1.0 and len(tickets) == n
+    seen = {}
+    deadline = time.time() + 20
+    while len(seen) < n and time.time() < deadline:
+        for t in b.poll(128, 50_000):
+            ids, sc, rc = b.take(t, k)
+            i = tickets[t]
+            assert rc == ffi.OK and i not in seen
+            seen[i] = (ids, sc)
+    assert len(seen) == n
+    for i, (ids, sc) in seen.items():
+        cnt = k - (i % 2)
+        assert ids.tolist() == [i + j for j in range(cnt)] and sc.tolist() == [i * 0.5 + j for j in range(cnt)]
+    st = b.stats()
+    assert st.queries == n and st.batches <= n / 8 and st.max_batch_seen == 64
+    assert b.poll(8, 1000) == []                                # every completion was announced exactly once
+    b.close()
+
+
+def test_take_blocks_until_done_and_rejects_unknown_or_spent_tickets():
+    log = []
+    b = Batcher(fn=_executor(log, delay=0.05), dim=DIM, max_batch=8, max_wait_us=1000)
+    t = b.submit(_q(6), 3, 9)
+    ids, sc, rc = b.take(t, 3)                                  # no poll needed: take waits for its query
+    assert rc == ffi.OK and ids.tolist() == [6, 7, 8]
+    assert b.take(t, 3)[2] == ffi.ERR_INVALID                   # a ticket is taken exactly once
+    assert b.take(123456789, 3)[2] == ffi.ERR_INVALID
+    assert b.poll(8, 1000) == [t]                               # the announcement is still delivered
+    b.close()
+
+
+def test_registered_filters_group_by_identity_and_reach_the_executor():
+    log = []
+    b = Batcher(fn=_executor(log, delay=0.03), dim=DIM, max_batch=256, max_wait_us=100_000)
+    a1 = np.array([0b1010, 7], np.uint64)
+    a3 = np.array([0b0110, 7], np.uint64)
+    f1, f3 = b.register_filter(a1), b.register_filter(a3)
+    b.submit(_q(0), 3, 10)                                      # occupies the executor so the rest queue up
+    ts = [b.submit(_q(10 + i), 3, 10, filter_id=f1 if i % 2 else f3) for i in range(20)]
+    ts += [b.submit(_q(40 + i), 3, 10, allowList=a1) for i in range(4)]   # raw bitset, same membership as f1
+    got = {}
+    while len(got) < len(ts) + 1:
+        for t in b.poll(64, 50_000):
+            got[t] = b.take(t, 3)
+    assert all(got[t][2] == ffi.OK for t in ts)
+    filters = [None if a is None else tuple(a.tolist()) for _, _, _, a in log]
+    assert set(filters) == {None, (0b1010, 7), (0b0110, 7)}
+    assert len(log) <= 5                                         # one batch per filter (+ raw / first), not one per query
+    with pytest.raises(ffi.GpuError):
+        b.submit(_q(1), 3, 10, filter_id=999)
+    b.release_filter(f1)
+    with pytest.raises(ffi.GpuError):
+        b.release_filter(f1)
+    b.close()
+
+
+def test_failed_batch_reaches_async_callers_as_empty_result_plus_code():
+    log = []
+    b = Batcher(fn=_executor(log, delay=0.01, fail_on=13.0), dim=DIM, max_batch=64, max_wait_us=1000)
+    t = b.submit(_q(13), 3, 3)
+    ids, sc, rc = b.take(t, 3)
+    assert rc == ffi.ERR_OVERFLOW and len(ids) == 0
+    assert b.take(b.submit(_q(2), 3, 3), 3)[0].tolist() == [2, 3, 4]
+    b.close()
+
+
+def test_native_async_driver_equals_blocking_callers():
+    """The load generator bench.py uses (tools/native): submit / poll / take from 4 submitter threads and one
+    dispatcher gives every query the result the blocking call shape gives."""
+    from tools.native import driver
+    log = []
+    b = Batcher(fn=_executor(log), dim=DIM, max_batch=32, max_wait_us=2000)
+    Q = np.stack([_q(i) for i in range(500)])
+    a = driver.run_async(b, Q, 4, 16, 4, 96)
+    c = driver.run_callers(b, Q, 4, 16, 48)
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]) and np.array_equal(a[2], c[2])
+    assert a[0][7].tolist()[:3] == [7, 8, 9] and a[2].tolist() == [4 - (i % 2) for i in range(500)]
+    b.close()

@@ -24,7 +24,8 @@ def test_shard_ranges_partition_the_corpus():
 
 
 def test_globalize_ids_and_reference_merge():
-    from kektordb_b200.sharding import globalize_ids, merge_reference
+    from kektordb_b200.sharding import globalize_ids
+    from tests.pyref import merge_reference
     ids = np.array([[3, 1, 0], [2, 0, 0]], dtype=np.uint32)
     g = globalize_ids(ids, np.array([2, 1]), 100)
     assert g.tolist() == [[103, 101, 0], [102, 0, 0]]
@@ -40,7 +41,8 @@ def _worker(rank, world, port, out_path):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    from kektordb_b200.sharding import globalize_ids, merge_reference, shard_range
+    from kektordb_b200.sharding import globalize_ids, shard_range
+    from tests.pyref import merge_reference
     from oracle import oracle as O
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -70,7 +72,8 @@ def _worker(rank, world, port, out_path):
 
 def test_two_rank_sharded_search_matches_single_process(tmp_path):
     import torch.multiprocessing as mp
-    from kektordb_b200.sharding import globalize_ids, merge_reference, shard_range
+    from kektordb_b200.sharding import globalize_ids, shard_range
+    from tests.pyref import merge_reference
     from oracle import oracle as O
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
