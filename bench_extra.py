@@ -137,18 +137,17 @@ def run_flat(args, torch, bench):
                      "queries_sent_to_exhaustive_scan": int(fallbacks)},
         "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
 
 
 def run_flat_sharded(args, torch, bench):
     """configs[2] over G GPUs (flat path): the corpus is split by contiguous id range, every rank
-    scans its N/G rows for the same queries (tensor-core pre-filter + exact float64 re-score), one NCCL
-    all-gather of the per-shard top-k {id, distance} and the merge kernel give the global exact top-k.
-    Work per rank shrinks with G, so this is reported with "scaling": "strong"."""
+    scans its N/G rows for the same queries (tensor-core pre-filter + exact float64 re-score), and the library's
+    shard group does the rest on the device: ONE ncclAllGather of the packed per-shard top-k and the merge kernel
+    (kdbgpu_shard_flat_search_batch — no host round trip between scan and merge).  Work per rank shrinks with G,
+    so this is reported with "scaling": "strong"."""
     import torch.distributed as dist
-    from kektordb_b200 import GpuIndex
-    from kektordb_b200.sharding import shard_range
+    from kektordb_b200 import GpuIndex, sharding
     ffi = bench_ffi()
     N, D, B = args.n, args.dim, args.batch
     k = args.k if args.k != 10 else 100
@@ -159,7 +158,7 @@ def run_flat_sharded(args, torch, bench):
     dist.init_process_group("nccl", device_id=dev)
     n_total = args.warmup + args.steps
     X = bench.make_data(torch, N, D, args.latent, args.noise, 42, dev)
-    base, n_local = shard_range(N, world, rank)
+    base, n_local = sharding.shard_range(N, world, rank)
     gi = GpuIndex(D, "euclidean", 8, n_local, device=local_rank)
     ffi.check(ffi.lib().kdbgpu_upload_vectors_device(gi._h, 1, n_local, X[base:base + n_local].data_ptr(), D))
     _rows_only_graph(gi, n_local)
@@ -169,56 +168,39 @@ def run_flat_sharded(args, torch, bench):
         ffi.check(ffi.lib().kdbgpu_upload_vectors_device(full._h, 1, N, X.data_ptr(), D))
         _rows_only_graph(full, N)
     del X
+    uid = [sharding.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    grp = sharding.ShardGroup.rank(gi, rank, world, uid[0], base)
     Qd = bench.make_data(torch, n_total * B, D, args.latent, args.noise, 4242, dev)
-    Q = Qd.cpu().numpy()
-    g_ids = torch.zeros((world, B, k), dtype=torch.int32, device=dev)
-    g_sc = torch.zeros((world, B, k), dtype=torch.float64, device=dev)
-    g_cnt = torch.zeros((world, B), dtype=torch.int32, device=dev)
-    m_ids = torch.zeros((B, k), dtype=torch.int32, device=dev)
-    m_sc = torch.zeros((B, k), dtype=torch.float64, device=dev)
-    m_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.Stream(device=dev)  # an explicit stream: a NULL stream would mean the library's own
-
-    def step(i):
-        ids, sc, cnt, st = gi.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True)
-        with torch.cuda.stream(stream):
-            l_ids = torch.from_numpy(np.where(ids > 0, ids.astype(np.int64) + base, 0).astype(np.int32)).to(dev)
-            l_sc = torch.from_numpy(sc).to(dev)
-            l_cnt = torch.from_numpy(cnt.astype(np.int32)).to(dev)
-            dist.all_gather_into_tensor(g_ids.view(world * B, k), l_ids)   # the one exchange step
-            dist.all_gather_into_tensor(g_sc.view(world * B, k), l_sc)
-            dist.all_gather_into_tensor(g_cnt.view(world * B), l_cnt)
-        ffi.check(ffi.lib().kdbgpu_merge_topk_device(gi._h, world, B, k, g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(),
-                                                     m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr(), stream.cuda_stream))
-        with torch.cuda.stream(stream):
-            out = (m_ids.cpu().numpy(), m_sc.cpu().numpy(), m_cnt.cpu().numpy())
-        stream.synchronize()
-        return out, st
-
+    Qh = torch.empty((n_total * B, D), dtype=torch.float32, pin_memory=True)
+    Qh.copy_(Qd)
+    torch.cuda.synchronize()
+    Q = Qh.numpy()
     for i in range(args.warmup):
-        step(i)
+        grp.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True)
     dist.barrier()
     torch.cuda.synchronize()
     sampler = bench.ClockSampler(local_rank, args.clock_sampler)
     if rank == 0:
         sampler.start()
-    comp_ms = 0.0
+    scan_ms = xch_ms = mrg_ms = 0.0
     t0 = time.perf_counter()
     for i in range(args.warmup, n_total):
-        out, st = step(i)
-        comp_ms += st.kernel_ms
+        out = grp.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True)
+        scan_ms += out[3].traversal_ms
+        xch_ms += out[3].exchange_ms
+        mrg_ms += out[3].merge_ms
     dist.barrier()
     torch.cuda.synchronize()
     wall_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([wall_s, comp_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([wall_s, scan_ms, xch_ms, mrg_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall_s, comp_ms = float(t[0]), float(t[1])
-    exact = None
+    wall_s, scan_ms, xch_ms, mrg_ms = (float(x) for x in t)
     if rank == 0:
         n_par = 64
         f = full.flat_search(Q[(n_total - 1) * B:(n_total - 1) * B + n_par], k, 0, prefilter=True)
-        exact = {"queries": n_par, "ids_equal_to_unsharded_scan": bool(np.array_equal(f[0], out[0][:n_par].astype(np.uint32))),
+        exact = {"queries": n_par, "ids_equal_to_unsharded_scan": bool(np.array_equal(f[0], out[0][:n_par])),
                  "scores_bit_equal": bool(np.array_equal(f[1], out[1][:n_par]))}
         pk = _peaks()
         line = {
@@ -227,14 +209,15 @@ def run_flat_sharded(args, torch, bench):
             "warmup": args.warmup, "ms_per_step": round(wall_s / args.steps * 1e3, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16 nomination (tcgen05) + f64 exact re-score", "data": "synthetic",
             "recall_at_k": 1.0 if exact["ids_equal_to_unsharded_scan"] else None,
-            "config": {"workload": f"{N}x{D} L2 flat, top-{k}, batch={B}; rows split by id range over {world} GPUs, NCCL "
-                                   f"all-gather of per-shard top-{k} + merge kernel",
-                       "value_is": "wall clock per step through the host-buffer call on every rank (H2D, scan, D2H, all-gather, "
+            "config": {"workload": f"{N}x{D} L2 flat, top-{k}, batch={B}; rows split by id range over {world} GPUs, library shard "
+                                   f"group: ONE ncclAllGather of the packed per-shard top-{k} + merge kernel, no host bounce",
+                       "value_is": "wall clock per step through the host-buffer call on every rank (H2D, scan, all-gather, "
                                    "merge, D2H), barrier on both sides, max over ranks",
-                       "per_shard_kernel_ms_per_step": round(comp_ms / args.steps, 4)},
+                       "per_shard_scan_ms_per_step": round(scan_ms / args.steps, 4),
+                       "allgather_ms_per_step": round(xch_ms / args.steps, 4), "merge_ms_per_step": round(mrg_ms / args.steps, 4)},
             "e2e": {"value": round(B * args.steps / wall_s, 1), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
-                    "d2h_bytes_per_step": B * k * 12 + B * 4},
-            "gpu_launches": 9 * args.steps,
+                    "d2h_bytes_per_step": B * k * 12 + B * 4 + 48},
+            "gpu_launches": 10 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "flat_tc_kernel", "achieved": None, "peak": pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": None, "traffic": None,
                          "note": "per-shard tensor passes; see the single-GPU line for the roofline of the kernel"},
@@ -242,6 +225,7 @@ def run_flat_sharded(args, torch, bench):
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
+    grp.close()
     dist.destroy_process_group()
     return 0
 
@@ -300,7 +284,7 @@ def _flat_reference_arm(args, gi, X, Q, k, ncores):
         oi.flat_search_batch(Q[i * B:(i + 1) * B], k, mode=0, threads=ncores)
     el = time.perf_counter() - t0
     v = B * args.steps / el
-    print(json.dumps({
+    return ({
         "impl": "reference", "metric": f"top-{k} queries/sec, exact, {args.n}x{args.dim}-d L2 flat brute force",
         "value": round(v, 2), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(el / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -310,8 +294,7 @@ def _flat_reference_arm(args, gi, X, Q, k, ncores):
         "cpu_baseline": {"value": round(v, 2), "unit": "queries/s", "cores": ncores, "kind": "port",
                          "sample": f"{args.steps} steps of {B} queries, oracle restatement of BruteForceIndex"},
         "e2e": {"value": round(v, 2), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
-    return 0
+        "gpu_launches": 0})
 
 
 
@@ -415,7 +398,7 @@ def run_hybrid(args, torch, bench):
             oi.search_batch(Q[i * B:(i + 1) * B], k, ef, allow=allow, threads=ncores)
         el = time.perf_counter() - t0
         v = B * args.steps / el
-        print(json.dumps({"impl": "reference", "metric": f"top-{k} queries/sec, {N}x{D}-d cosine HNSW + allow-list {sel:.0%}",
+        return ({"impl": "reference", "metric": f"top-{k} queries/sec, {N}x{D}-d cosine HNSW + allow-list {sel:.0%}",
                           "value": round(v, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -424,8 +407,7 @@ def run_hybrid(args, torch, bench):
                           "cpu_baseline": {"value": round(v, 1), "unit": "queries/s", "cores": ncores, "kind": "port",
                                            "sample": f"{args.steps} steps of {B} queries, oracle port"},
                           "e2e": {"value": round(v, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}), flush=True)
-        return 0
+                          "gpu_launches": 0})
 
     gi.prepare_search(B, k, ef)
     ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, allow, ef)
@@ -480,8 +462,7 @@ def run_hybrid(args, torch, bench):
                      "dist_evals_per_query": round(E / (B * args.steps), 1), "hops_per_query": round(H / (B * args.steps), 1)},
         "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
 
 
 # --------------------------------------------------------------------------------------------------
@@ -557,7 +538,7 @@ def run_quantized(args, torch, bench):
             oi.search_batch(Q[i * B:(i + 1) * B], k, ef, threads=ncores)
         el = time.perf_counter() - t1
         v = B * args.steps / el
-        print(json.dumps({"impl": "reference", "metric": metric_name, "value": round(v, 1), "unit": "queries/s",
+        return ({"impl": "reference", "metric": metric_name, "value": round(v, 1), "unit": "queries/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": prec, "data": "synthetic",
@@ -566,8 +547,7 @@ def run_quantized(args, torch, bench):
                           "cpu_baseline": {"value": round(v, 1), "unit": "queries/s", "cores": ncores, "kind": "port",
                                            "sample": f"{args.steps} steps of {B} queries, oracle port"},
                           "e2e": {"value": round(v, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}), flush=True)
-        return 0
+                          "gpu_launches": 0})
 
     gi.prepare_search(B, k, ef)
     ids0, sc0, cnt0, st0 = gi.SearchWithScores(Q[:B], k, None, ef)
@@ -629,5 +609,4 @@ def run_quantized(args, torch, bench):
                      "dist_evals_per_query": round(st.dist_evals / B, 1), "hops_per_query": round(st.hops / B, 1)},
         "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return line

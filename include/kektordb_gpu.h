@@ -124,6 +124,10 @@ int kdbgpu_arena_load_dir(kdbgpu_index *, const char *dir, const uint32_t *slot_
                           uint64_t *rows_staged);
 int kdbgpu_arena_stage_chunk(kdbgpu_index *, uint32_t chunk_id, const void *chunk, size_t chunk_bytes,
                              const uint32_t *slot_table, uint32_t table_len, uint32_t *rows_staged);
+/* kdbgpu_arena_stage_chunk page-locks the caller's mapping in place for the copy (cudaHostRegister) whenever the
+ * chunk pointer is page aligned — an mmap always is — so that the DMA engine reads the mapping directly; this
+ * counts the calls that did (0 for malloc'ed buffers or when registration is unavailable). */
+uint64_t kdbgpu_arena_chunks_registered(const kdbgpu_index *);
 /* Same, from device memory on the handle's device (row_stride in floats). */
 int kdbgpu_upload_vectors_device(kdbgpu_index *, uint32_t first_id, uint32_t count, const float *d_rows,
                                  size_t row_stride);
@@ -133,6 +137,22 @@ int kdbgpu_upload_vectors_device(kdbgpu_index *, uint32_t first_id, uint32_t cou
  * in the reference's order.  entry / max_level = entrypointID / maxLevel. */
 int kdbgpu_set_graph(kdbgpu_index *, uint32_t n, const int32_t *levels, const uint64_t *node_row,
                      const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level);
+/* The same topology through a flat binary sidecar file, so that a 1 M - 10 M-node graph does not have to be rebuilt
+ * in Go slices at every start (the reference keeps it inside its gob-encoded .kdb snapshot, pkg/core/core.go:177-306
+ * / SnapshotData hnsw_index.go:3064-3150, which only Go can decode).  Layout (little endian, sections 8-byte
+ * aligned): 64-byte header {u32 magic 0x4742444B, u32 version 1, u32 n, u32 entry, i32 max_level, u32 m, u64 n_rows,
+ * u64 n_edges}, then levels i32[n+1], node_row u64[n+2], row_off u64[n_rows+1], nbrs u32[n_edges] — the arguments of
+ * kdbgpu_set_graph.
+ *   kdbgpu_graph_file_write  writes one from host arrays (atomically: temp file + rename); host only;
+ *   kdbgpu_save_graph_file   writes the mirror's current topology (after kdbgpu_add_batch / a refresh);
+ *   kdbgpu_graph_file_probe  header fields of a file; host only, any out pointer may be NULL;
+ *   kdbgpu_set_graph_file    maps the file and stages it exactly as kdbgpu_set_graph would. */
+int kdbgpu_graph_file_write(const char *path, uint32_t n, int m, const int32_t *levels, const uint64_t *node_row,
+                            const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level);
+int kdbgpu_save_graph_file(kdbgpu_index *, const char *path);
+int kdbgpu_graph_file_probe(const char *path, uint32_t *n, int *m, uint64_t *n_rows, uint64_t *n_edges, uint32_t *entry,
+                            int *max_level);
+int kdbgpu_set_graph_file(kdbgpu_index *, const char *path);
 /* Incremental refresh — follow the CPU index without re-staging everything:
  *   kdbgpu_register_nodes  ids first_id .. first_id+count-1 (= nodeCounter+1 onwards) come to exist with
  *                          levels[i] = len(Connections)-1 and empty rows (Add phase 1, hnsw_index.go:559-655;
@@ -309,6 +329,7 @@ int kdbgpu_download_vectors(kdbgpu_index *, uint32_t first_id, uint32_t count, f
 int kdbgpu_last_search_stats(kdbgpu_index *, kdbgpu_stats *stats);
 int kdbgpu_index_device(const kdbgpu_index *);
 int kdbgpu_index_dim(const kdbgpu_index *);
+int kdbgpu_index_m(const kdbgpu_index *);
 uint32_t kdbgpu_index_count(const kdbgpu_index *);   /* n of the last kdbgpu_set_graph        */
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *);
 /* Resident CTAs the traversal kernel runs with for (k, ef) — queries in flight per launch. */

@@ -993,6 +993,36 @@ int kdbgpu_arena_stage_chunk(kdbgpu_index *h, uint32_t chunk_id, const void *chu
     CUDA_TRY(cudaMemcpyAsync(d_slot.p, slot_table, (size_t)table_len * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   }
   if (have < payload) CUDA_TRY(cudaMemsetAsync(d_stage.p + have, 0, payload - have, s));
+  // The chunk is the host's own mapping of arena_%04d.bin (VectorArena keeps every chunk mmap'ed, arena.go:307-376).
+  // Page-lock it in place for the duration of the copy, so the DMA engine reads the mapping directly instead of
+  // the driver bouncing it through its own pinned staging; a mapping that cannot be registered (not page
+  // aligned, read-only registration unsupported) is copied the ordinary way.
+  const uintptr_t page = 4096;
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(bytes);
+  const size_t span = (arena_header_size() + have + page - 1) & ~(size_t)(page - 1);  // whole pages of the mapping
+  bool registered = false;
+  if (have >= (1u << 20) && (lo & (page - 1)) == 0 && getenv("KDBGPU_ARENA_NO_REGISTER") == nullptr) {
+    cudaError_t re = cudaHostRegister(reinterpret_cast<void *>(lo), span, cudaHostRegisterReadOnly);
+    if (re != cudaSuccess) {
+      (void)cudaGetLastError();
+      re = cudaHostRegister(reinterpret_cast<void *>(lo), span, cudaHostRegisterDefault);  // a writable mapping
+    }
+    if (re == cudaSuccess)
+      registered = true;
+    else
+      (void)cudaGetLastError();
+  }
+  struct Unregister {
+    void *p;
+    bool on;
+    ~Unregister() {
+      if (on) {
+        cudaHostUnregister(p);
+        (void)cudaGetLastError();
+      }
+    }
+  } unreg{reinterpret_cast<void *>(lo), registered};
+  h->arena_chunks_registered += registered ? 1 : 0;
   CUDA_TRY(cudaMemcpyAsync(d_stage.p, bytes + arena_header_size(), have, cudaMemcpyHostToDevice, s));
   CUDA_TRY(launch_arena_scatter(d_stage.p, chunk_id, vpc, vb, slot_table ? d_slot.p : nullptr, 1, last_id, h->vecs.p,
                                 h->row_words, d_cnt.p, s));
@@ -1082,6 +1112,7 @@ int kdbgpu_arena_load_dir(kdbgpu_index *h, const char *dir, const uint32_t *slot
 }
 
 int kdbgpu_index_precision(const kdbgpu_index *h) { return h ? h->precision : -1; }
+uint64_t kdbgpu_arena_chunks_registered(const kdbgpu_index *h) { return h ? h->arena_chunks_registered : 0; }
 
 int kdbgpu_upload_vectors_device(kdbgpu_index *h, uint32_t first_id, uint32_t count, const float *d_rows,
                                  size_t row_stride) {
@@ -1534,6 +1565,7 @@ int kdbgpu_last_search_stats(kdbgpu_index *h, kdbgpu_stats *stats) {
 
 int kdbgpu_index_device(const kdbgpu_index *h) { return h ? h->device : -1; }
 int kdbgpu_index_dim(const kdbgpu_index *h) { return h ? h->dim : -1; }
+int kdbgpu_index_m(const kdbgpu_index *h) { return h ? h->m : -1; }
 uint32_t kdbgpu_index_count(const kdbgpu_index *h) { return h ? h->n : 0; }
 uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *h) {
   if (!h) return 0;

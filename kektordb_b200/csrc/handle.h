@@ -143,6 +143,7 @@ struct kdbgpu_index {
   DevBuf<unsigned long long> t_nres;
   bool tc_valid = false;
   uint32_t tc_n = 0;
+  uint64_t arena_chunks_registered = 0;  // kdbgpu_arena_stage_chunk calls that page-locked the caller's mapping in place
 
   DevIndex dev() const {
     DevIndex d;

@@ -64,12 +64,19 @@ SIGNATURES = {
     "kdbgpu_arena_probe": (_i32, [C.c_char_p, C.POINTER(_u32), C.POINTER(_i32), C.POINTER(_u32), C.POINTER(_u32)]),
     "kdbgpu_arena_load_dir": (_i32, [_vp, C.c_char_p, _vp, _u32, C.POINTER(C.c_uint64)]),
     "kdbgpu_arena_stage_chunk": (_i32, [_vp, _u32, _vp, _sz, _vp, _u32, C.POINTER(_u32)]),
+    "kdbgpu_arena_chunks_registered": (C.c_uint64, [_vp]),
     "kdbgpu_upload_rows_raw": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_download_rows_raw": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_download_norms": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_upload_vectors": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_upload_vectors_device": (_i32, [_vp, _u32, _u32, _vp, _sz]),
     "kdbgpu_set_graph": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _i32]),
+    "kdbgpu_graph_file_write": (_i32, [C.c_char_p, _u32, _i32, _vp, _vp, _vp, _vp, _u32, _i32]),
+    "kdbgpu_save_graph_file": (_i32, [_vp, C.c_char_p]),
+    "kdbgpu_graph_file_probe": (_i32, [C.c_char_p, C.POINTER(_u32), C.POINTER(_i32), C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64), C.POINTER(_u32), C.POINTER(_i32)]),
+    "kdbgpu_set_graph_file": (_i32, [_vp, C.c_char_p]),
+    "kdbgpu_index_m": (_i32, [_vp]),
     "kdbgpu_register_nodes": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_patch_rows": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp]),
     "kdbgpu_remove_nodes": (_i32, [_vp, _u32, _vp]),

@@ -193,6 +193,14 @@ class GpuIndex:
         ffi.check(self._lib.kdbgpu_set_graph(self._handle(), n, _ptr(levels), _ptr(node_row), _ptr(row_off),
                                              _ptr(nbrs), entry, max_level))
 
+    def save_graph_file(self, path: str) -> None:
+        """The mirror's topology as a flat sidecar file (layout in include/kektordb_gpu.h)."""
+        ffi.check(self._lib.kdbgpu_save_graph_file(self._handle(), path.encode()))
+
+    def set_graph_file(self, path: str) -> None:
+        """kdbgpu_set_graph from a sidecar file: mapped and staged inside the library."""
+        ffi.check(self._lib.kdbgpu_set_graph_file(self._handle(), path.encode()))
+
     # -- incremental refresh (follow the CPU index's Add / Vacuum / Refine) ----------------------------
     def register_nodes(self, first_id: int, levels) -> None:
         lv = np.ascontiguousarray(levels, dtype=np.int32)

@@ -286,7 +286,7 @@ def test_removed_node_named_by_a_stale_row_is_skipped_at_search_time():
     gi = _mirror(oi, O.METRIC_COSINE, 8)
     base_ids = gi.SearchWithScores(Q, k, None, ef)[0]
     victims = np.unique(base_ids[:, 0])
-    victims = victims[victims != oi.entry()][:5].astype(np.uint32)  # nodes the queries certainly reach
+    victims = victims[victims != oi.entry][:5].astype(np.uint32)  # nodes the queries certainly reach
     gi.remove_nodes(victims)  # rows naming them are NOT re-patched
     ids, sc, cnt, _ = gi.SearchWithScores(Q, k, None, ef)
     assert not np.isin(ids[ids > 0], victims).any()
