@@ -169,6 +169,38 @@ int kdbgpu_patch_rows(kdbgpu_index *, uint32_t count, const uint32_t *ids, const
                       const uint64_t *row_off, const uint32_t *nbrs);
 int kdbgpu_remove_nodes(kdbgpu_index *, uint32_t count, const uint32_t *ids);
 int kdbgpu_set_entry(kdbgpu_index *, uint32_t entry, int max_level);
+/* The staleness policy on top of those calls (csrc/refresher.cpp).  Each of them takes the handle exclusively and
+ * drains the searches in flight, so a host that mirrored every single Add would starve its own queries.  A
+ * refresher QUEUES the changes — adjacency rows per (node, level) with last-write-wins, new nodes with their stored
+ * vector, removals, Node.Deleted flips, the entry point — and applies them in ONE exclusive section when the queue
+ * holds max_pending_rows rows, when the oldest queued change is max_lag_ms old (a background thread watches the
+ * clock; 0 = no clock, flush by size / by call only), or when kdbgpu_refresher_flush is called.  Between flushes
+ * searches see the mirror as of the last flush (bounded staleness: at most max_lag_ms / max_pending_rows behind).
+ *   add_node      Add phase 1 (hnsw_index.go:559-655): id (> the mirror's count; skipped ids stay nil), level =
+ *                 len(Connections)-1, row_raw = the vector in stored form (dim x 4 / 2 / 1 bytes, VectorArena bytes)
+ *   set_row       Connections[level] of node id := nbrs (forward / reverse links :717-783, reconnectNode
+ *                 optimizer.go:195-222, Refine :288-468)
+ *   remove_node   nodes[id] = nil (optimizer.go:252-274);  set_deleted  Node.Deleted (:2303-2336)
+ *   set_entry     entrypointID / maxLevel (:793-801, optimizer.go:231-249)
+ * destroy flushes what is queued.  Errors of a background flush are kept in stats.last_error. */
+typedef struct kdbgpu_refresher kdbgpu_refresher;
+typedef struct {
+  uint64_t pending_rows, pending_nodes;
+  uint64_t flushes, flushes_by_rows, flushes_by_lag, flushes_by_call;
+  uint64_t rows_queued, rows_applied; /* queued minus applied = rewrites coalesced by last-write-wins */
+  uint64_t nodes_applied;
+  float oldest_pending_ms, last_flush_ms;
+  int last_error;
+} kdbgpu_refresher_stats_t;
+int kdbgpu_refresher_create(kdbgpu_index *, uint32_t max_pending_rows, uint32_t max_lag_ms, kdbgpu_refresher **out);
+int kdbgpu_refresher_destroy(kdbgpu_refresher *);
+int kdbgpu_refresher_add_node(kdbgpu_refresher *, uint32_t id, int level, const void *row_raw);
+int kdbgpu_refresher_set_row(kdbgpu_refresher *, uint32_t id, int level, const uint32_t *nbrs, uint32_t count);
+int kdbgpu_refresher_remove_node(kdbgpu_refresher *, uint32_t id);
+int kdbgpu_refresher_set_deleted(kdbgpu_refresher *, uint32_t id, int is_deleted);
+int kdbgpu_refresher_set_entry(kdbgpu_refresher *, uint32_t entry, int max_level);
+int kdbgpu_refresher_flush(kdbgpu_refresher *);
+int kdbgpu_refresher_stats(kdbgpu_refresher *, kdbgpu_refresher_stats_t *out);
 /* Node.Deleted flags as a dense bitset over ids (bit i of word i/64); NULL clears all. */
 int kdbgpu_set_deleted(kdbgpu_index *, const uint64_t *bitset, size_t words);
 

@@ -8,5 +8,6 @@ from .index import Cosine, Euclidean, Float16, Float32, Int8, GpuIndex, SearchSt
 
 from .batcher import Batcher, BatcherStats  # noqa: E402,F401
 from .sharding import ShardGroup, ShardStats, shard_range  # noqa: E402,F401
+from .refresher import Refresher, RefresherStats  # noqa: E402,F401
 
-__all__ = ["Batcher", "BatcherStats", "ShardGroup", "ShardStats", "shard_range", "GpuIndex", "SearchStats", "arena_probe", "Cosine", "Euclidean", "Float32", "Float16", "Int8", "dense_allow_list", "effective_ef"]
+__all__ = ["Batcher", "BatcherStats", "ShardGroup", "ShardStats", "shard_range", "Refresher", "RefresherStats", "GpuIndex", "SearchStats", "arena_probe", "Cosine", "Euclidean", "Float32", "Float16", "Int8", "dense_allow_list", "effective_ef"]

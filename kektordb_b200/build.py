@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkektordb_gpu.so")
-SOURCES = ["api.cu", "search.cu", "search_k0.cu", "search_k1.cu", "search_k2.cu", "search_k3.cu", "flat.cu", "flat_tc.cu", "build.cu", "arena.cu", "shard.cu", "batcher.cpp", "graphfile.cpp"]
+SOURCES = ["api.cu", "search.cu", "search_k0.cu", "search_k1.cu", "search_k2.cu", "search_k3.cu", "flat.cu", "flat_tc.cu", "build.cu", "arena.cu", "shard.cu", "batcher.cpp", "graphfile.cpp", "refresher.cpp"]
 HEADERS = ["kdb_internal.cuh", "handle.h", "searcher.cuh", "search_inst.cuh", os.path.join("..", "..", "include", "kektordb_gpu.h")]
 
 

@@ -40,6 +40,13 @@ class Stats(C.Structure):
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("heap_pass_queries", C.c_uint32)]
 
 
+class RefresherStats(C.Structure):
+    _fields_ = [("pending_rows", C.c_uint64), ("pending_nodes", C.c_uint64), ("flushes", C.c_uint64),
+                ("flushes_by_rows", C.c_uint64), ("flushes_by_lag", C.c_uint64), ("flushes_by_call", C.c_uint64),
+                ("rows_queued", C.c_uint64), ("rows_applied", C.c_uint64), ("nodes_applied", C.c_uint64),
+                ("oldest_pending_ms", C.c_float), ("last_flush_ms", C.c_float), ("last_error", C.c_int)]
+
+
 class ShardStats(C.Structure):
     _fields_ = [("dist_evals", C.c_uint64), ("hops", C.c_uint64), ("hops_l0", C.c_uint64),
                 ("traversal_ms", C.c_float), ("exchange_ms", C.c_float), ("merge_ms", C.c_float),
@@ -77,6 +84,15 @@ SIGNATURES = {
                                        C.POINTER(C.c_uint64), C.POINTER(_u32), C.POINTER(_i32)]),
     "kdbgpu_set_graph_file": (_i32, [_vp, C.c_char_p]),
     "kdbgpu_index_m": (_i32, [_vp]),
+    "kdbgpu_refresher_create": (_i32, [_vp, _u32, _u32, C.POINTER(_vp)]),
+    "kdbgpu_refresher_destroy": (_i32, [_vp]),
+    "kdbgpu_refresher_add_node": (_i32, [_vp, _u32, _i32, _vp]),
+    "kdbgpu_refresher_set_row": (_i32, [_vp, _u32, _i32, _vp, _u32]),
+    "kdbgpu_refresher_remove_node": (_i32, [_vp, _u32]),
+    "kdbgpu_refresher_set_deleted": (_i32, [_vp, _u32, _i32]),
+    "kdbgpu_refresher_set_entry": (_i32, [_vp, _u32, _i32]),
+    "kdbgpu_refresher_flush": (_i32, [_vp]),
+    "kdbgpu_refresher_stats": (_i32, [_vp, C.POINTER(RefresherStats)]),
     "kdbgpu_register_nodes": (_i32, [_vp, _u32, _u32, _vp]),
     "kdbgpu_patch_rows": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp]),
     "kdbgpu_remove_nodes": (_i32, [_vp, _u32, _vp]),

@@ -126,3 +126,40 @@ def test_search_over_arena_staged_rows_is_bit_identical(tmp_path):
     oids, osc, ocnt, ost = oi.search_batch(Q, 10, 64, threads=8)
     assert np.array_equal(ids, oids) and np.array_equal(sc, osc) and stt.dist_evals == ost.dist_evals
     gi.close()
+
+
+def test_stage_chunk_from_the_hosts_own_mmap_page_locks_it_in_place(tmp_path):
+    """The Go side keeps every chunk mmap'ed (arena.go:307-376): kdbgpu_arena_stage_chunk reads that mapping
+    directly (cudaHostRegister for the duration of the copy) — no bounce through another pinned buffer."""
+    import mmap
+    from kektordb_b200 import ffi
+    GpuIndex = _gpu()
+    rng = np.random.default_rng(7)
+    n, dim = 30000, 768                                       # 92 MB of float32 rows: two chunks
+    rows = _rows(rng, n, dim, 0)
+    d = str(tmp_path / "arena")
+    n_chunks = A.write_arena(d, rows, 0, None)
+    assert n_chunks == 2
+    gi = GpuIndex(dim, "euclidean", 4, n)
+    maps, staged = [], 0
+    for c in range(n_chunks):
+        f = open(os.path.join(d, "arena_%04d.bin" % c), "rb")
+        mm = mmap.mmap(f.fileno(), 0, prot=mmap.PROT_READ)   # a read-only file mapping, as the reference holds it
+        maps.append((f, mm))
+        staged += gi.stage_arena_chunk(c, np.frombuffer(mm, dtype=np.uint8), None, n + 1)
+    assert staged == n
+    assert np.array_equal(gi.download_rows_raw(1, n), rows[1:])
+    assert ffi.lib().kdbgpu_arena_chunks_registered(gi._h) == n_chunks
+    # a malloc'ed, unaligned copy of the same bytes takes the ordinary copy path and stages the same rows
+    gj = GpuIndex(dim, "euclidean", 4, n)
+    for c in range(n_chunks):
+        buf = np.empty(len(maps[c][1]) + 1, np.uint8)[1:]
+        buf[:] = np.frombuffer(maps[c][1], dtype=np.uint8)
+        gj.stage_arena_chunk(c, buf, None, n + 1)
+    assert np.array_equal(gj.download_rows_raw(1, n), rows[1:])
+    assert ffi.lib().kdbgpu_arena_chunks_registered(gj._h) == 0
+    gi.close()
+    gj.close()
+    for f, mm in maps:
+        del mm
+        f.close()

@@ -189,3 +189,102 @@ def test_searches_and_refresh_calls_from_concurrent_threads():
         t.join()
     assert not bad
     gi.close()
+
+
+# ---- the staleness policy (csrc/refresher.cpp): queued changes, one exclusive section per flush ----------------
+def _replay_adds(oi, X, u, pos, step, rf, prev):
+    """`step` single Adds on the CPU index; every row they rewrote goes to the refresher, change by change."""
+    for i in range(pos, pos + step):
+        oi.add(X[i], u[i])
+        g = oi.export_graph()
+        cur = _rows(g)
+        nid = i + 1
+        rf.add_node(nid, int(g.levels[nid]), oi.vectors()[nid])
+        for key, row in cur.items():
+            if prev.get(key) != row:
+                rf.set_row(key[0], key[1], row)
+        rf.set_entry(g.entry, g.max_level)
+        prev = cur
+    return prev, g
+
+
+def test_refresher_batches_changes_and_ends_identical_to_a_fresh_mirror():
+    from kektordb_b200 import GpuIndex, Refresher
+    rng = np.random.default_rng(41)
+    n0, n1, dim, m = 1200, 1320, 32, 8
+    X = rng.standard_normal((n1, dim)).astype(np.float32)
+    u = rng.random(n1)
+    oi = O.OracleIndex(dim, O.METRIC_COSINE, m, 60, O.ARITH_KERNEL, n1)
+    oi.build_batched(X[:n0], u[:n0], batch=400, threads=8)
+    g0 = oi.export_graph()
+    gi = GpuIndex(dim, "cosine", m, n1)
+    gi.upload_vectors(1, oi.vectors()[1:])
+    gi.set_graph(g0.n, g0.levels, g0.node_row, g0.row_off, g0.nbrs, g0.entry, g0.max_level)
+    Q = rng.standard_normal((48, dim)).astype(np.float32)
+    before = gi.SearchWithScores(Q, 10, None, 64)
+    rf = Refresher(gi, max_pending_rows=100_000, max_lag_ms=0)       # no clock, no size trigger: flush by call only
+    prev, g = _replay_adds(oi, X, u, n0, 60, rf, _rows(g0))
+    st = rf.stats()
+    assert st.flushes == 0 and st.pending_nodes == 60 and st.pending_rows > 60
+    assert st.rows_queued > st.pending_rows                           # hub rows rewritten repeatedly: last write wins
+    mid = gi.SearchWithScores(Q, 10, None, 64)                        # the mirror is still the old snapshot
+    assert np.array_equal(mid[0], before[0]) and gi.count == n0
+    rf.flush()
+    _same_graph(gi, g)
+    want = oi.search_batch(Q, 10, 64, threads=8)
+    got = gi.SearchWithScores(Q, 10, None, 64)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    st = rf.stats()
+    assert st.flushes == 1 and st.flushes_by_call == 1 and st.nodes_applied == 60 and st.pending_rows == 0
+    # size trigger: a small max_pending_rows flushes on its own while changes stream in
+    rf.close()
+    rf = Refresher(gi, max_pending_rows=64, max_lag_ms=0)
+    prev, g = _replay_adds(oi, X, u, n0 + 60, 60, rf, prev)
+    assert rf.stats().flushes_by_rows >= 2
+    rf.close()                                                        # destroy flushes the rest
+    _same_graph(gi, g)
+    want = oi.search_batch(Q, 10, 64, threads=8)
+    got = gi.SearchWithScores(Q, 10, None, 64)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    gi.close()
+
+
+def test_refresher_lag_bound_deletes_and_removals():
+    import time
+    from kektordb_b200 import GpuIndex, Refresher
+    rng = np.random.default_rng(42)
+    n, dim, m = 1500, 24, 8
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    oi = O.OracleIndex(dim, O.METRIC_L2, m, 60, O.ARITH_KERNEL, n)
+    oi.build_batched(X, rng.random(n), batch=500, threads=8)
+    g = oi.export_graph()
+    gi = GpuIndex(dim, "euclidean", m, n)
+    gi.upload_vectors(1, oi.vectors()[1:])
+    gi.set_graph(g.n, g.levels, g.node_row, g.row_off, g.nbrs, g.entry, g.max_level)
+    Q = rng.standard_normal((40, dim)).astype(np.float32)
+    rf = Refresher(gi, max_pending_rows=1 << 20, max_lag_ms=30)
+    dead = [int(x) for x in rng.choice(np.arange(1, n + 1), 40, replace=False) if int(x) != g.entry]
+    for d in dead:                                                    # Delete = Node.Deleted (hnsw_index.go:2303-2336)
+        oi.delete(d)
+        rf.set_deleted(d)
+    deadline = time.time() + 5
+    while rf.stats().flushes_by_lag == 0 and time.time() < deadline:  # nobody calls flush: the clock does
+        time.sleep(0.01)
+    st = rf.stats()
+    assert st.flushes_by_lag >= 1 and st.last_error == 0
+    want = oi.search_batch(Q, 10, 64, threads=8)
+    got = gi.SearchWithScores(Q, 10, None, 64)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert not np.isin(got[0], dead).any()
+    # Vacuum's physical removal of the same nodes: rows naming them are patched, the nodes become nil
+    rows = _rows(g)
+    for (i, l), r in rows.items():
+        if i not in dead and any(x in dead for x in r):
+            rf.set_row(i, l, [x for x in r if x not in dead])
+    for d in dead:
+        rf.remove_node(d)
+    rf.flush()
+    got2 = gi.SearchWithScores(Q, 10, None, 64)
+    assert not np.isin(got2[0], dead).any() and (got2[2] == 10).all()
+    rf.close()
+    gi.close()
