@@ -138,7 +138,7 @@ def test_stage_chunk_from_the_hosts_own_mmap_page_locks_it_in_place(tmp_path):
     n, dim = 30000, 768                                       # 92 MB of float32 rows: two chunks
     rows = _rows(rng, n, dim, 0)
     d = str(tmp_path / "arena")
-    n_chunks = A.write_arena(d, rows, 0, None)
+    n_chunks = A.write_arena(d, rows, 0, A.sequential_slot_table(n))
     assert n_chunks == 2
     gi = GpuIndex(dim, "euclidean", 4, n)
     maps, staged = [], 0
