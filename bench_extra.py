@@ -98,7 +98,11 @@ def run_flat(args, torch, bench):
         rescored += st.dist_evals
         fallbacks += st.hops
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_one_s = time.perf_counter() - t0
+    # e2e: the same host-buffer calls from two caller threads — the library keeps two flat calls in flight (its own
+    # stream and staging each), so one call's copies and host-side work overlap the other's kernels
+    e2e_s = bench.e2e_threads(torch, local_rank, lambda i: gi.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True),
+                              2, args.warmup, args.steps)
     clocks = sampler.stop()
     pk = _peaks()
     value = B * args.steps / (comp_ms / 1e3)
@@ -126,7 +130,8 @@ def run_flat(args, torch, bench):
                    "pass_a_tile_stride": stride, "host_cores": ncores,
                    "value_is": "device time of every kernel of the call (CUDA events inside the library), copies excluded"},
         "e2e": {"value": round(e2e, 1), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
-                "d2h_bytes_per_step": B * k * 12 + B * 8, "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+                "d2h_bytes_per_step": B * k * 12 + B * 8, "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
+                "calls_in_flight": 2, "one_call_at_a_time": round(B * args.steps / e2e_one_s, 1)},
         "gpu_launches": 8 * args.steps,
         "roofline": {"bound": "tensor", "kernel": "flat_tc_kernel (threshold pass + nomination pass)",
                      "achieved": round(achieved, 1), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

@@ -262,36 +262,80 @@ int stage_allow(kdbgpu_index *h, DevBuf<uint32_t> &dst, const uint64_t *allow, s
 namespace {
 
 // ---- flat scan -------------------------------------------------------------------------------------
-// exhaustive float64 scan (flat.cu); caller holds the handle exclusively
-int flat_scan_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, const uint32_t *d_allow,
-                   uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
-  cudaStream_t s = h->stream;
+// Every flat call runs on one of the handle's two flat workspaces (FlatWs: its own stream, staging and result
+// buffers), under the handle's SHARED lock — so the copies and host-side work of one call overlap the kernels
+// of the next, and flat scans run next to traversals.  Results leave the device through a pinned staging blob
+// (one asynchronous copy per array, one synchronisation) or, for device-resident outputs, device-to-device.
+
+bool is_device_pointer(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// results of `c` queries: device buffers of the workspace -> the caller's arrays (+ per-query flags to `flags`, host)
+int flat_deliver(kdbgpu_index *h, kdbgpu_index::FlatWs &w, uint32_t c, int k, uint32_t *out_ids, double *out_scores,
+                 uint32_t *out_counts, uint32_t *flags, cudaStream_t s) {
+  const size_t nk = (size_t)c * k;
+  if (is_device_pointer(out_ids)) {
+    CUDA_TRY(cudaMemcpyAsync(out_ids, w.out_ids.p, nk * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(out_scores, w.out_scores.p, nk * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts, w.out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    if (flags) CUDA_TRY(cudaMemcpyAsync(flags, w.t_flags.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return KDBGPU_OK;
+  }
+  const size_t o_ids = nk * sizeof(double), o_cnt = o_ids + nk * sizeof(uint32_t), o_flags = o_cnt + (size_t)c * sizeof(uint32_t);
+  const size_t bytes = o_flags + (size_t)c * sizeof(uint32_t);
+  if (w.h_out_bytes < bytes) {
+    if (w.h_out) cudaFreeHost(w.h_out);
+    w.h_out = nullptr;
+    w.h_out_bytes = 0;
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&w.h_out), bytes + bytes / 4, cudaHostAllocDefault));
+    w.h_out_bytes = bytes + bytes / 4;
+  }
+  CUDA_TRY(cudaMemcpyAsync(w.h_out, w.out_scores.p, nk * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(w.h_out + o_ids, w.out_ids.p, nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(w.h_out + o_cnt, w.out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (flags) CUDA_TRY(cudaMemcpyAsync(w.h_out + o_flags, w.t_flags.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  memcpy(out_scores, w.h_out, nk * sizeof(double));
+  memcpy(out_ids, w.h_out + o_ids, nk * sizeof(uint32_t));
+  memcpy(out_counts, w.h_out + o_cnt, (size_t)c * sizeof(uint32_t));
+  if (flags) memcpy(flags, w.h_out + o_flags, (size_t)c * sizeof(uint32_t));
+  (void)h;
+  return KDBGPU_OK;
+}
+
+// exhaustive float64 scan (flat.cu)
+int flat_scan_impl(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *queries, uint32_t nq, int k, int mode,
+                   const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+  cudaStream_t s = w.stream;
   // bound the dist[chunk][n] workspace to ~2 GiB
   uint32_t chunk = (uint32_t)((2ull << 30) / ((size_t)h->n * sizeof(double)));
   if (chunk < 16) chunk = 16;
   chunk &= ~15u;
   if (chunk > nq) chunk = nq;
-  CUDA_TRY(h->q_raw.reserve((size_t)chunk * h->dim));
-  CUDA_TRY(h->q_prep.reserve((size_t)chunk * h->stride));
-  CUDA_TRY(h->out_ids.reserve((size_t)chunk * k));
-  CUDA_TRY(h->out_scores.reserve((size_t)chunk * k));
-  CUDA_TRY(h->out_counts.reserve(chunk));
-  CUDA_TRY(h->flat_dist.reserve((size_t)chunk * h->n));
+  CUDA_TRY(w.q_raw.reserve((size_t)chunk * h->dim));
+  CUDA_TRY(w.q_prep.reserve((size_t)chunk * h->stride));
+  CUDA_TRY(w.out_ids.reserve((size_t)chunk * k));
+  CUDA_TRY(w.out_scores.reserve((size_t)chunk * k));
+  CUDA_TRY(w.out_counts.reserve(chunk));
+  CUDA_TRY(w.flat_dist.reserve((size_t)chunk * h->n));
   DevIndex ix = h->dev();
   for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
     const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
-    CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries + (size_t)q0 * h->dim, (size_t)c * h->dim * sizeof(float),
+    CUDA_TRY(cudaMemcpyAsync(w.q_raw.p, queries + (size_t)q0 * h->dim, (size_t)c * h->dim * sizeof(float),
                              cudaMemcpyDefault, s));
-    CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
+    CUDA_TRY(launch_prep_queries(w.q_raw.p, (size_t)h->dim, w.q_prep.p, c, (uint32_t)h->dim, h->stride,
                                  mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
-    CUDA_TRY(launch_flat_distances(ix, h->q_raw.p, h->q_prep.p, c, mode, h->flat_dist.p, s));
-    CUDA_TRY(launch_flat_select(ix, h->flat_dist.p, c, k, d_allow, h->out_ids.p, h->out_scores.p, h->out_counts.p, s));
-    CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
-                             cudaMemcpyDefault, s));
-    CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
-                             cudaMemcpyDefault, s));
-    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDefault, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(launch_flat_distances(ix, w.q_raw.p, w.q_prep.p, c, mode, w.flat_dist.p, s));
+    CUDA_TRY(launch_flat_select(ix, w.flat_dist.p, c, k, d_allow, w.out_ids.p, w.out_scores.p, w.out_counts.p, s));
+    int rc = flat_deliver(h, w, c, k, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0, nullptr, s);
+    if (rc) return rc;
   }
   return KDBGPU_OK;
 }
@@ -303,8 +347,8 @@ struct TcPlan {
   float alpha;
 };
 
-// bf16 mirror of the rows (lazily), beta for this call's liveness / allow-list
-int tc_prepare(kdbgpu_index *h, int mode, const uint32_t *d_allow, int k, TcPlan *P, cudaStream_t s) {
+// bf16 mirror of the rows (built once, lazily, under tc_mu), beta for this call's liveness / allow-list
+int tc_prepare(kdbgpu_index *h, kdbgpu_index::FlatWs &w, int mode, const uint32_t *d_allow, TcPlan *P, cudaStream_t s) {
   P->bm = flat_tc_bm();
   P->bn = flat_tc_bn();
   P->n_pad = (h->n + P->bn - 1) / P->bn * P->bn;
@@ -312,45 +356,49 @@ int tc_prepare(kdbgpu_index *h, int mode, const uint32_t *d_allow, int k, TcPlan
   P->n_groups = P->n_pad / 32;
   P->use_norm = (mode == 0 || h->metric == KDBGPU_METRIC_L2) ? 1 : 0;
   P->alpha = P->use_norm ? -2.f : -1.f;  // L2: |x|^2 - 2<q,x> (+|q|^2) ; cosine: -<q^,x> (+1)
-  (void)k;
-  if (!h->tc_valid || h->tc_n != h->n) {
-    CUDA_TRY(h->x_bf16.reserve((size_t)P->n_pad * P->dp));
-    CUDA_TRY(h->x_sumsq.reserve(P->n_pad));
-    CUDA_TRY(h->x_resid2.reserve(P->n_pad));
-    CUDA_TRY(h->x_max.reserve(2));
-    CUDA_TRY(launch_to_bf16(h->vecs.p + h->stride, h->stride, h->n, (uint32_t)h->dim, h->x_bf16.p, P->dp, P->n_pad,
-                            h->x_sumsq.p, h->x_resid2.p, s));
-    CUDA_TRY(launch_tc_max(h->x_sumsq.p, h->x_resid2.p, h->n, h->x_max.p, s));
-    h->tc_valid = true;
-    h->tc_n = h->n;
+  {
+    std::lock_guard<std::mutex> tl(h->tc_mu);
+    if (!h->tc_valid || h->tc_n != h->n) {
+      CUDA_TRY(cudaDeviceSynchronize());  // the other flat workspace may still be reading the old mirror
+      CUDA_TRY(h->x_bf16.reserve((size_t)P->n_pad * P->dp));
+      CUDA_TRY(h->x_sumsq.reserve(P->n_pad));
+      CUDA_TRY(h->x_resid2.reserve(P->n_pad));
+      CUDA_TRY(h->x_max.reserve(2));
+      CUDA_TRY(launch_to_bf16(h->vecs.p + h->stride, h->stride, h->n, (uint32_t)h->dim, h->x_bf16.p, P->dp, P->n_pad,
+                              h->x_sumsq.p, h->x_resid2.p, s));
+      CUDA_TRY(launch_tc_max(h->x_sumsq.p, h->x_resid2.p, h->n, h->x_max.p, s));
+      CUDA_TRY(cudaStreamSynchronize(s));  // visible to every stream before tc_valid says so
+      h->tc_valid = true;
+      h->tc_n = h->n;
+    }
   }
-  CUDA_TRY(h->tc_beta.reserve(P->n_pad));
-  CUDA_TRY(launch_tc_beta(h->dev(), h->x_sumsq.p, d_allow, P->use_norm, P->n_pad, h->tc_beta.p, s));
+  CUDA_TRY(w.tc_beta.reserve(P->n_pad));
+  CUDA_TRY(launch_tc_beta(h->dev(), h->x_sumsq.p, d_allow, P->use_norm, P->n_pad, w.tc_beta.p, s));
   return KDBGPU_OK;
 }
 
 // H2D of `c` raw queries, normalisation where the mode asks for it, bf16 copy + norms
-int tc_stage_queries(kdbgpu_index *h, const float *queries, uint32_t c, uint32_t c_pad, int mode, const TcPlan &P,
-                     cudaStream_t s, cudaEvent_t after_h2d = nullptr) {
-  CUDA_TRY(h->q_raw.reserve((size_t)c * h->dim));
-  CUDA_TRY(h->q_prep.reserve((size_t)c * h->stride));
-  CUDA_TRY(h->tq_bf16.reserve((size_t)c_pad * P.dp));
-  CUDA_TRY(h->tq_sumsq.reserve(c_pad));
-  CUDA_TRY(h->tq_resid2.reserve(c_pad));
-  CUDA_TRY(cudaMemcpyAsync(h->q_raw.p, queries, (size_t)c * h->dim * sizeof(float), cudaMemcpyDefault, s));
+int tc_stage_queries(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *queries, uint32_t c, uint32_t c_pad, int mode,
+                     const TcPlan &P, cudaStream_t s, cudaEvent_t after_h2d = nullptr) {
+  CUDA_TRY(w.q_raw.reserve((size_t)c * h->dim));
+  CUDA_TRY(w.q_prep.reserve((size_t)c * h->stride));
+  CUDA_TRY(w.tq_bf16.reserve((size_t)c_pad * P.dp));
+  CUDA_TRY(w.tq_sumsq.reserve(c_pad));
+  CUDA_TRY(w.tq_resid2.reserve(c_pad));
+  CUDA_TRY(cudaMemcpyAsync(w.q_raw.p, queries, (size_t)c * h->dim * sizeof(float), cudaMemcpyDefault, s));
   if (after_h2d) CUDA_TRY(cudaEventRecord(after_h2d, s));
-  CUDA_TRY(launch_prep_queries(h->q_raw.p, (size_t)h->dim, h->q_prep.p, c, (uint32_t)h->dim, h->stride,
+  CUDA_TRY(launch_prep_queries(w.q_raw.p, (size_t)h->dim, w.q_prep.p, c, (uint32_t)h->dim, h->stride,
                                mode == 1 ? h->metric : KDBGPU_METRIC_L2, s));
   const bool prepared = mode == 1 && h->metric == KDBGPU_METRIC_COSINE;
-  CUDA_TRY(launch_to_bf16(prepared ? h->q_prep.p : h->q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim, c,
-                          (uint32_t)h->dim, h->tq_bf16.p, P.dp, c_pad, h->tq_sumsq.p, h->tq_resid2.p, s));
+  CUDA_TRY(launch_to_bf16(prepared ? w.q_prep.p : w.q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim, c,
+                          (uint32_t)h->dim, w.tq_bf16.p, P.dp, c_pad, w.tq_sumsq.p, w.tq_resid2.p, s));
   return KDBGPU_OK;
 }
 
-FlatTcLaunch tc_launch_desc(kdbgpu_index *h, const TcPlan &P, uint32_t c, uint32_t c_pad) {
+FlatTcLaunch tc_launch_desc(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const TcPlan &P, uint32_t c, uint32_t c_pad) {
   FlatTcLaunch L;
   memset(&L, 0, sizeof L);
-  L.q_bf16 = h->tq_bf16.p;
+  L.q_bf16 = w.tq_bf16.p;
   L.x_bf16 = h->x_bf16.p;
   L.nq = c;
   L.nq_pad = c_pad;
@@ -358,18 +406,18 @@ FlatTcLaunch tc_launch_desc(kdbgpu_index *h, const TcPlan &P, uint32_t c, uint32
   L.n_pad = P.n_pad;
   L.dp = P.dp;
   L.alpha = P.alpha;
-  L.beta = h->tc_beta.p;
+  L.beta = w.tc_beta.p;
   const uint64_t tiles = (uint64_t)(c_pad / P.bm) * (P.n_pad / P.bn);
   L.grid = tiles < (uint64_t)h->num_sms ? (int)tiles : h->num_sms;
   return L;
 }
 
-int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, const uint32_t *d_allow,
-                        uint32_t *out_ids, double *out_scores, uint32_t *out_counts, uint64_t *evals,
-                        uint64_t *fallbacks, float *gemm_ms, float *compute_ms) {
-  cudaStream_t s = h->stream;
+int flat_prefilter_impl(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *queries, uint32_t nq, int k, int mode,
+                        const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
+                        uint64_t *evals, uint64_t *fallbacks, float *gemm_ms, float *compute_ms) {
+  cudaStream_t s = w.stream;
   TcPlan P;
-  int rc = tc_prepare(h, mode, d_allow, k, &P, s);
+  int rc = tc_prepare(h, w, mode, d_allow, &P, s);
   if (rc) return rc;
   const uint32_t cap = 2048u;                      // spill slots per query beyond the per-(query, CTA) slots
   const uint32_t sub_slots = flat_tc_sub_slots();
@@ -389,7 +437,7 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     // too few rows for a threshold to exist (or to be worth it): the exhaustive scan answers
     *evals = (uint64_t)nq * h->n;
     *fallbacks = nq;
-    return flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
+    return flat_scan_impl(h, w, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
   }
   // chunk so that gmin[chunk][n_groups] stays within 512 MiB
   uint32_t chunk = (uint32_t)((512ull << 20) / ((size_t)n_groups * sizeof(float)));
@@ -399,43 +447,42 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
   const uint32_t nq_pad = (nq + P.bm - 1) / P.bm * P.bm;
   if (chunk > nq_pad) chunk = nq_pad;
   const uint32_t emit_grid = (uint32_t)h->num_sms;
-  CUDA_TRY(h->t_gmin.reserve((size_t)chunk * n_groups));
-  CUDA_TRY(h->t_theta.reserve(chunk));
-  CUDA_TRY(h->t_bound.reserve(chunk));
-  CUDA_TRY(h->t_thf.reserve(chunk));
-  CUDA_TRY(h->t_cnt.reserve(chunk));
-  CUDA_TRY(h->t_fcnt.reserve(chunk));
-  CUDA_TRY(h->t_flags.reserve(chunk));
-  CUDA_TRY(h->t_sub.reserve((size_t)chunk * emit_grid * sub_slots));
-  CUDA_TRY(h->t_subcnt.reserve((size_t)chunk * emit_grid));
-  CUDA_TRY(h->t_ovf.reserve((size_t)chunk * cap));
-  CUDA_TRY(h->t_fid.reserve((size_t)chunk * fcap));
-  CUDA_TRY(h->t_nres.reserve(1));
-  CUDA_TRY(h->out_ids.reserve((size_t)chunk * k));
-  CUDA_TRY(h->out_scores.reserve((size_t)chunk * k));
-  CUDA_TRY(h->out_counts.reserve(chunk));
-  CUDA_TRY(cudaMemsetAsync(h->t_nres.p, 0, sizeof(unsigned long long), s));
+  CUDA_TRY(w.t_gmin.reserve((size_t)chunk * n_groups));
+  CUDA_TRY(w.t_theta.reserve(chunk));
+  CUDA_TRY(w.t_bound.reserve(chunk));
+  CUDA_TRY(w.t_thf.reserve(chunk));
+  CUDA_TRY(w.t_cnt.reserve(chunk));
+  CUDA_TRY(w.t_fcnt.reserve(chunk));
+  CUDA_TRY(w.t_flags.reserve(chunk));
+  CUDA_TRY(w.t_sub.reserve((size_t)chunk * emit_grid * sub_slots));
+  CUDA_TRY(w.t_subcnt.reserve((size_t)chunk * emit_grid));
+  CUDA_TRY(w.t_ovf.reserve((size_t)chunk * cap));
+  CUDA_TRY(w.t_fid.reserve((size_t)chunk * fcap));
+  CUDA_TRY(w.t_nres.reserve(1));
+  CUDA_TRY(w.out_ids.reserve((size_t)chunk * k));
+  CUDA_TRY(w.out_scores.reserve((size_t)chunk * k));
+  CUDA_TRY(w.out_counts.reserve(chunk));
+  CUDA_TRY(cudaMemsetAsync(w.t_nres.p, 0, sizeof(unsigned long long), s));
   DevIndex ix = h->dev();
   const bool prepared = mode == 1 && h->metric == KDBGPU_METRIC_COSINE;
   std::vector<uint32_t> flags(nq, 0u);
   *gemm_ms = 0.f;
   *compute_ms = 0.f;
-  cudaEvent_t ev_c0 = h->sws[0].ev[0], ev_c1 = h->sws[0].ev[1];  // handle is held exclusively: no search uses them
   for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
     const uint32_t c = nq - q0 < chunk ? nq - q0 : chunk;
     const uint32_t c_pad = (c + P.bm - 1) / P.bm * P.bm;
-    rc = tc_stage_queries(h, queries + (size_t)q0 * h->dim, c, c_pad, mode, P, s, ev_c0);
+    rc = tc_stage_queries(h, w, queries + (size_t)q0 * h->dim, c, c_pad, mode, P, s, w.ev[2]);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(h->t_cnt.p, 0, (size_t)c_pad * sizeof(uint32_t), s));
-    FlatTcLaunch L = tc_launch_desc(h, P, c, c_pad);
-    L.gmin = h->t_gmin.p;
-    L.theta = h->t_theta.p;
-    L.sub = h->t_sub.p;
-    L.sub_cnt = h->t_subcnt.p;
-    L.ovf_cnt = h->t_cnt.p;
-    L.ovf = h->t_ovf.p;
+    CUDA_TRY(cudaMemsetAsync(w.t_cnt.p, 0, (size_t)c_pad * sizeof(uint32_t), s));
+    FlatTcLaunch L = tc_launch_desc(h, w, P, c, c_pad);
+    L.gmin = w.t_gmin.p;
+    L.theta = w.t_theta.p;
+    L.sub = w.t_sub.p;
+    L.sub_cnt = w.t_subcnt.p;
+    L.ovf_cnt = w.t_cnt.p;
+    L.ovf = w.t_ovf.p;
     L.cap = cap;
-    CUDA_TRY(cudaEventRecord(h->ev[1], s));
+    CUDA_TRY(cudaEventRecord(w.ev[3], s));
     L.epi = 1;  // pass A: group minima over the sampled tiles
     L.ct_stride = ct_stride;
     {
@@ -443,35 +490,31 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
       L.grid = tiles < (uint64_t)h->num_sms ? (int)tiles : h->num_sms;
     }
     CUDA_TRY(launch_flat_tc(L, s));
-    CUDA_TRY(launch_tc_threshold(h->t_gmin.p, n_groups, c, k, h->tq_sumsq.p, h->tq_resid2.p, h->x_max.p, P.alpha,
-                                 P.use_norm, P.dp, h->t_theta.p, h->t_bound.p, s));
+    CUDA_TRY(launch_tc_threshold(w.t_gmin.p, n_groups, c, k, w.tq_sumsq.p, w.tq_resid2.p, h->x_max.p, P.alpha,
+                                 P.use_norm, P.dp, w.t_theta.p, w.t_bound.p, s));
     L.epi = 2;  // pass B: ids + scores below theta, every tile
     L.ct_stride = 1;
-    L.grid = tc_launch_desc(h, P, c, c_pad).grid;
+    L.grid = tc_launch_desc(h, w, P, c, c_pad).grid;
     CUDA_TRY(launch_flat_tc(L, s));
     const uint32_t grid_b = (uint32_t)L.grid;
-    CUDA_TRY(cudaEventRecord(h->ev[2], s));
-    CUDA_TRY(launch_tc_refine(h->t_sub.p, h->t_subcnt.p, grid_b, h->t_cnt.p, h->t_ovf.p, cap, c, k, h->t_theta.p,
-                              h->t_bound.p, h->t_fcnt.p, h->t_fid.p, fcap, h->t_thf.p, h->t_flags.p, s));
-    CUDA_TRY(launch_tc_rescore(ix, mode, prepared ? h->q_prep.p : h->q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim,
-                               c, k, h->t_fcnt.p, h->t_fid.p, fcap, h->t_thf.p, h->t_bound.p, h->tq_sumsq.p,
-                               h->out_ids.p, h->out_scores.p, h->out_counts.p, h->t_flags.p, h->t_nres.p, s));
-    CUDA_TRY(cudaEventRecord(ev_c1, s));
-    CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, h->out_ids.p, (size_t)c * k * sizeof(uint32_t),
-                             cudaMemcpyDefault, s));
-    CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, h->out_scores.p, (size_t)c * k * sizeof(double),
-                             cudaMemcpyDefault, s));
-    CUDA_TRY(cudaMemcpyAsync(out_counts + q0, h->out_counts.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDefault, s));
-    CUDA_TRY(cudaMemcpyAsync(flags.data() + q0, h->t_flags.p, (size_t)c * sizeof(uint32_t), cudaMemcpyDefault, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaEventRecord(w.ev[4], s));
+    CUDA_TRY(launch_tc_refine(w.t_sub.p, w.t_subcnt.p, grid_b, w.t_cnt.p, w.t_ovf.p, cap, c, k, w.t_theta.p,
+                              w.t_bound.p, w.t_fcnt.p, w.t_fid.p, fcap, w.t_thf.p, w.t_flags.p, s));
+    CUDA_TRY(launch_tc_rescore(ix, mode, prepared ? w.q_prep.p : w.q_raw.p, prepared ? (size_t)h->stride : (size_t)h->dim,
+                               c, k, w.t_fcnt.p, w.t_fid.p, fcap, w.t_thf.p, w.t_bound.p, w.tq_sumsq.p,
+                               w.out_ids.p, w.out_scores.p, w.out_counts.p, w.t_flags.p, w.t_nres.p, s));
+    CUDA_TRY(cudaEventRecord(w.ev[5], s));
+    rc = flat_deliver(h, w, c, k, out_ids + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0, flags.data() + q0, s);
+    if (rc) return rc;
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&ms, w.ev[3], w.ev[4]);
     *gemm_ms += ms;
-    cudaEventElapsedTime(&ms, ev_c0, ev_c1);
+    cudaEventElapsedTime(&ms, w.ev[2], w.ev[5]);
     *compute_ms += ms;
   }
   unsigned long long nres = 0;
-  CUDA_TRY(cudaMemcpy(&nres, h->t_nres.p, sizeof nres, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpyAsync(&nres, w.t_nres.p, sizeof nres, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
   // queries whose certificate did not close (candidate buffer overflow) take the exhaustive scan
   std::vector<uint32_t> redo;
   for (uint32_t q = 0; q < nq; ++q)
@@ -485,7 +528,7 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
     for (size_t i = 0; i < r; ++i)
       CUDA_TRY(cudaMemcpy(&rq[i * h->dim], queries + (size_t)redo[i] * h->dim, (size_t)h->dim * sizeof(float),
                           cudaMemcpyDefault));
-    rc = flat_scan_impl(h, rq.data(), (uint32_t)r, k, mode, d_allow, rid.data(), rsc.data(), rcnt.data());
+    rc = flat_scan_impl(h, w, rq.data(), (uint32_t)r, k, mode, d_allow, rid.data(), rsc.data(), rcnt.data());
     if (rc) return rc;
     for (size_t i = 0; i < r; ++i) {
       CUDA_TRY(cudaMemcpy(out_ids + (size_t)redo[i] * k, &rid[i * k], (size_t)k * sizeof(uint32_t), cudaMemcpyDefault));
@@ -501,28 +544,47 @@ int flat_prefilter_impl(kdbgpu_index *h, const float *queries, uint32_t nq, int 
 }  // namespace
 
 namespace kdb {
-int flat_search_locked(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, bool prefilter,
-                       const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
-                       kdbgpu_stats *stats) {
-  cudaStream_t s = h->stream;
-  CUDA_TRY(cudaEventRecord(h->ev[0], s));
+int acquire_fws(kdbgpu_index *h) {
+  std::unique_lock<std::mutex> lk(h->fws_mu);
+  for (;;) {
+    for (int i = 0; i < kdbgpu_index::kNumFlatWs; ++i)
+      if (!h->fws[i].busy) {
+        h->fws[i].busy = true;
+        return i;
+      }
+    h->fws_cv.wait(lk);
+  }
+}
+void release_fws(kdbgpu_index *h, int i) {
+  {
+    std::lock_guard<std::mutex> lk(h->fws_mu);
+    h->fws[i].busy = false;
+  }
+  h->fws_cv.notify_one();
+}
+
+int flat_search_ws(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *queries, uint32_t nq, int k, int mode,
+                   bool prefilter, const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
+                   kdbgpu_stats *stats) {
+  cudaStream_t s = w.stream;
+  CUDA_TRY(cudaEventRecord(w.ev[0], s));
   uint64_t evals = 0, fallbacks = 0;
   float gemm_ms = 0.f, compute_ms = 0.f;
   int rc;
   if (prefilter)
-    rc = flat_prefilter_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts, &evals, &fallbacks,
+    rc = flat_prefilter_impl(h, w, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts, &evals, &fallbacks,
                              &gemm_ms, &compute_ms);
   else {
-    rc = flat_scan_impl(h, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
+    rc = flat_scan_impl(h, w, queries, nq, k, mode, d_allow, out_ids, out_scores, out_counts);
     evals = (uint64_t)nq * h->n;
   }
   if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  CUDA_TRY(cudaEventRecord(w.ev[1], s));
   CUDA_TRY(cudaStreamSynchronize(s));
   if (stats) {
     stats->dist_evals = evals;
     stats->hops = fallbacks;
-    cudaEventElapsedTime(&stats->total_ms, h->ev[0], h->ev[3]);
+    cudaEventElapsedTime(&stats->total_ms, w.ev[0], w.ev[1]);
     // pre-filter: kernel_ms = every kernel of the call (no copies); hops_l0 = the two tensor-core
     // passes + threshold alone, in nanoseconds
     stats->kernel_ms = prefilter && compute_ms > 0.f ? compute_ms : stats->total_ms;
@@ -621,6 +683,10 @@ int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&w.ev[i]);
   }
+  for (auto &w : h->fws) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&w.ev[i]);
+  }
   const size_t n1 = (size_t)capacity + 1;
   if (e == cudaSuccess) e = h->vecs.reserve(n1 * h->row_words + 128, true);
   if (e == cudaSuccess && precision == KDBGPU_PRECISION_INT8) e = h->norms.reserve(n1, true);
@@ -692,9 +758,13 @@ int kdbgpu_index_destroy(kdbgpu_index *h) {
   h->b_scratch_ids.release();
   h->b_slot_level.release();
   h->b_scratch_d.release();
-  h->x_bf16.release(); h->tq_bf16.release(); h->x_sumsq.release(); h->x_resid2.release(); h->x_max.release();
-  h->tc_beta.release(); h->tq_sumsq.release(); h->tq_resid2.release(); h->t_gmin.release(); h->t_theta.release();
-  h->t_bound.release(); h->t_fcnt.release(); h->t_fid.release(); h->t_sub.release(); h->t_ovf.release(); h->t_subcnt.release(); h->t_thf.release(); h->t_cnt.release(); h->t_flags.release(); h->t_nres.release();
+  h->x_bf16.release(); h->x_sumsq.release(); h->x_resid2.release(); h->x_max.release();
+  for (auto &w : h->fws) {
+    w.release();
+    for (auto &e : w.ev)
+      if (e) cudaEventDestroy(e);
+    if (w.stream) cudaStreamDestroy(w.stream);
+  }
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1460,28 +1530,34 @@ int kdbgpu_flat_search_batch(kdbgpu_index *h, const float *queries, uint32_t nq,
   const bool prefilter = (mode & KDBGPU_FLAT_PREFILTER) != 0;
   mode &= ~KDBGPU_FLAT_PREFILTER;
   if (mode != 0 && mode != 1) return fail(KDBGPU_ERR_INVALID, "mode %d", mode);
+  std::shared_lock<std::shared_mutex> lk(h->mu);  // two flat calls (and the traversals) may be in flight
   if (!h->has_graph) return fail(KDBGPU_ERR_STATE, "kdbgpu_set_graph has not been called (it defines the live rows)");
-  std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  cudaStream_t s = h->stream;
   if (h->n == 0) {
     memset(out_ids, 0, (size_t)nq * k * sizeof(uint32_t));
     memset(out_scores, 0, (size_t)nq * k * sizeof(double));
     memset(out_counts, 0, (size_t)nq * sizeof(uint32_t));
     return KDBGPU_OK;
   }
+  const int wi = acquire_fws(h);
+  kdbgpu_index::FlatWs &w = h->fws[wi];
+  struct Release {
+    kdbgpu_index *h;
+    int wi;
+    ~Release() { release_fws(h, wi); }
+  } releaser{h, wi};
   // BruteForceIndex treats an empty allow-list as unfiltered (vector_index.go:132)
   const uint32_t *d_allow = nullptr;
   if (allow) {
     bool found = false;
     (void)first_set_bit(allow, allow_words, &found);
     if (found) {
-      int rc = stage_allow(h, h->allow, allow, allow_words, s);
+      int rc = stage_allow(h, w.allow, allow, allow_words, w.stream);
       if (rc) return rc;
-      d_allow = h->allow.p;
+      d_allow = w.allow.p;
     }
   }
-  return flat_search_locked(h, queries, nq, k, mode, prefilter, d_allow, out_ids, out_scores, out_counts, stats);
+  return flat_search_ws(h, w, queries, nq, k, mode, prefilter, d_allow, out_ids, out_scores, out_counts, stats);
 }
 
 int kdbgpu_flat_prefilter_scores(kdbgpu_index *h, const float *queries, uint32_t nq, int mode, float *out_scores,
@@ -1492,34 +1568,41 @@ int kdbgpu_flat_prefilter_scores(kdbgpu_index *h, const float *queries, uint32_t
   if (!h->has_graph || h->n == 0) return fail(KDBGPU_ERR_STATE, "no rows staged");
   if (nq == 0) return KDBGPU_OK;
   if ((uint64_t)nq * h->n > (1ull << 30)) return fail(KDBGPU_ERR_INVALID, "validation hook: nq * n too large");
-  std::unique_lock<std::shared_mutex> lk(h->mu);
+  std::shared_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  cudaStream_t s = h->stream;
+  const int wi = acquire_fws(h);
+  kdbgpu_index::FlatWs &w = h->fws[wi];
+  struct Release {
+    kdbgpu_index *h;
+    int wi;
+    ~Release() { release_fws(h, wi); }
+  } releaser{h, wi};
+  cudaStream_t s = w.stream;
   TcPlan P;
-  int rc = tc_prepare(h, mode, nullptr, 1, &P, s);
+  int rc = tc_prepare(h, w, mode, nullptr, &P, s);
   if (rc) return rc;
   const uint32_t c_pad = (nq + P.bm - 1) / P.bm * P.bm;
-  rc = tc_stage_queries(h, queries, nq, c_pad, mode, P, s);
+  rc = tc_stage_queries(h, w, queries, nq, c_pad, mode, P, s);
   if (rc) return rc;
   DevBuf<float> S;
   CUDA_TRY(S.reserve((size_t)nq * h->n));
-  CUDA_TRY(h->t_gmin.reserve(1));
-  CUDA_TRY(h->t_theta.reserve(c_pad));
-  CUDA_TRY(h->t_bound.reserve(c_pad));
-  FlatTcLaunch L = tc_launch_desc(h, P, nq, c_pad);
+  CUDA_TRY(w.t_gmin.reserve(1));
+  CUDA_TRY(w.t_theta.reserve(c_pad));
+  CUDA_TRY(w.t_bound.reserve(c_pad));
+  FlatTcLaunch L = tc_launch_desc(h, w, P, nq, c_pad);
   L.epi = 0;
   L.S = S.p;
   L.ldS = h->n;
   cudaError_t e = launch_flat_tc(L, s);
   // bound[q] through the threshold kernel on a dummy one-group input
-  if (e == cudaSuccess) e = cudaMemsetAsync(h->t_gmin.p, 0, sizeof(float), s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(w.t_gmin.p, 0, sizeof(float), s);
   if (e == cudaSuccess)
-    e = launch_tc_threshold(h->t_gmin.p, 0, nq, 1, h->tq_sumsq.p, h->tq_resid2.p, h->x_max.p, P.alpha, P.use_norm, P.dp,
-                            h->t_theta.p, h->t_bound.p, s);
+    e = launch_tc_threshold(w.t_gmin.p, 0, nq, 1, w.tq_sumsq.p, w.tq_resid2.p, h->x_max.p, P.alpha, P.use_norm, P.dp,
+                            w.t_theta.p, w.t_bound.p, s);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(out_scores, S.p, (size_t)nq * h->n * sizeof(float), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess && out_bound)
-    e = cudaMemcpyAsync(out_bound, h->t_bound.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, s);
+    e = cudaMemcpyAsync(out_bound, w.t_bound.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   S.release();
   CUDA_TRY(e);
@@ -1576,7 +1659,8 @@ uint64_t kdbgpu_index_device_bytes(const kdbgpu_index *h) {
   return h->vecs.bytes() + h->norms.bytes() + h->adj0.bytes() + h->upper_adj.bytes() + h->upper_first.bytes() +
          h->upper_node.bytes() + h->upper_level.bytes() + h->deleted.bytes() + h->levels.bytes() + h->visited.bytes() +
          h->cand_overflow.bytes() + ws + h->flat_dist.bytes() + h->q_raw.bytes() + h->q_prep.bytes() + h->out_ids.bytes() +
-         h->out_scores.bytes() + h->allow.bytes() + h->x_bf16.bytes() + h->conv_tmp.bytes();
+         h->out_scores.bytes() + h->allow.bytes() + h->x_bf16.bytes() + h->conv_tmp.bytes() + h->fws[0].bytes() +
+         h->fws[1].bytes();
 }
 int kdbgpu_search_concurrency(kdbgpu_index *h, int k, int ef_search) {
   if (!h) return 0;

@@ -102,6 +102,39 @@ struct kdbgpu_index {
       stats.release(); err_flag.release();
     }
   };
+  // one flat-scan call in flight: its own stream, staging and result buffers (two of them, so that the copies and the
+  // host-side work of one call overlap the kernels of the next)
+  struct FlatWs {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool busy = false;
+    DevBuf<float> q_raw, q_prep, tq_sumsq, tq_resid2, tc_beta, t_gmin, t_theta, t_bound, t_thf;
+    DevBuf<uint16_t> tq_bf16;
+    DevBuf<uint32_t> out_ids, out_counts, allow, t_cnt, t_subcnt, t_flags, t_fcnt, t_fid;
+    DevBuf<double> out_scores, flat_dist;
+    DevBuf<uint2> t_sub, t_ovf;
+    DevBuf<unsigned long long> t_nres;
+    unsigned char *h_out = nullptr;  // pinned staging of one chunk's results
+    size_t h_out_bytes = 0;
+    void release() {
+      if (h_out) cudaFreeHost(h_out);
+      h_out = nullptr;
+      h_out_bytes = 0;
+      q_raw.release(); q_prep.release(); tq_sumsq.release(); tq_resid2.release(); tc_beta.release(); t_gmin.release();
+      t_theta.release(); t_bound.release(); t_thf.release(); tq_bf16.release(); out_ids.release(); out_counts.release();
+      allow.release(); t_cnt.release(); t_subcnt.release(); t_flags.release(); t_fcnt.release(); t_fid.release();
+      out_scores.release(); flat_dist.release(); t_sub.release(); t_ovf.release(); t_nres.release();
+    }
+    size_t bytes() const {
+      return q_raw.bytes() + q_prep.bytes() + tq_bf16.bytes() + tc_beta.bytes() + t_gmin.bytes() + t_sub.bytes() +
+             t_ovf.bytes() + t_fid.bytes() + out_ids.bytes() + out_scores.bytes() + flat_dist.bytes() + allow.bytes();
+    }
+  };
+  static constexpr int kNumFlatWs = 2;
+  FlatWs fws[kNumFlatWs];
+  std::mutex fws_mu;
+  std::condition_variable fws_cv;
+  std::mutex tc_mu;  // the lazy build of the bf16 mirror
   static constexpr int kNumSearchWs = 4;
   SearchWs sws[kNumSearchWs];
   std::mutex ws_mu;
@@ -135,12 +168,8 @@ struct kdbgpu_index {
   DevBuf<uint8_t> b_slot_level;
   DevBuf<double> b_scratch_d;
   // tensor-core flat pre-filter: bf16 mirror of the rows (built lazily, dropped when rows change)
-  DevBuf<uint16_t> x_bf16, tq_bf16;
-  DevBuf<float> x_sumsq, x_resid2, x_max, tc_beta, tq_sumsq, tq_resid2, t_gmin, t_theta, t_bound;
-  DevBuf<uint32_t> t_cnt, t_subcnt, t_flags, t_fcnt, t_fid;
-  DevBuf<uint2> t_sub, t_ovf;
-  DevBuf<float> t_thf;
-  DevBuf<unsigned long long> t_nres;
+  DevBuf<uint16_t> x_bf16;
+  DevBuf<float> x_sumsq, x_resid2, x_max;
   bool tc_valid = false;
   uint32_t tc_n = 0;
   uint64_t arena_chunks_registered = 0;  // kdbgpu_arena_stage_chunk calls that page-locked the caller's mapping in place
@@ -203,10 +232,12 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
 uint32_t first_set_bit(const uint64_t *bits, size_t words, bool *found);
 int stage_allow(kdbgpu_index *h, DevBuf<uint32_t> &dst, const uint64_t *allow, size_t allow_words,
                 cudaStream_t stream);
-// flat scan (exhaustive or tensor-core pre-filter) on the handle's own stream; `queries` and the outputs may be
-// host or device pointers (copies use cudaMemcpyDefault).  Caller holds h->mu exclusively.
-int flat_search_locked(kdbgpu_index *h, const float *queries, uint32_t nq, int k, int mode, bool prefilter,
-                       const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
-                       kdbgpu_stats *stats);
+// flat scan (exhaustive or tensor-core pre-filter) on flat workspace `w` (acquire_fws / release_fws); `queries` and the
+// outputs may be host or device pointers.  Caller holds h->mu shared.  Synchronises w.stream before returning.
+int acquire_fws(kdbgpu_index *h);
+void release_fws(kdbgpu_index *h, int i);
+int flat_search_ws(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *queries, uint32_t nq, int k, int mode,
+                   bool prefilter, const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
+                   kdbgpu_stats *stats);
 
 }  // namespace kdb

@@ -690,11 +690,18 @@ int kdbgpu_shard_flat_search_batch(kdbgpu_shard_group *g, const float *queries, 
     kdbgpu_index *h = mb.h;
     DeviceGuard dm(mb.device);
     if (h->precision != KDBGPU_PRECISION_F32) return set_error(KDBGPU_ERR_INVALID, "the flat scan exists for float32 indexes only");
+    std::shared_lock<std::shared_mutex> hl(h->mu);
     if (!h->has_graph) return set_error(KDBGPU_ERR_STATE, "shard %d: no rows staged", shard_index(g, m));
-    std::unique_lock<std::shared_mutex> hl(h->mu);
+    const int wi = acquire_fws(h);
+    kdbgpu_index::FlatWs &w = h->fws[wi];
+    struct Release {
+      kdbgpu_index *h;
+      int wi;
+      ~Release() { release_fws(h, wi); }
+    } releaser{h, wi};
     CUDA_TRY(s.send[m].reserve(s.L.bytes));
     unsigned char *blob = s.send[m].p;
-    cudaStream_t st = h->stream;
+    cudaStream_t st = w.stream;
     CUDA_TRY(cudaEventRecord(s.ev_m0[m], st));
     CUDA_TRY(cudaMemsetAsync(blob, 0, s.L.bytes, st));
     kdbgpu_stats fs;
@@ -705,14 +712,14 @@ int kdbgpu_shard_flat_search_batch(kdbgpu_shard_group *g, const float *queries, 
         const size_t g32 = allow_words * 2;
         const size_t need32 = ((size_t)h->capacity + 1 + 31) / 32 + 2;
         CUDA_TRY(s.allow_g[m].reserve(g32));
-        CUDA_TRY(h->allow.reserve(need32));
+        CUDA_TRY(w.allow.reserve(need32));
         CUDA_TRY(cudaMemcpyAsync(s.allow_g[m].p, allow, g32 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(launch_slice_bits(s.allow_g[m].p, g32, mb.id_base, h->allow.p, need32, st));
-        d_allow = h->allow.p;
+        CUDA_TRY(launch_slice_bits(s.allow_g[m].p, g32, mb.id_base, w.allow.p, need32, st));
+        d_allow = w.allow.p;
       }
-      int frc = flat_search_locked(h, queries, nq, k, fmode, prefilter, d_allow, reinterpret_cast<uint32_t *>(blob + s.L.o_ids),
-                                   reinterpret_cast<double *>(blob + s.L.o_scores),
-                                   reinterpret_cast<uint32_t *>(blob + s.L.o_counts), &fs);
+      int frc = flat_search_ws(h, w, queries, nq, k, fmode, prefilter, d_allow, reinterpret_cast<uint32_t *>(blob + s.L.o_ids),
+                               reinterpret_cast<double *>(blob + s.L.o_scores),
+                               reinterpret_cast<uint32_t *>(blob + s.L.o_counts), &fs);
       if (frc) return frc;
       CUDA_TRY(launch_add_id_base(reinterpret_cast<uint32_t *>(blob + s.L.o_ids), (size_t)nq * k, mb.id_base, st));
       const unsigned long long evals = fs.dist_evals;
@@ -727,6 +734,8 @@ int kdbgpu_shard_flat_search_batch(kdbgpu_shard_group *g, const float *queries, 
         CUDA_TRY(cudaMemcpyPeerAsync(dst, g->merge_device, blob, mb.device, s.L.bytes, st));
     }
     CUDA_TRY(cudaEventRecord(s.ev_m2[m], st));
+    // the workspace goes back to the pool when this returns: its stream must be drained first
+    CUDA_TRY(cudaStreamSynchronize(st));
     return KDBGPU_OK;
   };
   if (rc == KDBGPU_OK) {
