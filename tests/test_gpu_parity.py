@@ -178,7 +178,10 @@ def test_reference_order_agreement_at_benchmark_shape_100k_x_768():
     gi = GpuIndex(dim, "cosine", m, n)
     u = np.random.default_rng(1).random(n)
     pos = 0
-    for b in (200, 200, 400, 800, 1600, 3200, 6400, 12800, 16384, 16384, 16384, 16384, 8448):
+    sched = [efc]                      # AddBatch call sizes: never more rows than the index already holds
+    while sum(sched) < n:
+        sched.append(min(16384, sum(sched), n - sum(sched)))
+    for b in sched:
         gi.AddBatch(X[pos:pos + b], u[pos:pos + b], efc)
         pos += b
     assert pos == n
