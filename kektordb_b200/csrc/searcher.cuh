@@ -40,6 +40,7 @@ struct SmemPtrs {
   uint32_t *eval_id;
   uint32_t *eval_del;
   float *eval_norm;  // int8: stored norm of every neighbour to evaluate (quantizedNorms[id])
+  int *eval_thr;     // int8: dot <= eval_thr[j] proves "not admitted" without the float64 divide (see collect_neighbours)
   uint32_t *marked;
   Ctl *ctl;
 };
@@ -67,6 +68,8 @@ __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots
   off += (size_t)dm * sizeof(uint32_t);
   const size_t o_evalnorm = off;
   off += (size_t)dm * sizeof(float);
+  const size_t o_evalthr = off;
+  off += (size_t)dm * sizeof(int);
   const size_t o_marked = off;
   off += (size_t)kMarkCap * sizeof(uint32_t);
   const size_t o_ctl = off;
@@ -81,6 +84,7 @@ __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots
     p->eval_id = reinterpret_cast<uint32_t *>(base + o_evalid);
     p->eval_del = reinterpret_cast<uint32_t *>(base + o_evaldel);
     p->eval_norm = reinterpret_cast<float *>(base + o_evalnorm);
+    p->eval_thr = reinterpret_cast<int *>(base + o_evalthr);
     p->marked = reinterpret_cast<uint32_t *>(base + o_marked);
     p->ctl = reinterpret_cast<Ctl *>(base + o_ctl);
   }
@@ -315,17 +319,8 @@ struct Searcher {
   __device__ __forceinline__ void heap_update(float s, uint32_t j, int ef) {
     HeapEntry e;
     if (METRIC == KIND_COS_I8) {
-      // Once the result heap is full most neighbours are turned away (:2577).  That verdict does not
-      // need the float64 divide: with P = qNorm * storedNorm > 0 and w = the worst kept distance,
-      //   dot <= ((1 - w) - 1e-12) * P   ==>   1 - dot / P >= w + 1e-12   ==>   the reference's rounded
-      // distance (three roundings, <= 1e-15 off; the clamp only ever yields 2 >= w) is >= w: not admitted.
-      const float sn = sm.eval_norm[j];
-      if (res.n >= ef && sn != 0.f) {
-        const double P = __dmul_rn(static_cast<double>(qnorm), static_cast<double>(sn));
-        const double t = __dmul_rn(__dsub_rn(__dsub_rn(1.0, worst), 1e-12), P);
-        if (static_cast<double>(__float_as_int(s)) <= t) return;
-      }
-      e.d = int8_distance(__float_as_int(s), qnorm, sn);
+      if (__float_as_int(s) <= sm.eval_thr[j]) return;  // certainly not admitted (collect_neighbours)
+      e.d = int8_distance(__float_as_int(s), qnorm, sm.eval_norm[j]);
     } else {
       e.d = to_distance<METRIC>(s);
     }
@@ -367,8 +362,16 @@ struct Searcher {
   }
 
   // Phase B of a hop: the adjacency row of `cur` -> the ordered list of neighbours to evaluate
-  // (sm.eval_id / eval_del / eval_norm).  Returns their number (on every lane).
-  __device__ __forceinline__ uint32_t collect_neighbours(uint32_t cur, int level, bool log_marks, bool &expand) {
+  // (sm.eval_id / eval_del / eval_norm / eval_thr).  Returns their number (on every lane).
+  // full / worst_now (uniform): the result queue is full and its worst kept distance, as of the start of the hop.
+  // int8 only: with P = qNorm * storedNorm > 0 and w = the worst kept distance,
+  //   dot <= ((1 - w) - 1e-12) * P   ==>   1 - dot / P >= w + 1e-12   ==>   the reference's rounded distance (three
+  // roundings, <= 1e-15 off; the clamp only ever yields 2 >= w) is >= w: not admitted (:2577).  The bound is turned
+  // into an integer threshold per neighbour HERE, one lane per neighbour, so that the per-evaluation test is one
+  // integer compare.  w only decreases during the hop, so a threshold from the start of the hop rejects less than it
+  // could, never more: whatever passes it takes the exact float64 path.
+  __device__ __forceinline__ uint32_t collect_neighbours(uint32_t cur, int level, bool log_marks, bool &expand, bool full,
+                                                         double worst_now) {
     uint32_t n_eval = 0;
     // "level >= len(currentNode.Connections)" -> continue (:2521-2524)
     expand = (level == 0) || (ix.levels[cur] >= level);
@@ -382,6 +385,7 @@ struct Searcher {
         deg = ix.degu;
         row = ix.upper_adj + ((size_t)ix.upper_first[cur] + (uint32_t)(level - 1)) * deg;
       }
+      const double wmargin = __dsub_rn(__dsub_rn(1.0, worst_now), 1e-12);
       for (uint32_t base = 0; base < deg; base += 32) {  // :2537
         const uint32_t idx = base + lane;
         const uint32_t id = idx < deg ? row[idx] : 0u;  // plain load: build kernels mutate rows
@@ -391,8 +395,17 @@ struct Searcher {
         const uint32_t same = __match_any_sync(0xffffffffu, id);
         const bool leader = act && ((__ffs(same) - 1) == lane);
         // nodes[neighborID] == nil is tested at search time (:2553-2561): a row the host has not re-patched yet
-        // may still name a node Vacuum removed.  Loaded before the atomic so that the two latencies overlap.
-        const bool is_node = leader && id <= ix.n && ix.levels[id] >= 0;
+        // may still name a node Vacuum removed.  This load, the int8 norm and the deleted bit do not depend on the
+        // visited test: they are issued BEFORE the atomic so that all the latencies overlap.
+        const bool in_range = leader && id <= ix.n;
+        int8_t lvl = -1;
+        float sn = 0.f;
+        uint32_t del = 0u;
+        if (in_range) {
+          lvl = ix.levels[id];
+          if (METRIC == KIND_COS_I8) sn = ix.norms[id];
+          if (ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
+        }
         bool fresh = false;
         if (leader) {
           const uint32_t bit = 1u << (id & 31);
@@ -410,16 +423,20 @@ struct Searcher {
           if (lane == 0) sm.ctl->n_marked = m0 + __popc(fm);
           __syncwarp();
         }
-        // allow-list before any distance work (:2545-2549)
-        const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id)) && is_node;
-        uint32_t del = 0u;
-        if (keep && ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
+        // allow-list before any distance work (:2545-2549), then the nil test (:2553-2561)
+        const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id)) && lvl >= 0;
         const uint32_t km = __ballot_sync(0xffffffffu, keep);
         if (keep) {
           const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
           sm.eval_id[pos] = id;
           sm.eval_del[pos] = del;
-          if (METRIC == KIND_COS_I8) sm.eval_norm[pos] = ix.norms[id];
+          if (METRIC == KIND_COS_I8) {
+            sm.eval_norm[pos] = sn;
+            int thr = (int)0x80000000;  // nothing is rejected without the exact test
+            if (full && sn != 0.f)
+              thr = __double2int_rd(__dmul_rn(wmargin, __dmul_rn(static_cast<double>(qnorm), static_cast<double>(sn))));
+            sm.eval_thr[pos] = thr;
+          }
         }
         n_eval += __popc(km);
       }
@@ -472,7 +489,13 @@ struct Searcher {
       if (cur == 0xffffffffu) break;
       // ---- B: adjacency row -> ordered list of neighbours to evaluate
       bool expand;
-      const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand);
+      bool full = false;
+      double worst_now = 0.0;
+      if (METRIC == KIND_COS_I8) {  // the cheap-reject thresholds need the result queue's state on every lane
+        full = __shfl_sync(0xffffffffu, res.n >= ef ? 1 : 0, 0) != 0;
+        worst_now = __shfl_sync(0xffffffffu, worst, 0);
+      }
+      const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand, full, worst_now);
       // ---- C + D: stream the rows, two per iteration (independent reductions interleave), and
       // apply each heap update as soon as its distance exists
       if (lane == 0) {
@@ -485,24 +508,30 @@ struct Searcher {
         if (two) wait_slot(j + 1);
         float sa = lane_partial(j);  // :2566
         float sb = two ? lane_partial(j + 1) : 0.f;
+        // The first step of the reduction reads every lane's partial: once it has executed, every lane's reads of
+        // the two slots have returned, and the slots can be refilled — BEFORE the rest of the reduction and the
+        // heap updates, so that the next rows are in flight that much earlier.  (No proxy fence: the slot was only
+        // READ through the generic proxy; the bulk copy's completion is observed through the mbarrier.)
         if (METRIC == KIND_COS_I8) {
           sa = warp_sum<METRIC>(sa);
           sb = warp_sum<METRIC>(sb);
         } else {
+          sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, 16));
+          sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, 16));
+        }
+        __syncwarp();
+        if (lane == 0 && j + SLOTS < n_eval) {
+          issue_row(j + SLOTS, sm.eval_id[j + SLOTS]);
+          if (j + 1 + SLOTS < n_eval) issue_row(j + 1 + SLOTS, sm.eval_id[j + 1 + SLOTS]);
+        }
+        if (METRIC != KIND_COS_I8) {
 #pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) {
+          for (int o = 8; o >= 1; o >>= 1) {
             sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
             sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
           }
         }
-        __syncwarp();  // all lanes are done reading both slots
         if (lane == 0) {
-          // refill the slots first: keeps SLOTS rows in flight while the heaps are updated
-          if (j + SLOTS < n_eval) {
-            fence_proxy_async();  // generic-proxy reads of the slots precede the async-proxy overwrite
-            issue_row(j + SLOTS, sm.eval_id[j + SLOTS]);
-            if (j + 1 + SLOTS < n_eval) issue_row(j + 1 + SLOTS, sm.eval_id[j + 1 + SLOTS]);
-          }
           heap_update(sa, j, ef);
           if (two) heap_update(sb, j + 1, ef);
         }
@@ -619,13 +648,8 @@ struct Searcher {
   __device__ __forceinline__ void list_update(float s, uint32_t j, int ef) {
     double d;
     if (METRIC == KIND_COS_I8) {
-      const float sn = sm.eval_norm[j];
-      if (ln >= ef && sn != 0.f) {  // certain reject without the float64 divide (see heap_update)
-        const double P = __dmul_rn(static_cast<double>(qnorm), static_cast<double>(sn));
-        const double t = __dmul_rn(__dsub_rn(__dsub_rn(1.0, worst), 1e-12), P);
-        if (static_cast<double>(__float_as_int(s)) <= t) return;
-      }
-      d = int8_distance(__float_as_int(s), qnorm, sn);
+      if (__float_as_int(s) <= sm.eval_thr[j]) return;  // certainly not admitted (collect_neighbours)
+      d = int8_distance(__float_as_int(s), qnorm, sm.eval_norm[j]);
     } else {
       d = to_distance<METRIC>(s);
     }
@@ -667,7 +691,7 @@ struct Searcher {
       const uint32_t cur = tie ? 0xffffffffu : sl_pop_nearest();  // :2496-2506
       if (cur == 0xffffffffu) break;
       bool expand;
-      const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand);
+      const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand, ln >= ef, worst);
       if (lane == 0) {
         const uint32_t pro = n_eval < (uint32_t)SLOTS ? n_eval : (uint32_t)SLOTS;
         for (uint32_t j = 0; j < pro; ++j) issue_row(j, sm.eval_id[j]);
@@ -678,21 +702,24 @@ struct Searcher {
         if (two) wait_slot(j + 1);
         float sa = lane_partial(j);
         float sb = two ? lane_partial(j + 1) : 0.f;
-        if (METRIC == KIND_COS_I8) {
+        if (METRIC == KIND_COS_I8) {  // refill after the first reduction step, as in search_layer
           sa = warp_sum<METRIC>(sa);
           sb = warp_sum<METRIC>(sb);
         } else {
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) {
-            sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
-            sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
-          }
+          sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, 16));
+          sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, 16));
         }
         __syncwarp();
         if (lane == 0 && j + SLOTS < n_eval) {
-          fence_proxy_async();
           issue_row(j + SLOTS, sm.eval_id[j + SLOTS]);
           if (j + 1 + SLOTS < n_eval) issue_row(j + 1 + SLOTS, sm.eval_id[j + 1 + SLOTS]);
+        }
+        if (METRIC != KIND_COS_I8) {
+#pragma unroll
+          for (int o = 8; o >= 1; o >>= 1) {
+            sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
+            sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
+          }
         }
         list_update(sa, j, ef);
         if (two) list_update(sb, j + 1, ef);
