@@ -232,7 +232,7 @@ bool search_slots_supported(int slots) { return slots == 2 || slots == 4 || slot
 
 size_t search_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t) {
   return smem_layout(ix.stride, ef, t.slots, (uint32_t)t.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
-                     cpl_of(ix) == 0, nullptr, nullptr);
+                     cpl_of(ix) == 0, ix.kind, nullptr, nullptr);
 }
 
 int search_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
@@ -256,7 +256,7 @@ cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchT
 // hand_over: no heap arrays (ties go to the heap kernel); otherwise the heap kernel's own carve-up
 static size_t search_fast_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t, bool hand_over) {
   return smem_layout(ix.stride, hand_over ? 0 : ef, 4, hand_over ? 0u : (uint32_t)t.cand_smem,
-                     ix.deg0 > ix.degu ? ix.deg0 : ix.degu, cpl_of(ix) == 0, nullptr, nullptr);
+                     ix.deg0 > ix.degu ? ix.deg0 : ix.degu, cpl_of(ix) == 0, ix.kind, nullptr, nullptr);
 }
 bool search_fast_hands_over(const DevIndex &ix) { return ix.kind == KIND_COS_I8; }
 

@@ -48,8 +48,9 @@ struct SmemPtrs {
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // shared-memory carve-up of one warp-CTA, identical on host (sizing) and device (pointers)
+// kind = the index's distance kind: only int8 rows need the per-neighbour norm / threshold lists
 __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots, uint32_t cand_smem, uint32_t deg_max,
-                                              bool q_in_smem, unsigned char *base, SmemPtrs *p) {
+                                              bool q_in_smem, int kind, unsigned char *base, SmemPtrs *p) {
   const uint32_t dm = (deg_max + 31u) & ~31u;
   size_t off = 0;
   const size_t o_slots = off;
@@ -67,9 +68,9 @@ __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots
   const size_t o_evaldel = off;
   off += (size_t)dm * sizeof(uint32_t);
   const size_t o_evalnorm = off;
-  off += (size_t)dm * sizeof(float);
+  if (kind == KIND_COS_I8) off += (size_t)dm * sizeof(float);
   const size_t o_evalthr = off;
-  off += (size_t)dm * sizeof(int);
+  if (kind == KIND_COS_I8) off += (size_t)dm * sizeof(int);
   const size_t o_marked = off;
   off += (size_t)kMarkCap * sizeof(uint32_t);
   const size_t o_ctl = off;
@@ -224,7 +225,7 @@ struct Searcher {
   __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem, bool heaps_in_smem = true)
       : ix(ix_), a(a_), lane(threadIdx.x & 31), phase_bits(0), st_e(0), st_h(0), st_h0(0), overflow(false), qnorm(1.f), lexp(0), ln(0), tie(false) {
     smem_layout(ix.stride, heaps_in_smem ? a.ef : 0, SLOTS, heaps_in_smem ? a.cand_smem : 0u,
-                ix.deg0 > ix.degu ? ix.deg0 : ix.degu, CPL == 0, smem, &sm);
+                ix.deg0 > ix.degu ? ix.deg0 : ix.degu, CPL == 0, METRIC, smem, &sm);
     vis = a.visited + (size_t)blockIdx.x * a.vis_words;
     cand.s = sm.cand;
     cand.g = a.cand_overflow + (size_t)blockIdx.x * a.ovf_cap;
