@@ -45,6 +45,7 @@ struct TcArgs {
   uint32_t nq_tiles, n_ctiles, k_blocks;  // n_ctiles = corpus tiles this launch visits
   uint32_t ct_stride;                     // visited tile i is corpus tile i * ct_stride (pass A samples)
   uint32_t nq, n;
+  uint32_t nq_rows;  // rows the per-query arrays (theta, gmin, sub_cnt) hold (pair kernel: tiles may run past them)
   float alpha;
   const float *beta;  // [n_ctiles * BN], +inf = row excluded (padding, nil, deleted, not allowed)
   float *S;           // EPI_STORE: [nq_tiles*BM][ldS]
@@ -307,6 +308,273 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 
+// =====================================================================================================
+// The same GEMM on CTA PAIRS (tcgen05 cta_group::2): two CTAs of one cluster (same TPC) compute a 256-query x
+// 256-row tile together.  Each CTA stages its own 128 query rows (A) and only HALF of the corpus tile (B, 128
+// rows): the tensor core of the leader reads both halves, so the bytes per MMA that go L2 -> shared memory and
+// shared memory -> tensor core drop by a third, a stage shrinks from 48 KB to 32 KB and the ring grows from 4 to
+// 6 stages — 1.5x the prefetch distance in MMA time, which is what the single-CTA kernel lacked (tensor pipe 69 %
+// active with neither L2 nor the crossbar above 52 %, profiles/README.md).
+//   rank 0 (leader)  issues every tcgen05.mma.cta_group::2; its `full` barriers collect the bytes of BOTH CTAs'
+//                    TMA loads (.cta_group::2 loads signal the leader's barrier)
+//   both ranks       TMA producer for their own A rows + B half; epilogue over their own 128 TMEM lanes
+//   barriers         full[s]       leader only, 2 arrivals (leader's expect_tx + the peer's remote arrive)
+//                    empty[s]      per CTA, signalled by the leader's commit (multicast to both CTAs)
+//                    tmem_full[a]  per CTA, signalled by the leader's commit (multicast)
+//                    tmem_empty[a] leader only, 8 arrivals: the four epilogue warps of both CTAs (remote arrive)
+constexpr int STAGES2 = 6;
+constexpr uint32_t B2_BYTES = B_BYTES / 2;
+constexpr uint32_t STAGE2_BYTES = A_BYTES + B2_BYTES;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *tm, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {  // arrives on this barrier in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// instruction descriptor of the pair: D = f32, A = B = bf16, both K-major, N = 256, M = 256 (128 per CTA)
+__device__ __forceinline__ uint32_t make_idesc_pair() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+}
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    flat_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmXh, const TcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *tiles = smem;  // [STAGES2][A | B half], every tile 1024-byte aligned (SWIZZLE_128B atom)
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES2 * STAGE2_BYTES);
+  uint64_t *empty = full + STAGES2;
+  uint64_t *tmem_full = empty + STAGES2;
+  uint64_t *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *s_beta = reinterpret_cast<float *>(tmem_ptr + 4);          // [2][BN]
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_beta + 2 * BN);  // [nq_tiles * 2 * BM], EPI_EMIT only
+  const uint32_t q_rows = a.nq_tiles * 2u * BM;                     // a.nq_tiles = 256-query tile pairs here
+  if (EPI == EPI_EMIT)
+    for (uint32_t i = threadIdx.x; i < q_rows; i += TC_THREADS) s_cnt[i] = 0u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0u;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXh) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES2; ++i) {
+        mbar_init(&full[i], 2);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], 8);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t total_tiles = a.nq_tiles * a.n_ctiles;
+  const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs): own A rows + own half of B =====
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const uint32_t ct = (tile / a.nq_tiles) * a.ct_stride, qt = tile % a.nq_tiles;
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          const uint32_t leader_full = mapa_u32(smem_u32(&full[stage]), 0u);
+          if (leader)
+            mbar_expect_tx(&full[stage], 2u * STAGE2_BYTES);
+          else
+            mbar_arrive_cluster(leader_full);
+          unsigned char *sa = tiles + (size_t)stage * STAGE2_BYTES;
+          tma_load_2d_pair(sa, &tmQ, (int)(kb * BK), (int)(qt * 2u * BM + rank * BM), leader_full);
+          tma_load_2d_pair(sa + A_BYTES, &tmXh, (int)(kb * BK), (int)(ct * BN + rank * (BN / 2)), leader_full);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {  // ===== MMA issuer: the leader CTA only =====
+      const uint32_t idesc = make_idesc_pair();
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);  // BOTH epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);  // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          const unsigned char *sa = tiles + (size_t)stage * STAGE2_BYTES;
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | (uint32_t)k) != 0u);
+          tc_commit_pair(&empty[stage]);  // frees the stage in both CTAs once these MMAs retire
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit_pair(&tmem_full[acc]);  // accumulator complete -> both epilogues
+        acc ^= 1u;
+        if (acc == 0u) acc_phase ^= 1u;
+      }
+    }
+  } else {  // ===== epilogue warps 2..5 (both CTAs, each over its own 128 queries) =====
+    const uint32_t quarter = (uint32_t)warp & 3u;
+    const uint32_t et = (uint32_t)(threadIdx.x - 64);
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const uint32_t cti = tile / a.nq_tiles, qt = tile % a.nq_tiles;
+      const uint32_t ct = cti * a.ct_stride;
+      const uint32_t q = qt * 2u * BM + rank * BM + quarter * 32u + (uint32_t)lane;
+      const bool q_ok = q < a.nq_rows;  // rows the caller's per-query arrays hold
+      float *sb = s_beta + acc * BN;
+      sb[et] = a.beta[(size_t)ct * BN + et];
+      sb[et + 128] = a.beta[(size_t)ct * BN + et + 128];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      float theta = 0.f;
+      uint32_t my_cnt = 0u, my_cnt0 = 0u;
+      if (EPI == EPI_EMIT) {
+        theta = q_ok ? a.theta[q] : 0.f;
+        my_cnt = my_cnt0 = s_cnt[q];
+      }
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        float sc[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4 *>(sb + c0 + 4 * j4);
+          sc[4 * j4 + 0] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 0]), b4.x);
+          sc[4 * j4 + 1] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 1]), b4.y);
+          sc[4 * j4 + 2] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 2]), b4.z);
+          sc[4 * j4 + 3] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 3]), b4.w);
+        }
+        if (EPI == EPI_STORE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t col = ct * BN + c0 + (uint32_t)j;
+            if (q < a.nq && col < a.n) a.S[(size_t)q * a.ldS + col] = sc[j];
+          }
+        } else {
+          float m[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = fminf(sc[j], sc[j + 16]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = fminf(m[j], m[j + 8]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = fminf(m[j], m[j + 4]);
+          const float best = fminf(fminf(m[0], m[1]), fminf(m[2], m[3]));
+          if (EPI == EPI_GROUPMIN) {
+            if (q_ok)
+              a.gmin[(size_t)q * ((size_t)a.n_ctiles * GROUPS_PER_TILE) + (size_t)cti * GROUPS_PER_TILE + c0 / GROUP] = best;
+          } else if (best < theta && q < a.nq) {
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mask |= (sc[j] < theta) ? (1u << j) : 0u;
+            while (mask) {
+              const int j = __ffs((int)mask) - 1;
+              mask &= mask - 1u;
+              float v16[16], v8[8], v4[4];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v16[i] = (j & 16) ? sc[i + 16] : sc[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] = (j & 8) ? v16[i + 8] : v16[i];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v4[i] = (j & 4) ? v8[i + 4] : v8[i];
+              const float v2a = (j & 2) ? v4[2] : v4[0], v2b = (j & 2) ? v4[3] : v4[1];
+              const float v = (j & 1) ? v2b : v2a;
+              const uint2 rec = make_uint2(ct * BN + c0 + (uint32_t)j + 1u, __float_as_uint(v));
+              const uint32_t pos = my_cnt++;
+              if (pos < (uint32_t)SUB) {
+                a.sub[((size_t)q * gridDim.x + blockIdx.x) * SUB + pos] = rec;
+              } else {
+                const uint32_t p = atomicAdd(&a.ovf_cnt[q], 1u);
+                if (p < a.cap) a.ovf[(size_t)q * a.cap + p] = rec;
+              }
+            }
+          }
+        }
+      }
+      if (EPI == EPI_EMIT && my_cnt != my_cnt0) s_cnt[q] = my_cnt;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0u));  // the leader counts all 8 warps
+      acc ^= 1u;
+      if (acc == 0u) acc_phase ^= 1u;
+    }
+    if (EPI == EPI_EMIT) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // every query row of the launch is served by exactly one CTA of each pair: the other one reports 0 nominees
+      for (uint32_t i = et; i < q_rows; i += 128)
+        if (i < a.nq_rows) a.sub_cnt[(size_t)i * gridDim.x + blockIdx.x] = s_cnt[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA of the pair leaves while the other may still signal it or read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // f32 rows [rows][src_stride] -> bf16 [rows_pad][dp] (zero padded); per row, rounded UP to f32:
 // sumsq = sum v^2 and resid2 = sum (v - bf16(v))^2, both accumulated in f64 (they feed the error
 // certificate, so they must never under-estimate)
@@ -339,6 +607,10 @@ __global__ void to_bf16_kernel(const float *__restrict__ src, size_t src_stride,
 size_t tc_smem_bytes(uint32_t nq_pad_emit) {
   return 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * sizeof(uint64_t) + 16 + 2 * BN * sizeof(float) +
          (size_t)nq_pad_emit * sizeof(uint32_t);
+}
+size_t tc2_smem_bytes(uint32_t q_rows_emit) {
+  return 1024 + (size_t)STAGES2 * STAGE2_BYTES + (2 * STAGES2 + 4) * sizeof(uint64_t) + 16 + 2 * BN * sizeof(float) +
+         (size_t)q_rows_emit * sizeof(uint32_t);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -390,17 +662,26 @@ cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, u
   return cudaGetLastError();
 }
 
-cudaError_t launch_flat_tc(const FlatTcLaunch &L, cudaStream_t stream) {
+// CTA pairs (flat_tc2_kernel) whenever the batch has at least one full 256-query tile pair; KDBGPU_FLAT_2CTA=0 keeps
+// the single-CTA kernel.  L.grid is updated to the number of CTAs actually launched (the caller sizes / reads the
+// per-CTA nominee lists with it).
+cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream) {
+  static const bool pair_ok = [] {
+    const char *e = getenv("KDBGPU_FLAT_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  const bool pair = pair_ok && L.nq_pad >= 2u * BM;
   CUtensorMap tmQ, tmX;
-  if (!make_tmap(&tmQ, L.q_bf16, L.nq_pad, L.dp, BM) || !make_tmap(&tmX, L.x_bf16, L.n_pad, L.dp, BN))
+  if (!make_tmap(&tmQ, L.q_bf16, L.nq_pad, L.dp, BM) || !make_tmap(&tmX, L.x_bf16, L.n_pad, L.dp, pair ? BN / 2 : BN))
     return cudaErrorInvalidValue;
   TcArgs a;
-  a.nq_tiles = L.nq_pad / BM;
+  a.nq_tiles = pair ? (L.nq_pad + 2 * BM - 1) / (2 * BM) : L.nq_pad / BM;
   a.ct_stride = L.ct_stride ? L.ct_stride : 1u;
   a.n_ctiles = (L.n_pad / BN + a.ct_stride - 1) / a.ct_stride;
   a.k_blocks = L.dp / BK;
   a.nq = L.nq;
   a.n = L.n;
+  a.nq_rows = L.nq_pad;
   a.alpha = L.alpha;
   a.beta = L.beta;
   a.S = L.S;
@@ -413,8 +694,53 @@ cudaError_t launch_flat_tc(const FlatTcLaunch &L, cudaStream_t stream) {
   a.ovf = reinterpret_cast<uint2 *>(L.ovf);
   a.cap = L.cap;
   if (L.epi == EPI_EMIT && (L.nq_pad > MAX_Q_PER_LAUNCH || L.grid > 256)) return cudaErrorInvalidValue;
-  const size_t smem = tc_smem_bytes(L.epi == EPI_EMIT ? L.nq_pad : 0);
   cudaError_t e;
+  if (pair) {
+    const uint32_t q_rows = a.nq_tiles * 2u * BM;
+    const size_t smem = tc2_smem_bytes(L.epi == EPI_EMIT ? q_rows : 0);
+    const uint64_t tiles = (uint64_t)a.nq_tiles * a.n_ctiles;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t clusters = (uint32_t)(sms / 2);
+    if ((uint64_t)clusters > tiles) clusters = (uint32_t)tiles;
+    if ((int)(2 * clusters) > L.grid && L.grid >= 2) clusters = (uint32_t)L.grid / 2;
+    if (clusters == 0) clusters = 1;
+#define KDB_TC2_LAUNCH(EPIv)                                                                             \
+  {                                                                                                      \
+    auto kern = flat_tc2_kernel<EPIv>;                                                                   \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return e;                                                                      \
+    cudaLaunchConfig_t cfg = {};                                                                         \
+    cfg.gridDim = dim3(2 * clusters, 1, 1);                                                              \
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);                                                               \
+    cfg.dynamicSmemBytes = smem;                                                                         \
+    cfg.stream = stream;                                                                                 \
+    cudaLaunchAttribute at[1];                                                                           \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                      \
+    at[0].val.clusterDim.x = 2;                                                                          \
+    at[0].val.clusterDim.y = 1;                                                                          \
+    at[0].val.clusterDim.z = 1;                                                                          \
+    cfg.attrs = at;                                                                                      \
+    cfg.numAttrs = 1;                                                                                    \
+    int max_clusters = 0;                                                                                \
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0 &&  \
+        (uint32_t)max_clusters < clusters) {                                                             \
+      clusters = (uint32_t)max_clusters;                                                                 \
+      cfg.gridDim = dim3(2 * clusters, 1, 1);                                                            \
+    }                                                                                                    \
+    (void)cudaGetLastError();                                                                            \
+    e = cudaLaunchKernelEx(&cfg, kern, tmQ, tmX, a);                                                     \
+  }
+    if (L.epi == EPI_STORE) KDB_TC2_LAUNCH(EPI_STORE)
+    else if (L.epi == EPI_GROUPMIN) KDB_TC2_LAUNCH(EPI_GROUPMIN)
+    else KDB_TC2_LAUNCH(EPI_EMIT)
+#undef KDB_TC2_LAUNCH
+    L.grid = (int)(2 * clusters);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+  }
+  const size_t smem = tc_smem_bytes(L.epi == EPI_EMIT ? L.nq_pad : 0);
 #define KDB_TC_LAUNCH(EPIv)                                                                              \
   {                                                                                                      \
     auto kern = flat_tc_kernel<EPIv>;                                                                    \

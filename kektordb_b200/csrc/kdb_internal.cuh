@@ -192,7 +192,7 @@ uint32_t flat_tc_bk();
 uint32_t flat_tc_groups_per_tile();
 cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, uint32_t dim, void *dst, uint32_t dp,
                            uint32_t rows_pad, float *sumsq, float *resid2, cudaStream_t stream);
-cudaError_t launch_flat_tc(const FlatTcLaunch &L, cudaStream_t stream);
+cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream);  // L.grid <- CTAs actually launched
 cudaError_t launch_tc_beta(const DevIndex &ix, const float *sumsq, const uint32_t *allow, int use_norm, uint32_t n_pad,
                            float *beta, cudaStream_t stream);
 cudaError_t launch_tc_max(const float *sumsq, const float *resid2, uint32_t n, float *out2, cudaStream_t stream);

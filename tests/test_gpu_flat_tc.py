@@ -65,6 +65,29 @@ def test_tensor_core_scores_within_certified_bound(metric, mode, n, dim):
     assert np.all(bound < 200 * np.maximum(err, 1e-6))
 
 
+@pytest.mark.parametrize("nq", [256, 300, 1024])
+def test_cta_pair_kernel_is_bit_identical_on_full_and_ragged_query_tile_pairs(nq):
+    """Batches of 256+ queries take the cta_group::2 kernel (two CTAs share every corpus tile): full tile pairs,
+    a ragged last pair (300 -> 384 padded rows, the pair tile runs past them), and the benchmark's batch of 1024."""
+    n, dim = 30000, 200
+    X, rng = _data(n, dim, 77, lowrank=True)
+    Q = rng.standard_normal((nq, dim)).astype(np.float32)
+    Q[:10] = X[:10]
+    gi, _ = _flat_index(X, "euclidean")
+    S, bound = gi.flat_prefilter_scores(Q[:300] if nq > 300 else Q, 0)     # raw tensor-core scores of the pair kernel
+    Qd, Xd = Q[:S.shape[0]].astype(np.float64), X.astype(np.float64)
+    exact = (Xd * Xd).sum(1)[None, :] - 2.0 * (Qd @ Xd.T)
+    assert np.all(np.abs(S.astype(np.float64) - exact).max(axis=1) <= bound)
+    for k in (10, 100):
+        a = gi.flat_search(Q[:64], k, 0)                                   # exhaustive float64 scan (first 64: it is slow)
+        b = gi.flat_search(Q, k, 0, prefilter=True)
+        assert np.array_equal(a[0], b[0][:64]) and np.array_equal(a[1], b[1][:64]) and np.array_equal(a[2], b[2][:64])
+        c = gi.flat_search(Q[64:128], k, 0, prefilter=True)                # 64 queries: the single-CTA kernel
+        assert np.array_equal(c[0], b[0][64:128]) and np.array_equal(c[1], b[1][64:128])
+        assert b[3].hops <= 2
+    gi.close()
+
+
 @pytest.mark.parametrize("metric", ["euclidean", "cosine"])
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("k", [10, 100])
