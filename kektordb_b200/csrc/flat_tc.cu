@@ -668,7 +668,7 @@ cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, u
 cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream) {
   static const bool pair_ok = [] {
     const char *e = getenv("KDBGPU_FLAT_2CTA");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   const bool pair = pair_ok && L.nq_pad >= 2u * BM;
   CUtensorMap tmQ, tmX;

@@ -316,73 +316,6 @@ struct Searcher {
     return acc.lane_sum();
   }
 
-  // ---- direct rows: short rows (int8: 768 B at 768-d) are not worth a bulk copy each.  The copy engine serves a
-  // request in ~46 cycles per SM whatever its size (B300_MICROARCH.md, TMA service), i.e. ~6 G rows/s per chip: the
-  // int8 traversal ran at 4.9 G rows/s — 0.8 of THAT ceiling — with HBM at 0.58, and neither more slots nor more
-  // resident warps moved it (profiles/README.md, round 2).  So these kinds read their rows with plain 128-bit
-  // global loads straight into registers, kPF rows ahead: no shared-memory slot, no mbarrier, no copy-engine
-  // request, and ~3x fewer instructions per evaluation.  float32 rows (3 KB, at the HBM roofline) keep the bulk copies.
-  static constexpr bool kDirect = (METRIC == KIND_COS_I8) && CPL >= 1 && CPL <= 2;
-  static constexpr int kPF = 4;
-  static constexpr int CPLX = CPL > 0 ? CPL : 1;
-
-  __device__ __forceinline__ void direct_load(uint32_t id, float4 (&dst)[CPLX]) const {
-    const float4 *src = reinterpret_cast<const float4 *>(vec_bytes + (size_t)id * row_bytes);
-    const uint32_t valid = ix.row_words >> 2;
-#pragma unroll
-    for (int t = 0; t < CPLX; ++t) {
-      const uint32_t c = (uint32_t)lane + 32u * (uint32_t)t;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // beyond the row's pitch: contributes nothing
-      if (c < valid) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                     : "l"(src + c));
-      }
-      dst[t] = v;
-    }
-  }
-  __device__ __forceinline__ float direct_partial(const float4 (&row)[CPLX]) const {
-    LaneAcc<METRIC> acc;
-#pragma unroll
-    for (int t = 0; t < CPLX; ++t) acc.add(qreg[t], row[t]);
-    return acc.lane_sum();
-  }
-  // all lanes: the reduced value for stored row `id`
-  __device__ __forceinline__ float direct_row(uint32_t id) const {
-    float4 r[CPLX];
-    direct_load(id, r);
-    return warp_sum<METRIC>(direct_partial(r));
-  }
-  // the evaluation loop of a hop over sm.eval_id[0 .. n_eval): rows kPF ahead in registers.  Each round reduces kPF
-  // rows (independent chains, every consumed buffer refilled at once), then applies upd(s, j) in row order — the
-  // update code is NOT unrolled (its state, the sorted list / the heaps, would be replicated kPF times in registers).
-  template <class Update>
-  __device__ __forceinline__ void eval_rows_direct(uint32_t n_eval, Update upd) {
-    float4 buf[kPF][CPLX];
-#pragma unroll
-    for (int u = 0; u < kPF; ++u)
-      if ((uint32_t)u < n_eval) direct_load(sm.eval_id[u], buf[u]);
-    for (uint32_t j0 = 0; j0 < n_eval; j0 += (uint32_t)kPF) {
-      float sv[kPF];
-#pragma unroll
-      for (int u = 0; u < kPF; ++u) {
-        const uint32_t j = j0 + (uint32_t)u;
-        sv[u] = 0.f;
-        if (j < n_eval) {
-          const float part = direct_partial(buf[u]);
-          if (j + (uint32_t)kPF < n_eval) direct_load(sm.eval_id[j + kPF], buf[u]);  // refill what was just consumed
-          sv[u] = warp_sum<METRIC>(part);
-        }
-      }
-      const uint32_t cnt = n_eval - j0 < (uint32_t)kPF ? n_eval - j0 : (uint32_t)kPF;
-#pragma unroll 1
-      for (uint32_t u = 0; u < cnt; ++u) {
-        const float x = u == 0 ? sv[0] : (u == 1 ? sv[1] : (u == 2 ? sv[2] : sv[3]));
-        upd(x, j0 + u);
-      }
-    }
-  }
-
   // lane 0: the reference's per-neighbour result update (:2571-2591)
   __device__ __forceinline__ void heap_update(float s, uint32_t j, int ef) {
     HeapEntry e;
@@ -519,19 +452,13 @@ struct Searcher {
     const bool log_marks = level > 0;
     if (ep == 0 || ep > ix.n || ix.levels[ep] < 0) return -1;
     // dist(query, entry) (:2471)
-    float s0;
-    if (kDirect) {
-      if (lane == 0) sm.ctl->n_marked = 0;
-      s0 = direct_row(ep);
-    } else {
-      if (lane == 0) {
-        sm.ctl->n_marked = 0;
-        issue_row(0, ep);
-      }
-      __syncwarp();
-      wait_slot(0);
-      s0 = warp_sum<METRIC>(lane_partial(0));
+    if (lane == 0) {
+      sm.ctl->n_marked = 0;
+      issue_row(0, ep);
     }
+    __syncwarp();
+    wait_slot(0);
+    const float s0 = warp_sum<METRIC>(lane_partial(0));
     __syncwarp();  // all lanes are done reading the slot
     if (lane == 0) {
       cand.n = 0;
@@ -572,16 +499,11 @@ struct Searcher {
       const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand, full, worst_now);
       // ---- C + D: stream the rows, two per iteration (independent reductions interleave), and
       // apply each heap update as soon as its distance exists
-      if (kDirect) {
-        eval_rows_direct(n_eval, [&](float sv, uint32_t j) {
-          if (lane == 0) heap_update(sv, j, ef);
-        });
-      }
-      if (!kDirect && lane == 0) {
+      if (lane == 0) {
         const uint32_t pro = n_eval < (uint32_t)SLOTS ? n_eval : (uint32_t)SLOTS;
         for (uint32_t j = 0; j < pro; ++j) issue_row(j, sm.eval_id[j]);
       }
-      for (uint32_t j = 0; !kDirect && j < n_eval; j += 2) {
+      for (uint32_t j = 0; j < n_eval; j += 2) {
         const bool two = j + 1 < n_eval;
         wait_slot(j);
         if (two) wait_slot(j + 1);
@@ -750,19 +672,13 @@ struct Searcher {
   __device__ int search_layer_fast(const int level, const int ef, const uint32_t ep) {
     const bool log_marks = level > 0;
     if (ep == 0 || ep > ix.n || ix.levels[ep] < 0) return -1;
-    float s0;
-    if (kDirect) {
-      if (lane == 0) sm.ctl->n_marked = 0;
-      s0 = direct_row(ep);
-    } else {
-      if (lane == 0) {
-        sm.ctl->n_marked = 0;
-        issue_row(0, ep);
-      }
-      __syncwarp();
-      wait_slot(0);
-      s0 = warp_sum<METRIC>(lane_partial(0));
+    if (lane == 0) {
+      sm.ctl->n_marked = 0;
+      issue_row(0, ep);
     }
+    __syncwarp();
+    wait_slot(0);
+    const float s0 = warp_sum<METRIC>(lane_partial(0));
     __syncwarp();
     sl_clear();
     sl_insert(to_distance<METRIC>(s0, qnorm, METRIC == KIND_COS_I8 ? ix.norms[ep] : 0.f), ep, ef);  // :2478, :2487
@@ -777,12 +693,11 @@ struct Searcher {
       if (cur == 0xffffffffu) break;
       bool expand;
       const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand, ln >= ef, worst);
-      if (kDirect) eval_rows_direct(n_eval, [&](float sv, uint32_t j) { list_update(sv, j, ef); });
-      if (!kDirect && lane == 0) {
+      if (lane == 0) {
         const uint32_t pro = n_eval < (uint32_t)SLOTS ? n_eval : (uint32_t)SLOTS;
         for (uint32_t j = 0; j < pro; ++j) issue_row(j, sm.eval_id[j]);
       }
-      for (uint32_t j = 0; !kDirect && j < n_eval; j += 2) {
+      for (uint32_t j = 0; j < n_eval; j += 2) {
         const bool two = j + 1 < n_eval;
         wait_slot(j);
         if (two) wait_slot(j + 1);

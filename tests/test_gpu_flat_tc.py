@@ -66,7 +66,7 @@ def test_tensor_core_scores_within_certified_bound(metric, mode, n, dim):
 
 
 @pytest.mark.parametrize("nq", [256, 300, 1024])
-def test_cta_pair_kernel_is_bit_identical_on_full_and_ragged_query_tile_pairs(nq):
+def test_cta_pair_kernel_is_bit_identical_on_full_and_ragged_query_tile_pairs(nq, monkeypatch):
     """Batches of 256+ queries take the cta_group::2 kernel (two CTAs share every corpus tile): full tile pairs,
     a ragged last pair (300 -> 384 padded rows, the pair tile runs past them), and the benchmark's batch of 1024."""
     n, dim = 30000, 200
