@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 //   rank 0 (leader)  issues every tcgen05.mma.cta_group::2; its `full` barriers collect the bytes of BOTH CTAs'
 //                    TMA loads (.cta_group::2 loads signal the leader's barrier)
 //   both ranks       TMA producer for their own A rows + B half; epilogue over their own 128 TMEM lanes
-//   barriers         full[s]       leader only, 2 arrivals (leader's expect_tx + the peer's remote arrive)
+//   barriers         full[s]       leader only: its own expect_tx of both CTAs' bytes
 //                    empty[s]      per CTA, signalled by the leader's commit (multicast to both CTAs)
 //                    tmem_full[a]  per CTA, signalled by the leader's commit (multicast)
 //                    tmem_empty[a] leader only, 8 arrivals: the four epilogue warps of both CTAs (remote arrive)
@@ -341,8 +341,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// (default semantics — release at CTA scope: a cluster-scope release is a full fence, ~600 cycles per arrive, and what
+// the arrive orders here are tcgen05.ld's already fenced by tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *tm, int c0, int c1, uint32_t leader_bar) {
   asm volatile(
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES2; ++i) {
-        mbar_init(&full[i], 2);
+        mbar_init(&full[i], 1);  // the leader's expect_tx; the peer only contributes transaction bytes
         mbar_init(&empty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -430,10 +432,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           const uint32_t leader_full = mapa_u32(smem_u32(&full[stage]), 0u);
-          if (leader)
-            mbar_expect_tx(&full[stage], 2u * STAGE2_BYTES);
-          else
-            mbar_arrive_cluster(leader_full);
+          // the leader expects the bytes of BOTH CTAs; the peer's loads for this phase cannot be issued before the
+          // previous phase was consumed (its own empty barrier), so they never land in an earlier phase
+          if (leader) mbar_expect_tx(&full[stage], 2u * STAGE2_BYTES);
           unsigned char *sa = tiles + (size_t)stage * STAGE2_BYTES;
           tma_load_2d_pair(sa, &tmQ, (int)(kb * BK), (int)(qt * 2u * BM + rank * BM), leader_full);
           tma_load_2d_pair(sa + A_BYTES, &tmXh, (int)(kb * BK), (int)(ct * BN + rank * (BN / 2)), leader_full);
@@ -662,14 +663,12 @@ cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, u
   return cudaGetLastError();
 }
 
-// CTA pairs (flat_tc2_kernel) whenever the batch has at least one full 256-query tile pair; KDBGPU_FLAT_2CTA=0 keeps
-// the single-CTA kernel.  L.grid is updated to the number of CTAs actually launched (the caller sizes / reads the
+// CTA pairs (flat_tc2_kernel) when KDBGPU_FLAT_2CTA=1 and the batch has at least one full 256-query tile pair (the
+// pair kernel returns the same bits but measures slower than the single-CTA kernel so far).  L.grid is updated to the number of CTAs actually launched (the caller sizes / reads the
 // per-CTA nominee lists with it).
 cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream) {
-  static const bool pair_ok = [] {
-    const char *e = getenv("KDBGPU_FLAT_2CTA");
-    return e && e[0] == '1';
-  }();
+  const char *pair_env = getenv("KDBGPU_FLAT_2CTA");  // read per launch: tests switch it
+  const bool pair_ok = pair_env && pair_env[0] == '1';
   const bool pair = pair_ok && L.nq_pad >= 2u * BM;
   CUtensorMap tmQ, tmX;
   if (!make_tmap(&tmQ, L.q_bf16, L.nq_pad, L.dp, BM) || !make_tmap(&tmX, L.x_bf16, L.n_pad, L.dp, pair ? BN / 2 : BN))
