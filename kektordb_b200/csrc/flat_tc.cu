@@ -211,22 +211,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t quarter = (uint32_t)warp & 3u;  // the TMEM lane quarter this warp may read
     const uint32_t et = (uint32_t)(threadIdx.x - 64);  // 0..127
     uint32_t acc = 0, acc_phase = 0;
+    // beta of a tile is fetched one tile ahead (registers), so that its global-load latency is not paid between
+    // "accumulator ready" and the first tcgen05.ld of every tile
+    float nb0 = 0.f, nb1 = 0.f;
+    if (blockIdx.x < total_tiles) {
+      const uint32_t ct0 = (blockIdx.x / a.nq_tiles) * a.ct_stride;
+      nb0 = a.beta[(size_t)ct0 * BN + et];
+      nb1 = a.beta[(size_t)ct0 * BN + et + 128];
+    }
     for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const uint32_t cti = tile / a.nq_tiles, qt = tile % a.nq_tiles;
       const uint32_t ct = cti * a.ct_stride;
       const uint32_t q = qt * BM + quarter * 32u + (uint32_t)lane;
       float *sb = s_beta + acc * BN;
-      sb[et] = a.beta[(size_t)ct * BN + et];
-      sb[et + 128] = a.beta[(size_t)ct * BN + et + 128];
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      float theta = 0.f;
+      sb[et] = nb0;
+      sb[et + 128] = nb1;
+      if (tile + gridDim.x < total_tiles) {
+        const uint32_t ctn = ((tile + gridDim.x) / a.nq_tiles) * a.ct_stride;
+        nb0 = a.beta[(size_t)ctn * BN + et];
+        nb1 = a.beta[(size_t)ctn * BN + et + 128];
+      }
+      float theta = 0.f;  // fetched before the waits: its latency hides behind them
       uint32_t my_cnt = 0u, my_cnt0 = 0u;
       if (EPI == EPI_EMIT) {
         theta = a.theta[q];
         my_cnt = my_cnt0 = s_cnt[q];  // this thread is the only one in the CTA that serves query q
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
@@ -476,23 +489,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t quarter = (uint32_t)warp & 3u;
     const uint32_t et = (uint32_t)(threadIdx.x - 64);
     uint32_t acc = 0, acc_phase = 0;
+    float nb0 = 0.f, nb1 = 0.f;  // beta one tile ahead, as in the single-CTA kernel
+    if (cluster_id < total_tiles) {
+      const uint32_t ct0 = (cluster_id / a.nq_tiles) * a.ct_stride;
+      nb0 = a.beta[(size_t)ct0 * BN + et];
+      nb1 = a.beta[(size_t)ct0 * BN + et + 128];
+    }
     for (uint32_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       const uint32_t cti = tile / a.nq_tiles, qt = tile % a.nq_tiles;
       const uint32_t ct = cti * a.ct_stride;
       const uint32_t q = qt * 2u * BM + rank * BM + quarter * 32u + (uint32_t)lane;
       const bool q_ok = q < a.nq_rows;  // rows the caller's per-query arrays hold
       float *sb = s_beta + acc * BN;
-      sb[et] = a.beta[(size_t)ct * BN + et];
-      sb[et + 128] = a.beta[(size_t)ct * BN + et + 128];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      sb[et] = nb0;
+      sb[et + 128] = nb1;
+      if (tile + n_clusters < total_tiles) {
+        const uint32_t ctn = ((tile + n_clusters) / a.nq_tiles) * a.ct_stride;
+        nb0 = a.beta[(size_t)ctn * BN + et];
+        nb1 = a.beta[(size_t)ctn * BN + et + 128];
+      }
       float theta = 0.f;
       uint32_t my_cnt = 0u, my_cnt0 = 0u;
       if (EPI == EPI_EMIT) {
         theta = q_ok ? a.theta[q] : 0.f;
         my_cnt = my_cnt0 = s_cnt[q];
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
