@@ -255,7 +255,7 @@ cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchT
 
 // hand_over: no heap arrays (ties go to the heap kernel); otherwise the heap kernel's own carve-up
 static size_t search_fast_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t, bool hand_over) {
-  return smem_layout(ix.stride, hand_over ? 0 : ef, 4, hand_over ? 0u : (uint32_t)t.cand_smem,
+  return smem_layout(ix.stride, hand_over ? 0 : ef, t.slots, hand_over ? 0u : (uint32_t)t.cand_smem,
                      ix.deg0 > ix.degu ? ix.deg0 : ix.degu, cpl_of(ix) == 0, ix.kind, nullptr, nullptr);
 }
 bool search_fast_hands_over(const DevIndex &ix) { return ix.kind == KIND_COS_I8; }
@@ -266,14 +266,14 @@ bool search_fast_eligible(const DevIndex &ix, int ef, const SearchTuning &t) {
   // float64 ratios, no ties, +12 %).  On float32 / float16 rows (float32 sums: 2-3 % of the queries at
   // 1 M x 768 meet a relevant tie) it measures slower than the heaps; fast = 2 forces it.
   const bool kind_ok = t.fast >= 2 || (t.fast == 1 && ix.kind == KIND_COS_I8);
-  return kind_ok && t.slots == 4 && ef <= 128 && ix.deleted == nullptr &&
+  return kind_ok && ef <= 128 && ix.deleted == nullptr &&
          search_fast_smem_bytes(ix, ef, t, search_fast_hands_over(ix)) <= 227 * 1024;
 }
 
 int search_fast_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
   const size_t smem = search_fast_smem_bytes(ix, ef, t, search_fast_hands_over(ix));
   int nb = 0;
-  if (kind_fn(ix)(SEARCH_OP_OCCUPANCY_FAST, ix, nullptr, 4, cpl_of(ix), 0, smem, nullptr, &nb) != cudaSuccess) {
+  if (kind_fn(ix)(SEARCH_OP_OCCUPANCY_FAST, ix, nullptr, t.slots, cpl_of(ix), 0, smem, nullptr, &nb) != cudaSuccess) {
     (void)cudaGetLastError();
     return 0;
   }
@@ -284,7 +284,7 @@ int search_fast_occupancy(const DevIndex &ix, int ef, const SearchTuning &t) {
 cudaError_t launch_search_fast(const DevIndex &ix, const SearchArgs &a, const SearchTuning &t, int grid,
                                cudaStream_t stream) {
   const size_t smem = search_fast_smem_bytes(ix, a.ef, t, a.redo_list != nullptr);
-  return kind_fn(ix)(SEARCH_OP_LAUNCH_FAST, ix, &a, 4, cpl_of(ix), grid, smem, stream, nullptr);
+  return kind_fn(ix)(SEARCH_OP_LAUNCH_FAST, ix, &a, t.slots, cpl_of(ix), grid, smem, stream, nullptr);
 }
 
 cudaError_t launch_prep_queries(const float *in, size_t in_stride, float *out, uint32_t nq, uint32_t dim,

@@ -98,8 +98,7 @@ cudaError_t search_shape(int op, const DevIndex &ix, const SearchArgs *a, int gr
     kern<<<grid, 32, smem, stream>>>(ix, *a);
     return cudaGetLastError();
   }
-  if (SL != 4) return cudaErrorInvalidConfiguration;  // the fast pass exists for 4 slots
-  auto kern = hnsw_search_fast_kernel<4, KIND, CPL>;
+  auto kern = hnsw_search_fast_kernel<SL, KIND, CPL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (op == SEARCH_OP_OCCUPANCY_FAST) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 32, smem);

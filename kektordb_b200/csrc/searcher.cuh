@@ -9,10 +9,14 @@
 //                  bitset, applies the allow-list BEFORE any distance (:2537-2549) and compacts
 //                  the survivors in row order
 //   C. (all lanes) streams the survivors' rows HBM -> shared memory with 1-D bulk copies
-//                  (cp.async.bulk + mbarrier, SLOTS rows in flight), reduces query x row in the
-//                  fixed "kernel order" (kdb_internal.cuh) ...
-//   D. (lane 0)    ... and applies the heap update of each row right after its reduction, in row
-//                  order (:2571-2591), while the later rows of the hop are still in flight.
+//                  (cp.async.bulk + mbarrier) in GROUPS of G = SLOTS / 2 rows, two groups in flight,
+//                  ONE mbarrier per group; the G rows of a group are reduced against the query together
+//                  (G independent chains) in the fixed "kernel order" (kdb_internal.cuh), the warp
+//                  reduction of the G lane partials is done transposed (G - 1 + log2(32 / G) shuffles
+//                  for G rows instead of 5 G; same additions, same order), the group's slots are
+//                  refilled, and every row is pre-tested in parallel against the worst kept distance
+//   D. (lane 0)    the rows that pass get the reference's heap update (:2571-2591), in row order,
+//                  while the next groups of the hop are in flight.
 // No CTA-wide barrier exists on this path: a CTA is a single warp, the SM interleaves ~7 of them.
 // The two binary heaps are the reference's own algorithms run by lane 0, so ids, order and scores
 // are bit-identical to the oracle in KDBO_ARITH_KERNEL mode — ties included.
@@ -197,13 +201,14 @@ __device__ __forceinline__ bool bit_test(const uint32_t *bits, uint32_t id) {
 // registers, reduction fully unrolled); CPL == 0 is the generic path (query in shared memory).
 template <int SLOTS, int METRIC, int CPL>
 struct Searcher {
-  static_assert((SLOTS & (SLOTS - 1)) == 0, "SLOTS must be a power of two");
+  static_assert(SLOTS == 2 || SLOTS == 4 || SLOTS == 8 || SLOTS == 16, "SLOTS must be 2, 4, 8 or 16");
+  static constexpr int G = SLOTS / 2;  // rows per group; two groups (buffers) in flight
   const DevIndex &ix;
   const SearchArgs &a;
   SmemPtrs sm;
   uint32_t *vis;
   const int lane;
-  uint32_t phase_bits;  // parity of each slot barrier
+  uint32_t phase_bits;  // parity of each buffer's barrier
   CandHeap cand;        // meaningful on lane 0
   ResHeap res;          // meaningful on lane 0
   unsigned long long st_e, st_h, st_h0;
@@ -250,7 +255,7 @@ struct Searcher {
       fence_proxy_async();
     }
     if (lane == 0) {
-      for (int i = 0; i < SLOTS; ++i) mbar_init(&sm.bars[i], 1);
+      for (int i = 0; i < 2; ++i) mbar_init(&sm.bars[i], 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -286,45 +291,117 @@ struct Searcher {
     __syncwarp();
   }
 
-  __device__ __forceinline__ void issue_row(uint32_t j, uint32_t id) {  // lane 0
-    const uint32_t slot = j & (SLOTS - 1);
-    const uint32_t bar = bars_u32 + slot * 8u;
+  // ---- row streaming: groups of G rows, two group buffers, one mbarrier per buffer ------------------
+  __device__ __forceinline__ void issue_one(uint32_t buf, uint32_t id) {  // lane 0: a single row into buffer `buf`
+    const uint32_t bar = bars_u32 + buf * 8u;
     mbar_expect_tx_u32(bar, row_bytes);
-    bulk_g2s_u32(slots_u32 + slot * slot_bytes, vec_bytes + (size_t)id * row_bytes, row_bytes, bar);
+    bulk_g2s_u32(slots_u32 + buf * (uint32_t)G * slot_bytes, vec_bytes + (size_t)id * row_bytes, row_bytes, bar);
   }
-
-  __device__ __forceinline__ void wait_slot(uint32_t j) {
-    const uint32_t slot = j & (SLOTS - 1);
-    const uint32_t bar = bars_u32 + slot * 8u, parity = (phase_bits >> slot) & 1u;
+  // lane 0: rows eval_id[j0 .. j0 + cnt) into the slots of buffer (g & 1), all completing on that buffer's barrier
+  __device__ __forceinline__ void issue_group(uint32_t g, uint32_t j0, uint32_t cnt) {
+    const uint32_t buf = g & 1u;
+    const uint32_t bar = bars_u32 + buf * 8u;
+    uint32_t dst = slots_u32 + buf * (uint32_t)G * slot_bytes;
+    mbar_expect_tx_u32(bar, cnt * row_bytes);
+#pragma unroll
+    for (int r = 0; r < G; ++r) {
+      if ((uint32_t)r < cnt) bulk_g2s_u32(dst, vec_bytes + (size_t)sm.eval_id[j0 + r] * row_bytes, row_bytes, bar);
+      dst += slot_bytes;
+    }
+  }
+  __device__ __forceinline__ void wait_buf(uint32_t buf) {
+    const uint32_t bar = bars_u32 + buf * 8u, parity = (phase_bits >> buf) & 1u;
     while (!mbar_try_wait_u32(bar, parity)) {
     }
-    phase_bits ^= 1u << slot;
+    phase_bits ^= 1u << buf;
   }
 
-  // lane partial of query x row held in slot (j mod SLOTS), kernel order (LaneAcc, kdb_internal.cuh)
-  __device__ __forceinline__ float lane_partial(uint32_t j) const {
-    const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots + (size_t)(j & (SLOTS - 1)) * ix.stride);
+  // lane partials of query x the G rows of buffer `buf`, kernel order (LaneAcc, kdb_internal.cuh); the G chains
+  // are independent and interleave
+  __device__ __forceinline__ void group_partials(uint32_t buf, float (&p)[G]) const {
+    const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots + (size_t)buf * G * ix.stride);
+    const uint32_t pitch4 = ix.stride >> 2;
+    LaneAcc<METRIC> acc[G];
+    if (CPL > 0) {
+#pragma unroll
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) {
+#pragma unroll
+        for (int r = 0; r < G; ++r) acc[r].add(qreg[t], r4[r * pitch4 + lane + 32 * t]);
+      }
+    } else {
+      const uint32_t nchunks = ix.stride >> 2;
+#pragma unroll 2
+      for (uint32_t c = lane; c < nchunks; c += 32) {
+        const float4 q = sm.q4[c];
+#pragma unroll
+        for (int r = 0; r < G; ++r) acc[r].add(q, r4[r * pitch4 + c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < G; ++r) p[r] = acc[r].lane_sum();
+  }
+  // The xor-butterfly 16, 8, 4, 2, 1 of G rows at once.  While more than one row is left, a step at offset O pairs
+  // row i with row i + R/2: the lanes with bit O clear keep row i and hand their partial of row i + R/2 to the lane
+  // O away (and vice versa) — lane l still computes  own(l) + own(l ^ O)  for the row it keeps, which is exactly the
+  // butterfly's addition, so the totals are bit-identical.  reduce_head = the first step (after it every lane's
+  // shared-memory reads of the group have returned); reduce_tail = the rest.  Result: p[0] on lane l is the total
+  // of row l >> kRowShift (int8: exact integer totals of every row in p[0..G) on every lane).
+  static constexpr int kLog2G = G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : 3));
+  static constexpr int kRowShift = 5 - kLog2G;
+  template <int R, int O>
+  __device__ __forceinline__ void reduce_step(float (&p)[G]) const {
+    if (R > 1) {
+      const bool up = (lane & O) != 0;
+#pragma unroll
+      for (int i = 0; i < (R > 1 ? R / 2 : 1); ++i) {
+        const float keep = up ? p[i + R / 2] : p[i];
+        const float send = up ? p[i] : p[i + R / 2];
+        p[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, O));
+      }
+    } else {
+      p[0] = __fadd_rn(p[0], __shfl_xor_sync(0xffffffffu, p[0], O));
+    }
+  }
+  __device__ __forceinline__ void reduce_head(float (&p)[G]) const {
+    if (METRIC == KIND_COS_I8) {
+#pragma unroll
+      for (int r = 0; r < G; ++r) p[r] = __int_as_float(__reduce_add_sync(0xffffffffu, __float_as_int(p[r])));
+    } else {
+      reduce_step<G, 16>(p);
+    }
+  }
+  __device__ __forceinline__ void reduce_tail(float (&p)[G]) const {
+    if (METRIC != KIND_COS_I8) {
+      reduce_step<(G >= 2 ? G / 2 : 1), 8>(p);
+      reduce_step<(G >= 4 ? G / 4 : 1), 4>(p);
+      reduce_step<(G >= 8 ? G / 8 : 1), 2>(p);
+      reduce_step<1, 1>(p);
+    }
+  }
+
+  // dist(query, entry) (:2471): one row through buffer 0; the reduced value on every lane
+  __device__ __forceinline__ float entry_sum(uint32_t ep) {
+    if (lane == 0) issue_one(0, ep);
+    __syncwarp();
+    wait_buf(0);
+    const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots);
     LaneAcc<METRIC> acc;
     if (CPL > 0) {
 #pragma unroll
       for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) acc.add(qreg[t], r4[lane + 32 * t]);
     } else {
       const uint32_t nchunks = ix.stride >> 2;
-#pragma unroll 4
       for (uint32_t c = lane; c < nchunks; c += 32) acc.add(sm.q4[c], r4[c]);
     }
-    return acc.lane_sum();
+    const float s0 = warp_sum<METRIC>(acc.lane_sum());
+    __syncwarp();  // all lanes are done reading the slot
+    return s0;
   }
 
-  // lane 0: the reference's per-neighbour result update (:2571-2591)
-  __device__ __forceinline__ void heap_update(float s, uint32_t j, int ef) {
+  // lane 0: the reference's per-neighbour result update (:2571-2591) for neighbour j at distance d
+  __device__ __forceinline__ void heap_update(double d, uint32_t j, int ef) {
     HeapEntry e;
-    if (METRIC == KIND_COS_I8) {
-      if (__float_as_int(s) <= sm.eval_thr[j]) return;  // certainly not admitted (collect_neighbours)
-      e.d = int8_distance(__float_as_int(s), qnorm, sm.eval_norm[j]);
-    } else {
-      e.d = to_distance<METRIC>(s);
-    }
+    e.d = d;
     e.id = sm.eval_id[j];
     e.pad = 0;
     bool admit = res.n < ef;  // worstDist = MaxFloat64 while results is empty
@@ -335,6 +412,86 @@ struct Searcher {
         res.push(e);
         if (res.n > ef) (void)res.pop();  // :2587-2589
         worst = res.a[0].d;
+      }
+    }
+  }
+
+  // Phases C + D of a hop: the rows of eval_id[0 .. n_eval) through the group pipeline.  LIST = the sorted-list
+  // queues of the fast path (all lanes), otherwise the two heaps (lane 0).
+  // Pre-test: once the result queue is full its worst kept distance only decreases (:2587-2589), so a row that fails
+  // `d < worst` against the value at the START of its group fails the exact test (:2577) too — those rows cost
+  // nothing more.  The rows that pass are handed to the exact update one by one, in row order.
+  template <bool LIST>
+  __device__ __forceinline__ void stream_hop(const uint32_t n_eval, const int ef) {
+    if (n_eval == 0) return;
+    const uint32_t n_groups = (n_eval + (uint32_t)G - 1u) / (uint32_t)G;
+    if (lane == 0) {
+      issue_group(0, 0, n_eval < (uint32_t)G ? n_eval : (uint32_t)G);
+      if (n_groups > 1) issue_group(1, G, n_eval - G < (uint32_t)G ? n_eval - G : (uint32_t)G);
+    }
+    for (uint32_t g = 0, j0 = 0; g < n_groups; ++g, j0 += G) {
+      const uint32_t buf = g & 1u;
+      const uint32_t cnt = n_eval - j0 < (uint32_t)G ? n_eval - j0 : (uint32_t)G;
+      bool full;
+      double wst;
+      if (LIST) {
+        full = ln >= ef;
+        wst = worst;
+      } else {
+        full = __shfl_sync(0xffffffffu, res.n >= ef ? 1 : 0, 0) != 0;
+        wst = __shfl_sync(0xffffffffu, worst, 0);
+      }
+      wait_buf(buf);
+      float p[G];
+      group_partials(buf, p);
+      reduce_head(p);
+      // Every lane's reads of the group's slots have returned (the step above consumed every lane's partials): the
+      // slots are refilled BEFORE the rest of the reduction and the queue updates.  (No proxy fence: the slots were
+      // only READ through the generic proxy; the bulk copies' completion is observed through the mbarrier.)
+      __syncwarp();
+      if (lane == 0 && g + 2 < n_groups) {
+        const uint32_t j2 = j0 + 2u * G;
+        issue_group(g, j2, n_eval - j2 < (uint32_t)G ? n_eval - j2 : (uint32_t)G);
+      }
+      reduce_tail(p);
+      // distance + pre-test on the lane that holds the row
+      uint32_t r_mine;
+      bool holder;
+      float s_mine = p[0];
+      if (METRIC == KIND_COS_I8) {
+        r_mine = (uint32_t)lane;
+        holder = r_mine < cnt;
+#pragma unroll
+        for (int r = 1; r < G; ++r)
+          if (lane == r) s_mine = p[r];
+      } else {
+        r_mine = (uint32_t)lane >> kRowShift;
+        holder = (lane & ((1 << kRowShift) - 1)) == 0 && r_mine < cnt;
+      }
+      double d = 0.0;
+      bool pass = false;
+      if (holder) {
+        if (METRIC == KIND_COS_I8) {
+          if (__float_as_int(s_mine) > sm.eval_thr[j0 + r_mine]) {  // else: certainly not admitted (collect_neighbours)
+            d = int8_distance(__float_as_int(s_mine), qnorm, sm.eval_norm[j0 + r_mine]);
+            pass = !full || d < wst;
+          }
+        } else {
+          d = to_distance<METRIC>(s_mine);
+          pass = !full || d < wst;
+        }
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, pass);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const double dd = __shfl_sync(0xffffffffu, d, src);
+        const uint32_t j = j0 + (METRIC == KIND_COS_I8 ? (uint32_t)src : (uint32_t)src >> kRowShift);
+        if (LIST) {
+          list_update(dd, j, ef);
+        } else if (lane == 0) {
+          heap_update(dd, j, ef);
+        }
       }
     }
   }
@@ -451,15 +608,8 @@ struct Searcher {
   __device__ int search_layer(const int level, const int ef, const uint32_t ep) {
     const bool log_marks = level > 0;
     if (ep == 0 || ep > ix.n || ix.levels[ep] < 0) return -1;
-    // dist(query, entry) (:2471)
-    if (lane == 0) {
-      sm.ctl->n_marked = 0;
-      issue_row(0, ep);
-    }
-    __syncwarp();
-    wait_slot(0);
-    const float s0 = warp_sum<METRIC>(lane_partial(0));
-    __syncwarp();  // all lanes are done reading the slot
+    if (lane == 0) sm.ctl->n_marked = 0;
+    const float s0 = entry_sum(ep);  // dist(query, entry) (:2471)
     if (lane == 0) {
       cand.n = 0;
       res.n = 0;
@@ -497,46 +647,8 @@ struct Searcher {
         worst_now = __shfl_sync(0xffffffffu, worst, 0);
       }
       const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand, full, worst_now);
-      // ---- C + D: stream the rows, two per iteration (independent reductions interleave), and
-      // apply each heap update as soon as its distance exists
-      if (lane == 0) {
-        const uint32_t pro = n_eval < (uint32_t)SLOTS ? n_eval : (uint32_t)SLOTS;
-        for (uint32_t j = 0; j < pro; ++j) issue_row(j, sm.eval_id[j]);
-      }
-      for (uint32_t j = 0; j < n_eval; j += 2) {
-        const bool two = j + 1 < n_eval;
-        wait_slot(j);
-        if (two) wait_slot(j + 1);
-        float sa = lane_partial(j);  // :2566
-        float sb = two ? lane_partial(j + 1) : 0.f;
-        // The first step of the reduction reads every lane's partial: once it has executed, every lane's reads of
-        // the two slots have returned, and the slots can be refilled — BEFORE the rest of the reduction and the
-        // heap updates, so that the next rows are in flight that much earlier.  (No proxy fence: the slot was only
-        // READ through the generic proxy; the bulk copy's completion is observed through the mbarrier.)
-        if (METRIC == KIND_COS_I8) {
-          sa = warp_sum<METRIC>(sa);
-          sb = warp_sum<METRIC>(sb);
-        } else {
-          sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, 16));
-          sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, 16));
-        }
-        __syncwarp();
-        if (lane == 0 && j + SLOTS < n_eval) {
-          issue_row(j + SLOTS, sm.eval_id[j + SLOTS]);
-          if (j + 1 + SLOTS < n_eval) issue_row(j + 1 + SLOTS, sm.eval_id[j + 1 + SLOTS]);
-        }
-        if (METRIC != KIND_COS_I8) {
-#pragma unroll
-          for (int o = 8; o >= 1; o >>= 1) {
-            sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
-            sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
-          }
-        }
-        if (lane == 0) {
-          heap_update(sa, j, ef);
-          if (two) heap_update(sb, j + 1, ef);
-        }
-      }
+      // ---- C + D: stream the rows in groups, apply the heap updates of the rows that can be admitted
+      stream_hop<false>(n_eval, ef);
       if (lane == 0) {
         st_e += n_eval;
         if (expand) {
@@ -646,14 +758,7 @@ struct Searcher {
     return id;
   }
   // the per-neighbour result update (:2571-2591) on the sorted list; all lanes
-  __device__ __forceinline__ void list_update(float s, uint32_t j, int ef) {
-    double d;
-    if (METRIC == KIND_COS_I8) {
-      if (__float_as_int(s) <= sm.eval_thr[j]) return;  // certainly not admitted (collect_neighbours)
-      d = int8_distance(__float_as_int(s), qnorm, sm.eval_norm[j]);
-    } else {
-      d = to_distance<METRIC>(s);
-    }
+  __device__ __forceinline__ void list_update(double d, uint32_t j, int ef) {
     if (ln < ef || d < worst) {
       const bool evicts = ln >= ef;
       const double evicted = worst;
@@ -672,14 +777,8 @@ struct Searcher {
   __device__ int search_layer_fast(const int level, const int ef, const uint32_t ep) {
     const bool log_marks = level > 0;
     if (ep == 0 || ep > ix.n || ix.levels[ep] < 0) return -1;
-    if (lane == 0) {
-      sm.ctl->n_marked = 0;
-      issue_row(0, ep);
-    }
-    __syncwarp();
-    wait_slot(0);
-    const float s0 = warp_sum<METRIC>(lane_partial(0));
-    __syncwarp();
+    if (lane == 0) sm.ctl->n_marked = 0;
+    const float s0 = entry_sum(ep);
     sl_clear();
     sl_insert(to_distance<METRIC>(s0, qnorm, METRIC == KIND_COS_I8 ? ix.norms[ep] : 0.f), ep, ef);  // :2478, :2487
     if (ln >= ef) worst = sl_worst(ef);
@@ -693,38 +792,7 @@ struct Searcher {
       if (cur == 0xffffffffu) break;
       bool expand;
       const uint32_t n_eval = collect_neighbours(cur, level, log_marks, expand, ln >= ef, worst);
-      if (lane == 0) {
-        const uint32_t pro = n_eval < (uint32_t)SLOTS ? n_eval : (uint32_t)SLOTS;
-        for (uint32_t j = 0; j < pro; ++j) issue_row(j, sm.eval_id[j]);
-      }
-      for (uint32_t j = 0; j < n_eval; j += 2) {
-        const bool two = j + 1 < n_eval;
-        wait_slot(j);
-        if (two) wait_slot(j + 1);
-        float sa = lane_partial(j);
-        float sb = two ? lane_partial(j + 1) : 0.f;
-        if (METRIC == KIND_COS_I8) {  // refill after the first reduction step, as in search_layer
-          sa = warp_sum<METRIC>(sa);
-          sb = warp_sum<METRIC>(sb);
-        } else {
-          sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, 16));
-          sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, 16));
-        }
-        __syncwarp();
-        if (lane == 0 && j + SLOTS < n_eval) {
-          issue_row(j + SLOTS, sm.eval_id[j + SLOTS]);
-          if (j + 1 + SLOTS < n_eval) issue_row(j + 1 + SLOTS, sm.eval_id[j + 1 + SLOTS]);
-        }
-        if (METRIC != KIND_COS_I8) {
-#pragma unroll
-          for (int o = 8; o >= 1; o >>= 1) {
-            sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
-            sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
-          }
-        }
-        list_update(sa, j, ef);
-        if (two) list_update(sb, j + 1, ef);
-      }
+      stream_hop<true>(n_eval, ef);
       if (lane == 0) {
         st_e += n_eval;
         if (expand) {
