@@ -375,6 +375,10 @@ int kdbgpu_prepare_search(kdbgpu_index *, uint32_t nq, int k, int ef_search);
  * entries kept in shared memory, cap on resident query-warps per SM (0 = no cap).  A value <= 0
  * (< 0 for the cap) keeps the current setting.  Results never depend on the shape. */
 int kdbgpu_set_tuning(kdbgpu_index *, int slots, int cand_smem, int max_ctas_per_sm);
+/* Slot count of a launch that finds no other batch of the handle in flight (0 = same as `slots`): with more rows in
+ * flight per query a lone batch finishes sooner (batch latency), with fewer a stream of overlapping batches moves
+ * more queries per second.  The defaults are per precision. */
+int kdbgpu_set_idle_slots(kdbgpu_index *, int slots_idle);
 /* The reference's candidate heap is unbounded; ours holds cand_smem entries in shared memory and spills up to
  * spill_entries (default 32768) to HBM per query.  A query that would need more returns count 0 and the call
  * fails with KDBGPU_ERR_OVERFLOW (kdbgpu_search_batch: at once; the *_device forms: from

@@ -151,12 +151,36 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
                    uint32_t *d_counts, cudaStream_t stream, unsigned long long *d_stats, int *d_err,
                    uint32_t id_base) {
   DevIndex ix = h->dev();
-  const int occ = search_occupancy(ix, ef, h->tuning);
+  // the launch shape: the throughput shape while other batches of this handle are in flight (their query-warps
+  // fill this launch's straggler tail), the latency shape when this batch is alone on the device
+  SearchTuning tn = h->tuning;
+  if (tn.slots_idle > 0 && tn.slots_idle != tn.slots) {
+    // "in flight" = a launch of another workspace, queued on ANOTHER stream (launches of one stream run one after
+    // the other: nothing fills their tails), that has not finished on the device — every path records the
+    // workspace's `done` event behind its launch
+    int n_other = 0;
+    {
+      std::lock_guard<std::mutex> lk(h->ws_mu);
+      for (int i = 0; i < kdbgpu_index::kNumSearchWs; ++i) {
+        kdbgpu_index::SearchWs &o = h->sws[i];
+        if (&o == &w || o.launch_stream == nullptr || o.launch_stream == stream) continue;
+        if (o.done && cudaEventQuery(o.done) == cudaErrorNotReady) n_other++;
+      }
+      w.launch_stream = stream;
+    }
+    (void)cudaGetLastError();  // cudaErrorNotReady is an answer, not a failure
+    if (n_other == 0) tn.slots = tn.slots_idle;
+  }
+  int occ = search_occupancy(ix, ef, tn);
+  if (occ <= 0 && tn.slots != h->tuning.slots) {  // the latency shape does not fit: fall back
+    tn.slots = h->tuning.slots;
+    occ = search_occupancy(ix, ef, tn);
+  }
   if (occ <= 0)
     return fail(KDBGPU_ERR_INVALID, "search configuration does not fit shared memory (dim=%d ef=%d smem=%zu)", h->dim,
-                ef, search_smem_bytes(ix, ef, h->tuning));
-  const bool fast = search_fast_eligible(ix, ef, h->tuning);
-  const int occ_fast = fast ? search_fast_occupancy(ix, ef, h->tuning) : 0;
+                ef, search_smem_bytes(ix, ef, tn));
+  const bool fast = search_fast_eligible(ix, ef, tn);
+  const int occ_fast = fast ? search_fast_occupancy(ix, ef, tn) : 0;
   const int occ_max = occ_fast > occ ? occ_fast : occ;
   int rc = ensure_ws(h, w, occ_max * h->num_sms);
   if (rc) return rc;
@@ -184,7 +208,7 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
   a.vis_words = w.vis_words;
   a.cand_overflow = w.cand_overflow.p;
   a.ovf_cap = h->ovf_cap;
-  a.cand_smem = (uint32_t)h->tuning.cand_smem;
+  a.cand_smem = (uint32_t)tn.cand_smem;
   a.stats = d_stats;
   a.work_counter = w.work_counter.p;
   a.err_flag = d_err;
@@ -199,19 +223,19 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
     a.redo_count = w.work_counter.p + 2;
     if (search_fast_hands_over(ix)) {
       a.redo_list = w.redo.p;
-      CUDA_TRY(launch_search_fast(ix, a, h->tuning, gfast, stream));
+      CUDA_TRY(launch_search_fast(ix, a, tn, gfast, stream));
       a.work_counter = w.work_counter.p + 1;
       a.query_list = w.redo.p;
       a.query_count = w.work_counter.p + 2;
       a.redo_list = nullptr;
       a.redo_count = nullptr;
-      CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
+      CUDA_TRY(launch_search(ix, a, tn, grid, stream));
     } else {  // tied queries are re-run by the heap path inside the same launch
       a.redo_list = nullptr;
-      CUDA_TRY(launch_search_fast(ix, a, h->tuning, gfast, stream));
+      CUDA_TRY(launch_search_fast(ix, a, tn, gfast, stream));
     }
   } else {
-    CUDA_TRY(launch_search(ix, a, h->tuning, grid, stream));
+    CUDA_TRY(launch_search(ix, a, tn, grid, stream));
   }
   if (fast && occ_fast > 0)  // stats[3] = queries the heap pass answered after a tie in the fast pass
     CUDA_TRY(cudaMemcpyAsync(d_stats + 3, w.work_counter.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
@@ -670,6 +694,7 @@ int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m
   if (precision != KDBGPU_PRECISION_F32) h->tuning.cand_smem = 64;
   if ((env = getenv("KDBGPU_FAST"))) h->tuning.fast = atoi(env);
   if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
+  if ((env = getenv("KDBGPU_SLOTS_IDLE"))) h->tuning.slots_idle = atoi(env);
   if ((env = getenv("KDBGPU_CAND_SMEM"))) h->tuning.cand_smem = atoi(env);
   if ((env = getenv("KDBGPU_MAX_CTAS_PER_SM"))) h->tuning.max_ctas_per_sm = atoi(env);
   auto cleanup = [&](int rc) {
@@ -2175,6 +2200,15 @@ int kdbgpu_set_tuning(kdbgpu_index *h, int slots, int cand_smem, int max_ctas_pe
   if (!search_slots_supported(t.slots)) return fail(KDBGPU_ERR_INVALID, "unsupported slot count %d", t.slots);
   std::unique_lock<std::shared_mutex> lk(h->mu);
   h->tuning = t;
+  return KDBGPU_OK;
+}
+
+int kdbgpu_set_idle_slots(kdbgpu_index *h, int slots_idle) {
+  if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
+  if (slots_idle != 0 && !search_slots_supported(slots_idle))
+    return fail(KDBGPU_ERR_INVALID, "unsupported slot count %d", slots_idle);
+  std::unique_lock<std::shared_mutex> lk(h->mu);
+  h->tuning.slots_idle = slots_idle;
   return KDBGPU_OK;
 }
 

@@ -79,6 +79,7 @@ struct kdbgpu_index {
   struct SearchWs {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;  // completion of the last launch that used this workspace
+    cudaStream_t launch_stream = nullptr;  // ... and the stream it was queued on (guarded by ws_mu)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<float> q_raw, q_prep, qnorms;
     DevBuf<uint32_t> out_ids, out_counts, allow, visited, work_counter, redo;

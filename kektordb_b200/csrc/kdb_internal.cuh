@@ -84,7 +84,9 @@ struct SearchArgs {
 struct SearchTuning {
   int fast = 1;             // sorted-list fast pass with exact re-run on ties (searcher.cuh): 0 = heaps only,
                             // 1 = where ties are practically absent (int8), 2 = every kind
-  int slots = 4;            // row slots per query-warp (bulk copies in flight per query), power of two
+  int slots = 4;            // row slots per query-warp (two groups of slots / 2 rows in flight per query): 2, 4, 8, 16
+  int slots_idle = 0;       // > 0: shape of a launch that finds no other batch of the handle in flight (the latency
+                            // shape: more rows in flight per query, fewer resident queries); 0 = always `slots`
   int cand_smem = 192;      // candidate-heap entries held in shared memory (the rest spills to HBM)
   int max_ctas_per_sm = 0;  // 0 = whatever fits
 };
@@ -280,6 +282,22 @@ __device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity)
       : "memory");
   return ok != 0;
 }
+// true on exactly one lane of the (converged) warp.  A bulk copy issued under this predicate compiles to ONE
+// UBLKCP; under `if (lane == 0)` ptxas cannot see that a single lane is active and wraps every copy in an
+// elect-one-lane-at-a-time loop (ELECT / UBLKCP / PLOP3 / BRA.U.ANY).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -296,49 +314,85 @@ __device__ __forceinline__ void fence_proxy_async() {
 // Then the xor-butterfly 16,8,4,2,1 (integer add for int8).
 // Replaces dotProductAsDistanceGonum / squaredEuclideanDistanceGo / squaredEuclideanGoFloat16 /
 // dotProductGoInt8 and the Rust kernels behind native/compute/include/kektordb_compute.h:8-11.
+// Packed float32 pairs (sm_100 FFMA2 / FADD2): one instruction, two independent IEEE operations — the same
+// bits as two scalar __fmaf_rn / __fsub_rn, half the issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2_rn(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2_rn(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 template <int KIND>
 struct LaneAcc {
-  float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+  f32x2 axy = 0ull, azw = 0ull;  // accumulators (4l, 4l+1), (4l+2, 4l+3)
   __device__ __forceinline__ void add(const float4 &a, const float4 &b) {
     if (KIND == KIND_COS_F32) {
-      ax = __fmaf_rn(a.x, b.x, ax);
-      ay = __fmaf_rn(a.y, b.y, ay);
-      az = __fmaf_rn(a.z, b.z, az);
-      aw = __fmaf_rn(a.w, b.w, aw);
+      axy = fma2_rn(pack2(a.x, a.y), pack2(b.x, b.y), axy);
+      azw = fma2_rn(pack2(a.z, a.w), pack2(b.z, b.w), azw);
     } else {
-      const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z),
-                  dw = __fsub_rn(a.w, b.w);
-      ax = __fmaf_rn(dx, dx, ax);
-      ay = __fmaf_rn(dy, dy, ay);
-      az = __fmaf_rn(dz, dz, az);
-      aw = __fmaf_rn(dw, dw, aw);
+      const f32x2 dxy = sub2_rn(pack2(a.x, a.y), pack2(b.x, b.y)), dzw = sub2_rn(pack2(a.z, a.w), pack2(b.z, b.w));
+      axy = fma2_rn(dxy, dxy, axy);
+      azw = fma2_rn(dzw, dzw, azw);
     }
   }
-  __device__ __forceinline__ float lane_sum() const { return __fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw)); }
+  __device__ __forceinline__ float lane_sum() const {
+    float ax, ay, az, aw;
+    unpack2(axy, ax, ay);
+    unpack2(azw, az, aw);
+    return __fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw));
+  }
 };
 __device__ __forceinline__ float2 f16x2_widen(float word) {
   const uint32_t u = __float_as_uint(word);
   const __half2 h = *reinterpret_cast<const __half2 *>(&u);
   return __half22float2(h);  // .x = low half = even element
 }
+// a 16-byte column of 8 packed halves widened to float32: lo = elements 0..3, hi = elements 4..7
+__device__ __forceinline__ void f16x8_widen(const float4 &c, float4 &lo, float4 &hi) {
+  const float2 w0 = f16x2_widen(c.x), w1 = f16x2_widen(c.y), w2 = f16x2_widen(c.z), w3 = f16x2_widen(c.w);
+  lo = make_float4(w0.x, w0.y, w1.x, w1.y);
+  hi = make_float4(w2.x, w2.y, w3.x, w3.y);
+}
 template <>
 struct LaneAcc<KIND_L2_F16> {
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  __device__ __forceinline__ void add2(float qa, float xb, int w) {
-    const float2 q = f16x2_widen(qa), x = f16x2_widen(xb);
-    const float d0 = __fsub_rn(q.x, x.x), d1 = __fsub_rn(q.y, x.y);
-    a[2 * w] = __fmaf_rn(d0, d0, a[2 * w]);
-    a[2 * w + 1] = __fmaf_rn(d1, d1, a[2 * w + 1]);
+  f32x2 a[4] = {0ull, 0ull, 0ull, 0ull};  // a[w] = accumulators (8l + 2w, 8l + 2w + 1)
+  __device__ __forceinline__ void add2(const float2 &q, float xb, int w) {
+    const float2 x = f16x2_widen(xb);
+    const f32x2 d = sub2_rn(pack2(q.x, q.y), pack2(x.x, x.y));
+    a[w] = fma2_rn(d, d, a[w]);
   }
-  __device__ __forceinline__ void add(const float4 &q, const float4 &b) {
-    add2(q.x, b.x, 0);
-    add2(q.y, b.y, 1);
-    add2(q.z, b.z, 2);
-    add2(q.w, b.w, 3);
+  __device__ __forceinline__ void add(const float4 &q, const float4 &b) {  // q: 8 packed halves
+    add2(f16x2_widen(q.x), b.x, 0);
+    add2(f16x2_widen(q.y), b.y, 1);
+    add2(f16x2_widen(q.z), b.z, 2);
+    add2(f16x2_widen(q.w), b.w, 3);
+  }
+  // the query column already widened (f16x8_widen): the traversal keeps it in registers in this form
+  __device__ __forceinline__ void add_wide(const float4 &qlo, const float4 &qhi, const float4 &b) {
+    add2(make_float2(qlo.x, qlo.y), b.x, 0);
+    add2(make_float2(qlo.z, qlo.w), b.y, 1);
+    add2(make_float2(qhi.x, qhi.y), b.z, 2);
+    add2(make_float2(qhi.z, qhi.w), b.w, 3);
   }
   __device__ __forceinline__ float lane_sum() const {
-    return __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])),
-                     __fadd_rn(__fadd_rn(a[4], a[5]), __fadd_rn(a[6], a[7])));
+    float s[8];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) unpack2(a[w], s[2 * w], s[2 * w + 1]);
+    return __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3])),
+                     __fadd_rn(__fadd_rn(s[4], s[5]), __fadd_rn(s[6], s[7])));
   }
 };
 template <>

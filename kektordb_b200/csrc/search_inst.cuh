@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const DevIndex ix, cons
 // maintenance; a query that meets two equal distances is appended to redo_list and answered by
 // hnsw_search_kernel afterwards, so the output is always the reference's.
 template <int SLOTS, int METRIC, int CPL>
-__global__ void __launch_bounds__(32, (METRIC == KIND_COS_I8 && CPL >= 1 && CPL <= 3) ? 28 : 1) hnsw_search_fast_kernel(const DevIndex ix, const SearchArgs a) {
+// (int8 rows up to 1536-d: the register cap follows the number of query-warps shared memory admits per SM)
+__global__ void __launch_bounds__(32, (METRIC == KIND_COS_I8 && CPL >= 1 && CPL <= 3) ? (SLOTS <= 8 ? 24 : 16) : 1)
+    hnsw_search_fast_kernel(const DevIndex ix, const SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   // two shapes: without heap arrays in shared memory (more resident query-warps; ties are handed to the
   // heap kernel through redo_list — for rows whose distances practically never tie), or with them, the

@@ -67,10 +67,12 @@ __host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots
   off += (size_t)cand_smem * sizeof(HeapEntry);
   const size_t o_bars = off;
   off += (size_t)slots * sizeof(uint64_t);
+  off = align_up(off, 16);  // the ids of a group are fetched with one vector load
   const size_t o_evalid = off;
   off += (size_t)dm * sizeof(uint32_t);
   const size_t o_evaldel = off;
   off += (size_t)dm * sizeof(uint32_t);
+  off = align_up(off, 16);
   const size_t o_evalnorm = off;
   if (kind == KIND_COS_I8) off += (size_t)dm * sizeof(float);
   const size_t o_evalthr = off;
@@ -224,7 +226,9 @@ struct Searcher {
   bool tie;       // two equal distances met: the heaps' tie order is needed, the exact kernel re-runs the query
   uint32_t slots_u32, bars_u32, slot_bytes, row_bytes;  // shared-window addresses of the row slots / barriers
   const unsigned char *vec_bytes;
-  float4 qreg[CPL > 0 ? CPL : 1];
+  // the query in registers: CPL 16-byte columns per lane; float16 columns are kept WIDENED (two float4 per column)
+  static constexpr int kQRegs = CPL > 0 ? (METRIC == KIND_L2_F16 ? 2 * CPL : CPL) : 1;
+  float4 qreg[kQRegs];
 
   // heaps_in_smem = false: the fast kernel's carve-up (no result / candidate heap arrays)
   __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem, bool heaps_in_smem = true)
@@ -265,11 +269,27 @@ struct Searcher {
     const float4 *src = reinterpret_cast<const float4 *>(src_row);
     if (CPL > 0) {
 #pragma unroll
-      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) qreg[t] = src[lane + 32 * t];
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) set_qreg(t, src[lane + 32 * t]);
     } else {
       for (uint32_t c = lane; c < (ix.stride >> 2); c += 32) sm.q4[c] = src[c];
     }
     __syncwarp();
+  }
+  __device__ __forceinline__ void set_qreg(int t, const float4 &col) {
+    if (METRIC == KIND_L2_F16) {
+      f16x8_widen(col, qreg[(2 * t) % kQRegs], qreg[(2 * t + 1) % kQRegs]);
+    } else {
+      qreg[t % kQRegs] = col;
+    }
+  }
+  // accumulate query column t x row column `col`
+  template <class Acc>
+  __device__ __forceinline__ void acc_col(Acc &acc, int t, const float4 &col) const {
+    if constexpr (METRIC == KIND_L2_F16) {
+      acc.add_wide(qreg[(2 * t) % kQRegs], qreg[(2 * t + 1) % kQRegs], col);
+    } else {
+      acc.add(qreg[t % kQRegs], col);
+    }
   }
 
   // a stored row as the query (construction: currObj := storedVector, hnsw_index.go:674, :1806): the
@@ -280,7 +300,7 @@ struct Searcher {
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (CPL > 0) {
 #pragma unroll
-      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) qreg[t] = (uint32_t)(lane + 32 * t) < valid ? src[lane + 32 * t] : z;
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) set_qreg(t, (uint32_t)(lane + 32 * t) < valid ? src[lane + 32 * t] : z);
     } else {
       for (uint32_t c = lane; c < (ix.stride >> 2); c += 32) sm.q4[c] = c < valid ? src[c] : z;
     }
@@ -292,21 +312,39 @@ struct Searcher {
   }
 
   // ---- row streaming: groups of G rows, two group buffers, one mbarrier per buffer ------------------
-  __device__ __forceinline__ void issue_one(uint32_t buf, uint32_t id) {  // lane 0: a single row into buffer `buf`
-    const uint32_t bar = bars_u32 + buf * 8u;
-    mbar_expect_tx_u32(bar, row_bytes);
-    bulk_g2s_u32(slots_u32 + buf * (uint32_t)G * slot_bytes, vec_bytes + (size_t)id * row_bytes, row_bytes, bar);
+  // (both called by the whole, converged warp; one elected lane issues — see elect_one)
+  __device__ __forceinline__ void issue_one(uint32_t buf, uint32_t id) {  // a single row into buffer `buf`
+    if (elect_one()) {
+      const uint32_t bar = bars_u32 + buf * 8u;
+      mbar_expect_tx_u32(bar, row_bytes);
+      bulk_g2s_u32(slots_u32 + buf * (uint32_t)G * slot_bytes, vec_bytes + (size_t)id * row_bytes, row_bytes, bar);
+    }
   }
-  // lane 0: rows eval_id[j0 .. j0 + cnt) into the slots of buffer (g & 1), all completing on that buffer's barrier
+  // rows eval_id[j0 .. j0 + cnt) into the slots of buffer (g & 1), all completing on that buffer's barrier
   __device__ __forceinline__ void issue_group(uint32_t g, uint32_t j0, uint32_t cnt) {
-    const uint32_t buf = g & 1u;
-    const uint32_t bar = bars_u32 + buf * 8u;
-    uint32_t dst = slots_u32 + buf * (uint32_t)G * slot_bytes;
-    mbar_expect_tx_u32(bar, cnt * row_bytes);
+    if (elect_one()) {
+      const uint32_t buf = g & 1u;
+      const uint32_t bar = bars_u32 + buf * 8u;
+      uint32_t dst = slots_u32 + buf * (uint32_t)G * slot_bytes;
+      mbar_expect_tx_u32(bar, cnt * row_bytes);
+      if (cnt == (uint32_t)G) {  // a full group: straight-line code, the ids fetched with one shared-memory load
+        uint32_t id[G];
+        if (G == 4) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(sm.eval_id + j0);
+          id[0] = v.x, id[G > 1 ? 1 : 0] = v.y, id[G > 2 ? 2 : 0] = v.z, id[G > 3 ? 3 : 0] = v.w;
+        } else if (G == 2) {
+          const uint2 v = *reinterpret_cast<const uint2 *>(sm.eval_id + j0);
+          id[0] = v.x, id[G > 1 ? 1 : 0] = v.y;
+        } else {
 #pragma unroll
-    for (int r = 0; r < G; ++r) {
-      if ((uint32_t)r < cnt) bulk_g2s_u32(dst, vec_bytes + (size_t)sm.eval_id[j0 + r] * row_bytes, row_bytes, bar);
-      dst += slot_bytes;
+          for (int r = 0; r < G; ++r) id[r] = sm.eval_id[j0 + r];
+        }
+#pragma unroll
+        for (int r = 0; r < G; ++r) bulk_g2s_u32(dst + r * slot_bytes, vec_bytes + (size_t)id[r] * row_bytes, row_bytes, bar);
+      } else {
+        for (uint32_t r = 0; r < cnt; ++r, dst += slot_bytes)
+          bulk_g2s_u32(dst, vec_bytes + (size_t)sm.eval_id[j0 + r] * row_bytes, row_bytes, bar);
+      }
     }
   }
   __device__ __forceinline__ void wait_buf(uint32_t buf) {
@@ -326,7 +364,7 @@ struct Searcher {
 #pragma unroll
       for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) {
 #pragma unroll
-        for (int r = 0; r < G; ++r) acc[r].add(qreg[t], r4[r * pitch4 + lane + 32 * t]);
+        for (int r = 0; r < G; ++r) acc_col(acc[r], t, r4[r * pitch4 + lane + 32 * t]);
       }
     } else {
       const uint32_t nchunks = ix.stride >> 2;
@@ -381,14 +419,13 @@ struct Searcher {
 
   // dist(query, entry) (:2471): one row through buffer 0; the reduced value on every lane
   __device__ __forceinline__ float entry_sum(uint32_t ep) {
-    if (lane == 0) issue_one(0, ep);
-    __syncwarp();
+    issue_one(0, ep);
     wait_buf(0);
     const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots);
     LaneAcc<METRIC> acc;
     if (CPL > 0) {
 #pragma unroll
-      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) acc.add(qreg[t], r4[lane + 32 * t]);
+      for (int t = 0; t < (CPL > 0 ? CPL : 1); ++t) acc_col(acc, t, r4[lane + 32 * t]);
     } else {
       const uint32_t nchunks = ix.stride >> 2;
       for (uint32_t c = lane; c < nchunks; c += 32) acc.add(sm.q4[c], r4[c]);
@@ -425,21 +462,22 @@ struct Searcher {
   __device__ __forceinline__ void stream_hop(const uint32_t n_eval, const int ef) {
     if (n_eval == 0) return;
     const uint32_t n_groups = (n_eval + (uint32_t)G - 1u) / (uint32_t)G;
-    if (lane == 0) {
-      issue_group(0, 0, n_eval < (uint32_t)G ? n_eval : (uint32_t)G);
-      if (n_groups > 1) issue_group(1, G, n_eval - G < (uint32_t)G ? n_eval - G : (uint32_t)G);
+    issue_group(0, 0, n_eval < (uint32_t)G ? n_eval : (uint32_t)G);
+    if (n_groups > 1) issue_group(1, G, n_eval - G < (uint32_t)G ? n_eval - G : (uint32_t)G);
+    // the admission state every lane pre-tests against: uniform copies of lane 0's (heap path), refreshed after a
+    // group that admitted something
+    bool full = false;
+    double wst = 0.0;
+    if (!LIST) {
+      full = __shfl_sync(0xffffffffu, res.n >= ef ? 1 : 0, 0) != 0;
+      wst = __shfl_sync(0xffffffffu, worst, 0);
     }
     for (uint32_t g = 0, j0 = 0; g < n_groups; ++g, j0 += G) {
       const uint32_t buf = g & 1u;
       const uint32_t cnt = n_eval - j0 < (uint32_t)G ? n_eval - j0 : (uint32_t)G;
-      bool full;
-      double wst;
       if (LIST) {
         full = ln >= ef;
         wst = worst;
-      } else {
-        full = __shfl_sync(0xffffffffu, res.n >= ef ? 1 : 0, 0) != 0;
-        wst = __shfl_sync(0xffffffffu, worst, 0);
       }
       wait_buf(buf);
       float p[G];
@@ -449,49 +487,74 @@ struct Searcher {
       // slots are refilled BEFORE the rest of the reduction and the queue updates.  (No proxy fence: the slots were
       // only READ through the generic proxy; the bulk copies' completion is observed through the mbarrier.)
       __syncwarp();
-      if (lane == 0 && g + 2 < n_groups) {
+      if (g + 2 < n_groups) {
         const uint32_t j2 = j0 + 2u * G;
         issue_group(g, j2, n_eval - j2 < (uint32_t)G ? n_eval - j2 : (uint32_t)G);
       }
       reduce_tail(p);
-      // distance + pre-test on the lane that holds the row
-      uint32_t r_mine;
-      bool holder;
-      float s_mine = p[0];
       if (METRIC == KIND_COS_I8) {
-        r_mine = (uint32_t)lane;
-        holder = r_mine < cnt;
+        // int8: every lane holds the exact integer dot of every row of the group.  The thresholds of
+        // collect_neighbours reject with one integer compare per row; what passes takes the float64 path.
+        int thr[G];
+        if (G == 4) {  // (16-byte aligned: j0 is a multiple of G and the list starts on a 128-byte boundary)
+          const int4 v = *reinterpret_cast<const int4 *>(sm.eval_thr + j0);
+          thr[0] = v.x, thr[G > 1 ? 1 : 0] = v.y, thr[G > 2 ? 2 : 0] = v.z, thr[G > 3 ? 3 : 0] = v.w;
+        } else if (G == 2) {
+          const int2 v = *reinterpret_cast<const int2 *>(sm.eval_thr + j0);
+          thr[0] = v.x, thr[G > 1 ? 1 : 0] = v.y;
+        } else {
 #pragma unroll
-        for (int r = 1; r < G; ++r)
-          if (lane == r) s_mine = p[r];
-      } else {
-        r_mine = (uint32_t)lane >> kRowShift;
-        holder = (lane & ((1 << kRowShift) - 1)) == 0 && r_mine < cnt;
+          for (int r = 0; r < G; ++r) thr[r] = sm.eval_thr[j0 + r];
+        }
+        uint32_t m = 0u;
+#pragma unroll
+        for (int r = 0; r < G; ++r)
+          if ((uint32_t)r < cnt && __float_as_int(p[r]) > thr[r]) m |= 1u << r;
+        const bool any_i8 = m != 0u;
+        if (any_i8) {
+#pragma unroll
+          for (int r = 0; r < G; ++r) {
+            if ((m >> r) & 1u) {
+              const double d = int8_distance(__float_as_int(p[r]), qnorm, sm.eval_norm[j0 + r]);
+              if (LIST) {
+                list_update(d, j0 + r, ef);
+              } else if (lane == 0) {
+                heap_update(d, j0 + r, ef);
+              }
+            }
+          }
+          if (!LIST) {
+            full = __shfl_sync(0xffffffffu, res.n >= ef ? 1 : 0, 0) != 0;
+            wst = __shfl_sync(0xffffffffu, worst, 0);
+          }
+        }
+        continue;
       }
+      // float rows: distance + pre-test on the lane that holds the row
+      const uint32_t r_mine = (uint32_t)lane >> kRowShift;
+      const bool holder = (lane & ((1 << kRowShift) - 1)) == 0 && r_mine < cnt;
       double d = 0.0;
       bool pass = false;
       if (holder) {
-        if (METRIC == KIND_COS_I8) {
-          if (__float_as_int(s_mine) > sm.eval_thr[j0 + r_mine]) {  // else: certainly not admitted (collect_neighbours)
-            d = int8_distance(__float_as_int(s_mine), qnorm, sm.eval_norm[j0 + r_mine]);
-            pass = !full || d < wst;
-          }
-        } else {
-          d = to_distance<METRIC>(s_mine);
-          pass = !full || d < wst;
-        }
+        d = to_distance<METRIC>(p[0]);
+        pass = !full || d < wst;
       }
       uint32_t mask = __ballot_sync(0xffffffffu, pass);
+      const bool any = mask != 0u;
       while (mask) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1u;
         const double dd = __shfl_sync(0xffffffffu, d, src);
-        const uint32_t j = j0 + (METRIC == KIND_COS_I8 ? (uint32_t)src : (uint32_t)src >> kRowShift);
+        const uint32_t j = j0 + ((uint32_t)src >> kRowShift);
         if (LIST) {
           list_update(dd, j, ef);
         } else if (lane == 0) {
           heap_update(dd, j, ef);
         }
+      }
+      if (!LIST && any) {
+        full = __shfl_sync(0xffffffffu, res.n >= ef ? 1 : 0, 0) != 0;
+        wst = __shfl_sync(0xffffffffu, worst, 0);
       }
     }
   }
@@ -544,59 +607,97 @@ struct Searcher {
         row = ix.upper_adj + ((size_t)ix.upper_first[cur] + (uint32_t)(level - 1)) * deg;
       }
       const double wmargin = __dsub_rn(__dsub_rn(1.0, worst_now), 1e-12);
-      for (uint32_t base = 0; base < deg; base += 32) {  // :2537
-        const uint32_t idx = base + lane;
-        const uint32_t id = idx < deg ? row[idx] : 0u;  // plain load: build kernels mutate rows
-        const bool act = id != 0u;                      // rows are compacted at upload; 0 = padding
-        if (__ballot_sync(0xffffffffu, act) == 0u) break;
-        // a repeated id inside the row is visited by its first occurrence (:2539-2542)
-        const uint32_t same = __match_any_sync(0xffffffffu, id);
-        const bool leader = act && ((__ffs(same) - 1) == lane);
-        // nodes[neighborID] == nil is tested at search time (:2553-2561): a row the host has not re-patched yet
-        // may still name a node Vacuum removed.  This load, the int8 norm and the deleted bit do not depend on the
-        // visited test: they are issued BEFORE the atomic so that all the latencies overlap.
-        const bool in_range = leader && id <= ix.n;
-        int8_t lvl = -1;
-        float sn = 0.f;
-        uint32_t del = 0u;
-        if (in_range) {
-          lvl = ix.levels[id];
-          if (METRIC == KIND_COS_I8) sn = ix.norms[id];
-          if (ix.deleted != nullptr) del = bit_test(ix.deleted, id) ? 1u : 0u;
+      // 64 neighbours per pass (two per lane: slot a = idx, slot b = idx + 32, a before b in row order).  Everything
+      // that depends only on the ids — nil test, int8 norm, deleted bit, allow-list bit — is loaded for both slots
+      // BEFORE the two visited test-and-sets, which are issued back to back: one round trip instead of two.
+      for (uint32_t base = 0; base < deg; base += 64) {  // :2537
+        uint32_t idv[2];
+        bool act[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t idx = base + 32u * h + lane;
+          idv[h] = idx < deg ? row[idx] : 0u;  // plain load: build kernels mutate rows
         }
-        bool fresh = false;
-        if (leader) {
-          const uint32_t bit = 1u << (id & 31);
-          const uint32_t old = atomicOr(&vis[id >> 5], bit);  // visited.Has + visited.Add
-          fresh = (old & bit) == 0u;
-        }
-        if (log_marks) {
-          const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
-          const uint32_t m0 = sm.ctl->n_marked;
-          if (fresh) {
-            const uint32_t pos = m0 + __popc(fm & ((1u << lane) - 1u));
-            if (pos < (uint32_t)kMarkCap) sm.marked[pos] = id;
+        act[0] = idv[0] != 0u;  // rows are compacted at upload; 0 = padding
+        act[1] = idv[1] != 0u;
+        if (__ballot_sync(0xffffffffu, act[0]) == 0u) break;
+        const bool any_b = __ballot_sync(0xffffffffu, act[1]) != 0u;
+        bool leader[2], fresh[2] = {false, false}, allowed[2] = {true, true};
+        int8_t lvl[2] = {-1, -1};
+        float sn[2] = {0.f, 0.f};
+        uint32_t del[2] = {0u, 0u};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          // a repeated id inside the row is visited by its first occurrence (:2539-2542)
+          const uint32_t same = __match_any_sync(0xffffffffu, idv[h]);
+          leader[h] = act[h] && ((__ffs(same) - 1) == lane);
+          // nodes[neighborID] == nil is tested at search time (:2553-2561): a row the host has not re-patched yet
+          // may still name a node Vacuum removed
+          if (leader[h] && idv[h] <= ix.n) {
+            lvl[h] = ix.levels[idv[h]];
+            if (METRIC == KIND_COS_I8) sn[h] = ix.norms[idv[h]];
+            if (ix.deleted != nullptr) del[h] = bit_test(ix.deleted, idv[h]) ? 1u : 0u;
+            if (a.allow != nullptr) allowed[h] = bit_test(a.allow, idv[h]);
           }
-          __syncwarp();
-          if (lane == 0) sm.ctl->n_marked = m0 + __popc(fm);
-          __syncwarp();
+          if (h == 0 && !any_b) break;
         }
-        // allow-list before any distance work (:2545-2549), then the nil test (:2553-2561)
-        const bool keep = fresh && (a.allow == nullptr || bit_test(a.allow, id)) && lvl >= 0;
-        const uint32_t km = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
-          sm.eval_id[pos] = id;
-          sm.eval_del[pos] = del;
-          if (METRIC == KIND_COS_I8) {
-            sm.eval_norm[pos] = sn;
-            int thr = (int)0x80000000;  // nothing is rejected without the exact test
-            if (full && sn != 0.f)
-              thr = __double2int_rd(__dmul_rn(wmargin, __dmul_rn(static_cast<double>(qnorm), static_cast<double>(sn))));
-            sm.eval_thr[pos] = thr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (leader[h]) {
+            const uint32_t bit = 1u << (idv[h] & 31);
+            const uint32_t old = atomicOr(&vis[idv[h] >> 5], bit);  // visited.Has + visited.Add
+            fresh[h] = (old & bit) == 0u;
+          }
+          if (h == 0 && !any_b) break;
+        }
+        if (any_b) {
+          // An id that occurs in BOTH slots is visited by its a-occurrence.  The two test-and-sets of such a pair
+          // are not ordered: if the b-lane won, hand the visit over to the a-lane.  Only an a-lane that found its
+          // bit set can be the loser of such a race, so those (few) ids are compared with the fresh b ids.
+          uint32_t lost = __ballot_sync(0xffffffffu, leader[0] && !fresh[0]);
+          const uint32_t won_b = __ballot_sync(0xffffffffu, fresh[1]);
+          while (lost != 0u && won_b != 0u) {
+            const int src = __ffs(lost) - 1;
+            lost &= lost - 1u;
+            const uint32_t x = __shfl_sync(0xffffffffu, idv[0], src);
+            const bool hit = fresh[1] && idv[1] == x;
+            if (__any_sync(0xffffffffu, hit)) {
+              if (hit) fresh[1] = false;
+              if (lane == src) fresh[0] = true;
+            }
           }
         }
-        n_eval += __popc(km);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (log_marks) {
+            const uint32_t fm = __ballot_sync(0xffffffffu, fresh[h]);
+            const uint32_t m0 = sm.ctl->n_marked;
+            if (fresh[h]) {
+              const uint32_t pos = m0 + __popc(fm & ((1u << lane) - 1u));
+              if (pos < (uint32_t)kMarkCap) sm.marked[pos] = idv[h];
+            }
+            __syncwarp();
+            if (lane == 0) sm.ctl->n_marked = m0 + __popc(fm);
+            __syncwarp();
+          }
+          // allow-list before any distance work (:2545-2549), then the nil test (:2553-2561)
+          const bool keep = fresh[h] && allowed[h] && lvl[h] >= 0;
+          const uint32_t km = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            const uint32_t pos = n_eval + __popc(km & ((1u << lane) - 1u));
+            sm.eval_id[pos] = idv[h];
+            sm.eval_del[pos] = del[h];
+            if (METRIC == KIND_COS_I8) {
+              sm.eval_norm[pos] = sn[h];
+              int thr = (int)0x80000000;  // nothing is rejected without the exact test
+              if (full && sn[h] != 0.f)
+                thr = __double2int_rd(__dmul_rn(wmargin, __dmul_rn(static_cast<double>(qnorm), static_cast<double>(sn[h]))));
+              sm.eval_thr[pos] = thr;
+            }
+          }
+          n_eval += __popc(km);
+          if (h == 0 && !any_b) break;
+        }
       }
       __syncwarp();
     }

@@ -132,6 +132,7 @@ SIGNATURES = {
     "kdbgpu_prepare_search": (_i32, [_vp, _u32, _i32, _i32]),
     "kdbgpu_set_fast_path": (_i32, [_vp, _i32]),
     "kdbgpu_set_tuning": (_i32, [_vp, _i32, _i32, _i32]),
+    "kdbgpu_set_idle_slots": (_i32, [_vp, _i32]),
     "kdbgpu_set_candidate_bound": (_i32, [_vp, _u32]),
     "kdbgpu_shard_unique_id": (_i32, [_vp]),
     "kdbgpu_shard_group_create_rank": (_i32, [_vp, _i32, _i32, _vp, _u32, C.POINTER(_vp)]),

@@ -268,6 +268,10 @@ class GpuIndex:
     def set_tuning(self, slots: int = 0, cand_smem: int = 0, max_ctas_per_sm: int = -1) -> None:
         ffi.check(self._lib.kdbgpu_set_tuning(self._handle(), slots, cand_smem, max_ctas_per_sm))
 
+    def set_idle_slots(self, slots_idle: int) -> None:
+        """Slot count of a launch that finds no other batch in flight (0 = same as the throughput shape)."""
+        ffi.check(self._lib.kdbgpu_set_idle_slots(self._handle(), slots_idle))
+
     # -- query -----------------------------------------------------------------------------
     def SearchWithScores(self, query, k: int, allowList: np.ndarray | None = None, efSearch: int = 0):
         """Batched (*Index).SearchWithScores.  `query` is [nq, dim] (or [dim]); allowList a dense

@@ -1,7 +1,8 @@
 """Traversal-kernel shape sweep on the benchmark workload (1M x 768 cosine, M=32, ef=128, k=10, 1024 queries):
 isolated launch time and pipelined step interval for every (slots, cand_smem, max CTAs/SM) asked for.
   gpurun -- 'python profiles/tools/sweep_tuning.py 4,192,0 8,192,0 8,192,7 16,128,0'
-Env: PREC=float32|int8|float16, N, OV (batches in flight, default 3), FAST (kdbgpu_set_fast_path)."""
+Env: PREC=float32|int8|float16, N, OV (batches in flight, default 3), FAST (kdbgpu_set_fast_path).
+A fourth field is the idle shape (kdbgpu_set_idle_slots): 4,192,0,8 = slots 4 with batches in flight, 8 alone."""
 import os
 import sys
 
@@ -14,7 +15,7 @@ import bench  # noqa: E402
 from kektordb_b200 import GpuIndex  # noqa: E402
 
 N = int(os.environ.get("N", 1_000_000))
-D, M, EFC, EF, K, B = 768, 32, 200, 128, 10, 1024
+D, M, EFC, EF, K, B = 768, 32, 200, 128, 10, int(os.environ.get("B", 1024))
 prec = os.environ.get("PREC", "float32")
 ov = int(os.environ.get("OV", 3))
 dev = torch.device("cuda", 0)
@@ -34,13 +35,15 @@ torch.cuda.synchronize()
 del X
 if "FAST" in os.environ:
     gi.set_fast_path(int(os.environ["FAST"]))
-nb = 24
+nb = max(4, 24 * 1024 // B)
 Qd = bench.make_data(torch, nb * B, D, 32, 0.1, 4242, dev)
 esz = {"float32": 4, "float16": 2, "int8": 1}[prec]
 row_bytes = (D * esz + 127) // 128 * 128 + (4 if prec == "int8" else 0)
 shapes = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]] or [(4, 192, 0)]
-for slots, cs, cap in shapes:
+for shape in shapes:
+    slots, cs, cap = shape[:3]
     gi.set_tuning(slots, cs, cap)
+    gi.set_idle_slots(shape[3] if len(shape) > 3 else slots)
     gi.prepare_search(B, K, EF)
     conc = gi.search_concurrency(K, EF)
     for n_ov in (1, ov):
@@ -51,5 +54,5 @@ for slots, cs, cap in shapes:
         ms = run.timed(4, 20, torch.cuda.synchronize) / 20
         st = gi.last_search_stats()
         byts = st.dist_evals * row_bytes + st.hops_l0 * 2 * M * 4 + (st.hops - st.hops_l0) * M * 4
-        print(f"{prec} slots={slots} cand_smem={cs} cap={cap} resident={conc} in_flight={n_ov}: {ms:.3f} ms/step "
+        print(f"{prec} slots={slots}{'/idle ' + str(shape[3]) if len(shape) > 3 else ''} cand_smem={cs} cap={cap} resident={conc} in_flight={n_ov}: {ms:.3f} ms/step "
               f"{B / ms * 1e3:,.0f} q/s  hbm_frac={byts / (ms / 1e3) / 1e9 / 6550.4:.3f}", flush=True)
