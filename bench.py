@@ -298,6 +298,16 @@ def workload_string(args):
             f"batch={args.batch} queries/step")
 
 
+def shared_config(args):
+    """`config` = the workload, identical on both arms (the driver compares the two arms' config); what is specific to
+    an arm (how many GPUs / host threads, batches in flight, build time) goes under `arm`."""
+    return {"workload": workload_string(args),
+            "data_model": (f"random-normal, low-rank covariance (latent {args.latent}, noise {args.noise}), "
+                           if args.latent > 0 else "random-normal, i.i.d. isotropic, ") + "seeds 42/4242, levels seed 1",
+            "graph": "built on the GPU by kdbgpu_add_batch (bit-identical to the oracle's AddBatch, tests/test_gpu_build.py)",
+            "l2_policy": f"inputs larger than L2: {args.n * ((args.dim + 127) // 128 * 128) * 4 / 1e9:.2f} GB corpus, new query batch every step"}
+
+
 class DeviceRunner:
     """Device-resident stepping: batch i goes to stream i mod n_ov, so that one batch's straggler tail overlaps the
     next one's head.  `search` is GpuIndex.search_device or ShardGroup.search_device (same leading arguments)."""
@@ -627,17 +637,13 @@ def main():
 
     if rank == 0:
         line.update({
-            "config": {"workload": workload_string(args),
-                       "parallelism": "1 GPU" if world == 1 else
-                                      (f"`value`: {world} replicas (full corpus per GPU), queries split, NO collective; " if do_replica else "") +
-                                      (f"`shard`: corpus split by id range over {world} GPUs, library shard group: ONE ncclAllGather "
-                                       f"of the packed per-shard top-{k} per batch + merge kernel" if do_shard else ""),
-                       "per_rank": "1xB200 per rank, batch per GPU per step" if world > 1 else "1xB200",
-                       "data_model": (f"random-normal, low-rank covariance (latent {args.latent}, noise {args.noise}), "
-                                      if args.latent > 0 else "random-normal, i.i.d. isotropic, ") +
-                                     "seeds 42/4242; graph built on GPU (kdbgpu_add_batch), levels seed 1",
-                       "l2_policy": "inputs larger than L2: 3.07 GB corpus, new query batch every step",
-                       "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "host_cores": ncores},
+            "config": shared_config(args),
+            "arm": {"parallelism": "1 GPU" if world == 1 else
+                                   (f"`value`: {world} replicas (full corpus per GPU), queries split, NO collective; " if do_replica else "") +
+                                   (f"`shard`: corpus split by id range over {world} GPUs, library shard group: ONE ncclAllGather "
+                                    f"of the packed per-shard top-{k} per batch + merge kernel" if do_shard else ""),
+                    "per_rank": "1xB200 per rank, batch per GPU per step" if world > 1 else "1xB200",
+                    "batches_in_flight": n_ov, "build_seconds": round(build_s, 2), "host_cores": ncores},
             "shard": shard, "cpu_baseline": cpu_baseline, "parity": parity, "extras": extras, "clocks": clocks})
         print(json.dumps(line), flush=True)
     if gi is not None:
@@ -980,9 +986,9 @@ def run_reference_arm(args, gi, Qh_np, ncores, build_s):
         "value": round(value, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "recall_at_10": round(recall, 4),
-        "config": {"workload": workload_string(args), "parallelism": f"CPU only, {ncores} threads",
-                   "graph": "built on the GPU by kdbgpu_add_batch (bit-identical to the oracle's AddBatch), "
-                            "searched on the CPU only", "build_seconds": round(build_s, 2)},
+        "config": shared_config(args),
+        "arm": {"parallelism": f"CPU only, {ncores} threads (the graph is searched on the CPU only)",
+                "build_seconds": round(build_s, 2), "host_cores": ncores},
         "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": ncores, "kind": "port",
                          "sample": f"{args.steps} steps of {B} queries; Go/Rust reference not buildable here "
                                    "(no go/rustc): oracle port, AVX2-FMA 8-lane distance order"},

@@ -692,6 +692,11 @@ int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m
   // float16 / int8 rows: the traversal is latency-bound, so resident query-warps matter more than
   // shared-memory heap capacity (measured: profiles/README.md, quantized sweep)
   if (precision != KDBGPU_PRECISION_F32) h->tuning.cand_smem = 64;
+  // launch shapes measured at 1 M x 768 (profiles/README.md): rows per group = slots / 2.  float32 / float16 rows are
+  // HBM-bound with batches in flight (more resident query-warps win: 4 slots) and latency-bound alone (8 slots);
+  // int8 rows are issue-bound either way (8 slots halve the per-row overhead, 16 when alone)
+  h->tuning.slots = precision == KDBGPU_PRECISION_INT8 ? 8 : 4;
+  h->tuning.slots_idle = precision == KDBGPU_PRECISION_INT8 ? 16 : 8;
   if ((env = getenv("KDBGPU_FAST"))) h->tuning.fast = atoi(env);
   if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
   if ((env = getenv("KDBGPU_SLOTS_IDLE"))) h->tuning.slots_idle = atoi(env);
@@ -1691,7 +1696,13 @@ int kdbgpu_search_concurrency(kdbgpu_index *h, int k, int ef_search) {
   if (!h) return 0;
   DeviceGuard g(h->device);
   const int ef = ef_search < k ? k : ef_search;
-  return search_occupancy(h->dev(), ef, h->tuning) * h->num_sms;
+  const DevIndex ix = h->dev();
+  int occ = search_occupancy(ix, ef, h->tuning);
+  if (search_fast_eligible(ix, ef, h->tuning)) {  // the pass that answers (nearly) every query of such an index
+    const int occ_fast = search_fast_occupancy(ix, ef, h->tuning);
+    if (occ_fast > occ) occ = occ_fast;
+  }
+  return occ * h->num_sms;
 }
 
 }  // extern "C"

@@ -687,12 +687,12 @@ cudaError_t launch_to_bf16(const float *src, size_t src_stride, uint32_t rows, u
   return cudaGetLastError();
 }
 
-// CTA pairs (flat_tc2_kernel) when KDBGPU_FLAT_2CTA=1 and the batch has at least one full 256-query tile pair (the
-// pair kernel returns the same bits but measures slower than the single-CTA kernel so far).  L.grid is updated to the number of CTAs actually launched (the caller sizes / reads the
-// per-CTA nominee lists with it).
+// CTA pairs (flat_tc2_kernel) whenever the batch has at least one full 256-query tile pair; KDBGPU_FLAT_2CTA=0 keeps
+// the single-CTA kernel (same bits; the pair kernel measures 2-3 % faster at 1 M x 768, profiles/README.md).  L.grid is
+// updated to the number of CTAs actually launched (the caller sizes / reads the per-CTA nominee lists with it).
 cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream) {
   const char *pair_env = getenv("KDBGPU_FLAT_2CTA");  // read per launch: tests switch it
-  const bool pair_ok = pair_env && pair_env[0] == '1';
+  const bool pair_ok = !(pair_env && pair_env[0] == '0');
   const bool pair = pair_ok && L.nq_pad >= 2u * BM;
   CUtensorMap tmQ, tmX;
   if (!make_tmap(&tmQ, L.q_bf16, L.nq_pad, L.dp, BM) || !make_tmap(&tmX, L.x_bf16, L.n_pad, L.dp, pair ? BN / 2 : BN))

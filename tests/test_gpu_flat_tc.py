@@ -69,7 +69,7 @@ def test_tensor_core_scores_within_certified_bound(metric, mode, n, dim):
 def test_cta_pair_kernel_is_bit_identical_on_full_and_ragged_query_tile_pairs(nq, monkeypatch):
     """Batches of 256+ queries take the cta_group::2 kernel (two CTAs share every corpus tile): full tile pairs,
     a ragged last pair (300 -> 384 padded rows, the pair tile runs past them), and the benchmark's batch of 1024."""
-    monkeypatch.setenv("KDBGPU_FLAT_2CTA", "1")  # the pair kernel is opt-in (read per launch)
+    monkeypatch.delenv("KDBGPU_FLAT_2CTA", raising=False)  # the pair kernel is the default (the switch is read per launch)
     n, dim = 30000, 200
     X, rng = _data(n, dim, 77, lowrank=True)
     Q = rng.standard_normal((nq, dim)).astype(np.float32)
@@ -87,7 +87,7 @@ def test_cta_pair_kernel_is_bit_identical_on_full_and_ragged_query_tile_pairs(nq
         assert np.array_equal(c[0], b[0][64:128]) and np.array_equal(c[1], b[1][64:128])
         assert b[3].hops <= 2
     monkeypatch.setenv("KDBGPU_FLAT_2CTA", "0")
-    d = gi.flat_search(Q, 10, 0, prefilter=True)                           # the default single-CTA kernel, same batch
+    d = gi.flat_search(Q, 10, 0, prefilter=True)                           # the single-CTA kernel, same batch
     e = gi.flat_search(Q[:64], 10, 0)
     assert np.array_equal(d[0][:64], e[0]) and np.array_equal(d[1][:64], e[1])
     gi.close()
