@@ -213,6 +213,7 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
   a.work_counter = w.work_counter.p;
   a.err_flag = d_err;
   a.id_base = id_base;
+  a.rows_evict_first = tn.rows_evict_first;
   int grid = occ * h->num_sms;
   if ((uint32_t)grid > nq) grid = (int)nq;
   if (fast && occ_fast > 0) {
@@ -700,6 +701,7 @@ int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m
   if ((env = getenv("KDBGPU_FAST"))) h->tuning.fast = atoi(env);
   if ((env = getenv("KDBGPU_SLOTS"))) h->tuning.slots = atoi(env);
   if ((env = getenv("KDBGPU_SLOTS_IDLE"))) h->tuning.slots_idle = atoi(env);
+  if ((env = getenv("KDBGPU_ROWS_EVICT_FIRST"))) h->tuning.rows_evict_first = atoi(env);
   if ((env = getenv("KDBGPU_CAND_SMEM"))) h->tuning.cand_smem = atoi(env);
   if ((env = getenv("KDBGPU_MAX_CTAS_PER_SM"))) h->tuning.max_ctas_per_sm = atoi(env);
   auto cleanup = [&](int rc) {

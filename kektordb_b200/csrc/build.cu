@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(32) seq_add_kernel(const DevIndex ix_in, const
   extern __shared__ __align__(128) unsigned char smem[];
   DevIndex ix = ix_in;
   Searcher<kSeqSlots, METRIC, 0> s(ix, a, smem);
-  const size_t base = smem_layout(ix.stride, a.ef, kSeqSlots, a.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
+  const size_t base = smem_layout(ix.stride, slot_pitch_words(ix.stride, ix.row_words, ix.kind), a.ef, kSeqSlots, a.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
                                   true, ix.kind, nullptr, nullptr);
   float4 *q2 = reinterpret_cast<float4 *>(smem + base);
   const int LL = (b.efc + kMaxDeg + 3) & ~1;  // list length, even so the f64 array after it stays aligned
@@ -638,7 +638,7 @@ size_t commit_smem_bytes(const DevIndex &ix) {
 }
 
 size_t seq_add_smem_bytes(const DevIndex &ix, int efc, uint32_t cand_smem) {
-  const size_t base = smem_layout(ix.stride, efc, kSeqSlots, cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, true, ix.kind,
+  const size_t base = smem_layout(ix.stride, slot_pitch_words(ix.stride, ix.row_words, ix.kind), efc, kSeqSlots, cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu, true, ix.kind,
                                   nullptr, nullptr);
   const size_t lists = (size_t)((efc + kMaxDeg + 3) & ~1) + 2;
   return base + (size_t)ix.stride * sizeof(float) + lists * (sizeof(double) + 3 * sizeof(uint32_t)) +
@@ -646,7 +646,7 @@ size_t seq_add_smem_bytes(const DevIndex &ix, int efc, uint32_t cand_smem) {
 }
 
 size_t build_search_smem(const DevIndex &ix, int efc, uint32_t cand_smem) {
-  return smem_layout(ix.stride, efc, kBuildSlots, cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
+  return smem_layout(ix.stride, slot_pitch_words(ix.stride, ix.row_words, ix.kind), efc, kBuildSlots, cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
                      build_cpl_of(ix) == 0, ix.kind, nullptr, nullptr);
 }
 

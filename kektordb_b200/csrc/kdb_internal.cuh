@@ -79,6 +79,7 @@ struct SearchArgs {
   // id-range shards: returned ids are local id + id_base, so that the per-shard results can be
   // gathered and merged without another pass (empty slots stay 0)
   uint32_t id_base;
+  int rows_evict_first;  // row copies carry an L2 evict_first hint (SearchTuning.rows_evict_first)
 };
 
 struct SearchTuning {
@@ -89,6 +90,7 @@ struct SearchTuning {
                             // shape: more rows in flight per query, fewer resident queries); 0 = always `slots`
   int cand_smem = 192;      // candidate-heap entries held in shared memory (the rest spills to HBM)
   int max_ctas_per_sm = 0;  // 0 = whatever fits
+  int rows_evict_first = 0; // row bulk copies carry an L2 evict_first hint
 };
 bool search_slots_supported(int slots);
 
@@ -267,6 +269,19 @@ __device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void *src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// L2 eviction-priority hint for data that is read once (the corpus rows of a traversal: 99 % of the traffic, no reuse),
+// so that what IS re-read — adjacency rows, visited words, levels, norms — survives in L2 longer
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_u32_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
 }
 // (a suspend-time hint on try_wait was measured and rejected: the coarser wake-up cost 3-5 % of throughput)
 __device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {

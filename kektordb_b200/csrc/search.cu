@@ -231,7 +231,7 @@ search_kind_fn kind_fn(const DevIndex &ix) {
 bool search_slots_supported(int slots) { return slots == 2 || slots == 4 || slots == 8 || slots == 16; }
 
 size_t search_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t) {
-  return smem_layout(ix.stride, ef, t.slots, (uint32_t)t.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
+  return smem_layout(ix.stride, slot_pitch_words(ix.stride, ix.row_words, ix.kind), ef, t.slots, (uint32_t)t.cand_smem, ix.deg0 > ix.degu ? ix.deg0 : ix.degu,
                      cpl_of(ix) == 0, ix.kind, nullptr, nullptr);
 }
 
@@ -255,7 +255,7 @@ cudaError_t launch_search(const DevIndex &ix, const SearchArgs &a, const SearchT
 
 // hand_over: no heap arrays (ties go to the heap kernel); otherwise the heap kernel's own carve-up
 static size_t search_fast_smem_bytes(const DevIndex &ix, int ef, const SearchTuning &t, bool hand_over) {
-  return smem_layout(ix.stride, hand_over ? 0 : ef, t.slots, hand_over ? 0u : (uint32_t)t.cand_smem,
+  return smem_layout(ix.stride, slot_pitch_words(ix.stride, ix.row_words, ix.kind), hand_over ? 0 : ef, t.slots, hand_over ? 0u : (uint32_t)t.cand_smem,
                      ix.deg0 > ix.degu ? ix.deg0 : ix.degu, cpl_of(ix) == 0, ix.kind, nullptr, nullptr);
 }
 bool search_fast_hands_over(const DevIndex &ix) { return ix.kind == KIND_COS_I8; }

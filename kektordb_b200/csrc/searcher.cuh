@@ -53,12 +53,19 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // shared-memory carve-up of one warp-CTA, identical on host (sizing) and device (pointers)
 // kind = the index's distance kind: only int8 rows need the per-neighbour norm / threshold lists
-__host__ __device__ inline size_t smem_layout(uint32_t stride, int ef, int slots, uint32_t cand_smem, uint32_t deg_max,
-                                              bool q_in_smem, int kind, unsigned char *base, SmemPtrs *p) {
+// slot pitch of a row in shared memory (32-bit words).  float rows: the padded stride (the tail of a shorter row is
+// zeroed once and must stay zero: 0 x garbage could be NaN).  int8 rows: the row's own pitch — the query's padding
+// columns are zero and an integer 0 x anything is 0, so whatever the last column pass reads past the row (the next
+// slot, or the regions behind the slots) contributes nothing; 768-byte rows then take 768, not 1024 bytes per slot.
+__host__ __device__ inline uint32_t slot_pitch_words(uint32_t stride, uint32_t row_words, int kind) {
+  return kind == KIND_COS_I8 ? row_words : stride;
+}
+__host__ __device__ inline size_t smem_layout(uint32_t stride, uint32_t slot_words, int ef, int slots, uint32_t cand_smem,
+                                              uint32_t deg_max, bool q_in_smem, int kind, unsigned char *base, SmemPtrs *p) {
   const uint32_t dm = (deg_max + 31u) & ~31u;
   size_t off = 0;
   const size_t o_slots = off;
-  off += (size_t)slots * stride * sizeof(float);
+  off += (size_t)slots * slot_words * sizeof(float);
   const size_t o_q = off;
   if (q_in_smem) off += (size_t)stride * sizeof(float);
   const size_t o_res = off;
@@ -224,7 +231,8 @@ struct Searcher {
   uint32_t lexp;  // bit r: entry r of this lane has been expanded (popped from the candidate queue)
   int ln;         // live entries (uniform)
   bool tie;       // two equal distances met: the heaps' tie order is needed, the exact kernel re-runs the query
-  uint32_t slots_u32, bars_u32, slot_bytes, row_bytes;  // shared-window addresses of the row slots / barriers
+  uint32_t slots_u32, bars_u32, slot_bytes, row_bytes, slot_words;
+  uint64_t row_policy;  // L2 cache hint of the row copies (0 = none)  // shared-window addresses of the row slots / barriers
   const unsigned char *vec_bytes;
   // the query in registers: CPL 16-byte columns per lane; float16 columns are kept WIDENED (two float4 per column)
   static constexpr int kQRegs = CPL > 0 ? (METRIC == KIND_L2_F16 ? 2 * CPL : CPL) : 1;
@@ -233,7 +241,8 @@ struct Searcher {
   // heaps_in_smem = false: the fast kernel's carve-up (no result / candidate heap arrays)
   __device__ Searcher(const DevIndex &ix_, const SearchArgs &a_, unsigned char *smem, bool heaps_in_smem = true)
       : ix(ix_), a(a_), lane(threadIdx.x & 31), phase_bits(0), st_e(0), st_h(0), st_h0(0), overflow(false), qnorm(1.f), lexp(0), ln(0), tie(false) {
-    smem_layout(ix.stride, heaps_in_smem ? a.ef : 0, SLOTS, heaps_in_smem ? a.cand_smem : 0u,
+    slot_words = slot_pitch_words(ix.stride, ix.row_words, METRIC);
+    smem_layout(ix.stride, slot_words, heaps_in_smem ? a.ef : 0, SLOTS, heaps_in_smem ? a.cand_smem : 0u,
                 ix.deg0 > ix.degu ? ix.deg0 : ix.degu, CPL == 0, METRIC, smem, &sm);
     vis = a.visited + (size_t)blockIdx.x * a.vis_words;
     cand.s = sm.cand;
@@ -245,7 +254,8 @@ struct Searcher {
     res.n = 0;
     slots_u32 = smem_u32(sm.slots);
     bars_u32 = smem_u32(sm.bars);
-    slot_bytes = ix.stride * (uint32_t)sizeof(float);
+    slot_bytes = slot_words * (uint32_t)sizeof(float);
+    row_policy = a.rows_evict_first ? l2_policy_evict_first() : 0ull;
     row_bytes = ix.row_words * (uint32_t)sizeof(float);
     vec_bytes = reinterpret_cast<const unsigned char *>(ix.vecs);
   }
@@ -253,9 +263,9 @@ struct Searcher {
   __device__ __forceinline__ void init_barriers() {
     // rows shorter than a slot (row_words < stride, float16 / int8 pitches) never overwrite the slot
     // tail: zero it once so the padded columns contribute nothing
-    if (ix.row_words < ix.stride) {
+    if (ix.row_words < slot_words) {
       for (int sl = 0; sl < SLOTS; ++sl)
-        for (uint32_t w = ix.row_words + lane; w < ix.stride; w += 32) sm.slots[(size_t)sl * ix.stride + w] = 0.f;
+        for (uint32_t w = ix.row_words + lane; w < slot_words; w += 32) sm.slots[(size_t)sl * slot_words + w] = 0.f;
       fence_proxy_async();
     }
     if (lane == 0) {
@@ -312,12 +322,19 @@ struct Searcher {
   }
 
   // ---- row streaming: groups of G rows, two group buffers, one mbarrier per buffer ------------------
+  __device__ __forceinline__ void copy_row(uint32_t dst, uint32_t id, uint32_t bar) const {
+    const unsigned char *src = vec_bytes + (size_t)id * row_bytes;
+    if (row_policy != 0ull)
+      bulk_g2s_u32_hint(dst, src, row_bytes, bar, row_policy);
+    else
+      bulk_g2s_u32(dst, src, row_bytes, bar);
+  }
   // (both called by the whole, converged warp; one elected lane issues — see elect_one)
   __device__ __forceinline__ void issue_one(uint32_t buf, uint32_t id) {  // a single row into buffer `buf`
     if (elect_one()) {
       const uint32_t bar = bars_u32 + buf * 8u;
       mbar_expect_tx_u32(bar, row_bytes);
-      bulk_g2s_u32(slots_u32 + buf * (uint32_t)G * slot_bytes, vec_bytes + (size_t)id * row_bytes, row_bytes, bar);
+      copy_row(slots_u32 + buf * (uint32_t)G * slot_bytes, id, bar);
     }
   }
   // rows eval_id[j0 .. j0 + cnt) into the slots of buffer (g & 1), all completing on that buffer's barrier
@@ -339,11 +356,17 @@ struct Searcher {
 #pragma unroll
           for (int r = 0; r < G; ++r) id[r] = sm.eval_id[j0 + r];
         }
+        if (row_policy != 0ull) {
 #pragma unroll
-        for (int r = 0; r < G; ++r) bulk_g2s_u32(dst + r * slot_bytes, vec_bytes + (size_t)id[r] * row_bytes, row_bytes, bar);
+          for (int r = 0; r < G; ++r)
+            bulk_g2s_u32_hint(dst + r * slot_bytes, vec_bytes + (size_t)id[r] * row_bytes, row_bytes, bar, row_policy);
+        } else {
+#pragma unroll
+          for (int r = 0; r < G; ++r) bulk_g2s_u32(dst + r * slot_bytes, vec_bytes + (size_t)id[r] * row_bytes, row_bytes, bar);
+        }
       } else {
         for (uint32_t r = 0; r < cnt; ++r, dst += slot_bytes)
-          bulk_g2s_u32(dst, vec_bytes + (size_t)sm.eval_id[j0 + r] * row_bytes, row_bytes, bar);
+          copy_row(dst, sm.eval_id[j0 + r], bar);
       }
     }
   }
@@ -357,8 +380,8 @@ struct Searcher {
   // lane partials of query x the G rows of buffer `buf`, kernel order (LaneAcc, kdb_internal.cuh); the G chains
   // are independent and interleave
   __device__ __forceinline__ void group_partials(uint32_t buf, float (&p)[G]) const {
-    const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots + (size_t)buf * G * ix.stride);
-    const uint32_t pitch4 = ix.stride >> 2;
+    const float4 *r4 = reinterpret_cast<const float4 *>(sm.slots + (size_t)buf * G * slot_words);
+    const uint32_t pitch4 = slot_words >> 2;
     LaneAcc<METRIC> acc[G];
     if (CPL > 0) {
 #pragma unroll
