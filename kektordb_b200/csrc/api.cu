@@ -692,7 +692,7 @@ int kdbgpu_index_create_ex(int device, int dim, int metric, int precision, int m
   const char *env;
   // float16 / int8 rows: the traversal is latency-bound, so resident query-warps matter more than
   // shared-memory heap capacity (measured: profiles/README.md, quantized sweep)
-  if (precision != KDBGPU_PRECISION_F32) h->tuning.cand_smem = 64;
+  if (precision != KDBGPU_PRECISION_F32) h->tuning.cand_smem = precision == KDBGPU_PRECISION_F16 ? 128 : 64;
   // launch shapes measured at 1 M x 768 (profiles/README.md): rows per group = slots / 2.  float32 / float16 rows are
   // HBM-bound with batches in flight (more resident query-warps win: 4 slots) and latency-bound alone (8 slots);
   // int8 rows are issue-bound either way (8 slots halve the per-row overhead, 16 when alone)
@@ -1832,6 +1832,21 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   }
   // the new nodes are registered (visible to id-range checks) but unlinked
   h->n = start_id + count - 1;
+  // a recoverable failure below (no memory for a workspace, a shape that does not fit) must leave the mirror as it
+  // was before the call: the ids go back to nil and the id range shrinks again; the host-side levels, upper-row
+  // cursor, entry point and max level are only committed at the end
+  struct Rollback {
+    kdbgpu_index *h;
+    uint32_t start, count;
+    bool armed;
+    ~Rollback() {
+      if (!armed) return;
+      h->n = start - 1;
+      cudaMemsetAsync(h->levels.p + start, 0xff, count, h->stream);  // level -1 = nil node
+      cudaStreamSynchronize(h->stream);
+      (void)cudaGetLastError();
+    }
+  } rollback{h, start_id, count, true};
   DevIndex ix = h->dev();
   ix.entry = pre_entry;
   ix.max_level = pre_max;
@@ -1939,6 +1954,7 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
   if (sequential) CUDA_TRY(cudaMemcpyAsync(io_back, h->b_scalars.p + 2, sizeof io_back, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   // commit host-side state
+  rollback.armed = false;
   for (uint32_t i = 0; i < count; ++i) {
     h->h_levels[start_id + i] = lv[i];
     h->h_upper_first[start_id + i] = uf[i];

@@ -159,3 +159,30 @@ def test_int8_construction_needs_a_trained_quantizer():
     with pytest.raises(ffi.GpuError):
         gi.AddBatch(rng.standard_normal((10, 8)).astype(np.float32), rng.random(10), 10)
     gi.close()
+
+
+def test_failed_add_batch_leaves_the_mirror_as_it_was():
+    """A recoverable failure inside kdbgpu_add_batch must not leave half-registered nodes behind.  At 8192-d the batch
+    path's construction search (8 row slots of 32 KB) does not fit shared memory while the single-Add fallback
+    (4 slots) does: the first efConstruction nodes go in, the next batch fails AFTER the library has registered its
+    ids — and the id range, levels, entry point and every search answer must be those of the last successful call."""
+    from kektordb_b200 import GpuIndex, ffi
+    n0, dim, m, efc = 25, 8192, 4, 20
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((80, dim)).astype(np.float32)
+    u = rng.random(80)
+    oi = O.OracleIndex(dim, O.METRIC_L2, m, efc, O.ARITH_KERNEL, 80)
+    gi = GpuIndex(dim, "euclidean", m, 80)
+    gi.AddBatch(X[:n0], u[:n0], efc)  # n < efConstruction: the sequential single-Add path (:1502-1513)
+    oi.add_batch(X[:n0], u[:n0], efc, threads=4)
+    before = gi.get_graph()
+    with pytest.raises(ffi.GpuError):
+        gi.AddBatch(X[n0:], u[n0:], efc)
+    after = gi.get_graph()
+    assert before[0] == after[0] == n0 and before[5:] == after[5:]
+    assert all(np.array_equal(a, b) for a, b in zip(before[1:5], after[1:5]))
+    Q = rng.standard_normal((8, dim)).astype(np.float32)
+    got = gi.SearchWithScores(Q, 5, None, 20)
+    want = oi.search_batch(Q, 5, 20, threads=4)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    gi.close()
