@@ -346,6 +346,62 @@ def test_nil_slots_in_the_graph():
     gi.close()
 
 
+def test_repeated_ids_inside_adjacency_rows():
+    """A neighbour list that names an id twice: the second occurrence finds the id visited and is skipped
+    (hnsw_index.go:2539-2542), so the id is evaluated at the position of its FIRST occurrence.  With M = 32 a
+    level-0 row spans both halves of the kernel's 64-neighbour pass; copies are planted inside one half, across the
+    two halves (slot < 32 and slot >= 32, whose two visited test-and-sets are not ordered against each other) and in
+    front of their original, on tie-heavy integer-grid data where the evaluation order decides the answer."""
+    n, dim, m, efc = 2500, 12, 32, 60
+    rng = np.random.default_rng(77)
+    X = rng.integers(-2, 3, (n, dim)).astype(np.float32)
+    X[np.all(X == 0, axis=1), 0] = 1.0
+    om = O.METRIC_COSINE
+    oi = O.OracleIndex(dim, om, m, efc, O.ARITH_KERNEL, n)
+    oi.build_batched(X, rng.random(n), batch=500, threads=8)
+    g = oi.export_graph()
+    node_row, row_off, nbrs = [0], [0], []
+    planted = 0
+    for i in range(g.n + 1):
+        for l in range(g.levels[i] + 1 if g.levels[i] >= 0 else 0):
+            row = g.row(i, l).tolist()
+            cap = 2 * m if l == 0 else m
+            if l == 0 and len(row) >= 34 and i % 3 == 0:
+                row = row[:cap - 3]
+                row.insert(33, row[5])    # across the halves: slot 5 and slot 33
+                row.insert(20, row[2])    # inside the first half
+                row.append(row[40])       # inside the second half
+                planted += 1
+            elif l == 0 and len(row) >= 34 and i % 3 == 1:
+                row = row[:cap - 1]
+                row.insert(3, row[45])    # the copy comes FIRST (slot 3), the original sits in the second half
+                planted += 1
+            nbrs.extend(row)
+            row_off.append(len(nbrs))
+        node_row.append(len(row_off) - 1)
+    assert planted > 200
+    g2 = O.Graph(g.n, g.levels, np.array(node_row, np.uint64), np.array(row_off, np.uint64), np.array(nbrs, np.uint32),
+                 g.deleted, g.entry, g.max_level)
+    o2 = O.OracleIndex(dim, om, m, efc, O.ARITH_KERNEL, g.n)
+    o2.import_graph(oi.vectors(), g2)
+    GpuIndex = _gpu()
+    gi = GpuIndex(dim, "cosine", m, g.n)
+    gi.upload_vectors(1, oi.vectors()[1:])
+    Q = (X[rng.integers(0, n, 96)] + rng.integers(-1, 2, (96, dim))).astype(np.float32)
+    Q[np.all(Q == 0, axis=1), 0] = 1.0
+    gi.set_graph(g2.n, g2.levels, g2.node_row, g2.row_off, g2.nbrs, g2.entry, g2.max_level)
+    for ef in (16, 64, 200):
+        got = gi.SearchWithScores(Q, 10, None, ef)
+        want = o2.search_batch(Q, 10, ef, threads=4)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        assert got[3].dist_evals == want[3].dist_evals and got[3].hops == want[3].hops
+    allow = O.dense_bitset(np.where(rng.random(g.n + 1) < 0.5)[0][1:], g.n)
+    got = gi.SearchWithScores(Q, 10, allow, 64)
+    want = o2.search_batch(Q, 10, 64, allow=allow, threads=4)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    gi.close()
+
+
 @pytest.mark.parametrize("name", ["cosine_d48_m8", "l2_d20_m6_filtered"])
 def test_golden_fixtures(name):
     """Committed fixtures (tests/golden/make_golden.py): stored rows, topology, queries and the
