@@ -476,7 +476,7 @@ int flat_prefilter_impl(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *q
   CUDA_TRY(w.t_theta.reserve(chunk));
   CUDA_TRY(w.t_bound.reserve(chunk));
   CUDA_TRY(w.t_thf.reserve(chunk));
-  CUDA_TRY(w.t_cnt.reserve(chunk));
+  CUDA_TRY(w.t_cnt.reserve(chunk + 4));  // [chunk] spill counters + the two tile counters of the tensor passes
   CUDA_TRY(w.t_fcnt.reserve(chunk));
   CUDA_TRY(w.t_flags.reserve(chunk));
   CUDA_TRY(w.t_sub.reserve((size_t)chunk * emit_grid * sub_slots));
@@ -498,8 +498,9 @@ int flat_prefilter_impl(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *q
     const uint32_t c_pad = (c + P.bm - 1) / P.bm * P.bm;
     rc = tc_stage_queries(h, w, queries + (size_t)q0 * h->dim, c, c_pad, mode, P, s, w.ev[2]);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(w.t_cnt.p, 0, (size_t)c_pad * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemsetAsync(w.t_cnt.p, 0, (size_t)(chunk + 4) * sizeof(uint32_t), s));
     FlatTcLaunch L = tc_launch_desc(h, w, P, c, c_pad);
+    L.tile_counter = w.t_cnt.p + chunk;
     L.gmin = w.t_gmin.p;
     L.theta = w.t_theta.p;
     L.sub = w.t_sub.p;
@@ -518,6 +519,7 @@ int flat_prefilter_impl(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *q
     CUDA_TRY(launch_tc_threshold(w.t_gmin.p, n_groups, c, k, w.tq_sumsq.p, w.tq_resid2.p, h->x_max.p, P.alpha,
                                  P.use_norm, P.dp, w.t_theta.p, w.t_bound.p, s));
     L.epi = 2;  // pass B: ids + scores below theta, every tile
+    L.tile_counter = w.t_cnt.p + chunk + 1;
     L.ct_stride = 1;
     L.grid = tc_launch_desc(h, w, P, c, c_pad).grid;
     CUDA_TRY(launch_flat_tc(L, s));

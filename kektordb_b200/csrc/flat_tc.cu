@@ -59,6 +59,7 @@ struct TcArgs {
   uint32_t *ovf_cnt;   // [nq_pad]
   uint2 *ovf;          // [nq_pad][cap]
   uint32_t cap;
+  uint32_t *tile_counter;  // pair kernel, dynamic schedule: zeroed before the launch (see flat_tc2_kernel)
 };
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
@@ -113,6 +114,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Epilogue arithmetic of one 32-column chunk (thread = query): scores S = alpha * acc + beta with packed FFMA2
+// (16 instructions for 32 scores), minimum of the 32 with three-input min (16 instead of 31 instructions).
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void epi_scores(const uint32_t (&r)[32], const float *sb, float alpha, float (&sc)[32]) {
+  const f32x2 a2 = pack2(alpha, alpha);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {  // beta: 8 broadcast LDS.128 instead of 32 dependent LDS.32
+    const float4 b4 = *reinterpret_cast<const float4 *>(sb + 4 * j4);
+    const f32x2 s01 = fma2_rn(a2, pack2(__uint_as_float(r[4 * j4 + 0]), __uint_as_float(r[4 * j4 + 1])), pack2(b4.x, b4.y));
+    const f32x2 s23 = fma2_rn(a2, pack2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), pack2(b4.z, b4.w));
+    unpack2(s01, sc[4 * j4 + 0], sc[4 * j4 + 1]);
+    unpack2(s23, sc[4 * j4 + 2], sc[4 * j4 + 3]);
+  }
+}
+__device__ __forceinline__ float epi_min32(const float (&sc)[32]) {
+  float m[11];  // 32 -> 11 -> 4 -> 2 -> 1
+#pragma unroll
+  for (int j = 0; j < 10; ++j) m[j] = min3f(sc[3 * j], sc[3 * j + 1], sc[3 * j + 2]);
+  m[10] = fminf(sc[30], sc[31]);
+  const float a0 = min3f(m[0], m[1], m[2]), a1 = min3f(m[3], m[4], m[5]), a2 = min3f(m[6], m[7], m[8]);
+  return min3f(a0, a1, min3f(a2, m[9], m[10]));
 }
 
 template <int EPI>
@@ -246,14 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         float sc[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {  // beta: 8 broadcast LDS.128 instead of 32 dependent LDS.32
-          const float4 b4 = *reinterpret_cast<const float4 *>(sb + c0 + 4 * j4);
-          sc[4 * j4 + 0] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 0]), b4.x);
-          sc[4 * j4 + 1] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 1]), b4.y);
-          sc[4 * j4 + 2] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 2]), b4.z);
-          sc[4 * j4 + 3] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 3]), b4.w);
-        }
+        epi_scores(r, sb + c0, a.alpha, sc);
         if (EPI == EPI_STORE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -261,14 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (q < a.nq && col < a.n) a.S[(size_t)q * a.ldS + col] = sc[j];
           }
         } else {
-          float m[16];  // min tree: independent chains
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = fminf(sc[j], sc[j + 16]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) m[j] = fminf(m[j], m[j + 8]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = fminf(m[j], m[j + 4]);
-          const float best = fminf(fminf(m[0], m[1]), fminf(m[2], m[3]));
+          const float best = epi_min32(sc);
           if (EPI == EPI_GROUPMIN) {
             a.gmin[(size_t)q * ((size_t)a.n_ctiles * GROUPS_PER_TILE) + (size_t)cti * GROUPS_PER_TILE + c0 / GROUP] = best;
           } else if (best < theta && q < a.nq) {  // a group holding at least one nominee of this query
@@ -387,7 +401,87 @@ __device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t adesc, uint6
       : "memory");
 }
 
-template <int EPI>
+// ---- dynamic tile schedule of the pair kernel ---------------------------------------------------------
+// With a static schedule (tile = cluster + i * clusters) every pair visits the same number of tiles, but pairs do not
+// run at the same speed (ncu, profiles/r2_flat_tc2_kernel_raw.csv: sm__cycles_active min / avg / max = 1.60 / 1.71 /
+// 1.82 M cycles for the nomination pass): the launch lasts as long as its slowest pair and 6-7 % of the SM time idles
+// at the end.  DYN: the leader's producer lane draws the next tile from a global counter (one atomicAdd per tile, issued
+// a tile ahead) and publishes it through a TQ-deep ring that exists in both CTAs of the pair:
+//   s_tile[slot]     the tile index, written locally and into the peer (st.shared::cluster)
+//   tq_full[slot]    per CTA, 1 arrival: the scheduler (release at cluster scope for the peer)
+//   tq_empty[slot]   leader only, 10 arrivals: everyone who reads the ring — the peer's producer, the MMA lane and the
+//                    four epilogue warps of both CTAs — once they hold the value
+// Tiles are still handed out in order, so the pairs working at the same moment keep sharing corpus tiles in L2.
+constexpr int TQ = 4;
+constexpr uint32_t kNoTile = 0x7fffffffu;
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// "I hold ring value v": the barrier address is made to depend on v (v < 2^31, so v >> 31 is 0), which keeps the
+// arrive behind the completion of the shared-memory read it announces
+__device__ __forceinline__ void mbar_arrive_cluster_after(uint32_t cluster_addr, uint32_t v) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 t;\n"
+      "shr.u32 t, %1, 31;\n"
+      "add.u32 t, t, %0;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [t];\n"
+      "}\n" ::"r"(cluster_addr),
+      "r"(v)
+      : "memory");
+}
+// One reader of the tile sequence: next_lane() from a single lane, next_warp() from a converged warp (lane 0 reads
+// and signals, the value is broadcast).
+template <bool DYN>
+struct TileReader {
+  uint32_t t, step, total;  // static schedule
+  uint32_t *s_tile;
+  uint64_t *tq_full;
+  uint32_t empty0;  // shared::cluster address of the leader's tq_empty[0]
+  uint32_t slot, ph;
+  bool leader;
+  __device__ __forceinline__ uint32_t next_lane() {
+    if (!DYN) {
+      const uint32_t r = t < total ? t : kNoTile;
+      t += step;
+      return r;
+    }
+    if (leader) mbar_wait(&tq_full[slot], ph);
+    else mbar_wait_cluster_acquire(&tq_full[slot], ph);
+    const uint32_t r = *reinterpret_cast<volatile uint32_t *>(&s_tile[slot]);
+    mbar_arrive_cluster_after(empty0 + 8u * slot, r);
+    if (++slot == (uint32_t)TQ) {
+      slot = 0;
+      ph ^= 1u;
+    }
+    return r;
+  }
+  __device__ __forceinline__ uint32_t next_warp(int lane) {
+    if (!DYN) return next_lane();
+    uint32_t r = 0u;
+    if (lane == 0) r = next_lane();
+    return __shfl_sync(0xffffffffu, r, 0);
+  }
+};
+
+template <int EPI, bool DYN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     flat_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmXh, const TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -397,8 +491,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t *empty = full + STAGES2;
   uint64_t *tmem_full = empty + STAGES2;
   uint64_t *tmem_empty = tmem_full + 2;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-  float *s_beta = reinterpret_cast<float *>(tmem_ptr + 4);          // [2][BN]
+  uint64_t *tq_full = tmem_empty + 2;   // tile ring (DYN)
+  uint64_t *tq_empty = tq_full + TQ;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tq_empty + TQ);
+  uint32_t *s_tile = tmem_ptr + 4;                                  // [TQ]
+  float *s_beta = reinterpret_cast<float *>(s_tile + TQ);           // [2][BN]
   uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_beta + 2 * BN);  // [nq_tiles * 2 * BM], EPI_EMIT only
   const uint32_t q_rows = a.nq_tiles * 2u * BM;                     // a.nq_tiles = 256-query tile pairs here
   if (EPI == EPI_EMIT)
@@ -421,6 +518,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_init(&tmem_full[i], 1);
         mbar_init(&tmem_empty[i], 8);
       }
+      for (int i = 0; i < TQ; ++i) {
+        mbar_init(&tq_full[i], 1);
+        mbar_init(&tq_empty[i], 10);
+      }
       mbar_fence_init();
     }
     __syncwarp();
@@ -436,11 +537,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t total_tiles = a.nq_tiles * a.n_ctiles;
   const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  TileReader<DYN> feed;
+  feed.t = cluster_id;
+  feed.step = n_clusters;
+  feed.total = total_tiles;
+  feed.s_tile = s_tile;
+  feed.tq_full = tq_full;
+  feed.empty0 = mapa_u32(smem_u32(&tq_empty[0]), 0u);
+  feed.slot = 0u;
+  feed.ph = 0u;
+  feed.leader = leader;
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer (both CTAs): own A rows + own half of B =====
       uint32_t stage = 0, phase = 0;
-      for (uint32_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      // the scheduler (DYN, leader): draws tiles from the global counter one ahead of their use and publishes them
+      uint32_t drawn = 0u, pslot = 0u, pph = 0u;
+      if (DYN && leader) drawn = atomicAdd(a.tile_counter, 1u);
+      for (;;) {
+        uint32_t tile;
+        if (DYN && leader) {
+          tile = drawn < total_tiles ? drawn : kNoTile;
+          mbar_wait(&tq_empty[pslot], pph ^ 1u);  // every reader holds what this slot carried a ring ago
+          s_tile[pslot] = tile;
+          st_cluster_u32(mapa_u32(smem_u32(&s_tile[pslot]), 1u), tile);
+          mbar_arrive(&tq_full[pslot]);
+          mbar_arrive_cluster_release(mapa_u32(smem_u32(&tq_full[pslot]), 1u));
+          if (++pslot == (uint32_t)TQ) {
+            pslot = 0u;
+            pph ^= 1u;
+          }
+          if (tile != kNoTile) drawn = atomicAdd(a.tile_counter, 1u);
+        } else {
+          tile = feed.next_lane();
+        }
+        if (tile == kNoTile) break;
         const uint32_t ct = (tile / a.nq_tiles) * a.ct_stride, qt = tile % a.nq_tiles;
         for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
@@ -462,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (lane == 0 && leader) {  // ===== MMA issuer: the leader CTA only =====
       const uint32_t idesc = make_idesc_pair();
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (uint32_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      while (feed.next_lane() != kNoTile) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);  // BOTH epilogues have drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -490,12 +621,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t et = (uint32_t)(threadIdx.x - 64);
     uint32_t acc = 0, acc_phase = 0;
     float nb0 = 0.f, nb1 = 0.f;  // beta one tile ahead, as in the single-CTA kernel
-    if (cluster_id < total_tiles) {
-      const uint32_t ct0 = (cluster_id / a.nq_tiles) * a.ct_stride;
+    uint32_t tile = feed.next_warp(lane);
+    if (tile != kNoTile) {
+      const uint32_t ct0 = (tile / a.nq_tiles) * a.ct_stride;
       nb0 = a.beta[(size_t)ct0 * BN + et];
       nb1 = a.beta[(size_t)ct0 * BN + et + 128];
     }
-    for (uint32_t tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+    // (DYN: the scheduler runs at least the operand ring — half a tile of MMAs — ahead of the accumulator this warp
+    // is about to read, so the next tile is normally published already when it is asked for here)
+    for (uint32_t tile_next; tile != kNoTile; tile = tile_next) {
+      tile_next = feed.next_warp(lane);
       const uint32_t cti = tile / a.nq_tiles, qt = tile % a.nq_tiles;
       const uint32_t ct = cti * a.ct_stride;
       const uint32_t q = qt * 2u * BM + rank * BM + quarter * 32u + (uint32_t)lane;
@@ -503,8 +638,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       float *sb = s_beta + acc * BN;
       sb[et] = nb0;
       sb[et + 128] = nb1;
-      if (tile + n_clusters < total_tiles) {
-        const uint32_t ctn = ((tile + n_clusters) / a.nq_tiles) * a.ct_stride;
+      if (tile_next != kNoTile) {
+        const uint32_t ctn = (tile_next / a.nq_tiles) * a.ct_stride;
         nb0 = a.beta[(size_t)ctn * BN + et];
         nb1 = a.beta[(size_t)ctn * BN + et + 128];
       }
@@ -523,14 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         float sc[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b4 = *reinterpret_cast<const float4 *>(sb + c0 + 4 * j4);
-          sc[4 * j4 + 0] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 0]), b4.x);
-          sc[4 * j4 + 1] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 1]), b4.y);
-          sc[4 * j4 + 2] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 2]), b4.z);
-          sc[4 * j4 + 3] = __fmaf_rn(a.alpha, __uint_as_float(r[4 * j4 + 3]), b4.w);
-        }
+        epi_scores(r, sb + c0, a.alpha, sc);
         if (EPI == EPI_STORE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -538,14 +666,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (q < a.nq && col < a.n) a.S[(size_t)q * a.ldS + col] = sc[j];
           }
         } else {
-          float m[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = fminf(sc[j], sc[j + 16]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) m[j] = fminf(m[j], m[j + 8]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) m[j] = fminf(m[j], m[j + 4]);
-          const float best = fminf(fminf(m[0], m[1]), fminf(m[2], m[3]));
+          const float best = epi_min32(sc);
           if (EPI == EPI_GROUPMIN) {
             if (q_ok)
               a.gmin[(size_t)q * ((size_t)a.n_ctiles * GROUPS_PER_TILE) + (size_t)cti * GROUPS_PER_TILE + c0 / GROUP] = best;
@@ -634,8 +755,8 @@ size_t tc_smem_bytes(uint32_t nq_pad_emit) {
          (size_t)nq_pad_emit * sizeof(uint32_t);
 }
 size_t tc2_smem_bytes(uint32_t q_rows_emit) {
-  return 1024 + (size_t)STAGES2 * STAGE2_BYTES + (2 * STAGES2 + 4) * sizeof(uint64_t) + 16 + 2 * BN * sizeof(float) +
-         (size_t)q_rows_emit * sizeof(uint32_t);
+  return 1024 + (size_t)STAGES2 * STAGE2_BYTES + (2 * STAGES2 + 4 + 2 * TQ) * sizeof(uint64_t) + 16 + TQ * sizeof(uint32_t) +
+         2 * BN * sizeof(float) + (size_t)q_rows_emit * sizeof(uint32_t);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -716,6 +837,8 @@ cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream) {
   a.ovf_cnt = L.ovf_cnt;
   a.ovf = reinterpret_cast<uint2 *>(L.ovf);
   a.cap = L.cap;
+  const char *dyn_env = getenv("KDBGPU_FLAT_DYNAMIC");  // 0 = static tile schedule (same bits)
+  a.tile_counter = (dyn_env && dyn_env[0] == '0') ? nullptr : L.tile_counter;
   if (L.epi == EPI_EMIT && (L.nq_pad > MAX_Q_PER_LAUNCH || L.grid > 256)) return cudaErrorInvalidValue;
   cudaError_t e;
   if (pair) {
@@ -729,9 +852,9 @@ cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream) {
     if ((uint64_t)clusters > tiles) clusters = (uint32_t)tiles;
     if ((int)(2 * clusters) > L.grid && L.grid >= 2) clusters = (uint32_t)L.grid / 2;
     if (clusters == 0) clusters = 1;
-#define KDB_TC2_LAUNCH(EPIv)                                                                             \
+#define KDB_TC2_LAUNCH(EPIv, DYNv)                                                                       \
   {                                                                                                      \
-    auto kern = flat_tc2_kernel<EPIv>;                                                                   \
+    auto kern = flat_tc2_kernel<EPIv, DYNv>;                                                             \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
     if (e != cudaSuccess) return e;                                                                      \
     cudaLaunchConfig_t cfg = {};                                                                         \
@@ -755,9 +878,12 @@ cudaError_t launch_flat_tc(FlatTcLaunch &L, cudaStream_t stream) {
     (void)cudaGetLastError();                                                                            \
     e = cudaLaunchKernelEx(&cfg, kern, tmQ, tmX, a);                                                     \
   }
-    if (L.epi == EPI_STORE) KDB_TC2_LAUNCH(EPI_STORE)
-    else if (L.epi == EPI_GROUPMIN) KDB_TC2_LAUNCH(EPI_GROUPMIN)
-    else KDB_TC2_LAUNCH(EPI_EMIT)
+    // the caller zeroes *tile_counter on this stream before the launch
+    if (L.epi == EPI_STORE) KDB_TC2_LAUNCH(EPI_STORE, false)
+    else if (L.epi == EPI_GROUPMIN && a.tile_counter) KDB_TC2_LAUNCH(EPI_GROUPMIN, true)
+    else if (L.epi == EPI_GROUPMIN) KDB_TC2_LAUNCH(EPI_GROUPMIN, false)
+    else if (a.tile_counter) KDB_TC2_LAUNCH(EPI_EMIT, true)
+    else KDB_TC2_LAUNCH(EPI_EMIT, false)
 #undef KDB_TC2_LAUNCH
     L.grid = (int)(2 * clusters);
     if (e != cudaSuccess) return e;

@@ -189,6 +189,7 @@ struct FlatTcLaunch {
   void *ovf;          // [nq_pad][cap]
   uint32_t cap;
   int grid;
+  uint32_t *tile_counter;  // pair kernel: one zeroed word per launch = dynamic tile schedule; null = static
 };
 uint32_t flat_tc_bm();
 uint32_t flat_tc_bn();

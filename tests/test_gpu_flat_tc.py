@@ -70,6 +70,7 @@ def test_cta_pair_kernel_is_bit_identical_on_full_and_ragged_query_tile_pairs(nq
     """Batches of 256+ queries take the cta_group::2 kernel (two CTAs share every corpus tile): full tile pairs,
     a ragged last pair (300 -> 384 padded rows, the pair tile runs past them), and the benchmark's batch of 1024."""
     monkeypatch.delenv("KDBGPU_FLAT_2CTA", raising=False)  # the pair kernel is the default (the switch is read per launch)
+    monkeypatch.delenv("KDBGPU_FLAT_DYNAMIC", raising=False)  # and so is its dynamic tile schedule (tile counter + ring)
     n, dim = 30000, 200
     X, rng = _data(n, dim, 77, lowrank=True)
     Q = rng.standard_normal((nq, dim)).astype(np.float32)
@@ -86,6 +87,10 @@ def test_cta_pair_kernel_is_bit_identical_on_full_and_ragged_query_tile_pairs(nq
         c = gi.flat_search(Q[64:128], k, 0, prefilter=True)                # 64 queries: the single-CTA kernel
         assert np.array_equal(c[0], b[0][64:128]) and np.array_equal(c[1], b[1][64:128])
         assert b[3].hops <= 2
+    monkeypatch.setenv("KDBGPU_FLAT_DYNAMIC", "0")                         # static tile schedule of the pair kernel
+    s_ = gi.flat_search(Q, 100, 0, prefilter=True)
+    assert np.array_equal(s_[0], b[0]) and np.array_equal(s_[1], b[1]) and np.array_equal(s_[2], b[2])
+    monkeypatch.delenv("KDBGPU_FLAT_DYNAMIC")
     monkeypatch.setenv("KDBGPU_FLAT_2CTA", "0")
     d = gi.flat_search(Q, 10, 0, prefilter=True)                           # the single-CTA kernel, same batch
     e = gi.flat_search(Q[:64], 10, 0)
