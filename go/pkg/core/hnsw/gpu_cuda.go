@@ -62,6 +62,7 @@ type gpuMirror struct {
 	refresher *C.kdbgpu_refresher
 	dim       int
 	capacity  uint32
+	opt       GPUOptions // as resolved by AttachGPU: GPUHealth re-attaches with the same settings
 
 	mu      sync.Mutex
 	waiting map[uint64]chan gpuResult // ticket -> the goroutine parked on it
@@ -139,6 +140,8 @@ func (h *Index) AttachGPU(opt GPUOptions) error {
 	g := &gpuMirror{dim: h.vectorDim, capacity: n + opt.CapacitySlack,
 		waiting: map[uint64]chan gpuResult{}, early: map[uint64]struct{}{}, filters: map[*roaring.Bitmap]gpuFilter{},
 		stop: make(chan struct{}), done: make(chan struct{})}
+	g.opt = opt
+	g.opt.CapacitySlack = 0 // sized again from the node count at re-attach time
 	if err := gpuErr(C.kdbgpu_index_create_ex(C.int(opt.Device), C.int(h.vectorDim), metric, prec, C.int(h.m),
 		C.uint32_t(g.capacity), &g.h)); err != nil {
 		return err
@@ -470,7 +473,28 @@ func (h *Index) gpuNoteEntry() {
 // GPUFlush applies every queued change now (read-your-writes for callers that need it, e.g. tests).
 func (h *Index) GPUFlush() error {
 	if g := gpuOf(h); g != nil {
-		return gpuErr(C.kdbgpu_refresher_flush(g.refresher))
+		if err := gpuErr(C.kdbgpu_refresher_flush(g.refresher)); err != nil {
+			return errors.Join(err, h.GPUHealth())
+		}
 	}
 	return nil
+}
+
+// GPUHealth re-stages the mirror from the CPU index when a flush has failed.  A flush that fails part-way (device out
+// of memory, an id the mirror already holds) has consumed its batch (include/kektordb_gpu.h, refresher), so the mirror
+// is behind the CPU index by those changes; background flushes report through stats.last_error only.  Call it from
+// the maintenance ticker (optimizer.go:60-116) and after a failed GPUFlush.  nil = the mirror is current or absent.
+func (h *Index) GPUHealth() error {
+	g := gpuOf(h)
+	if g == nil {
+		return nil
+	}
+	var st C.kdbgpu_refresher_stats_t
+	if C.kdbgpu_refresher_stats(g.refresher, &st) != C.KDBGPU_OK || st.last_error == C.KDBGPU_OK {
+		return nil
+	}
+	slog.Error("GPU mirror refresh failed; re-staging from the CPU index", "code", int(st.last_error))
+	opt := g.opt
+	h.DetachGPU()
+	return h.AttachGPU(opt)
 }

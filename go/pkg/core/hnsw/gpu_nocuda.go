@@ -26,6 +26,7 @@ func (h *Index) AttachGPU(GPUOptions) error {
 }
 func (h *Index) DetachGPU()      {}
 func (h *Index) GPUFlush() error { return nil }
+func (h *Index) GPUHealth() error { return nil }
 func (h *Index) searchWithScoresGPU([]float32, int, *roaring.Bitmap, int) ([]types.SearchResult, bool) {
 	return nil, false
 }

@@ -182,7 +182,10 @@ int kdbgpu_set_entry(kdbgpu_index *, uint32_t entry, int max_level);
  *                 optimizer.go:195-222, Refine :288-468)
  *   remove_node   nodes[id] = nil (optimizer.go:252-274);  set_deleted  Node.Deleted (:2303-2336)
  *   set_entry     entrypointID / maxLevel (:793-801, optimizer.go:231-249)
- * destroy flushes what is queued.  Errors of a background flush are kept in stats.last_error. */
+ * destroy flushes what is queued (no other call may race it).  Errors of a background flush are kept in
+ * stats.last_error.  A flush that fails part-way (device out of memory, an id the mirror already holds) has consumed
+ * its batch: the mirror is then behind the CPU index by those changes and must be re-staged (kdbgpu_set_graph /
+ * kdbgpu_set_graph_file) before it is trusted again — the Go shim does exactly that when last_error is set. */
 typedef struct kdbgpu_refresher kdbgpu_refresher;
 typedef struct {
   uint64_t pending_rows, pending_nodes;

@@ -78,7 +78,8 @@ struct Group {
   GroupBuf buf;
   uint32_t n = 0;                    // slots handed out (guarded by the batcher mutex)
   std::atomic<uint32_t> filled{0};   // queries copied into buf.q
-  std::vector<uint8_t> notify;       // per slot: announce completion through the poll queue
+  // per slot: 0 = blocking caller, 1 = ticket outstanding (announced through the poll queue), 2 = ticket taken
+  std::unique_ptr<std::atomic<uint8_t>[]> notify;
   Clock::time_point deadline;
   bool open = true;  // still accepting members (guarded by the batcher mutex)
   // completion is signalled under the group's own mutex, so that a thousand blocked callers waking up contend
@@ -235,7 +236,7 @@ void worker_main(kdbgpu_batcher *b) {
     {
       std::lock_guard<std::mutex> ql(b->cq_mu);
       for (uint32_t i = 0; i < nq; ++i)
-        if (g->notify[i]) {
+        if (g->notify[i].load(std::memory_order_relaxed)) {
           b->cq.push_back((g->seq << 16) | i);
           any = true;
         }
@@ -272,7 +273,7 @@ int enqueue(kdbgpu_batcher *b, const float *query, int k, int ef, std::shared_pt
           continue;
         }
         idx = og->n++;
-        og->notify[idx] = notify ? 1 : 0;
+        og->notify[idx].store(notify ? 1 : 0, std::memory_order_relaxed);
         g = og;
         if (og->n >= b->max_batch) b->work_cv.notify_all();
         break;
@@ -291,10 +292,10 @@ int enqueue(kdbgpu_batcher *b, const float *query, int k, int ef, std::shared_pt
           nf->hash = raw_hash;
           ng->filter = nf;
         }
-        ng->notify.assign(b->max_batch, 0);
+        ng->notify.reset(new std::atomic<uint8_t>[b->max_batch]());
         ng->deadline = Clock::now() + std::chrono::microseconds(b->max_wait_us);
         idx = ng->n++;
-        ng->notify[idx] = notify ? 1 : 0;
+        ng->notify[idx].store(notify ? 1 : 0, std::memory_order_relaxed);
         b->open_groups.push_back(ng);
         if (notify) b->live[ng->seq] = ng;
         g = ng;
@@ -310,7 +311,7 @@ int enqueue(kdbgpu_batcher *b, const float *query, int k, int ef, std::shared_pt
         std::unique_lock<std::mutex> lk(b->mu);
         if (cand->open && cand->n < b->max_batch) {
           idx = cand->n++;
-          cand->notify[idx] = notify ? 1 : 0;
+          cand->notify[idx].store(notify ? 1 : 0, std::memory_order_relaxed);
           if (notify) b->live[cand->seq] = cand;
           g = cand;
           if (cand->n >= b->max_batch) b->work_cv.notify_all();
@@ -506,14 +507,18 @@ int kdbgpu_batcher_take(kdbgpu_batcher *b, uint64_t ticket, uint32_t *out_ids, d
   *out_count = 0;
   Inside inside(b);
   std::shared_ptr<Group> g;
+  const uint32_t idx = (uint32_t)(ticket & 0xffffu);
   {
     std::lock_guard<std::mutex> lk(b->mu);
     auto it = b->live.find(ticket >> 16);
     if (it == b->live.end()) return KDBGPU_ERR_INVALID;
     g = it->second;
+    if (idx >= g->n) return KDBGPU_ERR_INVALID;  // a slot that was never handed out
   }
-  const uint32_t idx = (uint32_t)(ticket & 0xffffu);
-  if (idx >= b->max_batch) return KDBGPU_ERR_INVALID;
+  // a ticket is good for ONE take: a second one would count the group's results out early and recycle its staging
+  // while other callers are still copying
+  uint8_t outstanding = 1;
+  if (!g->notify[idx].compare_exchange_strong(outstanding, 2)) return KDBGPU_ERR_INVALID;
   return copy_out(b, g, idx, out_ids, out_scores, out_count);
 }
 

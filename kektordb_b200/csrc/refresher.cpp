@@ -69,8 +69,22 @@ void touch(kdbgpu_refresher *r) {  // caller holds r->mu
   }
 }
 
+int flush_locked(kdbgpu_refresher *r, int why);
+
+// Nothing unwinds across the C boundary or out of the clock thread: a std::bad_alloc while the batch is assembled is
+// reported like a failed mirror call (last_error; the batch is gone, see kdbgpu_refresher_flush in the header).
 int flush_impl(kdbgpu_refresher *r, int why) {
   std::lock_guard<std::mutex> fl(r->flush_mu);
+  try {
+    return flush_locked(r, why);
+  } catch (...) {
+    std::lock_guard<std::mutex> lk(r->mu);
+    r->last_error = KDBGPU_ERR_NOMEM;
+    return KDBGPU_ERR_NOMEM;
+  }
+}
+
+int flush_locked(kdbgpu_refresher *r, int why) {
   std::map<uint32_t, NewNode> new_nodes;
   std::map<std::pair<uint32_t, int>, std::vector<uint32_t>> rows;
   std::vector<uint32_t> removed;

@@ -191,6 +191,22 @@ def test_take_blocks_until_done_and_rejects_unknown_or_spent_tickets():
     b.close()
 
 
+def test_a_ticket_is_spent_by_one_take_while_its_group_still_has_results_outstanding():
+    """A second take of the same ticket must not count the group's results out early (its staging would be
+    recycled under the members that have not copied yet), and a slot nobody was given is not a ticket."""
+    log = []
+    b = Batcher(fn=_executor(log, delay=0.05), dim=DIM, max_batch=8, max_wait_us=200_000)
+    hold = b.submit(_q(2), 3, 9)                                # dispatched as soon as a worker wakes up (idle device)
+    t1, t2, t3 = (b.submit(_q(i), 3, 9) for i in (10, 20, 30))  # these collect in ONE group (with or behind `hold`)
+    assert t1 >> 16 == t2 >> 16 == t3 >> 16
+    assert b.take(t1, 3)[0].tolist() == [10, 11, 12]
+    assert b.take(t1, 3)[2] == ffi.ERR_INVALID and b.take(t1, 3)[2] == ffi.ERR_INVALID
+    assert b.take(((t1 >> 16) << 16) | 7, 3)[2] == ffi.ERR_INVALID   # slot 7 of that group was never handed out
+    assert b.take(t2, 3)[0].tolist() == [20, 21, 22] and b.take(t3, 3)[0].tolist() == [30, 31, 32]
+    assert b.take(hold, 3)[0].tolist() == [2, 3, 4]
+    b.close()
+
+
 def test_registered_filters_group_by_identity_and_reach_the_executor():
     log = []
     b = Batcher(fn=_executor(log, delay=0.03), dim=DIM, max_batch=256, max_wait_us=100_000)
