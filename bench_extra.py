@@ -99,6 +99,17 @@ def run_flat(args, torch, bench):
         fallbacks += st.hops
     torch.cuda.synchronize()
     e2e_one_s = time.perf_counter() - t0
+    # sustained: the same steps repeated for --sustain-seconds (the K-step region above lasts ~30 ms: too short for
+    # the clock sampler and for the power cap to show); device time of every kernel of the call, as `value`
+    sustained = None
+    if args.sustain_seconds > 0:
+        sus_ms, sus_steps, t1 = 0.0, 0, time.perf_counter()
+        while time.perf_counter() - t1 < args.sustain_seconds:
+            i = args.warmup + sus_steps % args.steps
+            sus_ms += gi.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True)[3].kernel_ms
+            sus_steps += 1
+        sustained = {"value": round(B * sus_steps / (sus_ms / 1e3), 1), "steps": sus_steps,
+                     "seconds": round(time.perf_counter() - t1, 2)}
     # e2e: the same host-buffer calls from two caller threads — the library keeps two flat calls in flight (its own
     # stream and staging each), so one call's copies and host-side work overlap the other's kernels
     e2e_s = bench.e2e_threads(torch, local_rank, lambda i: gi.flat_search(Q[i * B:(i + 1) * B], k, 0, prefilter=True),
@@ -122,7 +133,7 @@ def run_flat(args, torch, bench):
         "value": round(value, 1), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(comp_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 nomination (tcgen05, f32 accumulate) + f64 exact re-score", "data": "synthetic",
-        "recall_at_k": 1.0 if parity["vs_exhaustive_f64_scan"]["ids_equal"] else None,
+        "recall_at_k": 1.0 if parity["vs_exhaustive_f64_scan"]["ids_equal"] else None, "sustained": sustained,
         "config": {"workload": f"{N}x{D} L2 flat, top-{k}, batch={B} queries/step, 1xB200 (BASELINE configs[2])",
                    "data_model": "random-normal, i.i.d. isotropic" if args.latent <= 0 else
                                  f"random-normal, low-rank covariance (latent {args.latent})",

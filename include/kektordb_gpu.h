@@ -134,7 +134,11 @@ int kdbgpu_upload_vectors_device(kdbgpu_index *, uint32_t first_id, uint32_t cou
 /* Topology snapshot (what SnapshotData() exposes, hnsw_index.go:3064): n = nodeCounter;
  * levels[i] = len(Connections)-1 of node i or -1 for a nil slot; node i owns rows
  * node_row[i] .. node_row[i+1]-1 (level 0 first); row r lists nbrs[row_off[r] .. row_off[r+1]-1]
- * in the reference's order.  entry / max_level = entrypointID / maxLevel. */
+ * in the reference's order.  entry / max_level = entrypointID / maxLevel.
+ * The rows are padded to their fixed degree (2M / M) and nil neighbours dropped on the device, slice by slice.  Per-node
+ * errors (level, row count, entry point) are reported before the mirror is touched; a row with more than 2M / M live
+ * neighbours or offsets out of order is found while the rows are written and leaves the mirror WITHOUT a graph
+ * (searches return KDBGPU_ERR_STATE until a kdbgpu_set_graph succeeds). */
 int kdbgpu_set_graph(kdbgpu_index *, uint32_t n, const int32_t *levels, const uint64_t *node_row,
                      const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level);
 /* The same topology through a flat binary sidecar file, so that a 1 M - 10 M-node graph does not have to be rebuilt

@@ -1250,15 +1250,32 @@ int kdbgpu_upload_vectors_device(kdbgpu_index *h, uint32_t first_id, uint32_t co
   return KDBGPU_OK;
 }
 
-int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const uint64_t *node_row,
-                     const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level) {
-  if (!h || !levels || !node_row || !row_off) return fail(KDBGPU_ERR_INVALID, "NULL argument");
-  if (n > h->capacity) return fail(KDBGPU_ERR_INVALID, "n %u exceeds capacity %u", n, h->capacity);
-  if (max_level >= 0 && (entry == 0 || entry > n || levels[entry] < 0))
-    return fail(KDBGPU_ERR_INVALID, "entry point %u is not a live node", entry);
+namespace {
+
+// One slice of whole nodes [a, b) of the caller's CSR, as it travels to the device in one copy:
+// [node_row[a..b]] [row_off[row(a)..row(b)]] [nbrs[edge(a)..edge(b))]
+struct GraphSlice {
+  uint32_t a, b;
+  uint64_t r0, r1, e0, e1;
+  size_t bytes() const { return ((size_t)(b - a) + 1 + (size_t)(r1 - r0) + 1) * sizeof(uint64_t) + (size_t)(e1 - e0) * sizeof(uint32_t); }
+};
+constexpr uint64_t kSliceRows = 1ull << 21;
+// <= 92 MB per slice; KDBGPU_GRAPH_SLICE_NODES / _EDGES shrink the slices (tests walk the multi-slice path on small graphs)
+uint64_t slice_limit(const char *env, uint64_t dflt) {
+  const char *v = getenv(env);
+  const long long x = v ? atoll(v) : 0;
+  return x >= 1 && (uint64_t)x < dflt ? (uint64_t)x : dflt;
+}
+
+// The topology is staged ON THE DEVICE: the host walks the per-node arrays once (levels, row counts: O(n)), the
+// O(edges) work — dropping nil neighbours, padding every row to its fixed degree — is graph_scatter_kernel's, fed
+// slice by slice through two pinned buffers so that filling one overlaps the DMA of the other.  (The first version
+// built the padded rows on the host: 4.9 s for the 2.76 GB sidecar of a 10 M-node graph, profiles/r2_cold_start.jsonl.)
+int set_graph_impl(kdbgpu_index *h, uint32_t n, const int32_t *levels, const uint64_t *node_row, const uint64_t *row_off,
+                   const uint32_t *nbrs, uint32_t entry, int max_level) {
   const uint32_t deg0 = (uint32_t)(2 * h->m), degu = (uint32_t)h->m;
   const size_t n1 = (size_t)n + 1;
-  std::vector<uint32_t> adj0(n1 * deg0, 0u), upper_first(n1, 0u), upper, upper_node;
+  std::vector<uint32_t> upper_first(n1, 0u), upper_node;
   std::vector<uint8_t> upper_level;
   std::vector<int8_t> lv(n1, (int8_t)-1);
   size_t upper_rows = 0;
@@ -1277,25 +1294,31 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
     }
     upper_rows += (size_t)L;
   }
-  upper.assign((upper_rows + 1) * degu, 0u);
-  for (uint32_t id = 1; id <= n; ++id) {
-    const int32_t L = levels[id];
-    for (int32_t l = 0; l <= L; ++l) {
-      const uint64_t r = node_row[id] + (uint64_t)l;
-      const uint64_t b = row_off[r], e = row_off[r + 1];
-      const uint32_t cap = l == 0 ? deg0 : degu;
-      uint32_t *dst = l == 0 ? &adj0[(size_t)id * deg0] : &upper[((size_t)upper_first[id] + (size_t)(l - 1)) * degu];
-      uint32_t w = 0;
-      for (uint64_t i = b; i < e; ++i) {
-        const uint32_t nb = nbrs[i];
-        // nil / out-of-range neighbours are skipped by the reference with no side effect on
-        // results (hnsw_index.go:2553-2561); drop them here so rows hold live ids only
-        if (nb == 0 || nb > n || levels[nb] < 0) continue;
-        if (w >= cap)
-          return fail(KDBGPU_ERR_INVALID, "node %u level %d has more than %u neighbours", id, l, cap);
-        dst[w++] = nb;
-      }
+  // slices of whole nodes within the limits above (every measure is monotone in b for a well-formed CSR)
+  std::vector<GraphSlice> slices;
+  size_t slice_bytes = 0;
+  const uint64_t kSliceNodes = slice_limit("KDBGPU_GRAPH_SLICE_NODES", 1ull << 20);
+  const uint64_t kSliceEdges = slice_limit("KDBGPU_GRAPH_SLICE_EDGES", 1ull << 24);
+  for (uint32_t a = 1; a <= n;) {
+    const uint64_t r0 = node_row[a], e0 = row_off[r0];
+    auto fits = [&](uint32_t b) {
+      const uint64_t r1 = node_row[b];
+      return r1 >= r0 && r1 - r0 <= kSliceRows && row_off[r1] >= e0 && row_off[r1] - e0 <= kSliceEdges;
+    };
+    uint32_t lo = a, hi = (uint64_t)a + kSliceNodes < (uint64_t)n + 1 ? a + (uint32_t)kSliceNodes : n + 1;  // b in (lo, hi]
+    if (!fits(a + 1))
+      return fail(KDBGPU_ERR_INVALID, "node %u: row / neighbour offsets out of order or beyond %llu neighbours", a,
+                  (unsigned long long)kSliceEdges);
+    lo = a + 1;
+    while (lo < hi) {  // largest b that fits
+      const uint32_t mid = lo + (hi - lo + 1) / 2;
+      if (fits(mid)) lo = mid;
+      else hi = mid - 1;
     }
+    GraphSlice sl{a, lo, r0, node_row[lo], e0, row_off[node_row[lo]]};
+    if (sl.bytes() > slice_bytes) slice_bytes = sl.bytes();
+    slices.push_back(sl);
+    a = lo;
   }
   std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
@@ -1309,11 +1332,34 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
     CUDA_TRY(h->upper_node.reserve(rows, true));
     CUDA_TRY(h->upper_level.reserve(rows, true));
   }
+  DevBuf<unsigned char> d_stage[2];
+  DevBuf<int> d_err;
+  unsigned char *pinned[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  struct Free {
+    DevBuf<unsigned char> *st;
+    DevBuf<int> &er;
+    unsigned char **pin;
+    cudaEvent_t *ev;
+    ~Free() {
+      st[0].release(); st[1].release(); er.release();
+      for (int i = 0; i < 2; ++i) {
+        if (pin[i]) cudaFreeHost(pin[i]);
+        if (ev[i]) cudaEventDestroy(ev[i]);
+      }
+    }
+  } freer{d_stage, d_err, pinned, ev};
+  const int n_buf = slices.size() > 1 ? 2 : (slices.empty() ? 0 : 1);
+  for (int i = 0; i < n_buf; ++i) {
+    CUDA_TRY(d_stage[i].reserve(slice_bytes + 16));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pinned[i]), slice_bytes + 16, cudaHostAllocDefault));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(d_err.reserve(4, true));
   cudaStream_t s = h->stream;
+  h->has_graph = false;  // until every row is in place
   CUDA_TRY(cudaMemsetAsync(h->adj0.p, 0, h->adj0.bytes(), s));
   CUDA_TRY(cudaMemsetAsync(h->upper_adj.p, 0, h->upper_adj.bytes(), s));
-  CUDA_TRY(cudaMemcpyAsync(h->adj0.p, adj0.data(), adj0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->upper_adj.p, upper.data(), upper.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   if (upper_rows) {
     CUDA_TRY(cudaMemcpyAsync(h->upper_node.p, upper_node.data(), upper_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(h->upper_level.p, upper_level.data(), upper_rows, cudaMemcpyHostToDevice, s));
@@ -1322,6 +1368,24 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
   CUDA_TRY(cudaMemcpyAsync(h->upper_first.p, upper_first.data(), n1 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemsetAsync(h->levels.p, 0xff, (size_t)h->capacity + 1, s));
   CUDA_TRY(cudaMemcpyAsync(h->levels.p, lv.data(), n1, cudaMemcpyHostToDevice, s));
+  for (size_t c = 0; c < slices.size(); ++c) {
+    const GraphSlice &sl = slices[c];
+    const int b = (int)(c & 1);
+    CUDA_TRY(cudaEventSynchronize(ev[b]));  // the copy that last read this pinned buffer is done
+    const size_t nn = (size_t)(sl.b - sl.a) + 1, nr = (size_t)(sl.r1 - sl.r0) + 1, ne = (size_t)(sl.e1 - sl.e0);
+    unsigned char *p = pinned[b];
+    memcpy(p, node_row + sl.a, nn * sizeof(uint64_t));
+    memcpy(p + nn * sizeof(uint64_t), row_off + sl.r0, nr * sizeof(uint64_t));
+    if (ne) memcpy(p + (nn + nr) * sizeof(uint64_t), nbrs + sl.e0, ne * sizeof(uint32_t));
+    CUDA_TRY(cudaMemcpyAsync(d_stage[b].p, p, sl.bytes(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(ev[b], s));
+    const uint64_t *d_node_row = reinterpret_cast<const uint64_t *>(d_stage[b].p);
+    CUDA_TRY(launch_graph_scatter(d_node_row, d_node_row + nn, reinterpret_cast<const uint32_t *>(d_node_row + nn + nr), sl.a,
+                                  sl.b - sl.a, sl.r0, sl.e0, sl.e1, n, h->levels.p, h->upper_first.p, deg0, degu,
+                                  h->adj0.p, h->upper_adj.p, d_err.p, s));
+  }
+  int err[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(err, d_err.p, sizeof err, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   std::fill(h->h_levels.begin(), h->h_levels.end(), (int8_t)-1);
   std::fill(h->h_upper_first.begin(), h->h_upper_first.end(), 0u);
@@ -1331,8 +1395,27 @@ int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const u
   h->n = n;
   h->entry = entry;
   h->max_level = max_level;
+  if (err[0] == 1)
+    return fail(KDBGPU_ERR_INVALID, "node %d level %d has more than %u neighbours", err[1], err[2], err[2] == 0 ? deg0 : degu);
+  if (err[0])
+    return fail(KDBGPU_ERR_INVALID, "node %d level %d: neighbour offsets out of order", err[1], err[2]);
   h->has_graph = true;
   return KDBGPU_OK;
+}
+
+}  // namespace
+
+int kdbgpu_set_graph(kdbgpu_index *h, uint32_t n, const int32_t *levels, const uint64_t *node_row,
+                     const uint64_t *row_off, const uint32_t *nbrs, uint32_t entry, int max_level) {
+  if (!h || !levels || !node_row || !row_off) return fail(KDBGPU_ERR_INVALID, "NULL argument");
+  if (n > h->capacity) return fail(KDBGPU_ERR_INVALID, "n %u exceeds capacity %u", n, h->capacity);
+  if (max_level >= 0 && (entry == 0 || entry > n || levels[entry] < 0))
+    return fail(KDBGPU_ERR_INVALID, "entry point %u is not a live node", entry);
+  try {
+    return set_graph_impl(h, n, levels, node_row, row_off, nbrs, entry, max_level);
+  } catch (...) {  // std::bad_alloc of the per-node arrays: nothing unwinds across the C boundary
+    return fail(KDBGPU_ERR_NOMEM, "out of host memory staging the topology");
+  }
 }
 
 int kdbgpu_set_deleted(kdbgpu_index *h, const uint64_t *bitset, size_t words) {

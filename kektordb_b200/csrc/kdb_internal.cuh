@@ -125,6 +125,11 @@ cudaError_t launch_abs_hist(const float *rows, size_t row_stride, uint32_t n_sam
                             uint32_t prefix, int hi_shift, int shift, int bits, unsigned long long *hist,
                             cudaStream_t stream);
 // arena chunk payload (device) -> mirror rows of the ids whose physical slot lives in that chunk
+// CSR slice of whole nodes -> fixed-degree adjacency rows of the mirror (search.cu: graph_scatter_kernel)
+cudaError_t launch_graph_scatter(const uint64_t *node_row, const uint64_t *row_off, const uint32_t *nbrs,
+                                 uint32_t first_node, uint32_t n_nodes, uint64_t row0, uint64_t edge0, uint64_t edge1,
+                                 uint32_t n, const int8_t *levels, const uint32_t *upper_first, uint32_t deg0,
+                                 uint32_t degu, uint32_t *adj0, uint32_t *upper, int *err, cudaStream_t stream);
 cudaError_t launch_arena_scatter(const unsigned char *chunk, uint32_t chunk_id, uint32_t vecs_per_chunk,
                                  uint32_t vector_bytes, const uint32_t *slot_table, uint32_t first_id, uint32_t last_id,
                                  float *vecs, size_t row_words, unsigned int *n_staged, cudaStream_t stream);

@@ -182,6 +182,57 @@ __global__ void arena_scatter_kernel(const unsigned char *__restrict__ chunk, ui
   if (lane == 0) atomicAdd(n_staged, 1u);
 }
 
+// Topology staging (kdbgpu_set_graph / kdbgpu_set_graph_file): the adjacency arrives as the reference-shaped CSR
+// (node i owns rows node_row[i] .. node_row[i+1]-1, level 0 first; row r holds nbrs[row_off[r] .. row_off[r+1])) in
+// slices of whole nodes [first_node, first_node + n_nodes).  One warp per node writes every row into the fixed-degree
+// mirror (level 0: adj0[id][2M], upper levels: upper[upper_first[id] + l - 1][M]), dropping nil / out-of-range
+// neighbours in place with an order-preserving warp compaction — the reference skips them at search time with no
+// effect on results (hnsw_index.go:2553-2561).  err[0..2] = {code, node, level}: 1 = more live neighbours than the row
+// holds, 2 = row offsets outside the slice / not monotone.
+__global__ void graph_scatter_kernel(const uint64_t *__restrict__ node_row, const uint64_t *__restrict__ row_off,
+                                     const uint32_t *__restrict__ nbrs, uint32_t first_node, uint32_t n_nodes,
+                                     uint64_t row0, uint64_t edge0, uint64_t edge1, uint32_t n,
+                                     const int8_t *__restrict__ levels, const uint32_t *__restrict__ upper_first,
+                                     uint32_t deg0, uint32_t degu, uint32_t *__restrict__ adj0,
+                                     uint32_t *__restrict__ upper, int *__restrict__ err) {
+  const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= n_nodes) return;
+  const uint32_t id = first_node + w;
+  const int L = levels[id];
+  if (L < 0) return;
+  const uint64_t r_first = node_row[w] - row0;
+  for (int l = 0; l <= L; ++l) {
+    const uint64_t eb = row_off[r_first + (uint64_t)l], ee = row_off[r_first + (uint64_t)l + 1];
+    if (eb < edge0 || ee > edge1 || eb > ee) {
+      if (lane == 0 && atomicCAS(&err[0], 0, 2) == 0) {
+        err[1] = (int)id;
+        err[2] = l;
+      }
+      return;
+    }
+    const uint32_t cap = l == 0 ? deg0 : degu;
+    uint32_t *dst = l == 0 ? adj0 + (size_t)id * deg0 : upper + ((size_t)upper_first[id] + (size_t)(l - 1)) * degu;
+    uint32_t kept = 0;
+    for (uint64_t i0 = eb; i0 < ee; i0 += 32) {
+      const uint64_t i = i0 + (uint64_t)lane;
+      const uint32_t nb = i < ee ? nbrs[i - edge0] : 0u;
+      const bool keep = nb != 0u && nb <= n && levels[nb] >= 0;
+      const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+      const uint32_t pos = kept + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+      if (keep && pos < cap) dst[pos] = nb;
+      kept += (uint32_t)__popc(mask);
+    }
+    if (kept > cap) {
+      if (lane == 0 && atomicCAS(&err[0], 0, 1) == 0) {
+        err[1] = (int)id;
+        err[2] = l;
+      }
+      return;
+    }
+  }
+}
+
 // Incremental topology refresh: adjacency row dst_row[i] of `base` (deg slots) := src[src_off[i] ..
 // +src_cnt[i]), zero padded — the rewritten node.Connections[level] of Add's forward / reverse links
 // (hnsw_index.go:717-783), Vacuum's reconnectNode and Refine's commits (optimizer.go).
@@ -355,6 +406,18 @@ cudaError_t launch_arena_scatter(const unsigned char *chunk, uint32_t chunk_id, 
   arena_scatter_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, stream>>>(chunk, chunk_id, vecs_per_chunk, vector_bytes,
                                                                       slot_table, first_id, last_id, vecs, row_words,
                                                                       n_staged);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_graph_scatter(const uint64_t *node_row, const uint64_t *row_off, const uint32_t *nbrs,
+                                 uint32_t first_node, uint32_t n_nodes, uint64_t row0, uint64_t edge0, uint64_t edge1,
+                                 uint32_t n, const int8_t *levels, const uint32_t *upper_first, uint32_t deg0,
+                                 uint32_t degu, uint32_t *adj0, uint32_t *upper, int *err, cudaStream_t stream) {
+  if (n_nodes == 0) return cudaSuccess;
+  const uint32_t wpb = 8;
+  graph_scatter_kernel<<<(n_nodes + wpb - 1) / wpb, wpb * 32, 0, stream>>>(node_row, row_off, nbrs, first_node, n_nodes, row0,
+                                                                      edge0, edge1, n, levels, upper_first, deg0, degu, adj0,
+                                                                      upper, err);
   return cudaGetLastError();
 }
 
