@@ -129,7 +129,7 @@ def run_flat(args, torch, bench):
     dp = (D + 63) // 64 * 64
     n_pad = (N + 255) // 256 * 256
     flops_full = 2.0 * B * n_pad * dp                      # one full Q x K^T pass (pass B, the dominant kernel)
-    stride = int(os.environ.get("KDBGPU_FLAT_SAMPLE", "0")) or max(1, min(8, 8192 // (6 * k)))
+    stride = int(os.environ.get("KDBGPU_FLAT_SAMPLE", "0")) or max(1, min(12, 8192 // (6 * k)))
     flops_step = flops_full * (1.0 + 1.0 / stride)         # + the sampled threshold pass
     achieved = flops_step * args.steps / (tens_ms / 1e3) / 1e12
     cpu = None

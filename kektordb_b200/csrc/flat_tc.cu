@@ -1164,8 +1164,10 @@ __device__ __forceinline__ double exact_term(float qf, float xf) {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_CHUNK = 64;            // floats of every row per step: 256 contiguous bytes per request
-constexpr int RS_LD = RS_CHUNK + 4;     // padded tile row (conflict-free LDS.128 with lane = row)
+// floats of every row per pipeline step (template parameter RS_CHUNK): 64 = 256 contiguous bytes per request and
+// 139 KB of row tiles per CTA (one CTA per SM); 32 halves the tiles so that two CTAs share an SM and one's waits hide
+// behind the other's sums.  Tile rows are padded by 4 floats (conflict-free LDS.128 with lane = row).
+constexpr int RS_CHUNK_DEFAULT = 32;
 
 // One CTA per query: exact distances of the surviving rows in the reference's arithmetic (flat.cu's
 // flat_distances_kernel order: sequential in the element index, float64), ascending (distance, id),
@@ -1173,7 +1175,7 @@ constexpr int RS_LD = RS_CHUNK + 4;     // padded tile row (conflict-free LDS.12
 //   theta' - bound  >  (k-th exact distance) - qconst
 // i.e. every row that was dropped is provably farther than the k-th result.  flags[q] != 0 sends the
 // query to the exhaustive float64 scan.
-template <int MODE, int METRIC>
+template <int MODE, int METRIC, int RS_CHUNK>
 __global__ void __launch_bounds__(RS_THREADS)
     tc_rescore_kernel(const DevIndex ix, const float *__restrict__ queries, size_t q_stride, uint32_t nq, int k,
                       const uint32_t *__restrict__ fcnt, const uint32_t *__restrict__ fid, uint32_t fcap,
@@ -1181,6 +1183,7 @@ __global__ void __launch_bounds__(RS_THREADS)
                       const float *__restrict__ qsumsq, uint32_t *__restrict__ out_ids, double *__restrict__ out_scores,
                       uint32_t *__restrict__ out_counts, uint32_t *__restrict__ flags,
                       unsigned long long *__restrict__ n_rescored) {
+  constexpr int RS_LD = RS_CHUNK + 4;
   extern __shared__ __align__(16) unsigned char rs_smem[];
   const uint32_t q = blockIdx.x;
   if (q >= nq) return;
@@ -1342,33 +1345,49 @@ cudaError_t launch_tc_refine(const void *sub, const uint32_t *sub_cnt, uint32_t 
   return cudaGetLastError();
 }
 
-size_t tc_rescore_smem(uint32_t dim, uint32_t fcap) {
+namespace {
+int rescore_chunk() {  // KDBGPU_FLAT_RS_CHUNK = 16 | 32 | 64 (measurement switch, read per launch; same bits)
+  const char *v = getenv("KDBGPU_FLAT_RS_CHUNK");
+  const int c = v ? atoi(v) : 0;
+  return (c == 16 || c == 32 || c == 64) ? c : RS_CHUNK_DEFAULT;
+}
+size_t rescore_smem(uint32_t dim, uint32_t fcap, int chunk) {
   uint32_t cap2 = 1;
   while (cap2 < fcap) cap2 <<= 1;
-  return (size_t)cap2 * (sizeof(double) + sizeof(uint32_t)) +
-         (size_t)((dim + RS_CHUNK - 1) / RS_CHUNK) * RS_CHUNK * sizeof(float) +
-         (size_t)RS_WARPS * 2 * 32 * RS_LD * sizeof(float);
+  return (size_t)cap2 * (sizeof(double) + sizeof(uint32_t)) + (size_t)((dim + chunk - 1) / chunk) * chunk * sizeof(float) +
+         (size_t)RS_WARPS * 2 * 32 * (chunk + 4) * sizeof(float);
 }
+}  // namespace
+
+size_t tc_rescore_smem(uint32_t dim, uint32_t fcap) { return rescore_smem(dim, fcap, 64); }  // the largest shape
 
 cudaError_t launch_tc_rescore(const DevIndex &ix, int mode, const float *queries, size_t q_stride, uint32_t nq, int k,
                               const uint32_t *fcnt, const uint32_t *fid, uint32_t fcap, const float *theta_final,
                               const float *bound, const float *qsumsq, uint32_t *out_ids, double *out_scores,
                               uint32_t *out_counts, uint32_t *flags, unsigned long long *n_rescored,
                               cudaStream_t stream) {
-  const size_t smem = tc_rescore_smem(ix.dim, fcap);
+  const int chunk = rescore_chunk();
+  const size_t smem = rescore_smem(ix.dim, fcap, chunk);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e;
-#define KDB_RS_LAUNCH(MODEv, METRICv)                                                                              \
+#define KDB_RS_LAUNCH_C(MODEv, METRICv, CHUNKv)                                                                    \
   {                                                                                                                \
-    auto kern = tc_rescore_kernel<MODEv, METRICv>;                                                                 \
+    auto kern = tc_rescore_kernel<MODEv, METRICv, CHUNKv>;                                                         \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
     if (e != cudaSuccess) return e;                                                                                \
     kern<<<nq, RS_THREADS, smem, stream>>>(ix, queries, q_stride, nq, k, fcnt, fid, fcap, theta_final, bound,      \
                                            qsumsq, out_ids, out_scores, out_counts, flags, n_rescored);            \
   }
+#define KDB_RS_LAUNCH(MODEv, METRICv)                                                                              \
+  {                                                                                                                \
+    if (chunk == 16) KDB_RS_LAUNCH_C(MODEv, METRICv, 16)                                                           \
+    else if (chunk == 32) KDB_RS_LAUNCH_C(MODEv, METRICv, 32)                                                      \
+    else KDB_RS_LAUNCH_C(MODEv, METRICv, 64)                                                                       \
+  }
   if (mode == 0) KDB_RS_LAUNCH(0, KDBGPU_METRIC_L2)
   else if (ix.metric == KDBGPU_METRIC_COSINE) KDB_RS_LAUNCH(1, KDBGPU_METRIC_COSINE)
   else KDB_RS_LAUNCH(1, KDBGPU_METRIC_L2)
+#undef KDB_RS_LAUNCH_C
 #undef KDB_RS_LAUNCH
   return cudaGetLastError();
 }

@@ -25,6 +25,11 @@ ffi.check(ffi.lib().kdbgpu_upload_vectors_device(gi._h, 1, N, X.data_ptr(), D))
 bench_extra._rows_only_graph(gi, N)
 Q = bench.make_data(torch, (STEPS + 3) * B, D, 32, 0.1, 4242, dev).cpu().numpy()
 variants = {"static": {"KDBGPU_FLAT_DYNAMIC": "0"}, "dynamic": {}}
+if os.environ.get("AB") == "rescore":   # re-score row chunk (CTAs per SM) and the sampling stride of the threshold pass
+    variants = {"chunk64": {"KDBGPU_FLAT_RS_CHUNK": "64"}, "chunk32": {"KDBGPU_FLAT_RS_CHUNK": "32"},
+                "chunk16": {"KDBGPU_FLAT_RS_CHUNK": "16"},
+                "chunk32+sample12": {"KDBGPU_FLAT_RS_CHUNK": "32", "KDBGPU_FLAT_SAMPLE": "12"},
+                "chunk32+sample16": {"KDBGPU_FLAT_RS_CHUNK": "32", "KDBGPU_FLAT_SAMPLE": "16"}}
 keys = {k for v in variants.values() for k in v}
 acc = {name: [0.0, 0.0, 0] for name in variants}
 ref = {}
@@ -42,9 +47,9 @@ for i in range(STEPS + 3):
             acc[name][2] += 1
 names = list(variants)
 same = all(np.array_equal(ref[names[0]][j], ref[n][j]) for n in names[1:] for j in range(3))
-flops = 2.0 * B * ((N + 255) // 256 * 256) * D * (1 + 1 / 8)
 for name, (t, c, n) in acc.items():
-    print(f"{name:8s} tensor passes {t / n:.4f} ms/step = {flops / (t / n * 1e-3) / 1e12:7.1f} TFLOP/s   whole call {c / n:.4f} ms/step "
+    flops = 2.0 * B * ((N + 255) // 256 * 256) * D * (1 + 1 / int(variants[name].get("KDBGPU_FLAT_SAMPLE", 12)))
+    print(f"{name:18s} tensor passes {t / n:.4f} ms/step = {flops / (t / n * 1e-3) / 1e12:7.1f} TFLOP/s   whole call {c / n:.4f} ms/step "
           f"= {B / (c / n * 1e-3) / 1e3:6.1f} k queries/s   ({n} steps)")
 print("bit-identical across variants:", same)
 gi.close()
