@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round-2 evidence on one GPU box:  gpurun --timeout 3000 -- 'bash profiles/tools/r2_evidence.sh <tag> <sections>'
-# sections (any of): tests bench sweep launches ncu sanitize gather  -> gpurun_out/<tag>_*
+# sections (any of): tests bench sweep launches ncu flatncu cold sanitize gather  -> gpurun_out/<tag>_*
 # ncu reports are exported to CSV on the box and deleted (gpurun copies back at most 64 MiB).
 set -u
 T=${1:-r2}; shift || true
@@ -15,6 +15,20 @@ if has bench; then
   python bench.py --workload quantized --precision int8 --overlap 4 > $O/${T}_bench_int8.json 2> $O/${T}_bench_int8.err
   python bench.py --workload quantized --precision float16 --overlap 4 > $O/${T}_bench_f16.json 2> $O/${T}_bench_f16.err
   python bench.py --workload flat > $O/${T}_bench_flat.json 2> $O/${T}_bench_flat.err
+  python bench.py --workload hybrid > $O/${T}_bench_hybrid.json 2> $O/${T}_bench_hybrid.err
+fi
+if has flatncu; then  # the two tensor passes of one flat step under ncu --set full, and the launch list of a short flat run
+  ncu --set full --clock-control none --import-source on -k regex:flat_tc2_kernel -s 8 -c 2 -f -o /tmp/${T}_flat \
+    python bench.py --workload flat --steps 2 --warmup 3 --no-cpu-baseline --sustain-seconds 0 > $O/${T}_ncu_flat.log 2>&1
+  ncu -i /tmp/${T}_flat.ncu-rep --page raw --csv > $O/${T}_flat_tc2_kernel_raw.csv 2>/dev/null
+  rm -f /tmp/${T}_flat.ncu-rep
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_flat_launches.csv \
+    python bench.py --workload flat --steps 2 --warmup 3 --no-cpu-baseline --sustain-seconds 0 > $O/${T}_flat_launches_bench.log 2>&1
+fi
+if has cold; then
+  python profiles/tools/cold_start.py 1000000 float32 > $O/${T}_cold_start_1m_f32.json 2> $O/${T}_cold_start_1m_f32.err
+  python profiles/tools/cold_start.py 10000000 int8 > $O/${T}_cold_start_10m_int8.json 2> $O/${T}_cold_start_10m_int8.err
+  cat $O/${T}_cold_start_1m_f32.json $O/${T}_cold_start_10m_int8.json
 fi
 if has sweep; then
   python profiles/tools/sweep_tuning.py 4,192,0,4 8,192,0,8 4,192,0,8 > $O/${T}_sweep_f32.log 2>&1
