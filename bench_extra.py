@@ -179,6 +179,8 @@ def run_flat_sharded(args, torch, bench):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # the banner would land on stdout, before the JSON line
+        os.environ.pop("NCCL_DEBUG", None)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
     n_total = args.warmup + args.steps
