@@ -108,9 +108,13 @@ int kdbgpu_graph_file_write(const char *path, uint32_t n, int m, const int32_t *
                   write_all(fd, node_row, ((size_t)n + 2) * sizeof(uint64_t)) &&
                   write_all(fd, row_off, ((size_t)n_rows + 1) * sizeof(uint64_t)) &&
                   write_padded(fd, nbrs, (size_t)n_edges * sizeof(uint32_t));
-  const int e = errno;
+  int e = errno;
+  // the rename below must never publish a file whose pages did not reach the disk (a crash would leave a sidecar
+  // with a valid header and torn sections)
+  bool synced = ok && fsync(fd) == 0;
+  if (ok && !synced) e = errno;
   close(fd);
-  if (!ok) {
+  if (!ok || !synced) {
     unlink(tmp.c_str());
     return set_error(KDBGPU_ERR_INVALID, "%s: %s", tmp.c_str(), strerror(e));
   }
