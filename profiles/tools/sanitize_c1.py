@@ -1,6 +1,7 @@
 """compute-sanitizer target: the C1 shape (128-d cosine, M=16, efC=200, ef=64, k=10) at a size racecheck can
 finish — graph construction on the device (build_search / request / scan / commit / seq_add kernels), then the
-traversal (heap pass and sorted-list fast pass), the flat scan and a two-shard group; checked against the oracle.
+traversal (heap pass and sorted-list fast pass), the flat scan, the topology staging kernel, a two-shard group and
+(TC=1) the tensor-core pre-filter of the flat scan in both kernels; checked against the oracle.
   compute-sanitizer --tool memcheck  python profiles/tools/sanitize_c1.py
   compute-sanitizer --tool racecheck python profiles/tools/sanitize_c1.py"""
 import os
@@ -39,6 +40,22 @@ assert np.array_equal(got[0], wa[0]) and np.array_equal(got[1], wa[1]), "filtere
 fi = gi.flat_search(Q[:16], k, 1)
 fw = oi.flat_search_batch(Q[:16], k, mode=1, threads=8)
 assert np.array_equal(fi[0], fw[0]) and np.array_equal(fi[1], fw[1]), "flat scan differs"
+# the topology staged from host arrays (graph_scatter_kernel, several slices): same mirror, same answers
+os.environ["KDBGPU_GRAPH_SLICE_NODES"] = "500"
+g2 = GpuIndex(dim, "cosine", m, n)
+g2.upload_vectors(1, oi.vectors()[1:])
+g2.set_graph(g.n, g.levels, g.node_row, g.row_off, g.nbrs, g.entry, g.max_level)
+del os.environ["KDBGPU_GRAPH_SLICE_NODES"]
+assert np.array_equal(g2.get_graph()[4], g.nbrs), "staged topology differs"
+got = g2.SearchWithScores(Q, k, None, ef)
+assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), "search over the staged topology differs"
+if os.environ.get("TC", "0") == "1":  # tensor-core pre-filter of the flat scan: single-CTA kernel (64 queries), CTA pairs (256)
+    Q2 = rng.standard_normal((256, dim)).astype(np.float32)
+    for qq in (Q[:64], Q2):
+        a = g2.flat_search(qq[:16], k, 1)
+        b = g2.flat_search(qq, k, 1, prefilter=True)
+        assert np.array_equal(a[0], b[0][:16]) and np.array_equal(a[1], b[1][:16]), "pre-filtered flat scan differs"
+g2.close()
 grp = ShardGroup.local([gi, gi], [0, n])  # the same shard twice: exercises the exchange + merge kernels
 ids, sc, cnt, st = grp.SearchWithScores(Q, k, None, ef)
 assert st.n_shards == 2 and (cnt == k).all()
