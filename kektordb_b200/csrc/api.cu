@@ -81,6 +81,17 @@ int arena_fail(int code, const char *fmt, ...) {
 }  // namespace kdb
 
 #define fail kdb::set_error
+// Nothing unwinds across the C boundary: the entry points (and the helpers behind them) that size host arrays from the
+// caller's arguments run inside this pair.  RAII guards (workspace release, add_batch's rollback) have run by then.
+#define KDB_NOTHROW_BEGIN try {
+#define KDB_NOTHROW_END                                                             \
+  }                                                                                 \
+  catch (const std::bad_alloc &) {                                                  \
+    return fail(KDBGPU_ERR_NOMEM, "out of host memory");                            \
+  }                                                                                 \
+  catch (...) {                                                                     \
+    return fail(KDBGPU_ERR_CUDA, "unexpected C++ exception inside the library");    \
+  }
 
 namespace {
 
@@ -440,6 +451,7 @@ FlatTcLaunch tc_launch_desc(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const TcPl
 int flat_prefilter_impl(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *queries, uint32_t nq, int k, int mode,
                         const uint32_t *d_allow, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
                         uint64_t *evals, uint64_t *fallbacks, float *gemm_ms, float *compute_ms) {
+  KDB_NOTHROW_BEGIN
   cudaStream_t s = w.stream;
   TcPlan P;
   int rc = tc_prepare(h, w, mode, d_allow, &P, s);
@@ -568,6 +580,7 @@ int flat_prefilter_impl(kdbgpu_index *h, kdbgpu_index::FlatWs &w, const float *q
   *evals = nres + (uint64_t)redo.size() * h->n;
   *fallbacks = redo.size();
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 
 }  // namespace
@@ -935,6 +948,7 @@ void train_sample(uint32_t n, uint32_t *step, uint32_t *count) {
 // d_rows[i * step * row_stride ..].
 int train_select(kdbgpu_index *h, const float *d_rows, size_t row_stride, uint32_t count, uint32_t step,
                  float *abs_max) {
+  KDB_NOTHROW_BEGIN
   const uint64_t total = (uint64_t)count * (uint64_t)h->dim;
   long long qi = (long long)((double)total * 0.999);
   if (qi >= (long long)total) qi = (long long)total - 1;
@@ -979,6 +993,7 @@ int train_select(kdbgpu_index *h, const float *d_rows, size_t row_stride, uint32
   h->abs_max = v;
   if (abs_max) *abs_max = v;
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 }  // namespace
 
@@ -1149,6 +1164,7 @@ int kdbgpu_arena_stage_chunk(kdbgpu_index *h, uint32_t chunk_id, const void *chu
 
 int kdbgpu_arena_load_dir(kdbgpu_index *h, const char *dir, const uint32_t *slot_table, uint32_t table_len,
                           uint64_t *rows_staged) {
+  KDB_NOTHROW_BEGIN
   if (rows_staged) *rows_staged = 0;
   if (!h || !dir) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (table_len < 2) return KDBGPU_OK;
@@ -1221,6 +1237,7 @@ int kdbgpu_arena_load_dir(kdbgpu_index *h, const char *dir, const uint32_t *slot
   CUDA_TRY(cudaStreamSynchronize(s));
   if (rows_staged) *rows_staged = cnt;
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 
 int kdbgpu_index_precision(const kdbgpu_index *h) { return h ? h->precision : -1; }
@@ -1325,6 +1342,7 @@ int set_graph_impl(kdbgpu_index *h, uint32_t n, const int32_t *levels, const uin
   std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
   CUDA_TRY(cudaDeviceSynchronize());  // drain searches queued through the asynchronous entry point
+  h->has_graph = false;               // from here on the mirror is being rewritten: no graph until every row is in place
   if ((upper_rows + 1) * degu > h->upper_adj.n) {
     const size_t rows = (upper_rows + 1) + (upper_rows + 1) / 4 + 1024;
     h->upper_adj.release();
@@ -1359,7 +1377,6 @@ int set_graph_impl(kdbgpu_index *h, uint32_t n, const int32_t *levels, const uin
   }
   CUDA_TRY(d_err.reserve(4, true));
   cudaStream_t s = h->stream;
-  h->has_graph = false;  // until every row is in place
   CUDA_TRY(cudaMemsetAsync(h->adj0.p, 0, h->adj0.bytes(), s));
   CUDA_TRY(cudaMemsetAsync(h->upper_adj.p, 0, h->upper_adj.bytes(), s));
   if (upper_rows) {
@@ -1847,6 +1864,7 @@ uint32_t next_pow2(uint32_t v) {
 // rows: `count` raw vectors, on the host (row_stride == dim) or on the device
 int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t row_stride, bool rows_on_device,
                    const double *level_draws, int ef_const) {
+  KDB_NOTHROW_BEGIN
   if (!h) return fail(KDBGPU_ERR_INVALID, "NULL handle");
   if (count == 0) return KDBGPU_OK;
   if (!rows || !level_draws) return fail(KDBGPU_ERR_INVALID, "NULL argument");
@@ -2061,6 +2079,7 @@ int add_batch_impl(kdbgpu_index *h, uint32_t count, const float *rows, size_t ro
                 (int)io_back[1] - 1, new_entry, cur_max);
   if (err == KDBGPU_ERR_OVERFLOW) return fail(KDBGPU_ERR_OVERFLOW, "a construction-time list exceeded its bound");
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 
 }  // namespace
@@ -2080,6 +2099,7 @@ int kdbgpu_add_batch_device(kdbgpu_index *h, uint32_t count, const float *d_rows
 // ---- incremental mirror refresh: follow the CPU index's Add / Delete / Vacuum /
 // ---- Refine without re-staging the whole topology ------------------------------------------------
 int kdbgpu_register_nodes(kdbgpu_index *h, uint32_t first_id, uint32_t count, const int32_t *levels) {
+  KDB_NOTHROW_BEGIN
   if (!h || (!levels && count)) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (count == 0) return KDBGPU_OK;
   std::unique_lock<std::shared_mutex> lk(h->mu);
@@ -2126,10 +2146,12 @@ int kdbgpu_register_nodes(kdbgpu_index *h, uint32_t first_id, uint32_t count, co
   h->n = first_id + count - 1;
   h->has_graph = true;
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 
 int kdbgpu_patch_rows(kdbgpu_index *h, uint32_t count, const uint32_t *ids, const int32_t *row_levels,
                       const uint64_t *row_off, const uint32_t *nbrs) {
+  KDB_NOTHROW_BEGIN
   if (!h || (count && (!ids || !row_levels || !row_off))) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   if (count == 0) return KDBGPU_OK;
   std::unique_lock<std::shared_mutex> lk(h->mu);
@@ -2182,6 +2204,7 @@ int kdbgpu_patch_rows(kdbgpu_index *h, uint32_t count, const uint32_t *ids, cons
   }
   CUDA_TRY(cudaStreamSynchronize(s));
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 
 int kdbgpu_remove_nodes(kdbgpu_index *h, uint32_t count, const uint32_t *ids) {
@@ -2223,6 +2246,7 @@ int kdbgpu_set_entry(kdbgpu_index *h, uint32_t entry, int max_level) {
 
 int kdbgpu_get_graph_sizes(kdbgpu_index *h, uint32_t *n, uint64_t *n_rows, uint64_t *n_edges, uint32_t *entry,
                            int *max_level) {
+  KDB_NOTHROW_BEGIN
   if (!h || !n || !n_rows || !n_edges || !entry || !max_level) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
@@ -2247,9 +2271,11 @@ int kdbgpu_get_graph_sizes(kdbgpu_index *h, uint32_t *n, uint64_t *n_rows, uint6
   *entry = h->entry;
   *max_level = h->max_level;
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 
 int kdbgpu_get_graph(kdbgpu_index *h, int32_t *levels, uint64_t *node_row, uint64_t *row_off, uint32_t *nbrs) {
+  KDB_NOTHROW_BEGIN
   if (!h || !levels || !node_row || !row_off || !nbrs) return fail(KDBGPU_ERR_INVALID, "NULL argument");
   std::unique_lock<std::shared_mutex> lk(h->mu);
   DeviceGuard g(h->device);
@@ -2274,6 +2300,7 @@ int kdbgpu_get_graph(kdbgpu_index *h, int32_t *levels, uint64_t *node_row, uint6
   node_row[h->n + 1] = r;
   row_off[r] = e;
   return KDBGPU_OK;
+  KDB_NOTHROW_END
 }
 
 int kdbgpu_download_vectors(kdbgpu_index *h, uint32_t first_id, uint32_t count, float *rows) {

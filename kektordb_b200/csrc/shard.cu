@@ -743,16 +743,23 @@ int kdbgpu_shard_flat_search_batch(kdbgpu_shard_group *g, const float *queries, 
       rc = scan_one(0);
     } else {
       std::vector<std::future<int>> fut;
-      std::vector<std::string> errs(g->members.size());
-      for (size_t m = 0; m < g->members.size(); ++m)
-        fut.push_back(std::async(std::launch::async, [&, m]() -> int {
-          const int r = scan_one(m);
-          if (r) errs[m] = kdbgpu_last_error();  // the message lives in the worker thread
-          return r;
-        }));
-      for (size_t m = 0; m < fut.size(); ++m) {
-        const int r = fut[m].get();
-        if (r && rc == KDBGPU_OK) rc = set_error(r, "%s", errs[m].c_str());
+      try {
+        std::vector<std::string> errs(g->members.size());
+        for (size_t m = 0; m < g->members.size(); ++m)
+          fut.push_back(std::async(std::launch::async, [&, m]() -> int {
+            const int r = scan_one(m);
+            if (r) errs[m] = kdbgpu_last_error();  // the message lives in the worker thread
+            return r;
+          }));
+        for (size_t m = 0; m < fut.size(); ++m) {
+          const int r = fut[m].get();
+          if (r && rc == KDBGPU_OK) rc = set_error(r, "%s", errs[m].c_str());
+        }
+      } catch (...) {  // no thread / no memory: the scans already started are joined (the futures' destructors below),
+                       // the slot is handed back by the common exit, nothing unwinds across the C boundary
+        for (auto &f : fut)
+          if (f.valid()) f.wait();
+        rc = set_error(KDBGPU_ERR_NOMEM, "could not start one scan thread per local shard");
       }
     }
   }
