@@ -743,8 +743,10 @@ int kdbgpu_shard_flat_search_batch(kdbgpu_shard_group *g, const float *queries, 
       rc = scan_one(0);
     } else {
       std::vector<std::future<int>> fut;
+      std::vector<std::string> errs;  // outlives every scan thread (they are joined in the handler below)
       try {
-        std::vector<std::string> errs(g->members.size());
+        errs.resize(g->members.size());
+        fut.reserve(g->members.size());
         for (size_t m = 0; m < g->members.size(); ++m)
           fut.push_back(std::async(std::launch::async, [&, m]() -> int {
             const int r = scan_one(m);
