@@ -180,7 +180,18 @@ int enqueue_search(kdbgpu_index *h, kdbgpu_index::SearchWs &w, const float *d_q_
       w.launch_stream = stream;
     }
     (void)cudaGetLastError();  // cudaErrorNotReady is an answer, not a failure
-    if (n_other == 0) tn.slots = tn.slots_idle;
+    if (n_other == 0) {
+      tn.slots = tn.slots_idle;
+      // a lone batch small enough to be resident in ONE wave of the next larger shape takes it: only the per-query
+      // time counts then, and twice the rows in flight per query-warp shorten a hop (1 M x 768 float32, one call at a
+      // time: 2.39 -> 2.20 ms for 1 query, 3.24 -> 3.06 ms for 512; profiles/r2_latency_by_batch.json)
+      SearchTuning t2 = tn;
+      t2.slots = tn.slots * 2;
+      if (search_slots_supported(t2.slots)) {
+        const int o2 = search_occupancy(ix, ef, t2);
+        if (o2 > 0 && (uint64_t)nq <= (uint64_t)o2 * (uint64_t)h->num_sms) tn = t2;
+      }
+    }
   }
   int occ = search_occupancy(ix, ef, tn);
   if (occ <= 0 && tn.slots != h->tuning.slots) {  // the latency shape does not fit: fall back

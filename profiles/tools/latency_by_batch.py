@@ -2,7 +2,7 @@
 D2H, one stream synchronisation) by batch size, on the benchmark workload (1 M x 768 cosine, M=32, efC=200, ef=128,
 k=10).  The reference answers one query per call (SearchWithScores): nq = 1 is that call served by the GPU alone,
 with no batcher in front.  Prints one JSON line: wall-clock p50 / p99 / mean in ms over CALLS calls per batch size.
-  python profiles/tools/latency_by_batch.py [1,8,64,256,1024]"""
+  python profiles/tools/latency_by_batch.py [1,8,64,256,1024]        (IDLE=4,8,16: repeat per lone-batch launch shape)"""
 import json
 import os
 import sys
@@ -33,7 +33,10 @@ del X
 Q = bench.make_data(torch, 4096, D, 32, 0.1, 4242, dev).cpu().numpy()
 out = {"workload": f"{N}x{D} cosine HNSW M={M} efC={EFC} efSearch={EF} top-{K}; one blocking kdbgpu_search_batch call at a time, pageable host buffers",
        "calls_per_size": CALLS, "by_batch": []}
-for nq in sizes:
+shapes = [int(x) for x in os.environ.get("IDLE", "0").split(",")]  # IDLE=4,8,16: the lone-batch launch shape (row slots)
+for idle, nq in [(a, b) for a in shapes for b in sizes]:
+    if idle:
+        gi.set_idle_slots(idle)
     for i in range(8):
         gi.SearchWithScores(Q[i * nq % 2048:i * nq % 2048 + nq], K, None, EF)
     t = []
@@ -43,7 +46,7 @@ for nq in sizes:
         gi.SearchWithScores(Q[o:o + nq], K, None, EF)
         t.append((time.perf_counter() - t0) * 1e3)
     t = np.array(t)
-    out["by_batch"].append({"nq": nq, "p50_ms": round(float(np.percentile(t, 50)), 3), "p99_ms": round(float(np.percentile(t, 99)), 3),
+    out["by_batch"].append({"idle_slots": idle or "default", "nq": nq, "p50_ms": round(float(np.percentile(t, 50)), 3), "p99_ms": round(float(np.percentile(t, 99)), 3),
                             "mean_ms": round(float(t.mean()), 3), "queries_per_s": round(nq / (t.mean() / 1e3), 1)})
 print(json.dumps(out))
 gi.close()
