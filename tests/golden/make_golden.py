@@ -1,6 +1,8 @@
 """Generates tests/golden/*.npz with the CPU oracle (KDBO_ARITH_KERNEL): a small graph, its stored
 rows, queries and the expected SearchWithScores output.  The GPU parity tests replay these without
-rebuilding anything.  Run from the repo root:  python tests/golden/make_golden.py"""
+rebuilding anything.  These are REGRESSION fixtures written by this repo's own oracle, not vectors the reference
+holds: what pins the oracle to the reference is tests/test_oracle_golden.py (the known answers of the reference's
+own tests).  Run from the repo root:  python tests/golden/make_golden.py"""
 import os
 import sys
 
